@@ -1,0 +1,124 @@
+/* sad_b200.h — C ABI of the B200-native adaptive-distillation hot path (libsad_b200.so).
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All data pointers are DEVICE pointers on
+ * the current CUDA device unless a function name ends in _host.  `stream` is a cudaStream_t passed
+ * as void* (NULL = the legacy default stream).  Every function only ENQUEUES work on `stream` and
+ * never synchronises it (the reference contract: RunOnDevice must not synchronise,
+ * caffe2/caffe2/core/operator.h:373-413), except the *_host entry points, which return when the
+ * host output buffers are valid.
+ *
+ * Return value: 0 on success, SAD_ERR_* (<0) otherwise; sad_last_error() describes the failure for
+ * the calling thread.  There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with SAD_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).  The reference exposes these only as C++ operator classes registered with
+ * REGISTER_CUDA_OPERATOR; the operator library libcaffe2_detectron_ops_gpu.so in this repo keeps
+ * that C++ surface and forwards to this ABI.
+ */
+#ifndef SAD_B200_H_
+#define SAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAD_OK 0
+#define SAD_ERR_INVALID (-1)   /* bad argument (null pointer, shape, D % num_classes, scale < 0 ...) */
+#define SAD_ERR_CUDA (-2)      /* CUDA runtime/driver error, including "no device" */
+#define SAD_ERR_WORKSPACE (-3) /* workspace too small or misaligned */
+#define SAD_ERR_UNSUPPORTED (-4)
+
+#define SAD_MAX_LEVELS 8   /* FPN levels per fused launch (RetinaNet uses 5: P3..P7) */
+#define SAD_MAX_INPUTS 16  /* PowSum inputs per launch */
+
+const char* sad_last_error(void);
+/* "sad_b200 <version> sm_100a" — also proves which library was loaded */
+const char* sad_version(void);
+/* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
+uint64_t sad_launch_count(void);
+
+/* Workspaces.  The kernels below reduce in two stages and need caller-owned scratch (the role of
+ * the reference ops' member tensors losses_ / _buff, loss_op.h:54, pow_sum_op.h:38-40): 256-byte
+ * aligned device memory of at least sad_*_workspace_bytes().  Call sad_workspace_init ONCE after
+ * allocating it; afterwards it can be reused launch after launch by one caller at a time. */
+int sad_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PowSum — replaces PowSumOp<float, CUDAContext>::RunOnDevice
+ *   (caffe2/modules/detectron/pow_sum_op.cu:25-43; argument `power`, pow_sum_op.h:24-41).
+ * out[0] = sum_k sum_j powf(inputs[k][j], power), one fp32 scalar.  One launch for all inputs,
+ * 4 B/element of HBM traffic (the reference makes 1 + 3*n_inputs launches and 12 B/element).
+ * `inputs`/`sizes` are HOST arrays of n_inputs device pointers / element counts.
+ * ------------------------------------------------------------------------------------------ */
+size_t sad_pow_sum_workspace_bytes(const int64_t* sizes, int n_inputs);
+int sad_pow_sum_f32(const float* const* inputs, const int64_t* sizes, int n_inputs, float power,
+                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SigmoidAdaptiveDistillLoss (+Gradient) — replaces
+ *   SigmoidAdaptiveDistillLossOp<float, CUDAContext>::RunOnDevice          (...loss_op.cu:108-141)
+ *   SigmoidAdaptiveDistillLossGradientOp<float, CUDAContext>::RunOnDevice  (...loss_op.cu:144-171)
+ *   and their kernels (...loss_op.cu:28-67, 69-105), file
+ *   caffe2/modules/detectron/sigmoid_adaptive_distillation_loss_op.cu.
+ * One launch covers up to SAD_MAX_LEVELS FPN levels.  Per level, which outputs are non-NULL
+ * selects the work: loss only (the forward op), d_logits only (the gradient op), or both (fused,
+ * 12.05 B/element).  All levels of one call must request the same outputs.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sad_distill_level {
+  const float* logits;       /* X: (N, D = A*num_classes, H, W) fp32, NCHW        [Input(0)] */
+  const float* teacher_prob; /* T: same shape, teacher sigmoid probabilities      [Input(1)] */
+  const int32_t* labels;     /* G: (N, A, H, W) int32; only `!= ignored_label` matters [Input(2)] */
+  float* d_logits;           /* out: dX, same shape as X, or NULL                 [Gradient Output(0)] */
+  float* loss;               /* out: fp32 scalar, or NULL                         [Output(0)] */
+  const float* d_loss;       /* upstream gradient of `loss` (fp32 scalar), NULL = 1.0 [Gradient Input(4)] */
+  int32_t N, D, H, W;
+} sad_distill_level;
+
+typedef struct sad_distill_params {
+  float gamma;            /* arg "gamma", default 1.0 */
+  float alpha;            /* arg "alpha", default 0.25 */
+  float beta;             /* arg "beta", default 0.0 */
+  float scale;            /* arg "scale", default 1.0, must be >= 0 (loss_op.h:38) */
+  int32_t num_classes;    /* arg "num_classes", default 80 */
+  int32_t ignored_label;  /* arg "ignored_label", default -1 */
+} sad_distill_params;
+
+void sad_distill_default_params(sad_distill_params* p);
+size_t sad_distill_workspace_bytes(const sad_distill_level* levels, int n_levels);
+/* normalizer: device fp32, element 0 is read (Input(3): PowSum's output or retnet_fg_num). */
+int sad_distill_f32(const sad_distill_level* levels, int n_levels, const float* normalizer,
+                    const sad_distill_params* params, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole distillation-loss step on HOST buffers (what a host-memory caller of the reference's
+ * operators pays end to end): H2D of teacher probs / logits / labels, PowSum -> normaliser,
+ * fused loss + gradient for every level, D2H of the per-level losses, the normaliser and
+ * (if requested) the gradients.  Copies and kernels are pipelined over internal streams.
+ * The context owns device buffers, streams and events and is reused across calls.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sad_host_level {
+  const float* logits;       /* host, (N, D, H, W) */
+  const float* teacher_prob; /* host, (N, D, H, W) */
+  const int32_t* labels;     /* host, (N, A, H, W) */
+  float* d_logits;           /* host out, may be NULL (gradient stays on the device) */
+  int32_t N, D, H, W;
+} sad_host_level;
+
+typedef struct sad_ctx sad_ctx;
+int sad_ctx_create(int device, sad_ctx** out);
+void sad_ctx_destroy(sad_ctx* ctx);
+/* losses_out: host, n_levels floats.  normalizer_out: host, 1 float (may be NULL). */
+int sad_distill_step_host(sad_ctx* ctx, const sad_host_level* levels, int n_levels, float power,
+                          const sad_distill_params* params, float* losses_out, float* normalizer_out);
+/* device address of level i's gradient from the last sad_distill_step_host call */
+float* sad_ctx_device_d_logits(sad_ctx* ctx, int level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAD_B200_H_ */

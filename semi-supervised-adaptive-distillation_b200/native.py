@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/sad_b200.h.
+
+There is no fallback: if libsad_b200.so is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsad_b200.so")
+OPS_LIB_PATH = os.path.join(HERE, "libcaffe2_detectron_ops_gpu.so")
+
+SAD_MAX_LEVELS = 8
+SAD_MAX_INPUTS = 16
+
+
+class SadError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sad_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class DistillLevel(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("teacher_prob", C.c_void_p), ("labels", C.c_void_p),
+                ("d_logits", C.c_void_p), ("loss", C.c_void_p), ("d_loss", C.c_void_p),
+                ("N", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class DistillParams(C.Structure):
+    _fields_ = [("gamma", C.c_float), ("alpha", C.c_float), ("beta", C.c_float), ("scale", C.c_float),
+                ("num_classes", C.c_int32), ("ignored_label", C.c_int32)]
+
+
+class HostLevel(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("teacher_prob", C.c_void_p), ("labels", C.c_void_p),
+                ("d_logits", C.c_void_p),
+                ("N", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded libsad_b200.so (built in-tree by build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libsad_b200.so is missing (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or semi-supervised-adaptive-distillation_b200/build.py; there is no non-CUDA fallback." % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.sad_last_error.restype = C.c_char_p
+        l.sad_version.restype = C.c_char_p
+        l.sad_launch_count.restype = C.c_uint64
+        l.sad_workspace_init.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_pow_sum_workspace_bytes.restype = C.c_size_t
+        l.sad_pow_sum_workspace_bytes.argtypes = [C.POINTER(C.c_int64), C.c_int]
+        l.sad_pow_sum_f32.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_distill_default_params.argtypes = [C.POINTER(DistillParams)]
+        l.sad_distill_default_params.restype = None
+        l.sad_distill_workspace_bytes.restype = C.c_size_t
+        l.sad_distill_workspace_bytes.argtypes = [C.POINTER(DistillLevel), C.c_int]
+        l.sad_distill_f32.argtypes = [C.POINTER(DistillLevel), C.c_int, C.c_void_p, C.POINTER(DistillParams),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        l.sad_ctx_destroy.argtypes = [C.c_void_p]
+        l.sad_ctx_destroy.restype = None
+        l.sad_distill_step_host.argtypes = [C.c_void_p, C.POINTER(HostLevel), C.c_int, C.c_float,
+                                            C.POINTER(DistillParams), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        l.sad_ctx_device_d_logits.restype = C.c_void_p
+        l.sad_ctx_device_d_logits.argtypes = [C.c_void_p, C.c_int]
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SadError(rc, lib().sad_last_error().decode())
+
+
+def default_params(**kw):
+    p = DistillParams()
+    lib().sad_distill_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown distillation argument %r" % k)
+        setattr(p, k, v)
+    return p

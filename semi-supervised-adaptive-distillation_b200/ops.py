@@ -1,0 +1,188 @@
+"""torch-tensor convenience layer over the C ABI (torch supplies device memory and streams only).
+
+Every function enqueues on torch's current CUDA stream and returns device tensors; nothing here
+computes on the CPU and nothing falls back if the CUDA library is unavailable.
+"""
+import ctypes as C
+
+import torch
+
+from . import native
+from .native import DistillLevel, DistillParams, HostLevel, check, default_params, lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise ValueError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous (NCHW)" % name)
+
+
+class Workspace:
+    """Caller-owned kernel scratch (see include/sad_b200.h: sad_workspace_init)."""
+
+    def __init__(self, nbytes, device):
+        nbytes = max(256, (int(nbytes) + 255) // 256 * 256)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        assert self.buf.data_ptr() % 256 == 0
+        check(lib().sad_workspace_init(C.c_void_p(self.buf.data_ptr()), nbytes, _stream()))
+        self.nbytes = nbytes
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.buf.data_ptr())
+
+
+def pow_sum_workspace(tensors):
+    sizes = (C.c_int64 * len(tensors))(*[t.numel() for t in tensors])
+    return Workspace(lib().sad_pow_sum_workspace_bytes(sizes, len(tensors)), tensors[0].device)
+
+
+def pow_sum(tensors, power=1.0, out=None, workspace=None):
+    """PowSum operator: scalar sum of x**power over all inputs (reference pow_sum_op.cu:25-43)."""
+    tensors = list(tensors)
+    if not 1 <= len(tensors) <= native.SAD_MAX_INPUTS:
+        raise ValueError("PowSum takes 1..%d inputs" % native.SAD_MAX_INPUTS)
+    for i, t in enumerate(tensors):
+        _require_cuda(t, torch.float32, "input %d" % i)
+    if out is None:
+        out = torch.empty((), dtype=torch.float32, device=tensors[0].device)
+    if workspace is None:
+        workspace = pow_sum_workspace(tensors)
+    ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    sizes = (C.c_int64 * len(tensors))(*[t.numel() for t in tensors])
+    check(lib().sad_pow_sum_f32(ptrs, sizes, len(tensors), float(power), C.c_void_p(out.data_ptr()),
+                                workspace.ptr, workspace.nbytes, _stream()))
+    return out
+
+
+def _levels_struct(levels, want_loss, want_grad, d_loss):
+    n = len(levels)
+    arr = (DistillLevel * n)()
+    losses, grads = [], []
+    for i, (x, t, g) in enumerate(levels):
+        _require_cuda(x, torch.float32, "logits[%d]" % i)
+        _require_cuda(t, torch.float32, "teacher_prob[%d]" % i)
+        _require_cuda(g, torch.int32, "labels[%d]" % i)
+        if x.dim() != 4 or t.shape != x.shape:
+            raise ValueError("logits/teacher_prob must be 4-D of equal shape")
+        L = arr[i]
+        L.logits, L.teacher_prob, L.labels = x.data_ptr(), t.data_ptr(), g.data_ptr()
+        L.N, L.D, L.H, L.W = x.shape
+        if want_loss:
+            losses.append(torch.empty((), dtype=torch.float32, device=x.device))
+            L.loss = losses[-1].data_ptr()
+        if want_grad:
+            grads.append(torch.empty_like(x))
+            L.d_logits = grads[-1].data_ptr()
+            if d_loss is not None:
+                dl = d_loss[i] if isinstance(d_loss, (list, tuple)) else d_loss
+                _require_cuda(dl, torch.float32, "d_loss")
+                L.d_loss = dl.data_ptr()
+    return arr, losses, grads
+
+
+def distill_workspace(levels):
+    arr, _, _ = _levels_struct(levels, False, False, None)
+    return Workspace(lib().sad_distill_workspace_bytes(arr, len(levels)), levels[0][0].device)
+
+
+def distill(levels, normalizer, want_loss=True, want_grad=True, d_loss=None, workspace=None, **args):
+    """SigmoidAdaptiveDistillLoss and/or its gradient for a list of (logits, teacher_prob, labels)
+    levels in one launch.  Returns (losses, d_logits) lists (empty when not requested).
+    Keyword args are the operator arguments: gamma, alpha, beta, scale, num_classes, ignored_label."""
+    levels = list(levels)
+    params = default_params(**args)
+    _require_cuda(normalizer, torch.float32, "normalizer")
+    arr, losses, grads = _levels_struct(levels, want_loss, want_grad, d_loss)
+    if want_loss and workspace is None:
+        workspace = distill_workspace(levels)
+    wptr, wbytes = (workspace.ptr, workspace.nbytes) if workspace is not None else (None, 0)
+    check(lib().sad_distill_f32(arr, len(levels), C.c_void_p(normalizer.data_ptr()), C.byref(params), wptr, wbytes,
+                                _stream()))
+    return losses, grads
+
+
+class DistillPlan:
+    """Pre-bound PowSum + fused multi-level loss+grad for fixed device tensors: the launch
+    descriptors are built once so the timed loop only enqueues two kernels."""
+
+    def __init__(self, levels, power=1.8, **args):
+        self.levels = list(levels)
+        self.params = default_params(**args)
+        dev = self.levels[0][0].device
+        self.teacher = [t for (_, t, _) in self.levels]
+        n = len(self.levels)
+        self.power = float(power)
+        self.normalizer = torch.empty((), dtype=torch.float32, device=dev)
+        self.arr, self.losses, self.grads = _levels_struct(self.levels, True, True, None)
+        self.ws_pow = pow_sum_workspace(self.teacher)
+        self.ws_dist = distill_workspace(self.levels)
+        self._ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in self.teacher])
+        self._sizes = (C.c_int64 * n)(*[t.numel() for t in self.teacher])
+        self.n = n
+
+    def run(self):
+        st = _stream()
+        l = lib()
+        check(l.sad_pow_sum_f32(self._ptrs, self._sizes, self.n, self.power, C.c_void_p(self.normalizer.data_ptr()),
+                                self.ws_pow.ptr, self.ws_pow.nbytes, st))
+        check(l.sad_distill_f32(self.arr, self.n, C.c_void_p(self.normalizer.data_ptr()), C.byref(self.params),
+                                self.ws_dist.ptr, self.ws_dist.nbytes, st))
+
+    def run_pow_sum(self):
+        check(lib().sad_pow_sum_f32(self._ptrs, self._sizes, self.n, self.power,
+                                    C.c_void_p(self.normalizer.data_ptr()), self.ws_pow.ptr, self.ws_pow.nbytes, _stream()))
+
+    def run_distill(self):
+        check(lib().sad_distill_f32(self.arr, self.n, C.c_void_p(self.normalizer.data_ptr()), C.byref(self.params),
+                                    self.ws_dist.ptr, self.ws_dist.nbytes, _stream()))
+
+
+class HostStep:
+    """sad_distill_step_host: the whole loss step on HOST (ideally pinned) tensors."""
+
+    def __init__(self, device=0):
+        self.handle = C.c_void_p()
+        check(lib().sad_ctx_create(int(device), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            lib().sad_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bind(self, levels, grads_out, power=1.8, **args):
+        """levels: [(logits, teacher_prob, labels)] CPU tensors; grads_out: CPU tensors or None."""
+        n = len(levels)
+        self._keep = (levels, grads_out)
+        self._arr = (HostLevel * n)()
+        for i, (x, t, g) in enumerate(levels):
+            for name, ten, dt in (("logits", x, torch.float32), ("teacher_prob", t, torch.float32), ("labels", g, torch.int32)):
+                if ten.is_cuda or ten.dtype != dt or not ten.is_contiguous():
+                    raise ValueError("%s[%d] must be a contiguous CPU %s tensor" % (name, i, dt))
+            L = self._arr[i]
+            L.logits, L.teacher_prob, L.labels = x.data_ptr(), t.data_ptr(), g.data_ptr()
+            L.d_logits = grads_out[i].data_ptr() if grads_out is not None else None
+            L.N, L.D, L.H, L.W = x.shape
+        self._n = n
+        self._power = float(power)
+        self._params = default_params(**args)
+        self._losses = (C.c_float * n)()
+        self._norm = C.c_float()
+
+    def run(self):
+        check(lib().sad_distill_step_host(self.handle, self._arr, self._n, self._power, C.byref(self._params),
+                                          self._losses, C.byref(self._norm)))
+        return list(self._losses), self._norm.value

@@ -1,0 +1,141 @@
+"""CPU: host logic of the operator boundary — registration under the reference's names, schema
+arity, argument typing, gradient maker, NetDef text round trip, graph wiring and the fusion pass.
+No kernels run here."""
+import numpy as np
+import pytest
+
+from sad_b200 import c2, retinanet_heads
+
+
+@pytest.fixture(scope="module")
+def oplib():
+    return c2.OperatorLibrary()
+
+
+def test_operators_registered_under_reference_names(oplib):
+    # reference: pow_sum_op.cc:22-24, pow_sum_op.cu:45-46, ...loss_op.cc:21-24, ...loss_op.cu:174-177
+    for dev in (c2.CPU, c2.CUDA):
+        for name in ("PowSum", "SigmoidAdaptiveDistillLoss", "SigmoidAdaptiveDistillLossGradient"):
+            assert oplib.HasOperator(name, dev), (name, dev)
+    assert oplib.HasOperator("SigmoidAdaptiveDistillLossMultiLevel", c2.CUDA)
+
+
+def test_schema_arity_matches_reference(oplib):
+    assert oplib.SchemaArity("PowSum")[0] == 1 and oplib.SchemaArity("PowSum")[2:] == (1, 1)
+    assert oplib.SchemaArity("SigmoidAdaptiveDistillLoss") == (4, 4, 1, 1)
+    assert oplib.SchemaArity("SigmoidAdaptiveDistillLossGradient") == (5, 5, 1, 1)
+
+
+def test_schema_violation_is_an_enforce_failure(oplib):
+    ws = oplib.Workspace()
+    ws.FeedBlob("a", np.zeros((1, 4, 2, 2), np.float32))
+    op = c2.CreateOperator("SigmoidAdaptiveDistillLoss", ["a", "a", "a"], ["l"])  # 3 inputs, needs 4
+    with pytest.raises(c2.EnforceNotMet, match="schema"):
+        ws.RunOperatorOnce(op)
+
+
+def test_missing_input_blob_names_the_blob(oplib):
+    ws = oplib.Workspace()
+    op = c2.CreateOperator("PowSum", ["nope"], ["s"])
+    with pytest.raises(c2.EnforceNotMet, match="nope"):
+        ws.RunOperatorOnce(op)
+
+
+def test_cpu_operators_are_not_implemented_like_the_reference(oplib):
+    # pow_sum_op.h:33-36, ...loss_op.h:42-45: REGISTER_CPU_OPERATOR exists, RunOnDevice throws
+    ws = oplib.Workspace()
+    ws.FeedBlob("x", np.ones((1, 4, 2, 2), np.float32))
+    with pytest.raises(c2.EnforceNotMet, match="Not Implemented"):
+        ws.RunOperatorOnce(c2.CreateOperator("PowSum", ["x"], ["s"], power=1.8))
+    ws.FeedBlob("g", np.zeros((1, 1, 2, 2), np.int32))
+    ws.FeedBlob("wp", np.ones((1,), np.float32))
+    with pytest.raises(c2.EnforceNotMet, match="Not Implemented"):
+        ws.RunOperatorOnce(c2.CreateOperator("SigmoidAdaptiveDistillLoss", ["x", "x", "g", "wp"], ["l"], num_classes=4))
+
+
+def test_argument_fields_are_type_strict(oplib):
+    # proto_utils.cc:263-267: a float argument stored in `i` fails
+    ws = oplib.Workspace()
+    ws.FeedBlob("x", np.ones((4,), np.float32))
+    with pytest.raises(c2.EnforceNotMet, match="power"):
+        ws.RunOperatorOnce('input: "x" output: "s" type: "PowSum" arg { name: "power" i: 2 }')
+
+
+def test_negative_scale_rejected_at_construction(oplib):
+    ws = oplib.Workspace()
+    ws.FeedBlob("x", np.ones((1, 4, 2, 2), np.float32))
+    ws.FeedBlob("g", np.zeros((1, 1, 2, 2), np.int32))
+    ws.FeedBlob("wp", np.ones((1,), np.float32))
+    with pytest.raises(c2.EnforceNotMet, match="scale"):
+        ws.RunOperatorOnce(c2.CreateOperator("SigmoidAdaptiveDistillLoss", ["x", "x", "g", "wp"], ["l"], scale=-1.0))
+
+
+def test_gradient_maker_matches_reference(oplib):
+    # ...loss_op.cc:99-110: {I0, I1, I2, I3, GO0} -> {GI0}, arguments copied from the forward def
+    dev = c2.DeviceOption(c2.CUDA, 3)
+    op = c2.CreateOperator("SigmoidAdaptiveDistillLoss", ["X", "T", "G", "wp"], ["loss"], device_option=dev,
+                           gamma=2.0, alpha=0.5, scale=0.125, beta=0.0, num_classes=80, ignored_label=-1)
+    text = oplib.GetGradientDefs(op, ["loss_grad"])
+    assert 'type: "SigmoidAdaptiveDistillLossGradient"' in text
+    ins = [l.split('"')[1] for l in text.splitlines() if l.strip().startswith("input:")]
+    outs = [l.split('"')[1] for l in text.splitlines() if l.strip().startswith("output:")]
+    assert ins == ["X", "T", "G", "wp", "loss_grad"] and outs == ["X_grad"]
+    assert "cuda_gpu_id: 3" in text and "is_gradient_op: true" in text
+    for frag in ('name: "gamma"', "f: 2", 'name: "scale"', "f: 0.125", 'name: "num_classes"', "i: 80"):
+        assert frag in text
+    # only the student logits get a gradient (teacher probs, labels, normaliser do not)
+    assert [l.split('"')[1] for l in text.splitlines() if l.startswith("external_output")] == ["X_grad", "", "", ""]
+    with pytest.raises(c2.EnforceNotMet, match="PowSum"):
+        oplib.GetGradientDefs(c2.CreateOperator("PowSum", ["a"], ["s"]), ["s_grad"])  # no gradient registered
+
+
+def test_netdef_text_round_trip(oplib):
+    net, losses, grads = retinanet_heads.add_distill_loss(gpu_id=2, num_gpus=8)
+    text = net.to_text()
+    norm = oplib.NormalizeNetText(text)
+    assert oplib.NormalizeNetText(norm) == norm
+    assert norm.count("op {") == 1 + 5 + 5 + 5
+    assert 'f: 0.125' in norm  # scale = T^2 / NUM_GPUS (retinanet_heads.py:342)
+    assert 'f: 1.79999995' in norm or 'f: 1.8' in norm
+    with pytest.raises(c2.EnforceNotMet):
+        oplib.NormalizeNetText("op { type: \"X\" ")
+
+
+def test_graph_wiring_matches_reference_names():
+    net, losses, grads = retinanet_heads.add_distill_loss(gpu_id=0, num_gpus=1)
+    ps = net.op[0]
+    assert ps.type == "PowSum" and ps.output == ["gpu_0/distill_normalizer"]
+    assert ps.input == ["gpu_0/teacher/retnet_cls_prob_fpn%d" % l for l in range(3, 8)]
+    assert abs(ps.arg["power"] - 1.8) < 1e-12
+    l3 = net.op[1]
+    assert l3.type == "SigmoidAdaptiveDistillLoss"
+    assert l3.input == ["gpu_0/retnet_cls_pred_fpn3", "gpu_0/teacher/retnet_cls_prob_fpn3",
+                        "gpu_0/retnet_cls_labels_fpn3", "gpu_0/distill_normalizer"]
+    assert l3.arg == dict(gamma=2.0, alpha=0.5, scale=1.0, beta=0.0, num_classes=80, ignored_label=-1)
+    assert losses == ["gpu_0/fl_distill_fpn%d" % l for l in range(3, 8)]
+    assert grads == ["gpu_0/retnet_cls_pred_fpn%d_grad" % l for l in range(3, 8)]
+    # without the adaptive normaliser the foreground count is the normaliser (retinanet_heads.py:337)
+    net2, _, _ = retinanet_heads.add_distill_loss(cfg=dict(ADAPTIVE_NORMALIZER=False))
+    assert net2.op[0].type == "SigmoidAdaptiveDistillLoss" and net2.op[0].input[3] == "gpu_0/retnet_fg_num"
+
+
+def test_fusion_pass_groups_levels(oplib):
+    net, losses, grads = retinanet_heads.add_distill_loss(gpu_id=1, num_gpus=8)
+    fused, n = oplib.FuseAdaptiveDistillOps(net.to_text())
+    assert n == 1
+    assert fused.count('type: "SigmoidAdaptiveDistillLossMultiLevel"') == 1
+    assert fused.count('type: "SigmoidAdaptiveDistillLoss"') == 0
+    assert fused.count('type: "SigmoidAdaptiveDistillLossGradient"') == 0
+    assert fused.count('type: "PowSum"') == 1 and fused.count('type: "ConstantFill"') == 5
+    for b in losses + grads:  # blob names preserved
+        assert 'output: "%s"' % b in fused
+    # PowSum still precedes the fused op, which precedes the ConstantFills
+    assert fused.index("PowSum") < fused.index("MultiLevel") < fused.index("ConstantFill")
+    # different arguments -> not fusable
+    net.op[2].arg["alpha"] = 0.25
+    fused2, n2 = oplib.FuseAdaptiveDistillOps(net.to_text())
+    assert fused2.count('type: "SigmoidAdaptiveDistillLoss"') >= 1
+    # forward-only nets are left alone
+    net3, _, _ = retinanet_heads.add_distill_loss(with_gradients=False)
+    fused3, n3 = oplib.FuseAdaptiveDistillOps(net3.to_text())
+    assert n3 == 0 and fused3.count('type: "SigmoidAdaptiveDistillLoss"') == 5
