@@ -139,3 +139,14 @@ def test_oracle_matches_reference_cuda_ops_run_on_b200(oracle, name):
     grad = oracle.distill_grad(x, t, g, wp, d_loss=float(KAT[name + "_dloss"]), **a)
     assert_loss_close(loss, ref[name + "_loss"], "oracle vs reference loss")
     assert_grad_close(grad, ref[name + "_grad"], "oracle vs reference grad")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="reference-on-B200 vectors not generated yet")
+@pytest.mark.parametrize("power", [1.0, 1.8, 2.0, 3.0])
+def test_pow_sum_oracle_matches_reference_cuda_op_run_on_b200(oracle, power):
+    # the oracle follows the reference's fp32 summation ORDER (math_gpu.cu:1023-1057), so it agrees with
+    # the reference op run on the GPU to a few ulp (libm powf vs libdevice powf)
+    ref = np.load(REF_GPU)
+    ins = [KAT["ps_in%d" % i] for i in range(3)]
+    got = oracle.pow_sum(ins, power)
+    assert abs(got - float(ref["ps_%g" % power])) <= 2e-6 * abs(float(ref["ps_%g" % power]))
