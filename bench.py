@@ -290,7 +290,7 @@ def main():
                    "args": HEAD, "power": POWER,
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2; one step touches 236 MB" % (NSETS, NSETS * 3 * elements * 4 / 1e6),
                    "parallelism": "image-sharded x%d, no data-path collective" % world},
-        "roofline": {"bound": "hbm", "kernel": "distill_kernel<4,fast,loss,grad> (fused 5-level loss+grad)",
+        "roofline": {"bound": "hbm", "kernel": "distill_ring_kernel<fast,alpha=.5,loss,grad> (persistent TMA-ring, fused 5-level loss+grad)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic_per_launch(), "algorithmic_bytes_per_launch": BYTES_PER_ELEMENT * elements,
                      "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step},

@@ -22,128 +22,11 @@
 #include <cstdio>
 #include <string>
 
+#include "distill_math.cuh"
 #include "sad_b200.h"
 #include "sad_internal.h"
 
 namespace sad {
-
-// -------------------------------------------------------------------------------------------
-// small device helpers
-// -------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// streaming 128-bit load: read-only path, do not allocate in L1 (every X/T byte is used once)
-__device__ __forceinline__ float4 ld_stream4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float ld_stream1(const float* p) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// Sum of one value per thread over the CTA; result valid in thread 0.  kThreads % 32 == 0.
-template <int kThreads, typename T>
-__device__ __forceinline__ T block_sum(T v, T* smem /* kThreads/32 entries */) {
-  constexpr int kWarps = kThreads / 32;
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) smem[warp] = v;
-  __syncthreads();
-  T r = 0;
-  if (warp == 0) {
-    r = lane < kWarps ? smem[lane] : T(0);
-    r = warp_sum(r);
-  }
-  __syncthreads();
-  return r;
-}
-
-// -------------------------------------------------------------------------------------------
-// per-element math
-// -------------------------------------------------------------------------------------------
-// Given logit x and teacher probability pt, produce (both WITHOUT the ignore mask, 1/Np, scale):
-//   li = -AT^gamma * DLoss          (>= 0; the loss summand is li * keep / Np)
-//   g  = d*gamma*AT^(gamma-1)*E*DLoss - AT^gamma*g2   (the gradient is g * keep * d_loss / Np)
-// with, as in ...loss_op.cu:54-64 / :88-99,
-//   e = exp(-|x|), L = log(1+e), p = sigmoid(x), DL = -x*(pt-[x>=0]) + L + beta*(-H(pt)),
-//   E = exp(-DL), AT = 1-E, DLoss = alpha*pt*log(max(FLT_MIN,p)) + (1-alpha)(1-pt)*log(1-p),
-//   d = pt-p, g2 = alpha*d - (1-2alpha)(1-pt)p.
-// kFast = (gamma == 2 && beta == 0): 4 MUFU (ex2, lg2, rcp, ex2), no powf.  The beta term is
-// dropped from the arithmetic but its NaN is kept: the reference evaluates
-// beta*(pt*logf(pt)+(1-pt)*logf(1-pt)) even for beta == 0, which is NaN unless 0 < pt < 1.
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kLogFltMin = -87.33654475055310898657f;  // logf(FLT_MIN)
-
-template <bool kFast, bool kLoss, bool kGrad>
-__device__ __forceinline__ void distill_elem(float x, float pt, float gamma, float alpha, float beta,
-                                             float one_m_alpha, float one_m_2alpha, float& li, float& g) {
-  const float e = ex2_approx(-fabsf(x) * kLog2e);
-  const float u = 1.f + e;
-  const float L = lg2_approx(u) * kLn2;
-  const float mx = fmaxf(x, 0.f);
-  const float logp = fmaxf((x - mx) - L, kLogFltMin);
-  const float lq = -(mx + L);
-  float DL = fmaf(-x, pt, mx) + L;
-  const float q = 1.f - pt;
-  if (kFast) {
-    DL = (pt > 0.f && pt < 1.f) ? DL : __int_as_float(0x7fffffff);
-  } else {
-    DL += beta * (pt * logf(pt) + q * logf(q));
-  }
-  const float E = ex2_approx(-DL * kLog2e);
-  const float AT = 1.f - E;
-  const float DLoss = fmaf(alpha, pt * logp, one_m_alpha * (q * lq));
-  if (kFast) {
-    if (kLoss) li = -(AT * AT) * DLoss;
-    if (kGrad) {
-      const float r = rcp_approx(u);
-      const float p = x >= 0.f ? r : e * r;
-      const float d = pt - p;
-      const float g2 = fmaf(alpha, d, -one_m_2alpha * (q * p));
-      g = AT * fmaf(2.f * d * E, DLoss, -AT * g2);
-    }
-  } else {
-    const float atg = powf(AT, gamma);
-    if (kLoss) li = -atg * DLoss;
-    if (kGrad) {
-      const float r = rcp_approx(u);
-      const float p = x >= 0.f ? r : e * r;
-      const float d = pt - p;
-      const float g2 = fmaf(alpha, d, -one_m_2alpha * (q * p));
-      g = d * gamma * powf(AT, gamma - 1.f) * E * DLoss - atg * g2;
-    }
-  }
-}
 
 // -------------------------------------------------------------------------------------------
 // fused multi-level loss + gradient
@@ -460,7 +343,9 @@ static int pow_sum_plan(const int64_t* sizes, int n_inputs, uint32_t* begin, uin
 SAD_EXPORT size_t sad_pow_sum_workspace_bytes(const int64_t* sizes, int n_inputs) {
   uint32_t b[SAD_MAX_INPUTS], e[SAD_MAX_INPUTS], total = 0;
   if (pow_sum_plan(sizes, n_inputs, b, e, &total) != SAD_OK) return 0;
-  return 256 + (size_t)(total ? total : 1) * sizeof(float);
+  const size_t simt = (size_t)(total ? total : 1) * sizeof(float);
+  const size_t ring = (size_t)kMaxRingCtas * SAD_MAX_INPUTS * sizeof(float);
+  return 256 + (simt > ring ? simt : ring);
 }
 
 SAD_EXPORT int sad_pow_sum_f32(const float* const* inputs, const int64_t* sizes, int n_inputs, float power,
@@ -479,6 +364,8 @@ SAD_EXPORT int sad_pow_sum_f32(const float* const* inputs, const int64_t* sizes,
   if (total == 0) {  // every input empty: the reference's running sum stays 0
     return check_cuda(cudaMemsetAsync(out, 0, sizeof(float), st), "PowSum memset");
   }
+  if (pow_sum_ring_supported(inputs, sizes, n_inputs))  // 16-byte aligned inputs: persistent TMA ring
+    return launch_pow_sum_ring(inputs, sizes, n_inputs, power, out, workspace, workspace_bytes, st);
   const size_t need = 256 + (size_t)total * sizeof(float);
   if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return set_error(SAD_ERR_WORKSPACE, "PowSum: workspace must be 256-byte aligned and >= sad_pow_sum_workspace_bytes()");
@@ -550,7 +437,9 @@ SAD_EXPORT size_t sad_distill_workspace_bytes(const sad_distill_level* levels, i
     // a tile covers >= 1 class x up to kThreads rows; rows*classes <= elems, plus ragged last tiles
     tiles += elems / kThreads + (uint64_t)levels[l].D + 1;
   }
-  return 256 + (size_t)tiles * sizeof(float);
+  const size_t simt = (size_t)tiles * sizeof(float);
+  const size_t ring = (size_t)kMaxRingCtas * SAD_MAX_LEVELS * sizeof(float);
+  return 256 + (simt > ring ? simt : ring);
 }
 
 SAD_EXPORT int sad_distill_f32(const sad_distill_level* levels, int n_levels, const float* normalizer,
@@ -586,6 +475,9 @@ SAD_EXPORT int sad_distill_f32(const sad_distill_level* levels, int n_levels, co
       }
     return SAD_OK;
   }
+
+  if (vec == 4 && distill_ring_supported(levels, n_levels, params->num_classes))  // persistent TMA ring
+    return launch_distill_ring(levels, n_levels, normalizer, params, workspace, workspace_bytes, st);
 
   DistillArgs a{};
   uint32_t tiles = 0;

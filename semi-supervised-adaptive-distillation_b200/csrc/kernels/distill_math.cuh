@@ -1,0 +1,240 @@
+// Per-element arithmetic and reduction helpers shared by the SIMT kernels (distill_kernels.cu) and the
+// persistent bulk-copy-ring kernels (distill_ring.cu).
+#ifndef SAD_DISTILL_MATH_CUH_
+#define SAD_DISTILL_MATH_CUH_
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace sad {
+
+// -------------------------------------------------------------------------------------------
+// small device helpers
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// streaming 128-bit load: read-only path, do not allocate in L1 (every X/T byte is used once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum of one value per thread over the CTA; result valid in thread 0.  kThreads % 32 == 0.
+template <int kThreads, typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* kThreads/32 entries */) {
+  constexpr int kWarps = kThreads / 32;
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T r = 0;
+  if (warp == 0) {
+    r = lane < kWarps ? smem[lane] : T(0);
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// -------------------------------------------------------------------------------------------
+// per-element math
+// -------------------------------------------------------------------------------------------
+// Given logit x and teacher probability pt, produce (both WITHOUT the ignore mask, 1/Np, scale):
+//   li = -AT^gamma * DLoss          (>= 0; the loss summand is li * keep / Np)
+//   g  = d*gamma*AT^(gamma-1)*E*DLoss - AT^gamma*g2   (the gradient is g * keep * d_loss / Np)
+// with, as in ...loss_op.cu:54-64 / :88-99,
+//   e = exp(-|x|), L = log(1+e), p = sigmoid(x), DL = -x*(pt-[x>=0]) + L + beta*(-H(pt)),
+//   E = exp(-DL), AT = 1-E, DLoss = alpha*pt*log(max(FLT_MIN,p)) + (1-alpha)(1-pt)*log(1-p),
+//   d = pt-p, g2 = alpha*d - (1-2alpha)(1-pt)p.
+// kFast = (gamma == 2 && beta == 0): 4 MUFU (ex2, lg2, rcp, ex2), no powf.  The beta term is
+// dropped from the arithmetic but its NaN is kept: the reference evaluates
+// beta*(pt*logf(pt)+(1-pt)*logf(1-pt)) even for beta == 0, which is NaN unless 0 < pt < 1.
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kLogFltMin = -87.33654475055310898657f;  // logf(FLT_MIN)
+
+template <bool kFast, bool kLoss, bool kGrad>
+__device__ __forceinline__ void distill_elem(float x, float pt, float gamma, float alpha, float beta,
+                                             float one_m_alpha, float one_m_2alpha, float& li, float& g) {
+  const float e = ex2_approx(-fabsf(x) * kLog2e);
+  const float u = 1.f + e;
+  const float L = lg2_approx(u) * kLn2;
+  const float mx = fmaxf(x, 0.f);
+  const float logp = fmaxf((x - mx) - L, kLogFltMin);
+  const float lq = -(mx + L);
+  float DL = fmaf(-x, pt, mx) + L;
+  const float q = 1.f - pt;
+  if (kFast) {
+    DL = (pt > 0.f && pt < 1.f) ? DL : __int_as_float(0x7fffffff);
+  } else {
+    DL += beta * (pt * logf(pt) + q * logf(q));
+  }
+  const float E = ex2_approx(-DL * kLog2e);
+  const float AT = 1.f - E;
+  const float DLoss = fmaf(alpha, pt * logp, one_m_alpha * (q * lq));
+  if (kFast) {
+    if (kLoss) li = -(AT * AT) * DLoss;
+    if (kGrad) {
+      const float r = rcp_approx(u);
+      const float p = x >= 0.f ? r : e * r;
+      const float d = pt - p;
+      const float g2 = fmaf(alpha, d, -one_m_2alpha * (q * p));
+      g = AT * fmaf(2.f * d * E, DLoss, -AT * g2);
+    }
+  } else {
+    const float atg = powf(AT, gamma);
+    if (kLoss) li = -atg * DLoss;
+    if (kGrad) {
+      const float r = rcp_approx(u);
+      const float p = x >= 0.f ? r : e * r;
+      const float d = pt - p;
+      const float g2 = fmaf(alpha, d, -one_m_2alpha * (q * p));
+      g = d * gamma * powf(AT, gamma - 1.f) * E * DLoss - atg * g2;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// lean fast path (gamma == 2, beta == 0), base-2 logs: 4 MUFU + ~29 FP32 instructions per element
+// for loss + gradient with alpha == 0.5 (the headline configs), ~33 for general alpha.
+//   x2 = x*log2(e), e = 2^-|x2|, l = log2(1+e), a0 = log2 p, b = log2(1-p)
+//   S  = pt*a0 + (1-pt)*b = -DL*log2(e)  ->  E = 2^S = exp(-DL), AT = 1-E
+//   D2 = 2*DLoss = 2*ln2*(alpha*pt*a + (1-alpha)*(1-pt)*b),  a = max(a0, log2 FLT_MIN)  (...loss_op.cu:63)
+//   acc2 += -(AT^2)*D2*keep            (twice the loss summand; the caller halves the total)
+//   g    = AT*(d*E*D2 - AT*g2),  d = pt-p,  g2 = alpha*d - (1-2alpha)(1-pt)p   (...loss_op.cu:97-99)
+// a0 and b are formed from max(x2,0) separately (not b = a0 - x2) so neither cancels.
+struct FastConsts {
+  float ca2;   // 2*alpha*ln2
+  float cb2;   // 2*(1-alpha)*ln2
+  float alpha;
+  float om2a;  // 1 - 2*alpha
+};
+
+template <bool kAlphaHalf, bool kLoss, bool kGrad>
+__device__ __forceinline__ void distill_elem_fast(float x, float pt, float keep, float kk, const FastConsts& k,
+                                                  float& acc2, float& gout) {
+  const float x2 = x * kLog2e;
+  const float e = ex2_approx(-fabsf(x2));
+  const float u = 1.f + e;
+  const float l = lg2_approx(u);
+  const float mx = fmaxf(x2, 0.f);
+  const float a0 = (x2 - mx) - l;
+  const float b = -(mx + l);
+  const float q = 1.f - pt;
+  const float B = q * b;
+  float S = fmaf(pt, a0, B);
+  // the reference evaluates beta*(pt*logf(pt)+(1-pt)*logf(1-pt)) even for beta == 0: NaN unless 0 < pt < 1
+  S = (pt > 0.f && pt < 1.f) ? S : __int_as_float(0x7fffffff);
+  const float E = ex2_approx(S);
+  const float AT = 1.f - E;
+  const float a = fmaxf(a0, -126.f);
+  float D2;
+  if (kAlphaHalf) D2 = kLn2 * fmaf(pt, a, B);
+  else D2 = fmaf(k.ca2 * pt, a, k.cb2 * B);
+  if (kLoss) acc2 = fmaf(-(AT * AT) * D2, keep, acc2);  // NaN * 0 stays NaN, like the reference's `* (t != ignored)`
+  if (kGrad) {
+    const float r = rcp_approx(u);
+    const float p = x >= 0.f ? r : e * r;
+    const float d = pt - p;
+    float g;
+    if (kAlphaHalf) {
+      g = (AT * d) * fmaf(E, D2, -0.5f * AT);
+    } else {
+      const float g2 = fmaf(k.alpha, d, -k.om2a * (q * p));
+      g = AT * fmaf(d * E, D2, -AT * g2);
+    }
+    gout = g * kk;
+  }
+}
+
+// Sum over a group of kThreads threads that share named barrier `bar_id`; result valid in the group's thread 0.
+template <int kThreads, typename T>
+__device__ __forceinline__ T group_sum(T v, T* smem, int tid, uint32_t bar_id) {
+  constexpr int kWarps = kThreads / 32;
+  v = warp_sum(v);
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) smem[warp] = v;
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kThreads) : "memory");
+  T r = 0;
+  if (warp == 0) {
+    r = lane < kWarps ? smem[lane] : T(0);
+    r = warp_sum(r);
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kThreads) : "memory");
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-stage deterministic reduction tail shared by the ring kernels.
+// Stage 1: every CTA publishes kSlots sums (from shared memory) and takes a ticket.
+// Stage 2: the CTA holding the last ticket adds the published values per slot in a fixed order
+// (lane-strided over CTA index, then a butterfly), one WARP PER SLOT in parallel, in fp64.
+// The first version of this tail walked the slots one after the other with two block barriers and
+// block-wide fp64 shuffles each: ~12 k cycles (6 us) during which 147 SMs idled (ncu r01c:
+// sm__cycles_active max 89.6 k vs avg 77.6 k of 97.6 k elapsed).
+// ---------------------------------------------------------------------------------------------
+template <int kSlots>
+__device__ __forceinline__ bool publish_and_ticket(const float* vals_smem, float* partials, unsigned int* counter,
+                                                   bool* is_last_smem) {
+  __syncthreads();  // vals_smem complete
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    if (tid < kSlots) {
+      partials[(size_t)blockIdx.x * kSlots + tid] = vals_smem[tid];
+      __threadfence();
+    }
+    __syncwarp();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned int ticket = atomicAdd(counter, 1u);
+      *is_last_smem = ticket == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  return *is_last_smem;
+}
+
+// fp64 sum over CTAs of slot k, executed by one full warp; result valid in every lane
+template <int kSlots>
+__device__ __forceinline__ double warp_sum_partials(const float* partials, int k, int lane) {
+  double s = 0.0;
+  for (uint32_t b = lane; b < gridDim.x; b += 32) s += (double)__ldcg(partials + (size_t)b * kSlots + k);
+  return warp_sum(s);
+}
+
+}  // namespace sad
+#endif

@@ -7,12 +7,23 @@
 
 #include <string>
 
+#include "sad_b200.h"
+
 #define SAD_EXPORT __attribute__((visibility("default")))
 
 namespace sad {
 int set_error(int code, const std::string& msg);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(uint64_t n);
+
+// persistent bulk-copy-ring kernels (distill_ring.cu): the production path for 16-byte aligned tensors
+constexpr int kMaxRingCtas = 1024;  // upper bound of a ring grid (2 CTAs x #SMs); sizes the partial-sum scratch
+bool distill_ring_supported(const sad_distill_level* levels, int n_levels, int num_classes);
+int launch_distill_ring(const sad_distill_level* levels, int n_levels, const float* normalizer, const sad_distill_params* p,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st);
+bool pow_sum_ring_supported(const float* const* inputs, const int64_t* sizes, int n_inputs);
+int launch_pow_sum_ring(const float* const* inputs, const int64_t* sizes, int n_inputs, float power, float* out,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace sad
 
 #endif

@@ -40,3 +40,18 @@ def assert_grad_close(got, ref, what="grad"):
     bad = d > bound + 1e-30
     assert not bad.any(), "%s: %d of %d elements outside |d|<=1e-4|ref|+1e-6 max|ref| (worst %.3g vs %.3g)" % (
         what, int(bad.sum()), r.size, d[bad].max(), bound[bad][np.argmax(d[bad])])
+
+
+def assert_reduced_close(got, ref_order, exact, what="sum", exact_rtol=2e-5):
+    """Gate for a scalar that the reference obtains with its single-block fp32 Sum
+    (math_gpu.cu:1021-1058: 128 lanes, each adding up to 115 k terms sequentially at config-2 size).
+    That accumulation is itself up to ~1e-4 away from the exact sum of the same fp32 terms, so
+    comparing only against the reference-order value would test the reference's rounding noise.
+    `ref_order` is the oracle's value in the reference's summation order, `exact` the fp64 sum of the
+    oracle's per-element fp32 terms.  Required: within exact_rtol of the exact value, and within
+    1e-4 of the reference-order value once the reference's own deviation from exact is allowed for."""
+    got, ref_order, exact = float(got), float(ref_order), float(exact)
+    assert abs(got - exact) <= exact_rtol * abs(exact) + 1e-30, "%s: got %.9g exact %.9g rel %.3g" % (
+        what, got, exact, abs(got - exact) / max(abs(exact), 1e-30))
+    assert abs(got - ref_order) <= LOSS_RTOL * abs(ref_order) + abs(ref_order - exact) + 1e-30, \
+        "%s: got %.9g reference-order %.9g (exact %.9g)" % (what, got, ref_order, exact)

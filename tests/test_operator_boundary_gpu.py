@@ -92,7 +92,10 @@ def test_reference_graph_unfused_and_fused(oplib, oracle):
     for i, l in enumerate(host):
         assert_loss_close(lu[i], oracle.distill_loss(*l, wp, **HEAD), "level %d" % i)
         assert_grad_close(gu[i], oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)
-        assert lu[i] == lf[i] and np.array_equal(gu[i], gf[i])   # the pass does not change results
+        # the pass does not change results: gradients are element-wise (bit-equal); the loss is a sum whose
+        # partition over CTAs differs between the one-level and the all-levels launch (last-bit differences)
+        assert np.array_equal(gu[i], gf[i])
+        assert abs(float(lu[i]) - float(lf[i])) <= 1e-6 * abs(float(lu[i]))
 
 
 def test_against_unmodified_reference_cuda_ops(oplib, reflib, oracle):
