@@ -118,6 +118,43 @@ int sad_distill_step_host(sad_ctx* ctx, const sad_host_level* levels, int n_leve
 /* device address of level i's gradient from the last sad_distill_step_host call */
 float* sad_ctx_device_d_logits(sad_ctx* ctx, int level);
 
+/* ------------------------------------------------------------------------------------------
+ * RetinaNet head convolution: 3x3, stride 1, pad 1, NCHW fp32, weights shared by all FPN levels —
+ * replaces, for these shapes, the cuDNN calls of
+ *   CudnnConvOp::RunOnDevice / DoRunWithType          (caffe2/caffe2/operators/conv_op_cudnn.cc:293-643)
+ *   CudnnConvGradientOp::DoRunWithType                (caffe2/caffe2/operators/conv_op_cudnn.cc:645-1100)
+ * with the semantics of ConvOp<T>::RunOnDeviceWithOrderNCHW (caffe2/caffe2/operators/conv_op_impl.h:31-180)
+ * and the in-place Relu / ReluGradient that follow each tower conv (relu_op.cu:22-62,
+ * retinanet_heads.py:124,209).  tcgen05 kind::tf32 tensor-core tiles fed by TMA; one launch covers
+ * all levels.  fp32 tensors, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sad_conv_level {
+  const float* x_nhwc; /* input, channels-last (N, H, W, Cin): from sad_nchw_to_nhwc_f32 or a previous y_nhwc */
+  float* y_nchw;       /* output (N, Cout, H, W) — the operator's output blob — or NULL */
+  float* y_nhwc;       /* output channels-last (N, H, W, Cout), tf32-rounded, or NULL */
+  int32_t N, H, W;
+} sad_conv_level;
+
+/* The tensor-core kernels read activations channels-last (TMA cannot shift the innermost NCHW
+ * coordinate by one element).  One launch converts every level. */
+typedef struct sad_layout_level {
+  const float* src_nchw; /* (N, C, H, W) */
+  float* dst_nhwc;       /* (N, H, W, C), values rounded to tf32 */
+  int32_t N, H, W;
+} sad_layout_level;
+int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int channels, void* stream);
+
+/* Weights (Cout, Cin, 3, 3) are repacked once per step into [tap][M][K] (tf32-rounded):
+ *   mode 0: forward operator       M = Cout, K = Cin
+ *   mode 1: data gradient operator M = Cin,  K = Cout, taps flipped (dX = conv(dY, W^T flipped))
+ * sad_conv3x3_packed_bytes(cin, cout) bytes of 16-byte aligned device memory. */
+size_t sad_conv3x3_packed_bytes(int cin, int cout);
+int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int cout, int mode, float* packed, void* stream);
+/* y = conv3x3(x, packed) + bias (bias may be NULL), optionally followed by ReLU (relu != 0).
+ * `cin`/`cout` are the K/M of `packed` (for the data gradient pass cin = Cout_of_forward, cout = Cin_of_forward). */
+int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
+                        int cout, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

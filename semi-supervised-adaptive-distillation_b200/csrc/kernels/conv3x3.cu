@@ -1,0 +1,528 @@
+// 3x3 / stride 1 / pad 1 NCHW fp32 convolution of the RetinaNet head on the 5th-generation tensor
+// cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM), operands staged by TMA.
+//
+// Replaces, for the head's shapes, the reference's cuDNN calls
+//   CudnnConvOp::RunOnDevice            caffe2/caffe2/operators/conv_op_cudnn.cc:293-643  (Y = conv(X, W) + b)
+//   CudnnConvGradientOp (data gradient) caffe2/caffe2/operators/conv_op_cudnn.cc:645-1100 (dX = dY * W^T)
+// with the semantics of ConvOp<T>::RunOnDeviceWithOrderNCHW (conv_op_impl.h:31-180: cross-correlation,
+// zero padding) — weights (Cout, Cin, 3, 3), activations (N, C, H, W), all levels of the FPN pyramid in
+// ONE launch because the head's weights are shared across levels (retinanet_heads.py:90-152,171-245).
+//
+// Formulation: implicit GEMM per filter tap, no im2col buffer:
+//     D[co, pixel] = sum_tap sum_ci  Wp[tap][co][ci] * Xt[n][y + dy(tap)][x + dx(tap)][ci]
+//   * M = 128 output channels per tile, N = 256 pixels per tile (8 image rows x 32 columns),
+//     K = 32 input channels per pipeline stage, 9 * ceil(Cin/32) stages per tile.
+//   * A (weights): repacked once per step by conv3x3_pack_kernel to [tap][Cout][Cin] (K-major) and
+//     rounded to tf32 (round-to-nearest); one TMA box {32 ci, 128 co, 1 tap} per stage, 128B swizzle.
+//   * B (activations): a channels-last (N, H, W, C) copy of the input (nchw_to_nhwc_kernel, or the
+//     channels-last output a previous convolution wrote from its epilogue), read by ONE 4-D TMA box
+//     {32 ci, 32 x, 8 y, 1 n} per stage at the tap-shifted coordinate (c0, x0+dx, y0+dy, n).
+//     Out-of-bounds elements (negative or past the edge) are zero-filled by the TMA unit, which
+//     implements the padding and the ragged tile edges.  In shared memory that is 256 pixel rows of
+//     128 B = the canonical K-major 128B-swizzle UMMA operand.
+//     Why not straight from NCHW: measured on B200 (scripts/probe/tma_probe.cu), a TMA tile whose
+//     INNERMOST coordinate is not a multiple of 16 bytes raises "illegal instruction"; with NCHW the
+//     dx = +-1 taps shift the innermost (x) coordinate by 4 bytes.  Channels-last puts the shifts on
+//     outer dimensions, where any (also negative) coordinate is legal.
+//   * One elected thread issues 4 tcgen05.mma (128x256x8) per stage; accumulators are double-buffered
+//     in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * Epilogue warps: tcgen05.ld 32 lanes x 32 columns -> + bias (-> ReLU) -> NCHW (the operator's
+//     output blob; 128-bit stores) and/or channels-last (input of the next convolution / of the weight
+//     gradient; one coalesced 128 B line per pixel and warp).
+//   * Persistent grid (one CTA per SM), static round-robin tile order with the Cout-tile index fastest
+//     so concurrently running CTAs share activation tiles in L2.
+// Numerics: tf32 operands (10-bit mantissa, both rounded to nearest: weights in the pack kernel,
+// activations when the channels-last copy is written), fp32 accumulation. Tolerance vs the fp32
+// oracle is stated in tests/test_conv_gpu.py.
+//
+// Channel counts that are not a multiple of 4 (TMA needs 16-byte strides) take conv3x3_simt_kernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <string>
+
+#include "sad_b200.h"
+#include "sad_internal.h"
+#include "tc_utils.cuh"
+
+namespace sad {
+
+constexpr int kCvM = 128;
+constexpr int kCvRows = 8;
+constexpr int kCvCols = 32;
+constexpr int kCvN = kCvRows * kCvCols;  // 256
+constexpr int kCvKC = 32;
+constexpr int kCvStages = 4;
+constexpr int kCvABytes = kCvM * kCvKC * 4;            // 16 KB
+constexpr int kCvBBytes = kCvN * kCvKC * 4;            // 32 KB
+constexpr int kCvStageBytes = kCvABytes + kCvBBytes;   // 48 KB
+constexpr int kCvThreads = 192;                        // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
+constexpr int kCvTmemCols = 512;                       // 2 accumulator buffers x 256 columns
+constexpr size_t kCvSmemBytes = (size_t)kCvStages * kCvStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct ConvLevel {
+  float* y_nchw;  // may be null
+  float* y_nhwc;  // may be null
+  int32_t N, H, W;
+  int32_t pad;
+  uint32_t tiles_x, tiles_y, tile_begin, tile_end;
+};
+struct alignas(64) ConvArgs {
+  CUtensorMap tmap_w;
+  CUtensorMap tmap_x[SAD_MAX_LEVELS];
+  ConvLevel lv[SAD_MAX_LEVELS];
+  const float* bias;
+  int32_t n_levels, cin, cout, relu;
+  uint32_t m_tiles, k_blocks, total_tiles;
+};
+
+struct ConvTile {
+  int l, n, y0, x0, m0;
+};
+__device__ __forceinline__ ConvTile conv_decode_tile(const ConvArgs& a, uint32_t tile, int& l_hint) {
+  while (tile >= a.lv[l_hint].tile_end) ++l_hint;
+  const ConvLevel& L = a.lv[l_hint];
+  uint32_t r = tile - L.tile_begin;
+  const uint32_t mb = r % a.m_tiles;
+  r /= a.m_tiles;
+  const uint32_t xb = r % L.tiles_x;
+  r /= L.tiles_x;
+  const uint32_t yb = r % L.tiles_y;
+  const uint32_t n = r / L.tiles_y;
+  ConvTile t;
+  t.l = l_hint;
+  t.n = (int)n;
+  t.y0 = (int)yb * kCvRows;
+  t.x0 = (int)xb * kCvCols;
+  t.m0 = (int)mb * kCvM;
+  return t;
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __grid_constant__ ConvArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (128B-swizzle atoms are 1024 B), barriers behind it
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kCvStages * kCvStageBytes);
+  uint64_t* full_bar = bars;                    // [kCvStages] TMA -> MMA
+  uint64_t* empty_bar = bars + kCvStages;       // [kCvStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kCvStages;   // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;         // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&args.tmap_w);
+    for (int l = 0; l < args.n_levels; ++l)
+      tma_prefetch_desc(&args.tmap_x[l]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kCvStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full[b], 1);
+        mbar_init(&tmem_empty[b], 128);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<kCvTmemCols>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t k_blocks = args.k_blocks;  // ceil(Cin / 32)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      RingState rs;
+      int l_hint = 0;
+      for (uint32_t tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+        const ConvTile t = conv_decode_tile(args, tile, l_hint);
+        const CUtensorMap* mx = &args.tmap_x[t.l];
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
+            uint8_t* sa = smem + (size_t)rs.stage * kCvStageBytes;
+            uint8_t* sb = sa + kCvABytes;
+            mbar_arrive_expect_tx(&full_bar[rs.stage], kCvStageBytes);
+            tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kCvKC, t.m0, tap);
+            tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kCvKC, t.x0 + dx, t.y0 + dy, t.n);
+            rs.advance<kCvStages>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
+      RingState rs;
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[buf], aphase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * kCvN;
+        const uint32_t n_kb = 9u * k_blocks;
+        for (uint32_t kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full_bar[rs.stage], rs.phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kCvStageBytes);
+          const uint32_t b_addr = a_addr + kCvABytes;
+#pragma unroll
+          for (int k = 0; k < kCvKC / 8; ++k) {
+            // both operands K-major: rows of 128 B (32 tf32), 8-row groups 1024 B apart (SBO);
+            // one K step of 8 = +32 B inside the swizzled row
+            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+          }
+          umma_commit(&empty_bar[rs.stage]);  // frees the smem stage when these MMAs have read it
+          rs.advance<kCvStages>();
+        }
+        umma_commit(&tmem_full[buf]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps = 128 accumulator rows) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    int l_hint = 0;
+    for (uint32_t tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+      const ConvTile t = conv_decode_tile(args, tile, l_hint);
+      const ConvLevel& L = args.lv[t.l];
+      const int co = t.m0 + row;
+      const bool co_ok = co < args.cout;
+      const float b = (co_ok && args.bias) ? __ldg(args.bias + co) : 0.f;
+      mbar_wait(&tmem_full[buf], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kCvN;
+      const size_t HW = (size_t)L.H * L.W;
+      float* yrow = L.y_nchw ? L.y_nchw + ((size_t)t.n * args.cout + (co_ok ? co : 0)) * HW : nullptr;
+      float* ycl = L.y_nhwc ? L.y_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
+      const bool vec_ok = (L.W & 3) == 0;
+#pragma unroll 1
+      for (int j = 0; j < kCvRows; ++j) {
+        float v[32];
+        tmem_ld_32x32(taddr + j * kCvCols, v);
+        const int y = t.y0 + j;
+        if (co_ok && y < L.H) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] += b;
+            if (args.relu) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (yrow) {
+            float* dst = yrow + (size_t)y * L.W + t.x0;
+            if (vec_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                if (t.x0 + i < L.W) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (t.x0 + i < L.W) dst[i] = v[i];
+            }
+          }
+          if (ycl) {
+            // channels-last: for a fixed pixel the warp's 32 lanes (consecutive co) write one 128 B line
+            float* dst = ycl + ((size_t)y * L.W + t.x0) * args.cout;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (t.x0 + i < L.W) dst[(size_t)i * args.cout] = to_tf32_rna(v[i]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<kCvTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight repack: (Cout, Cin, 3, 3) fp32 -> [tap][M][K] tf32-rounded fp32
+//   mode 0 (forward):        M = Cout, K = Cin,  Wp[tap][co][ci] = W[co][ci][tap]
+//   mode 1 (data gradient):  M = Cin,  K = Cout, Wp[tap][ci][co] = W[co][ci][8 - tap]   (taps flipped)
+// ---------------------------------------------------------------------------------------------
+__global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int mode) {
+  const int M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
+  const size_t total = (size_t)9 * M * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int m = (int)((i / K) % M);
+    const int tap = (int)(i / ((size_t)K * M));
+    const float v = mode == 0 ? w[((size_t)m * cin + k) * 9 + tap] : w[((size_t)k * cin + m) * 9 + (8 - tap)];
+    out[i] = to_tf32_rna(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT fallback for channel counts the TMA path cannot address (C % 4 != 0): direct convolution from
+// the same packed weights and channels-last input.  One thread per output element.
+// ---------------------------------------------------------------------------------------------
+__global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* __restrict__ wp, const float* __restrict__ bias,
+                                    float* __restrict__ y_nchw, float* __restrict__ y_nhwc, int N, int cin, int cout, int H, int W,
+                                    int relu) {
+  const size_t total = (size_t)N * cout * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    const int xx = (int)((i / cout) % W);
+    const int yy = (int)((i / ((size_t)cout * W)) % H);
+    const int n = (int)(i / ((size_t)cout * W * H));
+    float acc = bias ? bias[co] : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+      const float* wrow = wp + ((size_t)tap * cout + co) * cin;
+      const float* xp = xt + (((size_t)n * H + sy) * W + sx) * cin;
+      for (int ci = 0; ci < cin; ++ci) acc = fmaf(wrow[ci], xp[ci], acc);
+    }
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (y_nchw) y_nchw[(((size_t)n * cout + co) * H + yy) * W + xx] = acc;
+    if (y_nhwc) y_nhwc[i] = to_tf32_rna(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> channels-last (N, H, W, C) fp32 rounded to tf32 (round-to-nearest), all levels in one
+// launch: per image a [C][HW] -> [HW][C] transpose in 32 x 32 tiles through shared memory.
+// ---------------------------------------------------------------------------------------------
+struct LayoutLevel {
+  const float* src;
+  float* dst;
+  uint32_t HW, tiles_hw, tile_begin, tile_end;  // tiles = N * tiles_c * tiles_hw
+};
+struct LayoutArgs {
+  LayoutLevel lv[SAD_MAX_LEVELS];
+  int32_t n_levels, C;
+  uint32_t tiles_c, total_tiles;
+};
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant__ LayoutArgs a) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  int l = 0;
+  for (uint32_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    while (t >= a.lv[l].tile_end) ++l;
+    const LayoutLevel& L = a.lv[l];
+    uint32_t r = t - L.tile_begin;
+    const uint32_t th = r % L.tiles_hw;
+    r /= L.tiles_hw;
+    const uint32_t tc = r % a.tiles_c;
+    const uint32_t n = r / a.tiles_c;
+    const uint32_t hw0 = th * 32, c0 = tc * 32;
+    const float* src = L.src + (size_t)n * a.C * L.HW;
+    float* dst = L.dst + (size_t)n * a.C * L.HW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t c = c0 + ty + k * 8, hw = hw0 + tx;
+      tile[ty + k * 8][tx] = (c < (uint32_t)a.C && hw < L.HW) ? __ldg(src + (size_t)c * L.HW + hw) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t hw = hw0 + ty + k * 8, c = c0 + tx;
+      if (c < (uint32_t)a.C && hw < L.HW) dst[(size_t)hw * a.C + c] = to_tf32_rna(tile[tx][ty + k * 8]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(SAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(SAD_ERR_CUDA, std::string("cuTensorMapEncodeTiled(") + what + ") failed: CUresult " + std::to_string((int)r));
+  return SAD_OK;
+}
+
+// channels-last activations (N, H, W, C): dims {C, W, H, N}, box {32 ci, 32 x, 8 y, 1}
+static int encode_x_map(CUtensorMap* m, const float* xt, int N, int C, int H, int W) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint32_t box[4] = {kCvKC, kCvCols, kCvRows, 1};
+  return encode_map(m, xt, 4, dims, str, box, "activations {C,W,H,N}");
+}
+
+static int sm_count(int* sms) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc != SAD_OK) return rc;
+  return check_cuda(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+}
+
+}  // namespace sad
+
+using namespace sad;
+
+extern "C" {
+
+SAD_EXPORT size_t sad_conv3x3_packed_bytes(int cin, int cout) {
+  if (cin < 1 || cout < 1) return 0;
+  return (size_t)9 * cin * cout * sizeof(float);
+}
+
+SAD_EXPORT int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int cout, int mode, float* packed, void* stream) {
+  if (!weight || !packed || cin < 1 || cout < 1 || (mode != 0 && mode != 1))
+    return set_error(SAD_ERR_INVALID, "conv3x3 pack: bad argument");
+  const size_t total = (size_t)9 * cin * cout;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 4096 ? (total + threads - 1) / threads : 4096);
+  conv3x3_pack_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(weight, packed, cout, cin, mode);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "conv3x3 pack launch");
+}
+
+SAD_EXPORT int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
+  if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || channels < 1) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: bad argument");
+  LayoutArgs a{};
+  a.n_levels = n_levels;
+  a.C = channels;
+  a.tiles_c = (uint32_t)((channels + 31) / 32);
+  uint64_t tiles = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_layout_level& L = levels[l];
+    if (L.N < 0 || L.H < 0 || L.W < 0) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: negative dimension");
+    const uint64_t HW = (uint64_t)L.H * L.W;
+    if ((uint64_t)L.N * HW && (!L.src_nchw || !L.dst_nhwc)) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: null tensor");
+    a.lv[l].src = L.src_nchw;
+    a.lv[l].dst = L.dst_nhwc;
+    a.lv[l].HW = (uint32_t)HW;
+    a.lv[l].tiles_hw = (uint32_t)((HW + 31) / 32);
+    a.lv[l].tile_begin = (uint32_t)tiles;
+    tiles += (uint64_t)L.N * a.tiles_c * a.lv[l].tiles_hw;
+    a.lv[l].tile_end = (uint32_t)tiles;
+    if (tiles > 0x7fffffffull) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: too many tiles");
+  }
+  if (tiles == 0) return SAD_OK;
+  a.total_tiles = (uint32_t)tiles;
+  int sms = 0, rc;
+  if ((rc = sm_count(&sms)) != SAD_OK) return rc;
+  const uint32_t grid = a.total_tiles < (uint32_t)sms * 8u ? a.total_tiles : (uint32_t)sms * 8u;
+  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
+}
+
+// `packed` has layout [tap][cout][cin] (sad_conv3x3_pack_weights_f32 mode 0 for the forward operator,
+// mode 1 — with cin/cout swapped by the caller — for the data gradient).
+SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
+                                   int cout, int relu, void* stream) {
+  if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3: n_levels must be in [1, 8]");
+  if (!packed || cin < 1 || cout < 1) return set_error(SAD_ERR_INVALID, "conv3x3: bad weights/channels");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvArgs a{};
+  uint64_t tiles = 0;
+  const uint32_t m_tiles = (uint32_t)((cout + kCvM - 1) / kCvM);
+  bool tma_ok = (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(packed) & 15) == 0);
+  int rc;
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_conv_level& L = levels[l];
+    if (L.N < 0 || L.H < 0 || L.W < 0) return set_error(SAD_ERR_INVALID, "conv3x3: negative dimension");
+    const uint64_t elems = (uint64_t)L.N * L.H * L.W;
+    if (elems && (!L.x_nhwc || (!L.y_nchw && !L.y_nhwc))) return set_error(SAD_ERR_INVALID, "conv3x3: null tensor");
+    if ((reinterpret_cast<uintptr_t>(L.x_nhwc) | reinterpret_cast<uintptr_t>(L.y_nchw)) & 15) tma_ok = false;
+    ConvLevel& D = a.lv[l];
+    D.y_nchw = L.y_nchw;
+    D.y_nhwc = L.y_nhwc;
+    D.N = L.N;
+    D.H = L.H;
+    D.W = L.W;
+    D.tiles_x = (uint32_t)((L.W + kCvCols - 1) / kCvCols);
+    D.tiles_y = (uint32_t)((L.H + kCvRows - 1) / kCvRows);
+    D.tile_begin = (uint32_t)tiles;
+    tiles += (uint64_t)L.N * D.tiles_y * D.tiles_x * m_tiles;
+    D.tile_end = (uint32_t)tiles;
+    if (tiles > 0x7fffffffull) return set_error(SAD_ERR_INVALID, "conv3x3: too many tiles");
+  }
+  if (tiles == 0) return SAD_OK;
+  if (!tma_ok) {  // channel count / alignment the TMA path cannot address
+    for (int l = 0; l < n_levels; ++l) {
+      const sad_conv_level& L = levels[l];
+      const size_t total = (size_t)L.N * cout * L.H * L.W;
+      if (total == 0) continue;
+      const size_t blocks = (total + 127) / 128;
+      conv3x3_simt_kernel<<<(unsigned)(blocks < 1048576 ? blocks : 1048576), 128, 0, st>>>(L.x_nhwc, packed, bias, L.y_nchw, L.y_nhwc, L.N,
+                                                                                           cin, cout, L.H, L.W, relu);
+      count_launch(1);
+      if ((rc = check_cuda(cudaGetLastError(), "conv3x3 simt launch")) != SAD_OK) return rc;
+    }
+    return SAD_OK;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
+    const cuuint64_t str[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cin * cout * 4};
+    const cuuint32_t box[3] = {kCvKC, kCvM, 1};
+    if ((rc = encode_map(&a.tmap_w, packed, 3, dims, str, box, "packed weights")) != SAD_OK) return rc;
+  }
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_conv_level& L = levels[l];
+    if ((uint64_t)L.N * L.H * L.W == 0) {  // empty level: a valid dummy map (never used, no tiles)
+      a.tmap_x[l] = a.tmap_w;
+      continue;
+    }
+    if ((rc = encode_x_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W)) != SAD_OK) return rc;
+  }
+  a.bias = bias;
+  a.n_levels = n_levels;
+  a.cin = cin;
+  a.cout = cout;
+  a.relu = relu;
+  a.m_tiles = m_tiles;
+  a.k_blocks = (uint32_t)((cin + kCvKC - 1) / kCvKC);
+  a.total_tiles = (uint32_t)tiles;
+
+  int sms = 0;
+  if ((rc = sm_count(&sms)) != SAD_OK) return rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(conv3x3_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
+                       "cudaFuncSetAttribute(conv3x3)")) != SAD_OK)
+    return rc;
+  const uint32_t grid = a.total_tiles < (uint32_t)sms ? a.total_tiles : (uint32_t)sms;
+  conv3x3_tf32_kernel<<<grid, kCvThreads, kCvSmemBytes, st>>>(a);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "conv3x3 launch");
+}
+
+}  // extern "C"

@@ -30,6 +30,15 @@ class DistillParams(C.Structure):
                 ("num_classes", C.c_int32), ("ignored_label", C.c_int32)]
 
 
+class ConvLevel(C.Structure):
+    _fields_ = [("x_nhwc", C.c_void_p), ("y_nchw", C.c_void_p), ("y_nhwc", C.c_void_p),
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class LayoutLevel(C.Structure):
+    _fields_ = [("src_nchw", C.c_void_p), ("dst_nhwc", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
 class HostLevel(C.Structure):
     _fields_ = [("logits", C.c_void_p), ("teacher_prob", C.c_void_p), ("labels", C.c_void_p),
                 ("d_logits", C.c_void_p),
@@ -69,6 +78,12 @@ def lib():
                                             C.POINTER(DistillParams), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         l.sad_ctx_device_d_logits.restype = C.c_void_p
         l.sad_ctx_device_d_logits.argtypes = [C.c_void_p, C.c_int]
+        l.sad_nchw_to_nhwc_f32.argtypes = [C.POINTER(LayoutLevel), C.c_int, C.c_int, C.c_void_p]
+        l.sad_conv3x3_packed_bytes.restype = C.c_size_t
+        l.sad_conv3x3_packed_bytes.argtypes = [C.c_int, C.c_int]
+        l.sad_conv3x3_pack_weights_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.sad_conv3x3_fwd_f32.argtypes = [C.POINTER(ConvLevel), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p]
         _lib = l
     return _lib
 

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import native
-from .native import DistillLevel, DistillParams, HostLevel, check, default_params, lib
+from .native import ConvLevel, DistillLevel, DistillParams, HostLevel, check, default_params, lib
 
 
 def _stream():
@@ -186,3 +186,77 @@ class HostStep:
         check(lib().sad_distill_step_host(self.handle, self._arr, self._n, self._power, C.byref(self._params),
                                           self._losses, C.byref(self._norm)))
         return list(self._losses), self._norm.value
+
+
+# ---------------------------------------------------------------------------------------------
+# RetinaNet head convolution (3x3, stride 1, pad 1, NCHW fp32; weights shared by all levels)
+# ---------------------------------------------------------------------------------------------
+def conv3x3_pack(weight, mode=0):
+    """Repack (Cout, Cin, 3, 3) weights for the tensor-core kernels: mode 0 forward, 1 data gradient."""
+    _require_cuda(weight, torch.float32, "weight")
+    cout, cin = weight.shape[0], weight.shape[1]
+    if tuple(weight.shape[2:]) != (3, 3):
+        raise ValueError("weight must be (Cout, Cin, 3, 3)")
+    packed = torch.empty(9 * cin * cout, dtype=torch.float32, device=weight.device)
+    check(lib().sad_conv3x3_pack_weights_f32(C.c_void_p(weight.data_ptr()), cin, cout, int(mode),
+                                             C.c_void_p(packed.data_ptr()), _stream()))
+    return packed
+
+
+def to_nhwc(xs):
+    """NCHW fp32 -> channels-last (N, H, W, C) fp32 rounded to tf32, every level in one launch."""
+    xs = list(xs)
+    arr = (native.LayoutLevel * len(xs))()
+    outs = []
+    for i, x in enumerate(xs):
+        _require_cuda(x, torch.float32, "x[%d]" % i)
+        if x.shape[1] != xs[0].shape[1]:
+            raise ValueError("all levels must have the same channel count")
+        n, c, h, w = x.shape
+        outs.append(torch.empty((n, h, w, c), dtype=torch.float32, device=x.device))
+        arr[i].src_nchw, arr[i].dst_nhwc = x.data_ptr(), outs[-1].data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = n, h, w
+    check(lib().sad_nchw_to_nhwc_f32(arr, len(xs), xs[0].shape[1], _stream()))
+    return outs
+
+
+def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc):
+    arr = (ConvLevel * len(xs_nhwc))()
+    ys, yts = [], []
+    for i, xt in enumerate(xs_nhwc):
+        _require_cuda(xt, torch.float32, "x_nhwc[%d]" % i)
+        n, h, w, c = xt.shape
+        if c != k:
+            raise ValueError("input channels do not match the weights")
+        arr[i].x_nhwc = xt.data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = n, h, w
+        if want_nchw:
+            ys.append(torch.empty((n, m, h, w), dtype=torch.float32, device=xt.device))
+            arr[i].y_nchw = ys[-1].data_ptr()
+        if want_nhwc:
+            yts.append(torch.empty((n, h, w, m), dtype=torch.float32, device=xt.device))
+            arr[i].y_nhwc = yts[-1].data_ptr()
+    b = C.c_void_p(bias.data_ptr()) if bias is not None else None
+    check(lib().sad_conv3x3_fwd_f32(arr, len(xs_nhwc), C.c_void_p(packed.data_ptr()), b, k, m, 1 if relu else 0, _stream()))
+    return ys, yts
+
+
+def conv3x3_forward(xs, weight, bias=None, relu=False, packed=None, xs_nhwc=None, want_nchw=True, want_nhwc=False):
+    """Conv (+bias, + optional fused ReLU) of every level in one launch.  xs: list of (N, Cin, H, W)
+    (or pass xs_nhwc, channels-last copies from to_nhwc / a previous call).  Returns (ys_nchw, ys_nhwc)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    if packed is None:
+        packed = conv3x3_pack(weight, 0)
+    if xs_nhwc is None:
+        xs_nhwc = to_nhwc(xs)
+    return _conv_run(xs_nhwc, packed, bias, cin, cout, relu, want_nchw, want_nhwc)
+
+
+def conv3x3_dgrad(dys, weight, packed=None, dys_nhwc=None, want_nchw=True, want_nhwc=False):
+    """Data gradient dX = conv(dY, W^T with flipped taps) of every level in one launch.  dys: (N, Cout, H, W)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    if packed is None:
+        packed = conv3x3_pack(weight, 1)
+    if dys_nhwc is None:
+        dys_nhwc = to_nhwc(dys)
+    return _conv_run(dys_nhwc, packed, None, cout, cin, False, want_nchw, want_nhwc)

@@ -1,0 +1,119 @@
+"""GPU parity of the tcgen05 3x3 convolution (forward and data gradient) against the CPU oracle
+(oracle/conv_oracle.c restating caffe2/caffe2/operators/conv_op_impl.h:31-180) and, at the head's full
+size, against torch's fp32 convolution used as an independent implementation.
+
+Tolerance: the tensor cores take tf32 operands (10-bit mantissa: activations truncated, weights rounded
+to nearest) and accumulate in fp32, the oracle is fp32 throughout.  With K = 9*Cin products per
+output the observed deviation is ~5e-4 of max|ref|; the gate is  max|d| <= 3e-3 * max|ref|  and
+rms(d) <= 1e-3 * rms(ref).  The SIMT fallback path (C % 4 != 0) meets the same gate.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TF32_MAX_TOL = 3e-3
+TF32_RMS_TOL = 1e-3
+
+
+def assert_conv_close(got, ref, what):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert np.isfinite(got).all(), what + ": non-finite output"
+    m = np.abs(ref).max()
+    d = np.abs(got - ref)
+    assert d.max() <= TF32_MAX_TOL * m, "%s: max|d| %.3g > %.1e * max|ref| %.3g (at %s)" % (
+        what, d.max(), TF32_MAX_TOL, m, np.unravel_index(d.argmax(), d.shape))
+    rms = np.sqrt((d ** 2).mean()) / max(np.sqrt((ref ** 2).mean()), 1e-30)
+    assert rms <= TF32_RMS_TOL, "%s: relative rms %.3g" % (what, rms)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from sad_b200 import ops as o
+    assert torch.cuda.is_available()
+    return o
+
+
+def _rand(rng, shape, relu_like=False, scale=1.0):
+    a = (rng.standard_normal(shape) * scale).astype(np.float32)
+    return np.maximum(a, 0).astype(np.float32) if relu_like else a
+
+
+CASES = [
+    # (N, Cin, Cout, H, W)  name
+    ((1, 32, 128, 8, 32), "one tile, one k-block per tap"),
+    ((2, 64, 128, 16, 64), "2x2 pixel tiles"),
+    ((1, 256, 256, 20, 32), "head tower shape, ragged rows (P5)"),
+    ((2, 256, 256, 10, 16), "P6: half-width tile"),
+    ((2, 256, 256, 5, 8), "P7"),
+    ((1, 48, 36, 12, 20), "K tail (Cin=48), M tail (Cout=36), ragged columns"),
+    ((1, 64, 720, 8, 40), "cls_pred Cout=720: 6 M tiles, last partial"),
+    ((1, 32, 64, 7, 14), "W % 4 != 0: scalar NCHW stores"),
+    ((1, 30, 20, 6, 10), "C % 4 != 0: SIMT fallback"),
+]
+
+
+@pytest.mark.parametrize("shape,name", CASES, ids=[c[1] for c in CASES])
+def test_forward_matches_oracle(ops, oracle, shape, name):
+    N, Cin, Cout, H, W = shape
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    x = _rand(rng, (N, Cin, H, W), relu_like=True)
+    w = _rand(rng, (Cout, Cin, 3, 3), scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand(rng, (Cout,))
+    ref = oracle.conv2d_fwd(x, w, b)
+    xd, wd, bd = (torch.from_numpy(a).cuda() for a in (x, w, b))
+    got = ops.conv3x3_forward([xd], wd, bd)[0][0]
+    torch.cuda.synchronize()
+    assert_conv_close(got.cpu().numpy(), ref, "conv fwd " + name)
+    got_relu, got_cl = (r[0] for r in ops.conv3x3_forward([xd], wd, bd, relu=True, want_nhwc=True))
+    assert_conv_close(got_relu.cpu().numpy(), oracle.relu(ref), "conv+relu fwd " + name)
+    assert_conv_close(got_cl.permute(0, 3, 1, 2).cpu().numpy(), oracle.relu(ref), "conv+relu fwd channels-last " + name)
+    got_nobias = ops.conv3x3_forward([xd], wd, None)[0][0]
+    assert_conv_close(got_nobias.cpu().numpy(), oracle.conv2d_fwd(x, w, None), "conv fwd (no bias) " + name)
+
+
+@pytest.mark.parametrize("shape,name", CASES[:6], ids=[c[1] for c in CASES[:6]])
+def test_dgrad_matches_oracle(ops, oracle, shape, name):
+    N, Cin, Cout, H, W = shape
+    rng = np.random.default_rng(7 + abs(hash(shape)) % (2 ** 31))
+    x = _rand(rng, (N, Cin, H, W), relu_like=True)
+    w = _rand(rng, (Cout, Cin, 3, 3), scale=1.0 / np.sqrt(9 * Cout))
+    dy = _rand(rng, (N, Cout, H, W))
+    _, _, ref_dx = oracle.conv2d_bwd(x, w, dy)
+    got = ops.conv3x3_dgrad([torch.from_numpy(dy).cuda()], torch.from_numpy(w).cuda())[0][0]
+    torch.cuda.synchronize()
+    assert_conv_close(got.cpu().numpy(), ref_dx, "conv dgrad " + name)
+
+
+def test_impulse_response_is_exact(ops):
+    # indexing check without rounding: x = one-hot pixels, weights = small integers (exact in tf32);
+    # the output must equal the fp64 convolution exactly
+    N, Cin, Cout, H, W = 1, 32, 128, 9, 36
+    rng = np.random.default_rng(3)
+    x = np.zeros((N, Cin, H, W), np.float32)
+    for _ in range(40):
+        x[0, rng.integers(Cin), rng.integers(H), rng.integers(W)] = float(rng.integers(1, 4))
+    w = rng.integers(-3, 4, size=(Cout, Cin, 3, 3)).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), padding=1).numpy()
+    got = ops.conv3x3_forward([torch.from_numpy(x).cuda()], torch.from_numpy(w).cuda())[0][0].cpu().numpy()
+    assert np.array_equal(got.astype(np.float64), ref)
+
+
+def test_all_levels_one_launch_head_shapes(ops):
+    # BASELINE.json configs[1] geometry: bs = 2, 600 px pyramid, 256 -> 256 tower conv, all 5 levels in
+    # one launch; reference = torch fp32 convolution (independent implementation, TF32 disabled)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(80, 128), (40, 64), (20, 32), (10, 16), (5, 8)]
+    xs = [torch.randn(2, 256, h, w, device="cuda", generator=g).clamp_(min=0) for (h, w) in shapes]
+    wt = torch.randn(256, 256, 3, 3, device="cuda", generator=g) / np.sqrt(9 * 256)
+    b = torch.randn(256, device="cuda", generator=g)
+    got = ops.conv3x3_forward(xs, wt, b, relu=True)[0]
+    torch.cuda.synchronize()
+    for x, y in zip(xs, got):
+        ref = torch.relu(torch.nn.functional.conv2d(x, wt, b, padding=1))
+        assert_conv_close(y.cpu().numpy(), ref.cpu().numpy(), "level %dx%d" % tuple(x.shape[2:]))
