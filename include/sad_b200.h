@@ -133,6 +133,9 @@ typedef struct sad_conv_level {
   float* y_nchw;       /* output (N, Cout, H, W) — the operator's output blob — or NULL */
   float* y_nhwc;       /* output channels-last (N, H, W, Cout), tf32-rounded, or NULL */
   int32_t N, H, W;
+  const float* relu_mask_nhwc; /* NULL, or channels-last (N, H, W, Cout): outputs are zeroed where mask <= 0.  Fuses the
+                                  tower's in-place ReluGradient (relu_op.cu:29-35, dX = Y > 0 ? dY : 0) into the data-gradient
+                                  pass of the NEXT convolution: mask = forward output Y of the layer whose dY is produced */
 } sad_conv_level;
 
 /* The tensor-core kernels read activations channels-last (TMA cannot shift the innermost NCHW
@@ -154,6 +157,24 @@ int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int cout, int mod
  * `cin`/`cout` are the K/M of `packed` (for the data gradient pass cin = Cout_of_forward, cout = Cin_of_forward). */
 int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                         int cout, int relu, void* stream);
+
+/* Weight and bias gradient — replaces the filter/bias half of CudnnConvGradientOp::DoRunWithType
+ *   (caffe2/caffe2/operators/conv_op_cudnn.cc:1011-1040: cudnnConvolutionBackwardBias / BackwardFilter)
+ * and the autograd Sum over the FPN levels that share the weight (caffe2/caffe2/python/core.py:695,706-842):
+ *   d_weight[co][ci][ky][kx] = sum over levels, images, pixels of dY[co][y][x] * X[ci][y+ky-1][x+kx-1]
+ *   d_bias[co]               = sum over levels, images, pixels of dY[co][y][x]
+ * Both operands are the channels-last tensors the forward / data-gradient passes already hold.  One
+ * tensor-core launch over all levels (pixels are the reduction axis, split across CTAs) + a fixed-order
+ * finish pass: deterministic.  accumulate != 0 adds into d_weight / d_bias instead of overwriting. */
+typedef struct sad_wgrad_level {
+  const float* x_nhwc;  /* forward input, channels-last (N, H, W, Cin) */
+  const float* dy_nhwc; /* output gradient, channels-last (N, H, W, Cout) */
+  int32_t N, H, W;
+} sad_wgrad_level;
+size_t sad_conv3x3_wgrad_workspace_bytes(const sad_wgrad_level* levels, int n_levels, int cin, int cout);
+/* d_weight: (Cout, Cin, 3, 3) fp32; d_bias: (Cout) fp32 or NULL; workspace: 256-byte aligned device memory */
+int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
+                          int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

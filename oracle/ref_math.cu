@@ -11,6 +11,7 @@
 //   Add    caffe2/caffe2/utils/math_gpu.cu:85-103      y = a + b
 //   Scale  caffe2/caffe2/utils/math_gpu.cu:1241-1247,1293-1302   y = x * alpha
 #include "caffe2/core/context_gpu.h"
+#include "caffe2/core/operator.h"
 #include "caffe2/utils/math.h"
 
 namespace caffe2 {
@@ -75,4 +76,26 @@ void Scale<float, CUDAContext>(const int N, const float alpha, const float* x, f
 }
 
 }  // namespace math
+
+// ConstantFill (subset: float value, output shaped like input 0) so the NetDef text Detectron emits
+// for the loss-gradient seeds (detectron/lib/utils/blob.py:166-172; caffe2/caffe2/operators/filler_op.h)
+// also runs through the GPU oracle's executor.  Uses the restated Set primitive above.
+class RefConstantFillOp final : public Operator<CUDAContext> {
+ public:
+  RefConstantFillOp(const OperatorDef& def, Workspace* ws)
+      : Operator<CUDAContext>(def, ws), value_(OperatorBase::GetSingleArgument<float>("value", 0.f)) {}
+  bool RunOnDevice() override {
+    auto* out = Output(0);
+    CAFFE_ENFORCE(InputSize() == 1, "GPU oracle ConstantFill: only the shape-from-input form is restated");
+    out->ResizeLike(Input(0));
+    math::Set<float, CUDAContext>(out->size(), value_, out->mutable_data<float>(), &context_);
+    return true;
+  }
+
+ private:
+  float value_;
+};
+REGISTER_CUDA_OPERATOR(ConstantFill, RefConstantFillOp);
+OPERATOR_SCHEMA(ConstantFill).NumInputs(0, 1).NumOutputs(1);
+
 }  // namespace caffe2

@@ -44,6 +44,7 @@
 #include <mutex>
 #include <string>
 
+#include "conv_common.cuh"
 #include "sad_b200.h"
 #include "sad_internal.h"
 #include "tc_utils.cuh"
@@ -64,8 +65,9 @@ constexpr int kCvTmemCols = 512;                       // 2 accumulator buffers 
 constexpr size_t kCvSmemBytes = (size_t)kCvStages * kCvStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct ConvLevel {
-  float* y_nchw;  // may be null
-  float* y_nhwc;  // may be null
+  float* y_nchw;            // may be null
+  float* y_nhwc;            // may be null
+  const float* mask_nhwc;   // may be null: ReluGradient fused into the data-gradient pass (out = mask > 0 ? out : 0)
   int32_t N, H, W;
   int32_t pad;
   uint32_t tiles_x, tiles_y, tile_begin, tile_end;
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
       const size_t HW = (size_t)L.H * L.W;
       float* yrow = L.y_nchw ? L.y_nchw + ((size_t)t.n * args.cout + (co_ok ? co : 0)) * HW : nullptr;
       float* ycl = L.y_nhwc ? L.y_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
+      const float* mcl = L.mask_nhwc ? L.mask_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
       const bool vec_ok = (L.W & 3) == 0;
 #pragma unroll 1
       for (int j = 0; j < kCvRows; ++j) {
@@ -225,6 +228,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
           for (int i = 0; i < 32; ++i) {
             v[i] += b;
             if (args.relu) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (mcl) {
+            // ReluGradient (relu_op.cu:29-35: dX = Y > 0 ? dY : 0) with Y the channels-last forward output
+            const float* msk = mcl + ((size_t)y * L.W + t.x0) * args.cout;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (t.x0 + i < L.W && !(__ldg(msk + (size_t)i * args.cout) > 0.f)) v[i] = 0.f;
           }
           if (yrow) {
             float* dst = yrow + (size_t)y * L.W + t.x0;
@@ -281,8 +291,8 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
 // the same packed weights and channels-last input.  One thread per output element.
 // ---------------------------------------------------------------------------------------------
 __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* __restrict__ wp, const float* __restrict__ bias,
-                                    float* __restrict__ y_nchw, float* __restrict__ y_nhwc, int N, int cin, int cout, int H, int W,
-                                    int relu) {
+                                    float* __restrict__ y_nchw, float* __restrict__ y_nhwc, const float* __restrict__ mask_nhwc, int N,
+                                    int cin, int cout, int H, int W, int relu) {
   const size_t total = (size_t)N * cout * H * W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % cout);
@@ -298,6 +308,7 @@ __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* _
       for (int ci = 0; ci < cin; ++ci) acc = fmaf(wrow[ci], xp[ci], acc);
     }
     if (relu) acc = fmaxf(acc, 0.f);
+    if (mask_nhwc && !(mask_nhwc[i] > 0.f)) acc = 0.f;
     if (y_nchw) y_nchw[(((size_t)n * cout + co) * H + yy) * W + xx] = acc;
     if (y_nhwc) y_nhwc[i] = to_tf32_rna(acc);
   }
@@ -350,49 +361,6 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const char* what) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return set_error(SAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(SAD_ERR_CUDA, std::string("cuTensorMapEncodeTiled(") + what + ") failed: CUresult " + std::to_string((int)r));
-  return SAD_OK;
-}
-
-// channels-last activations (N, H, W, C): dims {C, W, H, N}, box {32 ci, 32 x, 8 y, 1}
-static int encode_x_map(CUtensorMap* m, const float* xt, int N, int C, int H, int W) {
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  const cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  const cuuint32_t box[4] = {kCvKC, kCvCols, kCvRows, 1};
-  return encode_map(m, xt, 4, dims, str, box, "activations {C,W,H,N}");
-}
-
-static int sm_count(int* sms) {
-  int dev = 0;
-  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-  if (rc != SAD_OK) return rc;
-  return check_cuda(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
-}
-
 }  // namespace sad
 
 using namespace sad;
@@ -467,6 +435,7 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     ConvLevel& D = a.lv[l];
     D.y_nchw = L.y_nchw;
     D.y_nhwc = L.y_nhwc;
+    D.mask_nhwc = L.relu_mask_nhwc;
     D.N = L.N;
     D.H = L.H;
     D.W = L.W;
@@ -484,8 +453,8 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
       const size_t total = (size_t)L.N * cout * L.H * L.W;
       if (total == 0) continue;
       const size_t blocks = (total + 127) / 128;
-      conv3x3_simt_kernel<<<(unsigned)(blocks < 1048576 ? blocks : 1048576), 128, 0, st>>>(L.x_nhwc, packed, bias, L.y_nchw, L.y_nhwc, L.N,
-                                                                                           cin, cout, L.H, L.W, relu);
+      conv3x3_simt_kernel<<<(unsigned)(blocks < 1048576 ? blocks : 1048576), 128, 0, st>>>(L.x_nhwc, packed, bias, L.y_nchw, L.y_nhwc,
+                                                                                           L.relu_mask_nhwc, L.N, cin, cout, L.H, L.W, relu);
       count_launch(1);
       if ((rc = check_cuda(cudaGetLastError(), "conv3x3 simt launch")) != SAD_OK) return rc;
     }
@@ -503,7 +472,7 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
       a.tmap_x[l] = a.tmap_w;
       continue;
     }
-    if ((rc = encode_x_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W)) != SAD_OK) return rc;
+    if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows, "activations {C,W,H,N}")) != SAD_OK) return rc;
   }
   a.bias = bias;
   a.n_levels = n_levels;

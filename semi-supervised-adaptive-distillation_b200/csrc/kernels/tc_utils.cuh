@@ -105,6 +105,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major tf32 operands only exist with the "128-byte swizzle, 32-byte atom" layout (layout type 1; TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B = 32 consecutive M/N elements, the four 32-byte
+// chunks of a row XOR-ed with (K row & 3).  LBO = byte stride between 32-element M/N chunks,
+// SBO = byte stride between groups of 4 K rows.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 // instruction descriptor for kind::tf32, fp32 accumulate:
 //   [4,6) D format = 1 (f32) | [7,10) A format = 2 (tf32) | [10,13) B format = 2 (tf32)
 //   [15] A major (0 = K, 1 = MN) | [16] B major | [17,23) N >> 3 | [24,29) M >> 4

@@ -32,11 +32,15 @@ class DistillParams(C.Structure):
 
 class ConvLevel(C.Structure):
     _fields_ = [("x_nhwc", C.c_void_p), ("y_nchw", C.c_void_p), ("y_nhwc", C.c_void_p),
-                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu_mask_nhwc", C.c_void_p)]
 
 
 class LayoutLevel(C.Structure):
     _fields_ = [("src_nchw", C.c_void_p), ("dst_nhwc", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class WgradLevel(C.Structure):
+    _fields_ = [("x_nhwc", C.c_void_p), ("dy_nhwc", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
 
 
 class HostLevel(C.Structure):
@@ -84,6 +88,10 @@ def lib():
         l.sad_conv3x3_pack_weights_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.sad_conv3x3_fwd_f32.argtypes = [C.POINTER(ConvLevel), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p]
+        l.sad_conv3x3_wgrad_workspace_bytes.restype = C.c_size_t
+        l.sad_conv3x3_wgrad_workspace_bytes.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int]
+        l.sad_conv3x3_wgrad_f32.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = l
     return _lib
 

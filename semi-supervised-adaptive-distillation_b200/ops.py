@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import native
-from .native import ConvLevel, DistillLevel, DistillParams, HostLevel, check, default_params, lib
+from .native import ConvLevel, DistillLevel, DistillParams, HostLevel, WgradLevel, check, default_params, lib
 
 
 def _stream():
@@ -220,7 +220,7 @@ def to_nhwc(xs):
     return outs
 
 
-def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc):
+def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc, masks_nhwc=None):
     arr = (ConvLevel * len(xs_nhwc))()
     ys, yts = [], []
     for i, xt in enumerate(xs_nhwc):
@@ -230,6 +230,11 @@ def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc):
             raise ValueError("input channels do not match the weights")
         arr[i].x_nhwc = xt.data_ptr()
         arr[i].N, arr[i].H, arr[i].W = n, h, w
+        if masks_nhwc is not None:
+            _require_cuda(masks_nhwc[i], torch.float32, "relu_mask_nhwc[%d]" % i)
+            if tuple(masks_nhwc[i].shape) != (n, h, w, m):
+                raise ValueError("relu mask must be channels-last (N, H, W, Cout_of_this_pass)")
+            arr[i].relu_mask_nhwc = masks_nhwc[i].data_ptr()
         if want_nchw:
             ys.append(torch.empty((n, m, h, w), dtype=torch.float32, device=xt.device))
             arr[i].y_nchw = ys[-1].data_ptr()
@@ -252,11 +257,41 @@ def conv3x3_forward(xs, weight, bias=None, relu=False, packed=None, xs_nhwc=None
     return _conv_run(xs_nhwc, packed, bias, cin, cout, relu, want_nchw, want_nhwc)
 
 
-def conv3x3_dgrad(dys, weight, packed=None, dys_nhwc=None, want_nchw=True, want_nhwc=False):
-    """Data gradient dX = conv(dY, W^T with flipped taps) of every level in one launch.  dys: (N, Cout, H, W)."""
+def conv3x3_dgrad(dys, weight, packed=None, dys_nhwc=None, want_nchw=True, want_nhwc=False, relu_masks_nhwc=None):
+    """Data gradient dX = conv(dY, W^T with flipped taps) of every level in one launch.  dys: (N, Cout, H, W).
+    relu_masks_nhwc: channels-last forward outputs Y (N, H, W, Cin) of the layer below; fuses its ReluGradient."""
     cout, cin = weight.shape[0], weight.shape[1]
     if packed is None:
         packed = conv3x3_pack(weight, 1)
     if dys_nhwc is None:
         dys_nhwc = to_nhwc(dys)
-    return _conv_run(dys_nhwc, packed, None, cout, cin, False, want_nchw, want_nhwc)
+    return _conv_run(dys_nhwc, packed, None, cout, cin, False, want_nchw, want_nhwc, relu_masks_nhwc)
+
+
+def conv3x3_wgrad(xs_nhwc, dys_nhwc, want_bias=True, accumulate_into=None, workspace=None):
+    """Weight (+ bias) gradient summed over every level in one launch.  xs_nhwc: channels-last forward inputs
+    (N, H, W, Cin); dys_nhwc: channels-last output gradients (N, H, W, Cout).  Returns (dW (Cout, Cin, 3, 3), db)."""
+    n = len(xs_nhwc)
+    arr = (WgradLevel * n)()
+    cin, cout = xs_nhwc[0].shape[3], dys_nhwc[0].shape[3]
+    for i, (xt, dt) in enumerate(zip(xs_nhwc, dys_nhwc)):
+        _require_cuda(xt, torch.float32, "x_nhwc[%d]" % i)
+        _require_cuda(dt, torch.float32, "dy_nhwc[%d]" % i)
+        if xt.shape[:3] != dt.shape[:3] or xt.shape[3] != cin or dt.shape[3] != cout:
+            raise ValueError("level %d: x (N,H,W,Cin) and dy (N,H,W,Cout) do not match" % i)
+        arr[i].x_nhwc, arr[i].dy_nhwc = xt.data_ptr(), dt.data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = xt.shape[:3]
+    dev = xs_nhwc[0].device
+    if accumulate_into is not None:
+        dw, db = accumulate_into
+    else:
+        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
+        db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
+    if workspace is None:
+        nbytes = lib().sad_conv3x3_wgrad_workspace_bytes(arr, n, cin, cout)
+        workspace = torch.empty(max(256, nbytes), dtype=torch.uint8, device=dev)
+    check(lib().sad_conv3x3_wgrad_f32(arr, n, cin, cout, C.c_void_p(dw.data_ptr()),
+                                      C.c_void_p(db.data_ptr()) if db is not None else None,
+                                      1 if accumulate_into is not None else 0,
+                                      C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+    return dw, db

@@ -117,3 +117,98 @@ def test_all_levels_one_launch_head_shapes(ops):
     for x, y in zip(xs, got):
         ref = torch.relu(torch.nn.functional.conv2d(x, wt, b, padding=1))
         assert_conv_close(y.cpu().numpy(), ref.cpu().numpy(), "level %dx%d" % tuple(x.shape[2:]))
+
+
+# ---------------------------------------------------------------------------------------------
+# weight / bias gradient (tcgen05, pixels as the reduction axis) and the fused ReluGradient mask
+# ---------------------------------------------------------------------------------------------
+WGRAD_CASES = [
+    # (N, Cin, Cout, H, W)
+    ((1, 32, 128, 8, 32), "one tile, one segment per row"),
+    ((2, 64, 128, 16, 64), "two segments per row"),
+    ((1, 256, 256, 20, 32), "head tower shape (P5)"),
+    ((2, 256, 256, 10, 16), "P6: half-filled pixel block"),
+    ((2, 256, 256, 5, 8), "P7"),
+    ((1, 48, 36, 12, 20), "Cin=48 / Cout=36 tails, ragged columns"),
+    ((1, 64, 720, 8, 40), "cls_pred Cout=720: 6 M tiles, last partial"),
+    ((1, 30, 20, 6, 10), "C % 4 != 0: SIMT path"),
+]
+
+
+@pytest.mark.parametrize("shape,name", WGRAD_CASES, ids=[c[1] for c in WGRAD_CASES])
+def test_wgrad_matches_oracle(ops, oracle, shape, name):
+    N, Cin, Cout, H, W = shape
+    rng = np.random.default_rng(11 + abs(hash(shape)) % (2 ** 31))
+    x = _rand(rng, (N, Cin, H, W), relu_like=True)
+    w = _rand(rng, (Cout, Cin, 3, 3), scale=0.05)
+    dy = _rand(rng, (N, Cout, H, W))
+    ref_dw, ref_db, _ = oracle.conv2d_bwd(x, w, dy, need_dx=False)
+    xt = ops.to_nhwc([torch.from_numpy(x).cuda()])
+    dyt = ops.to_nhwc([torch.from_numpy(dy).cuda()])
+    dw, db = ops.conv3x3_wgrad(xt, dyt)
+    torch.cuda.synchronize()
+    assert_conv_close(dw.cpu().numpy(), ref_dw, "conv wgrad " + name)
+    assert_conv_close(db.cpu().numpy(), ref_db, "conv bias grad " + name)
+    # run to run bit-identical (fixed-order split reduction, no atomics)
+    dw2, db2 = ops.conv3x3_wgrad(xt, dyt)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    # accumulate: adding the same gradient again doubles it
+    ops.conv3x3_wgrad(xt, dyt, accumulate_into=(dw2, db2))
+    assert_conv_close(dw2.cpu().numpy(), 2 * ref_dw, "conv wgrad accumulate " + name)
+    assert_conv_close(db2.cpu().numpy(), 2 * ref_db, "conv bias grad accumulate " + name)
+
+
+def test_wgrad_impulse_is_exact(ops):
+    # indexing check without rounding: sparse integer x and dy (exact in tf32): dW must equal the fp64 result
+    N, Cin, Cout, H, W = 2, 64, 160, 9, 36
+    rng = np.random.default_rng(5)
+    x = np.zeros((N, Cin, H, W), np.float32)
+    dy = np.zeros((N, Cout, H, W), np.float32)
+    for _ in range(300):
+        x[rng.integers(N), rng.integers(Cin), rng.integers(H), rng.integers(W)] = float(rng.integers(1, 4))
+        dy[rng.integers(N), rng.integers(Cout), rng.integers(H), rng.integers(W)] = float(rng.integers(-3, 4))
+    xt64 = torch.from_numpy(x).double().requires_grad_(False)
+    w64 = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(xt64, w64, padding=1).backward(torch.from_numpy(dy).double())
+    dw, db = ops.conv3x3_wgrad(ops.to_nhwc([torch.from_numpy(x).cuda()]), ops.to_nhwc([torch.from_numpy(dy).cuda()]))
+    assert np.array_equal(dw.cpu().numpy().astype(np.float64), w64.grad.numpy())
+    assert np.array_equal(db.cpu().numpy().astype(np.float64), dy.astype(np.float64).sum(axis=(0, 2, 3)))
+
+
+def test_wgrad_sums_levels_in_one_launch(ops):
+    # the head's weights are shared by the 5 FPN levels: one launch must equal the sum of the per-level
+    # gradients (what Caffe2 autograd's Sum op computes); reference = torch fp32 autograd, TF32 disabled
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(9)
+    shapes = [(80, 128), (40, 64), (20, 32), (10, 16), (5, 8)]
+    xs = [torch.randn(2, 256, h, w, device="cuda", generator=g).clamp_(min=0) for (h, w) in shapes]
+    dys = [torch.randn(2, 256, h, w, device="cuda", generator=g) for (h, w) in shapes]
+    wt = torch.zeros(256, 256, 3, 3, device="cuda", requires_grad=True)
+    b = torch.zeros(256, device="cuda", requires_grad=True)
+    for x, dy in zip(xs, dys):
+        torch.nn.functional.conv2d(x, wt, b, padding=1).backward(dy)
+    dw, db = ops.conv3x3_wgrad(ops.to_nhwc(xs), ops.to_nhwc(dys))
+    torch.cuda.synchronize()
+    assert_conv_close(dw.cpu().numpy(), wt.grad.cpu().numpy(), "wgrad 5 levels")
+    assert_conv_close(db.cpu().numpy(), b.grad.cpu().numpy(), "bias grad 5 levels")
+
+
+@pytest.mark.parametrize("shape,name", CASES[:6] + CASES[8:], ids=[c[1] for c in CASES[:6] + CASES[8:]])
+def test_dgrad_with_fused_relu_gradient(ops, oracle, shape, name):
+    # tower backward: dX = ReluGradient(Y_prev, conv_dgrad(dY)) in one pass (relu_op.cu:29-35)
+    N, Cin, Cout, H, W = shape
+    rng = np.random.default_rng(23 + abs(hash(shape)) % (2 ** 31))
+    y_prev = _rand(rng, (N, Cin, H, W), relu_like=True)   # forward output of the layer below (post-ReLU)
+    w = _rand(rng, (Cout, Cin, 3, 3), scale=1.0 / np.sqrt(9 * Cout))
+    dy = _rand(rng, (N, Cout, H, W))
+    _, _, ref_dx = oracle.conv2d_bwd(y_prev, w, dy)
+    ref = oracle.relu_grad(y_prev, ref_dx)
+    mask = ops.to_nhwc([torch.from_numpy(y_prev).cuda()])
+    got_nchw, got_cl = ops.conv3x3_dgrad([torch.from_numpy(dy).cuda()], torch.from_numpy(w).cuda(), want_nhwc=True,
+                                         relu_masks_nhwc=mask)
+    torch.cuda.synchronize()
+    assert_conv_close(got_nchw[0].cpu().numpy(), ref, "dgrad+relu-grad " + name)
+    assert_conv_close(got_cl[0].permute(0, 3, 1, 2).cpu().numpy(), ref, "dgrad+relu-grad channels-last " + name)
+    # masked positions are exactly zero
+    assert np.all(got_nchw[0].cpu().numpy()[y_prev <= 0] == 0)
