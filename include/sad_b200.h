@@ -136,6 +136,8 @@ typedef struct sad_conv_level {
   const float* relu_mask_nhwc; /* NULL, or channels-last (N, H, W, Cout): outputs are zeroed where mask <= 0.  Fuses the
                                   tower's in-place ReluGradient (relu_op.cu:29-35, dX = Y > 0 ? dY : 0) into the data-gradient
                                   pass of the NEXT convolution: mask = forward output Y of the layer whose dY is produced */
+  int32_t accumulate_nchw;     /* != 0: y_nchw += result instead of = (the autograd Sum when a blob has two consumers,
+                                  caffe2/caffe2/python/core.py:695,792-842: fpn_L feeds both towers) */
 } sad_conv_level;
 
 /* The tensor-core kernels read activations channels-last (TMA cannot shift the innermost NCHW
@@ -153,6 +155,14 @@ int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int chann
  * sad_conv3x3_packed_bytes(cin, cout) bytes of 16-byte aligned device memory. */
 size_t sad_conv3x3_packed_bytes(int cin, int cout);
 int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int cout, int mode, float* packed, void* stream);
+/* The same for up to SAD_MAX_PACK_ITEMS weight tensors in ONE launch (all 10 head weights, both modes). */
+#define SAD_MAX_PACK_ITEMS 32
+typedef struct sad_pack_item {
+  const float* weight; /* (cout, cin, 3, 3) */
+  float* packed;       /* sad_conv3x3_packed_bytes(cin, cout) bytes */
+  int32_t cin, cout, mode;
+} sad_pack_item;
+int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, void* stream);
 /* y = conv3x3(x, packed) + bias (bias may be NULL), optionally followed by ReLU (relu != 0).
  * `cin`/`cout` are the K/M of `packed` (for the data gradient pass cin = Cout_of_forward, cout = Cin_of_forward). */
 int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
@@ -175,6 +185,69 @@ size_t sad_conv3x3_wgrad_workspace_bytes(const sad_wgrad_level* levels, int n_le
 /* d_weight: (Cout, Cin, 3, 3) fp32; d_bias: (Cout) fp32 or NULL; workspace: 256-byte aligned device memory */
 int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
                           int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The whole RetinaNet FPN head, forward and backward — replaces the operator chains emitted by
+ *   add_fpn_retinanet_outputs              (detectron/lib/modeling/retinanet_heads.py:63-245)
+ * and the gradient operators Caffe2 autograd appends for them (ConvGradient, ReluGradient, Sum of the
+ * per-level gradients of shared weights, Sum of both towers' gradients into fpn_L;
+ * caffe2/caffe2/python/core.py:695,706-842, caffe2/caffe2/operators/conv_gradient_op.cc:35-77).
+ * Per FPN level: num_convs x (Conv 3x3 dim->dim + Relu) + Conv 3x3 dim->cls_out, and the same tower +
+ * Conv 3x3 dim->bbox_out; weights shared by all levels (blob names retnet_{cls,bbox}_conv_n{i}_fpn{k_min}_{w,b},
+ * retnet_{cls,bbox}_pred_fpn{k_min}_{w,b}).  All tensors fp32; fpn_L, predictions and their gradients NCHW;
+ * weights (Cout, Cin, 3, 3).  The object owns the channels-last activations kept between forward and
+ * backward, the packed weights and the reduction scratch (sad_head_device_bytes()).
+ * ------------------------------------------------------------------------------------------ */
+#define SAD_HEAD_MAX_CONVS 8
+typedef struct sad_head_config {
+  int32_t n_levels;             /* k_max - k_min + 1 (5) */
+  int32_t N;                    /* images per GPU (TRAIN.IMS_PER_BATCH) */
+  int32_t H[SAD_MAX_LEVELS];    /* level 0 = finest (fpn3) */
+  int32_t W[SAD_MAX_LEVELS];
+  int32_t dim;                  /* FPN.DIM = 256 */
+  int32_t num_convs;            /* RETINANET.NUM_CONVS = 4 */
+  int32_t cls_out;              /* A * (NUM_CLASSES - 1) = 720 */
+  int32_t bbox_out;             /* A * 4 = 36 */
+} sad_head_config;
+typedef struct sad_head_weights {
+  const float* cls_tower_w[SAD_HEAD_MAX_CONVS];  /* (dim, dim, 3, 3) */
+  const float* cls_tower_b[SAD_HEAD_MAX_CONVS];  /* (dim) or NULL */
+  const float* bbox_tower_w[SAD_HEAD_MAX_CONVS];
+  const float* bbox_tower_b[SAD_HEAD_MAX_CONVS];
+  const float* cls_pred_w;   /* (cls_out, dim, 3, 3) */
+  const float* cls_pred_b;
+  const float* bbox_pred_w;  /* (bbox_out, dim, 3, 3) */
+  const float* bbox_pred_b;
+} sad_head_weights;
+typedef struct sad_head_grads {  /* same shapes as the weights; bias gradients may be NULL */
+  float* cls_tower_w[SAD_HEAD_MAX_CONVS];
+  float* cls_tower_b[SAD_HEAD_MAX_CONVS];
+  float* bbox_tower_w[SAD_HEAD_MAX_CONVS];
+  float* bbox_tower_b[SAD_HEAD_MAX_CONVS];
+  float* cls_pred_w;
+  float* cls_pred_b;
+  float* bbox_pred_w;
+  float* bbox_pred_b;
+} sad_head_grads;
+typedef struct sad_head sad_head;
+void sad_head_default_config(sad_head_config* cfg); /* dim 256, num_convs 4, cls_out 720, bbox_out 36; levels unset */
+int sad_head_create(const sad_head_config* cfg, sad_head** out); /* on the current device */
+void sad_head_destroy(sad_head* head);
+size_t sad_head_device_bytes(const sad_head* head);
+/* fpn_nchw[l]: (N, dim, H_l, W_l); cls_logits_nchw[l]: (N, cls_out, H_l, W_l); bbox_pred_nchw[l]: (N, bbox_out, H_l, W_l).
+ * training != 0 also prepares the data-gradient weights (required before sad_head_backward). */
+int sad_head_forward(sad_head* head, const sad_head_weights* weights, const float* const* fpn_nchw,
+                     float* const* cls_logits_nchw, float* const* bbox_pred_nchw, int training, void* stream);
+/* Introspection: copies a kept activation of the last forward into dst_nhwc (N, H_l, W_l, dim), channels-last,
+ * tf32-rounded as stored.  tower 0 = cls, 1 = bbox; conv = -1: the head's input fpn_L, 0..num_convs-1: output of
+ * that tower conv after ReLU (the blob retnet_{cls,bbox}_conv_n{conv}_fpn{L}). */
+int sad_head_copy_activation(const sad_head* head, int tower, int conv, int level, float* dst_nhwc, void* stream);
+/* d_cls_logits_nchw / d_bbox_pred_nchw: gradients of the two predictions (either may be NULL: that branch is
+ * skipped and its weight gradients are left untouched).  d_fpn_nchw: NULL, or (N, dim, H_l, W_l) receiving the sum
+ * of both towers' input gradients.  accumulate != 0 adds into the weight/bias gradients instead of overwriting. */
+int sad_head_backward(sad_head* head, const sad_head_weights* weights, const float* const* d_cls_logits_nchw,
+                      const float* const* d_bbox_pred_nchw, const sad_head_grads* grads, float* const* d_fpn_nchw,
+                      int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

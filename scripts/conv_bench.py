@@ -50,7 +50,8 @@ def main():
     xs = [rnd(a.bs, 256, h, w).clamp_(min=0) for h, w in SHAPES]
     res["to_nhwc_256_ms"] = timeit(lambda: ops.to_nhwc(xs), a.iters)
     xs_cl = ops.to_nhwc(xs)
-    for cout in (256, 720, 36):
+    couts = [int(c) for c in a.only.split(',')] if a.only else [256, 720, 36]
+    for cout in couts:
         w = rnd(cout, 256, 3, 3) * 0.02
         b = rnd(cout)
         packed = ops.conv3x3_pack(w, 0)
@@ -69,6 +70,9 @@ def main():
             ms = timeit(lambda: ops.conv3x3_wgrad(xs_cl, dys), a.iters)
             res["wgrad_256_%d" % cout] = {"ms": ms, "tflops": flops / ms / 1e9}
         res["pack_%d_ms" % cout] = timeit(lambda: ops.conv3x3_pack(w, 0), a.iters)
+    if a.only:
+        print(json.dumps(res, indent=1))
+        return
     # torch / cuDNN fp32 (TF32 allowed and not) for context: library call, not the product
     import torch.nn.functional as F
     w = rnd(256, 256, 3, 3) * 0.02

@@ -69,7 +69,7 @@ struct ConvLevel {
   float* y_nhwc;            // may be null
   const float* mask_nhwc;   // may be null: ReluGradient fused into the data-gradient pass (out = mask > 0 ? out : 0)
   int32_t N, H, W;
-  int32_t pad;
+  int32_t accumulate;       // y_nchw += result (the autograd Sum of two consumers' gradients, core.py:695,792-842)
   uint32_t tiles_x, tiles_y, tile_begin, tile_end;
 };
 struct alignas(64) ConvArgs {
@@ -241,11 +241,21 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             if (vec_ok) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
-                if (t.x0 + i < L.W) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (t.x0 + i < L.W) {
+                  float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                  if (L.accumulate) {
+                    const float4 p = *reinterpret_cast<const float4*>(dst + i);
+                    o.x += p.x;
+                    o.y += p.y;
+                    o.z += p.z;
+                    o.w += p.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + i) = o;
+                }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (t.x0 + i < L.W) dst[i] = v[i];
+                if (t.x0 + i < L.W) dst[i] = L.accumulate ? dst[i] + v[i] : v[i];
             }
           }
           if (ycl) {
@@ -286,13 +296,35 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+struct PackMulti {
+  const float* src[SAD_MAX_PACK_ITEMS];
+  float* dst[SAD_MAX_PACK_ITEMS];
+  int32_t cin[SAD_MAX_PACK_ITEMS], cout[SAD_MAX_PACK_ITEMS], mode[SAD_MAX_PACK_ITEMS];
+};
+// every weight tensor of the head in one launch: blockIdx.y selects the tensor
+__global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
+  const int k_ = blockIdx.y;
+  const float* __restrict__ w = p.src[k_];
+  float* __restrict__ out = p.dst[k_];
+  const int cout = p.cout[k_], cin = p.cin[k_], mode = p.mode[k_];
+  const int M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
+  const size_t total = (size_t)9 * M * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int m = (int)((i / K) % M);
+    const int tap = (int)(i / ((size_t)K * M));
+    const float v = mode == 0 ? w[((size_t)m * cin + k) * 9 + tap] : w[((size_t)k * cin + m) * 9 + (8 - tap)];
+    out[i] = to_tf32_rna(v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SIMT fallback for channel counts the TMA path cannot address (C % 4 != 0): direct convolution from
 // the same packed weights and channels-last input.  One thread per output element.
 // ---------------------------------------------------------------------------------------------
 __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* __restrict__ wp, const float* __restrict__ bias,
                                     float* __restrict__ y_nchw, float* __restrict__ y_nhwc, const float* __restrict__ mask_nhwc, int N,
-                                    int cin, int cout, int H, int W, int relu) {
+                                    int cin, int cout, int H, int W, int relu, int accumulate) {
   const size_t total = (size_t)N * cout * H * W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % cout);
@@ -309,7 +341,10 @@ __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* _
     }
     if (relu) acc = fmaxf(acc, 0.f);
     if (mask_nhwc && !(mask_nhwc[i] > 0.f)) acc = 0.f;
-    if (y_nchw) y_nchw[(((size_t)n * cout + co) * H + yy) * W + xx] = acc;
+    if (y_nchw) {
+      float* o = y_nchw + (((size_t)n * cout + co) * H + yy) * W + xx;
+      *o = accumulate ? *o + acc : acc;
+    }
     if (y_nhwc) y_nhwc[i] = to_tf32_rna(acc);
   }
 }
@@ -383,6 +418,28 @@ SAD_EXPORT int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int co
   return check_cuda(cudaGetLastError(), "conv3x3 pack launch");
 }
 
+SAD_EXPORT int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, void* stream) {
+  if (!items || n_items < 1 || n_items > SAD_MAX_PACK_ITEMS) return set_error(SAD_ERR_INVALID, "conv3x3 pack multi: n_items must be in [1, 32]");
+  PackMulti p{};
+  size_t most = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const sad_pack_item& it = items[i];
+    if (!it.weight || !it.packed || it.cin < 1 || it.cout < 1 || (it.mode != 0 && it.mode != 1))
+      return set_error(SAD_ERR_INVALID, "conv3x3 pack multi: bad item");
+    p.src[i] = it.weight;
+    p.dst[i] = it.packed;
+    p.cin[i] = it.cin;
+    p.cout[i] = it.cout;
+    p.mode[i] = it.mode;
+    const size_t total = (size_t)9 * it.cin * it.cout;
+    if (total > most) most = total;
+  }
+  const unsigned bx = (unsigned)((most + 255) / 256 < 1024 ? (most + 255) / 256 : 1024);
+  conv3x3_pack_multi_kernel<<<dim3(bx, (unsigned)n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "conv3x3 pack multi launch");
+}
+
 SAD_EXPORT int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || channels < 1) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: bad argument");
   LayoutArgs a{};
@@ -436,6 +493,7 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     D.y_nchw = L.y_nchw;
     D.y_nhwc = L.y_nhwc;
     D.mask_nhwc = L.relu_mask_nhwc;
+    D.accumulate = L.accumulate_nchw;
     D.N = L.N;
     D.H = L.H;
     D.W = L.W;
@@ -454,7 +512,8 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
       if (total == 0) continue;
       const size_t blocks = (total + 127) / 128;
       conv3x3_simt_kernel<<<(unsigned)(blocks < 1048576 ? blocks : 1048576), 128, 0, st>>>(L.x_nhwc, packed, bias, L.y_nchw, L.y_nhwc,
-                                                                                           L.relu_mask_nhwc, L.N, cin, cout, L.H, L.W, relu);
+                                                                                           L.relu_mask_nhwc, L.N, cin, cout, L.H, L.W, relu,
+                                                                                           L.accumulate_nchw);
       count_launch(1);
       if ((rc = check_cuda(cudaGetLastError(), "conv3x3 simt launch")) != SAD_OK) return rc;
     }

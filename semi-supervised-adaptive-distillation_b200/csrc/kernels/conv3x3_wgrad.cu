@@ -61,8 +61,10 @@ struct WgLevel {
   uint32_t block_begin, block_end;    // pixel blocks (n, y, xseg) of this level on the global K axis
 };
 struct alignas(64) WgArgs {
-  CUtensorMap tmap_dy[SAD_MAX_LEVELS];
+  CUtensorMap tmap_dy[SAD_MAX_LEVELS];   // 4-D {C, W, H, N}, box {32, 32, 1, 1}: one 32-channel chunk (tail tiles)
   CUtensorMap tmap_x[SAD_MAX_LEVELS];
+  CUtensorMap tmap_dy5[SAD_MAX_LEVELS];  // 5-D {32, W, H, N, C/32}, box {32, 32, 1, 1, 4}: a whole M tile in one copy
+  CUtensorMap tmap_x5[SAD_MAX_LEVELS];   // 5-D, box {32, 32, 1, 1, 8}: a whole N tile in one copy
   WgLevel lv[SAD_MAX_LEVELS];
   float* partial;                     // [splits][9][cout][cin]
   int32_t n_levels, cin, cout;
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
     for (int l = 0; l < args.n_levels; ++l) {
       tma_prefetch_desc(&args.tmap_dy[l]);
       tma_prefetch_desc(&args.tmap_x[l]);
+      tma_prefetch_desc(&args.tmap_dy5[l]);
+      tma_prefetch_desc(&args.tmap_x5[l]);
     }
   }
   if (warp == 1) {
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
         int n = (int)(r / (uint32_t)args.lv[l].H);
         const int a_left = (args.cout - it.m0 + 31) / 32, b_left = (args.cin - it.n0 + 31) / 32;
         const int a_chunks = a_left < kWgM / 32 ? a_left : kWgM / 32, b_chunks = b_left < kWgN / 32 ? b_left : kWgN / 32;
+        const bool a_full = it.m0 + kWgM <= args.cout, b_full = it.n0 + kWgN <= args.cin;  // whole tile inside the tensor
         for (uint32_t kb = it.kb_begin; kb < it.kb_end; ++kb) {
           mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
           uint8_t* sa = smem + (size_t)rs.stage * kWgStageBytes;
@@ -152,14 +157,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
           // 32-channel chunks that lie entirely past Cout / Cin are not loaded: whatever the stage holds there
           // only reaches accumulator rows / columns the epilogue never writes out
           mbar_arrive_expect_tx(&full_bar[rs.stage], (uint32_t)(a_chunks + b_chunks) * kWgChunkBytes);
+          if (a_full) {  // the tile's 4 chunks in one 5-D copy: [chunk][pixel][32 channels], chunks 4 KB apart
+            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y, n, it.m0 / 32);
+          } else {
 #pragma unroll
-          for (int j = 0; j < kWgM / 32; ++j)
-            if (j < a_chunks)
-              tma_load_4d(sa + j * kWgChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + 32 * j, xs * kWgKP, y, n);
+            for (int j = 0; j < kWgM / 32; ++j)
+              if (j < a_chunks)
+                tma_load_4d(sa + j * kWgChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + 32 * j, xs * kWgKP, y, n);
+          }
+          if (b_full) {
+            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y + dy, n, it.n0 / 32);
+          } else {
 #pragma unroll
-          for (int j = 0; j < kWgN / 32; ++j)
-            if (j < b_chunks)
-              tma_load_4d(sb + j * kWgChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + 32 * j, xs * kWgKP + dx, y + dy, n);
+            for (int j = 0; j < kWgN / 32; ++j)
+              if (j < b_chunks)
+                tma_load_4d(sb + j * kWgChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + 32 * j, xs * kWgKP + dx, y + dy, n);
+          }
           rs.advance<kWgStages>();
           if (++xs == (int)args.lv[l].xsegs) {
             xs = 0;
@@ -290,7 +303,8 @@ __global__ void conv3x3_wgrad_simt_kernel(const WgSimtArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // db partials: block b sums the pixels [b * chunk, (b + 1) * chunk) of the concatenated levels for every
-// channel (thread t owns channels t, t + 256, ...): coalesced rows of the channels-last dY.
+// channel.  256 threads = 4 pixel lanes x 64 channel quads: 128-bit loads along the channels-last rows,
+// the 4 pixel lanes are combined through shared memory in a fixed order.
 // ---------------------------------------------------------------------------------------------
 struct BgArgs {
   const float* dy[SAD_MAX_LEVELS];
@@ -300,44 +314,102 @@ struct BgArgs {
   uint32_t chunk;
 };
 __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgArgs a) {
+  __shared__ float4 red[kBgThreads];
   const uint32_t total = a.pix_begin[a.n_levels];
   const uint32_t p0 = blockIdx.x * a.chunk;
   const uint32_t p1 = p0 + a.chunk < total ? p0 + a.chunk : total;
-  for (int c = threadIdx.x; c < a.cout; c += kBgThreads) {
-    float acc = 0.f;
-    int l = 0;
-    for (uint32_t p = p0; p < p1; ++p) {
-      while (p >= a.pix_begin[l + 1]) ++l;
-      acc += __ldg(a.dy[l] + (size_t)(p - a.pix_begin[l]) * a.cout + c);
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  if ((a.cout & 3) == 0) {
+    const int quads = a.cout >> 2;
+    for (int q0 = 0; q0 < quads; q0 += 64) {
+      const int q = q0 + tx;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < quads) {
+        for (int l = 0; l < a.n_levels; ++l) {
+          const uint32_t lo = p0 > a.pix_begin[l] ? p0 : a.pix_begin[l];
+          const uint32_t hi = p1 < a.pix_begin[l + 1] ? p1 : a.pix_begin[l + 1];
+          const float* base = a.dy[l] - (size_t)a.pix_begin[l] * a.cout + (size_t)q * 4;
+#pragma unroll 4
+          for (uint32_t p = lo + ty; p < hi; p += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * a.cout));
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+          }
+        }
+      }
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      if (ty == 0 && q < quads) {
+        float4 r = red[tx];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const float4 o = red[tx + 64 * k];
+          r.x += o.x;
+          r.y += o.y;
+          r.z += o.z;
+          r.w += o.w;
+        }
+        *reinterpret_cast<float4*>(a.partial + (size_t)blockIdx.x * a.cout + (size_t)q * 4) = r;
+      }
+      __syncthreads();
     }
-    a.partial[(size_t)blockIdx.x * a.cout + c] = acc;
+  } else {  // channel counts that are not a multiple of 4: scalar loads, one thread per channel
+    for (int c = threadIdx.x; c < a.cout; c += kBgThreads) {
+      float acc = 0.f;
+      int l = 0;
+      for (uint32_t p = p0; p < p1; ++p) {
+        while (p >= a.pix_begin[l + 1]) ++l;
+        acc += __ldg(a.dy[l] + (size_t)(p - a.pix_begin[l]) * a.cout + c);
+      }
+      a.partial[(size_t)blockIdx.x * a.cout + c] = acc;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // finish: dW[co][ci][tap] (+)= sum_s partial[s][tap][co][ci];  db[co] (+)= sum_b bias_partial[b][co]
+// A block of 288 threads = 9 taps (one warp each) x 32 consecutive (co, ci): coalesced 128-byte partial
+// reads, fixed summation order, and the 288 results leave through shared memory as one contiguous
+// run of the (Cout, Cin, 3, 3) tensor.
 // ---------------------------------------------------------------------------------------------
-__global__ void conv3x3_wgrad_finish_kernel(const float* __restrict__ partial, int splits, int cin, int cout, float* __restrict__ d_weight,
-                                            const float* __restrict__ bias_partial, int bias_blocks, float* __restrict__ d_bias,
-                                            int accumulate) {
+constexpr int kFinThreads = 288;
+__global__ void __launch_bounds__(kFinThreads) conv3x3_wgrad_finish_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
+                                                                          float* __restrict__ d_weight,
+                                                                          const float* __restrict__ bias_partial, int bias_blocks,
+                                                                          float* __restrict__ d_bias, int accumulate) {
+  __shared__ float out[kFinThreads];
   const size_t plane = (size_t)cout * cin;
-  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = gtid; i < plane; i += gsz) {  // i = co * cin + ci
-    float out[9];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += __ldg(partial + ((size_t)s * 9 + tap) * plane + i);
-      out[tap] = acc;
+  const int tap = threadIdx.x >> 5, ii = threadIdx.x & 31;
+  const size_t groups = (plane + 31) / 32;
+  for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+    const size_t i = g * 32 + ii;  // i = co * cin + ci
+    float acc = 0.f;
+    if (i < plane) {
+      const float* src = partial + (size_t)tap * plane + i;
+#pragma unroll 4
+      for (int s = 0; s < splits; ++s) acc += __ldg(src + (size_t)s * 9 * plane);
     }
-    float* dst = d_weight + i * 9;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) dst[tap] = accumulate ? dst[tap] + out[tap] : out[tap];
+    out[ii * 9 + tap] = acc;
+    __syncthreads();
+    const size_t o = g * 288 + threadIdx.x;
+    if (o < 9 * plane) d_weight[o] = accumulate ? d_weight[o] + out[threadIdx.x] : out[threadIdx.x];
+    __syncthreads();
   }
   if (d_bias) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
     for (size_t c = gtid; c < (size_t)cout; c += gsz) {
-      float acc = 0.f;
-      for (int b = 0; b < bias_blocks; ++b) acc += __ldg(bias_partial + (size_t)b * cout + c);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four interleaved chains, combined in a fixed order
+      int b = 0;
+      for (; b + 3 < bias_blocks; b += 4) {
+        a0 += __ldg(bias_partial + (size_t)b * cout + c);
+        a1 += __ldg(bias_partial + (size_t)(b + 1) * cout + c);
+        a2 += __ldg(bias_partial + (size_t)(b + 2) * cout + c);
+        a3 += __ldg(bias_partial + (size_t)(b + 3) * cout + c);
+      }
+      for (; b < bias_blocks; ++b) a0 += __ldg(bias_partial + (size_t)b * cout + c);
+      const float acc = (a0 + a1) + (a2 + a3);
       d_bias[c] = accumulate ? d_bias[c] + acc : acc;
     }
   }
@@ -384,9 +456,8 @@ static int wg_plan(const sad_wgrad_level* levels, int n_levels, int cin, int cou
   if (s > (uint32_t)kWgMaxSplits) s = kWgMaxSplits;
   p->splits = s;
   p->partial_bytes = (size_t)s * 9 * cout * cin * sizeof(float);
-  uint32_t bb = (uint32_t)((pixels + 63) / 64);
+  uint32_t bb = (uint32_t)((pixels + 31) / 32);
   if (bb > (uint32_t)kBgMaxBlocks) bb = kBgMaxBlocks;
-  if (bb > (uint32_t)sms * 4u) bb = (uint32_t)sms * 4u;
   if (bb < 1) bb = 1;
   p->bias_chunk = (uint32_t)((pixels + bb - 1) / bb);
   if (p->bias_chunk < 1) p->bias_chunk = 1;
@@ -394,6 +465,15 @@ static int wg_plan(const sad_wgrad_level* levels, int n_levels, int cin, int cou
   if (p->bias_blocks < 1) p->bias_blocks = 1;
   p->bias_partial_bytes = (size_t)kBgMaxBlocks * cout * sizeof(float);
   return SAD_OK;
+}
+
+// channels-last (N, H, W, C) viewed as {32 c_lo, W, H, N, C/32 c_hi}: only whole 32-channel chunks are addressable,
+// a box {32, box_x, 1, 1, chunks} lands as [chunk][pixel][32 channels]
+static int encode_nhwc5_map(CUtensorMap* m, const float* xt, int N, int C, int H, int W, int box_x, int chunks, const char* what) {
+  const cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 32)};
+  const cuuint64_t str[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, 128};
+  const cuuint32_t box[5] = {32, (cuuint32_t)box_x, 1, 1, (cuuint32_t)chunks};
+  return encode_map(m, xt, 5, dims, str, box, what, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 static int wg_sms(int* sms) {
@@ -467,12 +547,19 @@ SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels
       if (D.block_end == D.block_begin) continue;
       if ((rc = encode_nhwc_map(&a.tmap_dy[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, 1, "wgrad dY {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
       if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, 1, "wgrad X {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
+      // 5-D views {32 c_lo, W, H, N, C/32 c_hi} (c_hi stride 128 B) so one copy brings a whole tile of full chunks
+      if (cout >= kWgM && (rc = encode_nhwc5_map(&a.tmap_dy5[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, kWgM / 32, "wgrad dY 5-D")) != SAD_OK) return rc;
+      if (cin >= kWgN && (rc = encode_nhwc5_map(&a.tmap_x5[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, kWgN / 32, "wgrad X 5-D")) != SAD_OK) return rc;
+      if (cout < kWgM) a.tmap_dy5[l] = a.tmap_dy[l];  // never used (no full tile)
+      if (cin < kWgN) a.tmap_x5[l] = a.tmap_x[l];
       if (first_valid < 0) first_valid = l;
     }
     for (int l = 0; l < n_levels; ++l)
       if (a.lv[l].block_end == a.lv[l].block_begin) {  // empty level: valid dummy maps, never dereferenced
         a.tmap_dy[l] = a.tmap_dy[first_valid];
         a.tmap_x[l] = a.tmap_x[first_valid];
+        a.tmap_dy5[l] = a.tmap_dy5[first_valid];
+        a.tmap_x5[l] = a.tmap_x5[first_valid];
       }
     a.partial = partial;
     a.n_levels = n_levels;
@@ -526,9 +613,9 @@ SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels
     count_launch(1);
     if ((rc = check_cuda(cudaGetLastError(), "bias grad launch")) != SAD_OK) return rc;
   }
-  const size_t plane = (size_t)cin * cout;
-  const unsigned fblocks = (unsigned)((plane + 255) / 256 < (size_t)sms * 8 ? (plane + 255) / 256 : (size_t)sms * 8);
-  conv3x3_wgrad_finish_kernel<<<fblocks, 256, 0, st>>>(partial, (int)p.splits, cin, cout, d_weight, bias_partial, (int)p.bias_blocks,
+  const size_t groups = ((size_t)cin * cout + 31) / 32;
+  const unsigned fblocks = (unsigned)(groups < (size_t)sms * 16 ? groups : (size_t)sms * 16);
+  conv3x3_wgrad_finish_kernel<<<fblocks, kFinThreads, 0, st>>>(partial, (int)p.splits, cin, cout, d_weight, bias_partial, (int)p.bias_blocks,
                                                        d_bias, accumulate);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "conv3x3 wgrad finish launch");

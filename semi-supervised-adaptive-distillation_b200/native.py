@@ -32,7 +32,8 @@ class DistillParams(C.Structure):
 
 class ConvLevel(C.Structure):
     _fields_ = [("x_nhwc", C.c_void_p), ("y_nchw", C.c_void_p), ("y_nhwc", C.c_void_p),
-                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu_mask_nhwc", C.c_void_p)]
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu_mask_nhwc", C.c_void_p),
+                ("accumulate_nchw", C.c_int32)]
 
 
 class LayoutLevel(C.Structure):
@@ -41,6 +42,21 @@ class LayoutLevel(C.Structure):
 
 class WgradLevel(C.Structure):
     _fields_ = [("x_nhwc", C.c_void_p), ("dy_nhwc", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+SAD_HEAD_MAX_CONVS = 8
+
+
+class HeadConfig(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("N", C.c_int32), ("H", C.c_int32 * SAD_MAX_LEVELS), ("W", C.c_int32 * SAD_MAX_LEVELS),
+                ("dim", C.c_int32), ("num_convs", C.c_int32), ("cls_out", C.c_int32), ("bbox_out", C.c_int32)]
+
+
+class HeadTensors(C.Structure):
+    """sad_head_weights / sad_head_grads (same layout: const-ness differs only in C)."""
+    _fields_ = [("cls_tower_w", C.c_void_p * SAD_HEAD_MAX_CONVS), ("cls_tower_b", C.c_void_p * SAD_HEAD_MAX_CONVS),
+                ("bbox_tower_w", C.c_void_p * SAD_HEAD_MAX_CONVS), ("bbox_tower_b", C.c_void_p * SAD_HEAD_MAX_CONVS),
+                ("cls_pred_w", C.c_void_p), ("cls_pred_b", C.c_void_p), ("bbox_pred_w", C.c_void_p), ("bbox_pred_b", C.c_void_p)]
 
 
 class HostLevel(C.Structure):
@@ -92,6 +108,19 @@ def lib():
         l.sad_conv3x3_wgrad_workspace_bytes.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int]
         l.sad_conv3x3_wgrad_f32.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_head_default_config.argtypes = [C.POINTER(HeadConfig)]
+        l.sad_head_default_config.restype = None
+        l.sad_head_create.argtypes = [C.POINTER(HeadConfig), C.POINTER(C.c_void_p)]
+        l.sad_head_destroy.argtypes = [C.c_void_p]
+        l.sad_head_destroy.restype = None
+        l.sad_head_device_bytes.argtypes = [C.c_void_p]
+        l.sad_head_device_bytes.restype = C.c_size_t
+        l.sad_head_forward.argtypes = [C.c_void_p, C.POINTER(HeadTensors), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        l.sad_head_backward.argtypes = [C.c_void_p, C.POINTER(HeadTensors), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(HeadTensors), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        l.sad_head_copy_activation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.sad_conv3x3_pack_weights_multi_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = l
     return _lib
 
