@@ -138,7 +138,14 @@ typedef struct sad_conv_level {
                                   pass of the NEXT convolution: mask = forward output Y of the layer whose dY is produced */
   int32_t accumulate_nchw;     /* != 0: y_nchw += result instead of = (the autograd Sum when a blob has two consumers,
                                   caffe2/caffe2/python/core.py:695,792-842: fpn_L feeds both towers) */
+  uint32_t* relu_bits_out;       /* NULL, or sad_conv3x3_sign_bits_bytes() bytes: receives one bit per output element,
+                                    set where the (bias-added, ReLU-ed) output is > 0 — 1/32 of the traffic of a float mask */
+  const uint32_t* relu_bits_in;  /* NULL, or such a bit plane (of a tensor shaped like THIS pass's output): outputs are
+                                    zeroed where the bit is clear — the compact form of relu_mask_nhwc */
 } sad_conv_level;
+/* bytes of a sign-bit plane for an (N, channels, H, W) output: layout [N][H][ceil(W/32)][channels] uint32,
+ * bit i of a word <-> x = 32 * segment + i */
+size_t sad_conv3x3_sign_bits_bytes(int N, int channels, int H, int W);
 
 /* The tensor-core kernels read activations channels-last (TMA cannot shift the innermost NCHW
  * coordinate by one element).  One launch converts every level. */

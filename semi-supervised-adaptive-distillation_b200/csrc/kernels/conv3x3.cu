@@ -68,6 +68,8 @@ struct ConvLevel {
   float* y_nchw;            // may be null
   float* y_nhwc;            // may be null
   const float* mask_nhwc;   // may be null: ReluGradient fused into the data-gradient pass (out = mask > 0 ? out : 0)
+  uint32_t* bits_out;       // may be null: sign bits of the output, [N][H][ceil(W/32)][Cout], bit i <-> x = 32 * xb + i
+  const uint32_t* bits_in;  // may be null: the same layout, applied like mask_nhwc (bit set = pass)
   int32_t N, H, W;
   int32_t accumulate;       // y_nchw += result (the autograd Sum of two consumers' gradients, core.py:695,792-842)
   uint32_t tiles_x, tiles_y, tile_begin, tile_end;
@@ -217,6 +219,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
       float* yrow = L.y_nchw ? L.y_nchw + ((size_t)t.n * args.cout + (co_ok ? co : 0)) * HW : nullptr;
       float* ycl = L.y_nhwc ? L.y_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
       const float* mcl = L.mask_nhwc ? L.mask_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
+      // sign-bit planes: one word per (image row, 32-pixel segment, channel); this tile owns segment t.x0 / 32
+      const size_t bits_row0 = (((size_t)t.n * L.H) * L.tiles_x + (t.x0 >> 5)) * args.cout + (co_ok ? co : 0);
       const bool vec_ok = (L.W & 3) == 0;
 #pragma unroll 1
       for (int j = 0; j < kCvRows; ++j) {
@@ -229,12 +233,29 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             v[i] += b;
             if (args.relu) v[i] = fmaxf(v[i], 0.f);
           }
-          if (mcl) {
-            // ReluGradient (relu_op.cu:29-35: dX = Y > 0 ? dY : 0) with Y the channels-last forward output
-            const float* msk = mcl + ((size_t)y * L.W + t.x0) * args.cout;
+          if (L.bits_in) {
+            // ReluGradient (relu_op.cu:29-35: dX = Y > 0 ? dY : 0) from the sign bits the forward pass left: 1 word per row
+            const uint32_t bits = __ldg(L.bits_in + bits_row0 + (size_t)y * L.tiles_x * args.cout);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (t.x0 + i < L.W && !(__ldg(msk + (size_t)i * args.cout) > 0.f)) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? v[i] : 0.f;
+          } else if (mcl) {
+            // the same from a channels-last float tensor Y.  The 32 loads are issued back to back (volatile asm keeps
+            // the compiler from chaining them through two registers, which serialises the memory latency)
+            const float* msk = mcl + ((size_t)y * L.W + t.x0) * args.cout;
+            float m[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              m[i] = 1.f;
+              if (t.x0 + i < L.W) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(m[i]) : "l"(msk + (size_t)i * args.cout));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = m[i] > 0.f ? v[i] : 0.f;
+          }
+          if (L.bits_out) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+            L.bits_out[bits_row0 + (size_t)y * L.tiles_x * args.cout] = bits;
           }
           if (yrow) {
             float* dst = yrow + (size_t)y * L.W + t.x0;
@@ -301,20 +322,23 @@ struct PackMulti {
   float* dst[SAD_MAX_PACK_ITEMS];
   int32_t cin[SAD_MAX_PACK_ITEMS], cout[SAD_MAX_PACK_ITEMS], mode[SAD_MAX_PACK_ITEMS];
 };
-// every weight tensor of the head in one launch: blockIdx.y selects the tensor
+// every weight tensor of the head in one launch: blockIdx.y selects the tensor; one thread per (row m, column k)
+// of the packed planes moves the 9 taps (writes coalesced along k in each tap plane)
 __global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
   const int k_ = blockIdx.y;
   const float* __restrict__ w = p.src[k_];
   float* __restrict__ out = p.dst[k_];
   const int cout = p.cout[k_], cin = p.cin[k_], mode = p.mode[k_];
-  const int M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
-  const size_t total = (size_t)9 * M * K;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % K);
-    const int m = (int)((i / K) % M);
-    const int tap = (int)(i / ((size_t)K * M));
-    const float v = mode == 0 ? w[((size_t)m * cin + k) * 9 + tap] : w[((size_t)k * cin + m) * 9 + (8 - tap)];
-    out[i] = to_tf32_rna(v);
+  const uint32_t M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
+  const uint32_t plane = M * K;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+    const uint32_t k = i % K, m = i / K;
+    const float* src = mode == 0 ? w + ((size_t)m * cin + k) * 9 : w + ((size_t)k * cin + m) * 9;
+    float v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) v[tap] = __ldg(src + tap);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) out[(size_t)tap * plane + i] = to_tf32_rna(mode == 0 ? v[tap] : v[8 - tap]);
   }
 }
 
@@ -323,8 +347,9 @@ __global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
 // the same packed weights and channels-last input.  One thread per output element.
 // ---------------------------------------------------------------------------------------------
 __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* __restrict__ wp, const float* __restrict__ bias,
-                                    float* __restrict__ y_nchw, float* __restrict__ y_nhwc, const float* __restrict__ mask_nhwc, int N,
-                                    int cin, int cout, int H, int W, int relu, int accumulate) {
+                                    float* __restrict__ y_nchw, float* __restrict__ y_nhwc, const float* __restrict__ mask_nhwc,
+                                    uint32_t* __restrict__ bits_out, const uint32_t* __restrict__ bits_in, int N, int cin, int cout,
+                                    int H, int W, int relu, int accumulate) {
   const size_t total = (size_t)N * cout * H * W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % cout);
@@ -341,6 +366,9 @@ __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* _
     }
     if (relu) acc = fmaxf(acc, 0.f);
     if (mask_nhwc && !(mask_nhwc[i] > 0.f)) acc = 0.f;
+    const size_t word = (((size_t)n * H + yy) * ((W + 31) / 32) + (xx >> 5)) * cout + co;
+    if (bits_in && !((bits_in[word] >> (xx & 31)) & 1u)) acc = 0.f;
+    if (bits_out && acc > 0.f) atomicOr(bits_out + word, 1u << (xx & 31));  // zeroed by the launcher
     if (y_nchw) {
       float* o = y_nchw + (((size_t)n * cout + co) * H + yy) * W + xx;
       *o = accumulate ? *o + acc : acc;
@@ -402,6 +430,11 @@ using namespace sad;
 
 extern "C" {
 
+SAD_EXPORT size_t sad_conv3x3_sign_bits_bytes(int N, int channels, int H, int W) {
+  if (N < 0 || channels < 0 || H < 0 || W < 0) return 0;
+  return (size_t)N * H * ((W + 31) / 32) * channels * sizeof(uint32_t);
+}
+
 SAD_EXPORT size_t sad_conv3x3_packed_bytes(int cin, int cout) {
   if (cin < 1 || cout < 1) return 0;
   return (size_t)9 * cin * cout * sizeof(float);
@@ -431,7 +464,7 @@ SAD_EXPORT int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, in
     p.cin[i] = it.cin;
     p.cout[i] = it.cout;
     p.mode[i] = it.mode;
-    const size_t total = (size_t)9 * it.cin * it.cout;
+    const size_t total = (size_t)it.cin * it.cout;
     if (total > most) most = total;
   }
   const unsigned bx = (unsigned)((most + 255) / 256 < 1024 ? (most + 255) / 256 : 1024);
@@ -493,6 +526,8 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     D.y_nchw = L.y_nchw;
     D.y_nhwc = L.y_nhwc;
     D.mask_nhwc = L.relu_mask_nhwc;
+    D.bits_out = L.relu_bits_out;
+    D.bits_in = L.relu_bits_in;
     D.accumulate = L.accumulate_nchw;
     D.N = L.N;
     D.H = L.H;
@@ -511,8 +546,13 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
       const size_t total = (size_t)L.N * cout * L.H * L.W;
       if (total == 0) continue;
       const size_t blocks = (total + 127) / 128;
+      if (L.relu_bits_out &&
+          (rc = check_cuda(cudaMemsetAsync(L.relu_bits_out, 0, (size_t)L.N * L.H * ((L.W + 31) / 32) * cout * sizeof(uint32_t), st),
+                           "conv3x3 simt: clear sign bits")) != SAD_OK)
+        return rc;
       conv3x3_simt_kernel<<<(unsigned)(blocks < 1048576 ? blocks : 1048576), 128, 0, st>>>(L.x_nhwc, packed, bias, L.y_nchw, L.y_nhwc,
-                                                                                           L.relu_mask_nhwc, L.N, cin, cout, L.H, L.W, relu,
+                                                                                           L.relu_mask_nhwc, L.relu_bits_out, L.relu_bits_in, L.N, cin, cout, L.H,
+                                                                                           L.W, relu,
                                                                                            L.accumulate_nchw);
       count_launch(1);
       if ((rc = check_cuda(cudaGetLastError(), "conv3x3 simt launch")) != SAD_OK) return rc;

@@ -398,19 +398,15 @@ __global__ void __launch_bounds__(kFinThreads) conv3x3_wgrad_finish_kernel(const
     __syncthreads();
   }
   if (d_bias) {
-    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = gtid; c < (size_t)cout; c += gsz) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four interleaved chains, combined in a fixed order
-      int b = 0;
-      for (; b + 3 < bias_blocks; b += 4) {
-        a0 += __ldg(bias_partial + (size_t)b * cout + c);
-        a1 += __ldg(bias_partial + (size_t)(b + 1) * cout + c);
-        a2 += __ldg(bias_partial + (size_t)(b + 2) * cout + c);
-        a3 += __ldg(bias_partial + (size_t)(b + 3) * cout + c);
-      }
-      for (; b < bias_blocks; ++b) a0 += __ldg(bias_partial + (size_t)b * cout + c);
-      const float acc = (a0 + a1) + (a2 + a3);
-      d_bias[c] = accumulate ? d_bias[c] + acc : acc;
+    // one warp per channel: lanes stride over the partial blocks, then a fixed-order shuffle tree
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t c = warp; c < (size_t)cout; c += warps) {
+      float acc = 0.f;
+      for (int b = lane; b < bias_blocks; b += 32) acc += __ldg(bias_partial + (size_t)b * cout + c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) d_bias[c] = accumulate ? d_bias[c] + acc : acc;
     }
   }
 }

@@ -13,7 +13,8 @@
 //   forward : 1 layout pass + 1 weight-pack launch + 10 convolution launches (all levels per launch,
 //             bias + ReLU fused, activations kept channels-last for the next layer and for backward)
 //   backward: 2 layout passes + per conv {1 weight-gradient launch + bias partials + finish, 1 data-gradient
-//             launch with ReluGradient fused}; the two towers run on two streams.
+//             launch with ReluGradient fused (from 1-bit sign planes the forward pass leaves)}; the two towers
+//             run on two streams.
 // Boundary tensors keep the operator contract: fpn_L, logits, box deltas and their gradients are NCHW
 // fp32; weights (Cout, Cin, 3, 3); gradients in the weights' layouts.
 #include <cuda_runtime.h>
@@ -36,6 +37,8 @@ struct sad_head {
   // channels-last activations: x0 = fpn input, act[t][i] = output of tower t's conv i (post-ReLU)
   float* x0[SAD_MAX_LEVELS] = {};
   float* act[2][SAD_HEAD_MAX_CONVS][SAD_MAX_LEVELS] = {};
+  // sign bits of act (1 bit per element): what the fused ReluGradient of the backward pass reads
+  uint32_t* bits[2][SAD_HEAD_MAX_CONVS][SAD_MAX_LEVELS] = {};
   // channels-last gradients: gpred[t] = d(prediction) (Cout = pred_out[t]); g[t][2] ping-pong (dim)
   float* gpred[2][SAD_MAX_LEVELS] = {};
   float* g[2][2][SAD_MAX_LEVELS] = {};
@@ -88,8 +91,9 @@ int pack_all(sad_head* h, const sad_head_weights* w, bool with_bwd, cudaStream_t
   return sad_conv3x3_pack_weights_multi_f32(items, n, st);
 }
 
-int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float* const* y_nhwc, float* const* mask, int accumulate,
-                const float* packed, const float* bias, int cin, int cout, int relu, cudaStream_t st) {
+int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float* const* y_nhwc, uint32_t* const* bits_out,
+                uint32_t* const* bits_in, int accumulate, const float* packed, const float* bias, int cin, int cout, int relu,
+                cudaStream_t st) {
   sad_conv_level lv[SAD_MAX_LEVELS];
   for (int l = 0; l < h->cfg.n_levels; ++l) {
     lv[l].x_nhwc = x[l];
@@ -98,7 +102,9 @@ int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float*
     lv[l].N = h->cfg.N;
     lv[l].H = h->cfg.H[l];
     lv[l].W = h->cfg.W[l];
-    lv[l].relu_mask_nhwc = mask ? mask[l] : nullptr;
+    lv[l].relu_mask_nhwc = nullptr;
+    lv[l].relu_bits_out = bits_out ? bits_out[l] : nullptr;
+    lv[l].relu_bits_in = bits_in ? bits_in[l] : nullptr;
     lv[l].accumulate_nchw = accumulate;
   }
   return sad_conv3x3_fwd_f32(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
@@ -195,7 +201,10 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
   for (int l = 0; l < L; ++l) {
     slot(&h->x0[l], h->pixels[l] * dim);
     for (int t = 0; t < 2; ++t) {
-      for (int i = 0; i < nc; ++i) slot(&h->act[t][i][l], h->pixels[l] * dim);
+      for (int i = 0; i < nc; ++i) {
+        slot(&h->act[t][i][l], h->pixels[l] * dim);
+        slot(reinterpret_cast<float**>(&h->bits[t][i][l]), sad_conv3x3_sign_bits_bytes(cfg->N, dim, cfg->H[l], cfg->W[l]) / sizeof(float));
+      }
       slot(&h->gpred[t][l], h->pixels[l] * pred_out(*cfg, t));
       for (int k = 0; k < 2; ++k) slot(&h->g[t][k][l], h->pixels[l] * dim);
     }
@@ -262,11 +271,14 @@ SAD_EXPORT int sad_head_forward(sad_head* h, const sad_head_weights* w, const fl
     float* const* in = h->x0;
     for (int i = 0; i < nc; ++i) {
       // Conv + in-place Relu (retinanet_heads.py:101-124, 188-209); only the channels-last copy is materialised
-      if ((rc = conv_levels(h, in, nullptr, h->act[t][i], nullptr, 0, h->packed[0][t][i], tower_b(w, t, i), dim, dim, 1, s)) != SAD_OK) return rc;
+      if ((rc = conv_levels(h, in, nullptr, h->act[t][i], training ? h->bits[t][i] : nullptr, nullptr, 0, h->packed[0][t][i],
+                            tower_b(w, t, i), dim, dim, 1, s)) != SAD_OK)
+        return rc;
       in = h->act[t][i];
     }
     float* const* out = t == 0 ? cls_logits_nchw : bbox_pred_nchw;
-    if ((rc = conv_levels(h, in, out, nullptr, nullptr, 0, h->packed[0][t][nc], pred_b(w, t), dim, pred_out(h->cfg, t), 0, s)) != SAD_OK) return rc;
+    if ((rc = conv_levels(h, in, out, nullptr, nullptr, nullptr, 0, h->packed[0][t][nc], pred_b(w, t), dim, pred_out(h->cfg, t), 0, s)) != SAD_OK)
+      return rc;
   }
   if ((rc = check_cuda(cudaEventRecord(h->ev_join, h->s_side), "cudaEventRecord")) != SAD_OK) return rc;
   return check_cuda(cudaStreamWaitEvent(st, h->ev_join, 0), "cudaStreamWaitEvent");
@@ -308,7 +320,7 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
       const bool last = i == 0;  // this pass produces d(fpn_L)
       if (last && !d_fpn_nchw) break;
       float* const* out_cl = last ? nullptr : h->g[t][i & 1];
-      float* const* mask = last ? nullptr : h->act[t][i - 1];
+      uint32_t* const* mask = last ? nullptr : h->bits[t][i - 1];
       int acc = 0;
       if (last) {
         if (t == 1 && two) {  // the other tower writes d_fpn first; this one adds to it
@@ -316,7 +328,8 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
         }
         acc = fpn_written ? 1 : 0;
       }
-      if ((rc = conv_levels(h, dy, last ? d_fpn_nchw : nullptr, out_cl, mask, acc, h->packed[1][t][i], nullptr, dy_c, dim, 0, s)) != SAD_OK) return rc;
+      if ((rc = conv_levels(h, dy, last ? d_fpn_nchw : nullptr, out_cl, nullptr, mask, acc, h->packed[1][t][i], nullptr, dy_c, dim, 0, s)) != SAD_OK)
+        return rc;
       if (last) {
         fpn_written = true;
         if (t == 0 && two && (rc = check_cuda(cudaEventRecord(h->ev_main, s), "cudaEventRecord")) != SAD_OK) return rc;

@@ -33,7 +33,7 @@ class DistillParams(C.Structure):
 class ConvLevel(C.Structure):
     _fields_ = [("x_nhwc", C.c_void_p), ("y_nchw", C.c_void_p), ("y_nhwc", C.c_void_p),
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu_mask_nhwc", C.c_void_p),
-                ("accumulate_nchw", C.c_int32)]
+                ("accumulate_nchw", C.c_int32), ("relu_bits_out", C.c_void_p), ("relu_bits_in", C.c_void_p)]
 
 
 class LayoutLevel(C.Structure):
@@ -120,6 +120,8 @@ def lib():
         l.sad_head_backward.argtypes = [C.c_void_p, C.POINTER(HeadTensors), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(HeadTensors), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         l.sad_head_copy_activation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.sad_conv3x3_sign_bits_bytes.restype = C.c_size_t
+        l.sad_conv3x3_sign_bits_bytes.argtypes = [C.c_int] * 4
         l.sad_conv3x3_pack_weights_multi_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = l
     return _lib

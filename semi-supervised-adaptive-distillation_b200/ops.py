@@ -220,9 +220,14 @@ def to_nhwc(xs):
     return outs
 
 
-def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc, masks_nhwc=None):
+def sign_bits_like(n, c, h, w, device):
+    nbytes = lib().sad_conv3x3_sign_bits_bytes(n, c, h, w)
+    return torch.empty(max(1, nbytes // 4), dtype=torch.int32, device=device)
+
+
+def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc, masks_nhwc=None, bits_in=None, want_bits=False):
     arr = (ConvLevel * len(xs_nhwc))()
-    ys, yts = [], []
+    ys, yts, bits = [], [], []
     for i, xt in enumerate(xs_nhwc):
         _require_cuda(xt, torch.float32, "x_nhwc[%d]" % i)
         n, h, w, c = xt.shape
@@ -235,6 +240,11 @@ def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc, masks_nhw
             if tuple(masks_nhwc[i].shape) != (n, h, w, m):
                 raise ValueError("relu mask must be channels-last (N, H, W, Cout_of_this_pass)")
             arr[i].relu_mask_nhwc = masks_nhwc[i].data_ptr()
+        if bits_in is not None:
+            arr[i].relu_bits_in = bits_in[i].data_ptr()
+        if want_bits:
+            bits.append(sign_bits_like(n, m, h, w, xt.device))
+            arr[i].relu_bits_out = bits[-1].data_ptr()
         if want_nchw:
             ys.append(torch.empty((n, m, h, w), dtype=torch.float32, device=xt.device))
             arr[i].y_nchw = ys[-1].data_ptr()
@@ -243,10 +253,10 @@ def _conv_run(xs_nhwc, packed, bias, k, m, relu, want_nchw, want_nhwc, masks_nhw
             arr[i].y_nhwc = yts[-1].data_ptr()
     b = C.c_void_p(bias.data_ptr()) if bias is not None else None
     check(lib().sad_conv3x3_fwd_f32(arr, len(xs_nhwc), C.c_void_p(packed.data_ptr()), b, k, m, 1 if relu else 0, _stream()))
-    return ys, yts
+    return (ys, yts, bits) if want_bits else (ys, yts)
 
 
-def conv3x3_forward(xs, weight, bias=None, relu=False, packed=None, xs_nhwc=None, want_nchw=True, want_nhwc=False):
+def conv3x3_forward(xs, weight, bias=None, relu=False, packed=None, xs_nhwc=None, want_nchw=True, want_nhwc=False, want_bits=False):
     """Conv (+bias, + optional fused ReLU) of every level in one launch.  xs: list of (N, Cin, H, W)
     (or pass xs_nhwc, channels-last copies from to_nhwc / a previous call).  Returns (ys_nchw, ys_nhwc)."""
     cout, cin = weight.shape[0], weight.shape[1]
@@ -254,10 +264,10 @@ def conv3x3_forward(xs, weight, bias=None, relu=False, packed=None, xs_nhwc=None
         packed = conv3x3_pack(weight, 0)
     if xs_nhwc is None:
         xs_nhwc = to_nhwc(xs)
-    return _conv_run(xs_nhwc, packed, bias, cin, cout, relu, want_nchw, want_nhwc)
+    return _conv_run(xs_nhwc, packed, bias, cin, cout, relu, want_nchw, want_nhwc, want_bits=want_bits)
 
 
-def conv3x3_dgrad(dys, weight, packed=None, dys_nhwc=None, want_nchw=True, want_nhwc=False, relu_masks_nhwc=None):
+def conv3x3_dgrad(dys, weight, packed=None, dys_nhwc=None, want_nchw=True, want_nhwc=False, relu_masks_nhwc=None, relu_bits=None):
     """Data gradient dX = conv(dY, W^T with flipped taps) of every level in one launch.  dys: (N, Cout, H, W).
     relu_masks_nhwc: channels-last forward outputs Y (N, H, W, Cin) of the layer below; fuses its ReluGradient."""
     cout, cin = weight.shape[0], weight.shape[1]
@@ -265,7 +275,7 @@ def conv3x3_dgrad(dys, weight, packed=None, dys_nhwc=None, want_nchw=True, want_
         packed = conv3x3_pack(weight, 1)
     if dys_nhwc is None:
         dys_nhwc = to_nhwc(dys)
-    return _conv_run(dys_nhwc, packed, None, cout, cin, False, want_nchw, want_nhwc, relu_masks_nhwc)
+    return _conv_run(dys_nhwc, packed, None, cout, cin, False, want_nchw, want_nhwc, relu_masks_nhwc, bits_in=relu_bits)
 
 
 def conv3x3_wgrad(xs_nhwc, dys_nhwc, want_bias=True, accumulate_into=None, workspace=None):

@@ -212,3 +212,30 @@ def test_dgrad_with_fused_relu_gradient(ops, oracle, shape, name):
     assert_conv_close(got_cl[0].permute(0, 3, 1, 2).cpu().numpy(), ref, "dgrad+relu-grad channels-last " + name)
     # masked positions are exactly zero
     assert np.all(got_nchw[0].cpu().numpy()[y_prev <= 0] == 0)
+
+
+@pytest.mark.parametrize("shape,name", [CASES[1], CASES[2], CASES[5], CASES[7], CASES[8]], ids=[c[1] for c in [CASES[1], CASES[2], CASES[5], CASES[7], CASES[8]]])
+def test_sign_bits_roundtrip(ops, oracle, shape, name):
+    # forward conv + ReLU leaves 1 bit per output element; the data-gradient pass of the layer above applies them
+    # (ReluGradient) and must equal the float-mask form exactly
+    N, Cin, Cout, H, W = shape
+    rng = np.random.default_rng(31 + abs(hash(shape)) % (2 ** 31))
+    x = _rand(rng, (N, Cin, H, W), relu_like=True)
+    w = _rand(rng, (Cout, Cin, 3, 3), scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand(rng, (Cout,))
+    xd, wd, bd = (torch.from_numpy(a).cuda() for a in (x, w, b))
+    ys, yts, bits = ops.conv3x3_forward([xd], wd, bd, relu=True, want_nhwc=True, want_bits=True)
+    # bit (n, y, seg, co) i  <->  y_nchw[n, co, y, 32 * seg + i] > 0
+    yb = (ys[0] > 0).cpu().numpy()
+    segs = (W + 31) // 32
+    words = bits[0].cpu().numpy().view(np.uint32).reshape(N, H, segs, Cout)
+    for i in range(min(W, 32 * segs)):
+        got = (words[:, :, i // 32, :] >> np.uint32(i % 32)) & 1
+        assert np.array_equal(got.astype(bool), yb[:, :, :, i].transpose(0, 2, 1)), "bit plane column %d" % i
+    # next layer's data gradient (Cout2 -> Cout channels) masked by bits == masked by the float tensor
+    w2 = _rand(rng, (40, Cout, 3, 3), scale=0.05)
+    dy2 = _rand(rng, (N, 40, H, W))
+    a_, _ = ops.conv3x3_dgrad([torch.from_numpy(dy2).cuda()], torch.from_numpy(w2).cuda(), relu_bits=bits)
+    b_, _ = ops.conv3x3_dgrad([torch.from_numpy(dy2).cuda()], torch.from_numpy(w2).cuda(), relu_masks_nhwc=yts)
+    torch.cuda.synchronize()
+    assert torch.equal(a_[0], b_[0])
