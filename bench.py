@@ -162,6 +162,80 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def _tensor_peak():
+    """tf32 tensor peak for a kernel timed inside a long step: half the measured sustained bf16 rate (tf32 runs at
+    half the bf16 rate on this part: 1.1 vs 2.25 PFLOP/s nominal, B200_PROFILING.md); MEASURED_PEAKS.json holds no tf32 figure."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2.0, "measured bf16_tflops_sustained / 2 (tf32 = half the bf16 rate)"
+        except Exception:
+            pass
+    return 1400.0 / 2.0, "fallback: 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) / 2"
+
+
+def run_head_step(args, rank, world, barrier, native):
+    """the widened path on every rank's own 2-image shard — student head forward, PowSum, fused
+    distillation loss + gradient, head backward (device work replayed from ONE CUDA graph), then the step's only
+    collective (SUM-allreduce of the 25.9 MB flat head-gradient buffer) and the momentum-SGD update."""
+    import torch
+    import torch.distributed as dist
+    from sad_b200.step import DistillHeadStep
+
+    K = args.head_steps or min(args.steps, 100)
+    st = DistillHeadStep(n_images=2, scale_px=600, world=world, rank=rank)
+    n0 = native.lib().sad_launch_count()
+    st.forward_backward()
+    per_step = int(native.lib().sad_launch_count() - n0)
+    st.capture()
+
+    def one():
+        st.run()
+        st.allreduce()
+        st.sgd()
+
+    for _ in range(5):
+        one()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev0.record()
+    for i in range(K):
+        st.run()
+        ar[i][0].record()
+        st.allreduce()
+        ar[i][1].record()
+        st.sgd()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) / K, sum(a.elapsed_time(b) for a, b in ar) / K], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0].item()), float(t[1].item())
+    losses = st.losses()
+    assert all(l == l and abs(l) < 1e30 for l in losses), ("non-finite distillation loss", losses)
+    fwd_f, bwd_f = st.flops()
+    dev_ms = ms - ar_ms
+    peak, src = _tensor_peak()
+    achieved = (fwd_f + bwd_f) / (ms * 1e-3) / 1e12
+    return {
+        "metric": "RetinaNet head distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s",
+        "ms_per_step": ms, "steps": K, "images_per_gpu": st.images, "scaling": "weak",
+        "workload": "student head fwd (10 convs, 5 levels) + PowSum + fused distill loss+grad + head bwd (dgrad + wgrad) at bs=2/GPU, "
+                    "600px, then ONE allreduce of %d head-gradient bytes + momentum SGD" % st.exchange.nbytes,
+        "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
+        "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
+        "conv_gflop_per_step": (fwd_f + bwd_f) / 1e9,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tf32_kernel + conv3x3_wgrad_tf32_kernel (tcgen05 kind::tf32, 30 launches/step)",
+                     "achieved": achieved, "peak": peak, "peak_source": src, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "note": "achieved = algorithmic conv flops of the step / WHOLE step time (loss kernels, layout passes, allreduce and "
+                             "SGD included); device-only step %.3f ms" % dev_ms},
+        "gpu_launches": per_step * (K + 5), "launches_per_step": per_step, "cuda_graph": True,
+        "dtype": "tf32 operands, fp32 accumulate (convs); f32 (loss)", "distill_losses": losses,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +244,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--head-steps", type=int, default=0, help="head distillation steps (0 = min(steps, 100); -1 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -275,6 +350,10 @@ def main():
         assert abs(a - b.item()) <= 1e-5 * abs(b.item()), ("e2e/device loss mismatch", a, b.item())
     step.close()
 
+    head_line = None
+    if args.head_steps >= 0:
+        head_line = run_head_step(args, rank, world, barrier, native)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,9 +376,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
                 "api": "sad_distill_step_host (pinned host buffers in, losses + normaliser + gradients out)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) + (head_line["gpu_launches"] if head_line else 0),
         "clocks": sampler.result(),
     }
+    if head_line:
+        line["head_step"] = head_line
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_oracle
         sample = host  # the full configs[1] batch, one pass (about 10-30 s of CPU work spread over the cores)

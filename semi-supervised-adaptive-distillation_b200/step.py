@@ -13,7 +13,7 @@ replayed with one host call — the reference synchronises the stream after ever
 """
 import torch
 
-from . import ops, synthetic
+from . import ops, parallel, synthetic
 from .head import RetinaNetHead
 
 
@@ -44,7 +44,8 @@ class DistillHeadStep:
             if with_bbox_branch else None
         self.d_fpn = [torch.empty_like(x) for x in self.fpn]
         self.plan = ops.DistillPlan(list(zip(self.cls, self.teacher, self.labels)), power=power, gamma=gamma, alpha=alpha, beta=beta,
-                                    scale=temperature ** 2 / self.world, num_classes=Cc, ignored_label=-1)
+                                    scale=parallel.distill_loss_scale(temperature, self.world), num_classes=Cc, ignored_label=-1)
+        self.exchange = parallel.GradientExchange(self.head.flat_grads, world=self.world)
         self.momentum = torch.zeros_like(self.head.flat_params)
         self.graph = None
         self.images = N
@@ -77,9 +78,8 @@ class DistillHeadStep:
             self.forward_backward()
 
     def allreduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.head.flat_grads, op=dist.ReduceOp.SUM)
+        """The step's only collective: SUM of the flat head-gradient buffer over the ranks."""
+        return self.exchange.allreduce()
 
     def sgd(self, lr=0.01, momentum=0.9, weight_decay=1e-4):
         """MomentumSGDUpdate with weight decay folded in (optimizer.py:95-130; biases get lr x2 and no decay there —
