@@ -175,6 +175,12 @@ int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, 
 int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                         int cout, int relu, void* stream);
 
+/* Relu / ReluGradient as stand-alone operators — replace ReluOp / ReluGradientOp<float, CUDAContext>::RunOnDevice
+ * (caffe2/caffe2/operators/relu_op.cu:22-62): y = x > 0 ? x : 0;  dx = y > 0 ? dy : 0.  In place allowed (y == x,
+ * dx == dy), as the towers use them (retinanet_heads.py:124,209). */
+int sad_relu_f32(const float* x, float* y, int64_t n, void* stream);
+int sad_relu_grad_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+
 /* Weight and bias gradient — replaces the filter/bias half of CudnnConvGradientOp::DoRunWithType
  *   (caffe2/caffe2/operators/conv_op_cudnn.cc:1011-1040: cudnnConvolutionBackwardBias / BackwardFilter)
  * and the autograd Sum over the FPN levels that share the weight (caffe2/caffe2/python/core.py:695,706-842):

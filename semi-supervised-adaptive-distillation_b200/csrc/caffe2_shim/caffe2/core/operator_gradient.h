@@ -72,6 +72,13 @@ class GradientMakerBase {
     if (CopyArguments()) for (const auto& a : def_.arg()) *g.add_arg() = a;
     return vector<OperatorDef>{g};
   }
+  // the overload with extra arguments (operator_gradient.h:216-234), used by the Conv gradient maker for no_bias
+  inline vector<OperatorDef> SingleGradientDef(const string& type, const string& name, const vector<string>& inputs,
+                                               const vector<string>& outputs, const vector<Argument>& extra_args) {
+    vector<OperatorDef> v = SingleGradientDef(type, name, inputs, outputs);
+    for (const auto& a : extra_args) *v[0].add_arg() = a;
+    return v;
+  }
 
  public:
   static string GradientName(const string& name) { return name + "_grad"; }

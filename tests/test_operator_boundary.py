@@ -139,3 +139,48 @@ def test_fusion_pass_groups_levels(oplib):
     net3, _, _ = retinanet_heads.add_distill_loss(with_gradients=False)
     fused3, n3 = oplib.FuseAdaptiveDistillOps(net3.to_text())
     assert n3 == 0 and fused3.count('type: "SigmoidAdaptiveDistillLoss"') == 5
+
+
+# ---------------------------------------------------------------------------------------------
+# head convolution operators (Conv / ConvGradient with and without engine CUDNN, Relu / ReluGradient)
+# ---------------------------------------------------------------------------------------------
+def test_head_conv_operators_registered(oplib):
+    # conv_op_cudnn.cc:1130-1131 registers the CUDNN engine; detector.py:56-60 makes Detectron ask for it
+    for name in ("Conv", "ConvGradient", "Relu", "ReluGradient"):
+        assert oplib.HasOperator(name, c2.CUDA), name
+    assert oplib.SchemaArity("Conv") == (2, 3, 1, 1)
+    assert oplib.SchemaArity("ConvGradient") == (2, 3, 1, 3)
+    assert oplib.SchemaArity("Relu") == (1, 1, 1, 1)
+    assert oplib.SchemaArity("ReluGradient") == (2, 2, 1, 1)
+
+
+def _grad_fields(text):
+    line = lambda key: [l.split('"')[1] for l in text.splitlines() if l.strip().startswith(key + ":")]
+    return line("type"), line("input"), line("output"), [l.split('"')[1] for l in text.splitlines() if l.startswith("external_output")]
+
+
+def test_conv_gradient_maker_follows_reference(oplib):
+    # conv_gradient_op.cc:35-77: inputs {X, W, dY}; outputs {dW, db, dX}; engine, device and arguments copied
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    op = c2.CreateOperator("Conv", ["x", "w", "b"], ["y"], device_option=dev, engine="CUDNN", kernel=3, pad=1, stride=1, order="NCHW")
+    text = oplib.GetGradientDefs(op, ["y_grad"])
+    types, ins, outs, gin = _grad_fields(text)
+    assert types == ["ConvGradient"] and 'engine: "CUDNN"' in text and "is_gradient_op: true" in text
+    assert ins == ["x", "w", "y_grad"] and outs == ["w_grad", "b_grad", "x_grad"]
+    for frag in ('name: "kernel"', "i: 3", 'name: "pad"', 'name: "order"', 's: "NCHW"'):
+        assert frag in text
+    assert gin == ["x_grad", "w_grad", "b_grad"]
+    # without bias: no_bias = 1 is appended and only {dW, dX} are produced
+    op = c2.CreateOperator("Conv", ["x", "w"], ["y"], device_option=dev, kernel=3, pad=1, stride=1)
+    text = oplib.GetGradientDefs(op, ["y_grad"])
+    assert _grad_fields(text)[2] == ["w_grad", "x_grad"] and 'name: "no_bias"' in text
+    # no_gradient_to_input (the first conv of a frozen body) drops dX
+    op = c2.CreateOperator("Conv", ["x", "w", "b"], ["y"], device_option=dev, kernel=3, pad=1, stride=1, no_gradient_to_input=1)
+    assert _grad_fields(oplib.GetGradientDefs(op, ["y_grad"]))[2] == ["w_grad", "b_grad"]
+
+
+def test_relu_gradient_maker_uses_the_output(oplib):
+    # relu_op.cc:98-108: ReluGradient(Y, dY) -> dX, which is what makes the in-place Relu of the towers legal
+    op = c2.CreateOperator("Relu", ["t"], ["t"], device_option=c2.DeviceOption(c2.CUDA, 0))
+    types, ins, outs, gin = _grad_fields(oplib.GetGradientDefs(op, ["t_grad"]))
+    assert types == ["ReluGradient"] and ins == ["t", "t_grad"] and outs == ["t_grad"]

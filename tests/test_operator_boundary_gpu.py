@@ -124,3 +124,72 @@ def test_reference_ops_on_golden_inputs_match_committed_vectors(reflib, oracle):
     stored = np.load(path)
     for k in stored.files:
         np.testing.assert_allclose(fresh[k], stored[k], rtol=1e-6, atol=1e-12, err_msg=k)
+
+
+# ---------------------------------------------------------------------------------------------
+# head convolutions through the registry: Conv (engine CUDNN, as Detectron requests) -> in-place Relu -> Conv,
+# then the gradient ops the makers emit, executed in reverse order — one FPN level of the classification
+# branch as Detectron builds it (retinanet_heads.py:101-152), against the CPU oracle.
+# ---------------------------------------------------------------------------------------------
+def _conv_close(got, ref, what, max_tol=3e-3, rms_tol=1e-3):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    d = np.abs(got - ref)
+    assert d.max() <= max_tol * np.abs(ref).max(), "%s: max|d| %.3g vs max|ref| %.3g" % (what, d.max(), np.abs(ref).max())
+    assert np.sqrt((d ** 2).mean()) <= rms_tol * np.sqrt((ref ** 2).mean()), what
+
+
+def test_head_conv_ops_by_name_forward_and_gradient(oplib, oracle):
+    from sad_b200 import c2
+    rng = np.random.default_rng(77)
+    N, C, M, H, W = 2, 64, 36, 10, 24
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    w0 = (rng.standard_normal((C, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32)
+    b0 = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    w1 = (rng.standard_normal((M, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32)
+    b1 = (0.1 * rng.standard_normal(M)).astype(np.float32)
+    dy = rng.standard_normal((N, M, H, W)).astype(np.float32)
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    conv_args = dict(kernel=3, pad=1, stride=1, order="NCHW")
+    fwd = [c2.CreateOperator("Conv", ["fpn", "w0", "b0"], ["t"], device_option=dev, engine="CUDNN", **conv_args),
+           c2.CreateOperator("Relu", ["t"], ["t"], device_option=dev),
+           c2.CreateOperator("Conv", ["t", "w1", "b1"], ["pred"], device_option=dev, engine="CUDNN", **conv_args)]
+    ws = oplib.Workspace()
+    for name, a in (("fpn", x), ("w0", w0), ("b0", b0), ("w1", w1), ("b1", b1), ("pred_grad", dy)):
+        ws.FeedBlob(name, torch.from_numpy(a).cuda())
+    for op in fwd:
+        ws.RunOperatorOnce(op)
+    t_ref = oracle.relu(oracle.conv2d_fwd(x, w0, b0))
+    pred_ref = oracle.conv2d_fwd(t_ref, w1, b1)
+    _conv_close(ws.FetchBlob("t"), t_ref, "tower activation")
+    _conv_close(ws.FetchBlob("pred"), pred_ref, "prediction")
+    # backward: gradient defs from the registered makers, run through the same registry
+    g_out = {"pred": "pred_grad"}
+    for op in reversed(fwd):
+        text = oplib.GetGradientDefs(op, [g_out.get(o, "") for o in op.output])
+        ws.CreateNet('name: "g"\n' + "\n".join(l for l in text.splitlines() if not l.startswith("external_output")), overwrite=True)
+        ws.RunNet("g")
+        gin = [l.split('"')[1] for l in text.splitlines() if l.startswith("external_output")]
+        for name, g in zip(op.input, gin):
+            if g:
+                g_out[name] = g
+    dw1, db1, dt = oracle.conv2d_bwd(ws.FetchBlob("t"), w1, dy)        # masks from the product's own activation
+    dt = oracle.relu_grad(ws.FetchBlob("t"), dt)
+    dw0, db0, dx = oracle.conv2d_bwd(x, w0, dt)
+    for name, ref in (("w1_grad", dw1), ("b1_grad", db1), ("w0_grad", dw0), ("b0_grad", db0), ("fpn_grad", dx)):
+        _conv_close(ws.FetchBlob(name), ref, name)
+
+
+def test_head_conv_op_rejects_shapes_outside_its_class(oplib):
+    from sad_b200 import c2
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    ws = oplib.Workspace()
+    ws.FeedBlob("x", torch.zeros(1, 8, 4, 4, device="cuda"))
+    ws.FeedBlob("w", torch.zeros(8, 8, 3, 3, device="cuda"))
+    for bad in (dict(kernel=1, pad=0, stride=1), dict(kernel=3, pad=1, stride=2), dict(kernel=3, pad=1, stride=1, group=2),
+                dict(kernel=3, pad=1, stride=1, order="NHWC")):
+        with pytest.raises(c2.EnforceNotMet, match="B200 head convolution"):
+            ws.RunOperatorOnce(c2.CreateOperator("Conv", ["x", "w"], ["y"], device_option=dev, **bad))
+    ws.FeedBlob("w5", torch.zeros(8, 4, 3, 3, device="cuda"))
+    with pytest.raises(c2.EnforceNotMet, match="channels"):
+        ws.RunOperatorOnce(c2.CreateOperator("Conv", ["x", "w5"], ["y"], device_option=dev, kernel=3, pad=1, stride=1))
