@@ -94,6 +94,18 @@ int sad_distill_f32(const sad_distill_level* levels, int n_levels, const float* 
                     const sad_distill_params* params, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* The whole loss step of add_distill_loss (detectron/lib/modeling/retinanet_heads.py:313-352) in ONE launch:
+ *   normalizer_out[0] = PowSum(levels[0..n).teacher_prob, power)           (pow_sum_op.cu:25-43)
+ *   levels[l].loss, levels[l].d_logits = SigmoidAdaptiveDistillLoss(+Gradient)(..., normalizer_out)  for every level
+ * i.e. exactly sad_pow_sum_f32 over the levels' teacher probabilities followed by sad_distill_f32 with that
+ * normaliser.  When gamma == 2, beta == 0, both outputs are requested and the tensors are 16-byte aligned with
+ * H*W % 4 == 0 this is one cooperative kernel (grid-wide barrier between the two phases, teacher probabilities
+ * re-read through L2, work units handed out dynamically); otherwise it runs as the two launches.  The workspace
+ * (sad_distill_fused_workspace_bytes, 256-byte aligned, sad_workspace_init once) is private to this entry point. */
+size_t sad_distill_fused_workspace_bytes(const sad_distill_level* levels, int n_levels, int num_classes);
+int sad_distill_fused_f32(const sad_distill_level* levels, int n_levels, float power, float* normalizer_out,
+                          const sad_distill_params* params, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole distillation-loss step on HOST buffers (what a host-memory caller of the reference's
  * operators pays end to end): H2D of teacher probs / logits / labels, PowSum -> normaliser,

@@ -1,0 +1,509 @@
+// PowSum + SigmoidAdaptiveDistillLoss + SigmoidAdaptiveDistillLossGradient for every FPN level in ONE cooperative
+// launch — the whole loss step of add_distill_loss (detectron/lib/modeling/retinanet_heads.py:313-352):
+//
+//   phase 1  normaliser = sum over levels of teacher_prob ^ power          (pow_sum_op.cu:25-43)
+//   ------   grid-wide barrier: every CTA adds the per-CTA partial sums in the same fixed order
+//   phase 2  per element loss and d(logits), loss reduced per level        (...loss_op.cu:28-67, 69-105, 108-171)
+//
+// Why one launch (measured on B200): the two-kernel step is 22 us (PowSum) + 51 us (loss + gradient); every SM is empty
+// for ~4 us of each launch (ramp + drain) and the teacher probabilities are read from DRAM twice.  Here there is one
+// ramp/drain, and phase 1 walks T backwards with an L2 evict-last policy while phase 2 walks forwards with evict-first
+// loads and streaming stores, so phase 2 finds T still in the 126 MB L2 (ncu: 172 MB read from DRAM per launch instead of
+// 236 MB; with evict-first in phase 1 it is 208 MB).
+// Work units are dealt round-robin (static): a dynamic hand-out through an atomic counter with per-unit loss slots was
+// measured too (globaltimer stamps per CTA): it narrows the spread of the CTAs' finish times from 5.3 to 3 us but its
+// per-unit overhead delays all of them by 4 us, and its fixed-order final reduction over 5220 slots costs another 7 us.
+//
+// Determinism: static unit assignment, per-CTA partial sums, fixed-order fp64 finish: bit-identical run to run.
+//
+// Restricted to the arithmetic fast path (gamma == 2, beta == 0: the reference's headline configs) with both outputs
+// requested; everything else runs as the two ring kernels of distill_ring.cu behind the same entry point.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdlib>
+#include <string>
+
+#include "distill_math.cuh"
+#include "ring.cuh"
+#include "sad_b200.h"
+#include "sad_internal.h"
+
+namespace sad {
+
+constexpr int kFHW = 512;           // hw positions per phase-2 unit
+constexpr int kFCT = 8;             // classes per phase-2 unit
+constexpr int kFStages = 3;
+constexpr int kFConsumers = 256;
+constexpr int kFWarps = kFConsumers / 32;
+constexpr int kFThreads = kFConsumers + 32;
+constexpr int kFPer = kFCT / 2;
+constexpr int kF1Chunk = 2048;      // floats per phase-1 unit (8 KB)
+constexpr int kF1Stages = 6;
+
+struct FusedLevel {
+  const float* X;
+  const float* T;
+  const int32_t* G;
+  float* dX;
+  float* loss;
+  const float* d_loss;
+  uint32_t HW, hw_tiles, unit_begin, unit_end;  // phase-2 units
+  uint32_t p1_begin, p1_end;                    // phase-1 units (chunks of T)
+  uint32_t elems;                               // N * D * HW
+};
+struct FusedArgs {
+  FusedLevel lv[SAD_MAX_LEVELS];
+  int32_t n_levels, num_classes, class_groups, ignored_label;
+  uint32_t total_units, p1_total;
+  float alpha, scale, power;
+  uint32_t dbg;  // experiment switches (SAD_FUSED_DEBUG): 1 = evict-first in phase 1, 2 = plain stores, 8 = globaltimer stamps
+  float* norm_out;
+  float* p1_partials;   // [gridDim.x][SAD_MAX_LEVELS]
+  float* p2_partials;   // [gridDim.x][SAD_MAX_LEVELS]
+  unsigned long long* stamps;  // debug (dbg & 8): [gridDim.x][5] globaltimer values
+  unsigned int* ctrl;   // [0] grid barrier, [1] final ticket; zero between launches
+};
+
+struct __align__(16) FUnitDesc {
+  float* dX;
+  uint32_t n_hw, n_cls, plane, unit;
+  int32_t level;
+  float kg;
+};
+struct __align__(128) FStage {
+  float X[kFCT][kFHW];
+  float T[kFCT][kFHW];
+  int32_t G[kFHW];
+};
+constexpr size_t kFusedSmemBytes = sizeof(FStage) * kFStages;
+static_assert(kFusedSmemBytes >= (size_t)kF1Chunk * 4 * kF1Stages, "phase-1 ring must fit in the phase-2 ring");
+
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool kAlphaHalf, bool kPowAccurate>
+__global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __grid_constant__ FusedArgs args) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FStage* stages = reinterpret_cast<FStage*>(smem_raw);
+  float(*p1_stages)[kF1Chunk] = reinterpret_cast<float(*)[kF1Chunk]>(smem_raw);
+  __shared__ FUnitDesc desc[kFStages];
+  __shared__ int32_t p1_desc[kF1Stages][2];  // {input, count}
+  __shared__ __align__(8) uint64_t full_bar[kFStages], empty_bar[kFStages], p1_full[kF1Stages], p1_empty[kF1Stages];
+  __shared__ float in_sum[SAD_MAX_LEVELS];
+  __shared__ float red_f[kFWarps];
+  __shared__ float lvl_sum[SAD_MAX_LEVELS];
+  __shared__ float np_smem;
+  __shared__ bool is_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kFStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kFWarps);
+    }
+#pragma unroll
+    for (int s = 0; s < kF1Stages; ++s) {
+      mbar_init(&p1_full[s], 1);
+      mbar_init(&p1_empty[s], kFWarps);
+    }
+    mbar_fence_init();
+  }
+  if (tid < SAD_MAX_LEVELS) {
+    in_sum[tid] = 0.f;
+    lvl_sum[tid] = 0.f;
+  }
+  __syncthreads();
+  const bool stamp = (args.dbg & 8u) && tid == 0;
+  if (stamp) args.stamps[blockIdx.x * 5 + 0] = gtimer();
+
+  // ================= phase 1: PowSum over the teacher probabilities, last chunk first =================
+  {
+    // unit j of this CTA = global chunk (p1_total - 1 - (blockIdx.x + j * gridDim.x))
+    if (tid == kFConsumers) {
+      const uint64_t pol = (args.dbg & 1u) ? policy_evict_first() : policy_evict_last();
+      RingState rs;
+      int k = args.n_levels - 1;
+#pragma unroll 1
+      for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
+        const uint32_t u = args.p1_total - 1u - r;
+        while (u < args.lv[k].p1_begin) --k;
+        const uint32_t start = (u - args.lv[k].p1_begin) * (uint32_t)kF1Chunk;
+        const uint32_t left = args.lv[k].elems - start;
+        const uint32_t cnt = left < (uint32_t)kF1Chunk ? left : (uint32_t)kF1Chunk;
+        mbar_wait(&p1_empty[rs.stage], rs.phase ^ 1u);
+        p1_desc[rs.stage][0] = k;
+        p1_desc[rs.stage][1] = (int32_t)cnt;
+        mbar_arrive_expect_tx(&p1_full[rs.stage], cnt * 4u);
+        bulk_g2s(p1_stages[rs.stage], args.lv[k].T + start, cnt * 4u, &p1_full[rs.stage], pol);
+        rs.advance<kF1Stages>();
+      }
+    } else if (tid < kFConsumers) {
+      const float power = args.power;
+      float acc = 0.f;
+      int cur = -1;
+      RingState rs;
+#pragma unroll 1
+      for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
+        mbar_wait(&p1_full[rs.stage], rs.phase);
+        const int input = p1_desc[rs.stage][0];
+        const uint32_t n4 = (uint32_t)p1_desc[rs.stage][1] >> 2;
+        if (input != cur) {
+          if (cur >= 0) {
+            const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
+            if (tid == 0) in_sum[cur] = s;
+            acc = 0.f;
+          }
+          cur = input;
+        }
+        const float4* src = reinterpret_cast<const float4*>(p1_stages[rs.stage]);
+#pragma unroll
+        for (int j = 0; j < kF1Chunk / 4 / kFConsumers; ++j) {
+          const uint32_t i = (uint32_t)tid + j * kFConsumers;
+          if (i < n4) {
+            const float4 v = src[i];
+            if (kPowAccurate) {
+              acc += powf(v.x, power) + powf(v.y, power);
+              acc += powf(v.z, power) + powf(v.w, power);
+            } else {  // x^p = 2^(p log2 x) for x >= 0 (NaN for x < 0, like powf with a non-integer exponent)
+              acc += ex2_approx(power * lg2_approx(v.x)) + ex2_approx(power * lg2_approx(v.y));
+              acc += ex2_approx(power * lg2_approx(v.z)) + ex2_approx(power * lg2_approx(v.w));
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p1_empty[rs.stage]);
+        rs.advance<kF1Stages>();
+      }
+      if (cur >= 0) {
+        const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
+        if (tid == 0) in_sum[cur] = s;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ================= grid barrier; every CTA derives the same normaliser =================
+  if (stamp) args.stamps[blockIdx.x * 5 + 1] = gtimer();
+  if (tid < SAD_MAX_LEVELS) args.p1_partials[(size_t)blockIdx.x * SAD_MAX_LEVELS + tid] = in_sum[tid];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(&args.ctrl[0], 1u);
+    while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+  // per input: fp64 sum of the CTA partials in a fixed order, rounded to float (one warp per input); then the
+  // reference's running float add over the inputs (pow_sum_op.cu:39)
+  for (int j = warp; j < args.n_levels; j += kFThreads / 32) {
+    const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p1_partials, j, lane);
+    if (lane == 0) in_sum[j] = (float)s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float res = 0.f;
+    for (int j = 0; j < args.n_levels; ++j) res = res + in_sum[j];
+    np_smem = res;
+    if (blockIdx.x == 0) args.norm_out[0] = res;
+  }
+  __syncthreads();
+  const float Np = fmaxf(np_smem, 1.0f);   // max(weight_pos[0], 1.0): ...loss_op.cu:49,87
+  if (stamp) args.stamps[blockIdx.x * 5 + 2] = gtimer();
+
+  // ================= phase 2: loss + gradient, units dealt round-robin =================
+  if (tid >= kFConsumers) {
+    if (tid == kFConsumers) {
+      const uint64_t pol = policy_evict_first();
+      const uint32_t C = (uint32_t)args.num_classes, cg = (uint32_t)args.class_groups;
+      RingState rs;
+      int l = 0;
+      float kg = 0.f;
+      int kg_level = -1;
+#pragma unroll 1
+      for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
+        mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
+        while (u >= args.lv[l].unit_end) ++l;
+        const FusedLevel& L = args.lv[l];
+        if (kg_level != l) {
+          kg = (L.d_loss ? __ldg(L.d_loss) : 1.f) * args.scale / Np;
+          kg_level = l;
+        }
+        const uint32_t local = u - L.unit_begin;
+        const uint32_t item = local / cg, chunk = local - item * cg;
+        const uint32_t na = item / L.hw_tiles, ht = item - na * L.hw_tiles;
+        const uint32_t hw0 = ht * kFHW;
+        const uint32_t n_hw = min((uint32_t)kFHW, L.HW - hw0);
+        const uint32_t c0 = chunk * kFCT;
+        const uint32_t n_cls = min((uint32_t)kFCT, C - c0);
+        const size_t off = ((size_t)na * C + c0) * L.HW + hw0;
+        FStage& st = stages[rs.stage];
+        FUnitDesc d;
+        d.dX = L.dX + off;
+        d.n_hw = n_hw;
+        d.n_cls = n_cls;
+        d.plane = L.HW;
+        d.unit = u;
+        d.level = l;
+        d.kg = kg;
+        desc[rs.stage] = d;
+        const uint32_t row_bytes = n_hw * 4u;
+        mbar_arrive_expect_tx(&full_bar[rs.stage], (2u * n_cls + 1u) * row_bytes);
+        const float* xs = L.X + off;
+        const float* ts = L.T + off;
+        for (uint32_t c = 0; c < n_cls; ++c) {
+          bulk_g2s(st.X[c], xs + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
+          bulk_g2s(st.T[c], ts + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
+        }
+        bulk_g2s(st.G, L.G + (size_t)na * L.HW + hw0, row_bytes, &full_bar[rs.stage], pol);
+        rs.advance<kFStages>();
+      }
+    }
+  } else {
+    const uint32_t h = (uint32_t)(tid & 127) * 4u;
+    const uint32_t cbase = (uint32_t)(tid >> 7) * kFPer;
+    const float alpha = args.alpha;
+    FastConsts fc;
+    fc.ca2 = 2.f * alpha * kLn2;
+    fc.cb2 = 2.f * (1.f - alpha) * kLn2;
+    fc.alpha = alpha;
+    fc.om2a = 1.f - 2.f * alpha;
+    const int32_t ignored = args.ignored_label;
+    RingState rs;
+    float acc = 0.f;
+    int cur_level = -1;
+#pragma unroll 1
+    for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
+      mbar_wait(&full_bar[rs.stage], rs.phase);
+      const FUnitDesc d = desc[rs.stage];
+      const FStage& st = stages[rs.stage];
+      if (d.level != cur_level) {
+        if (cur_level >= 0) {
+          const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
+          if (tid == 0) lvl_sum[cur_level] = s;
+          acc = 0.f;
+        }
+        cur_level = d.level;
+      }
+      if (h < d.n_hw) {
+        const int4 g = *reinterpret_cast<const int4*>(&st.G[h]);
+        float keep[4], kk[4];
+        keep[0] = g.x != ignored ? 1.f : 0.f;
+        keep[1] = g.y != ignored ? 1.f : 0.f;
+        keep[2] = g.z != ignored ? 1.f : 0.f;
+        keep[3] = g.w != ignored ? 1.f : 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) kk[v] = keep[v] * d.kg;
+        float4 xv[kFPer], tv[kFPer];
+#pragma unroll
+        for (int j = 0; j < kFPer; ++j) {
+          xv[j] = *reinterpret_cast<const float4*>(&st.X[cbase + j][h]);
+          tv[j] = *reinterpret_cast<const float4*>(&st.T[cbase + j][h]);
+        }
+        float* out = d.dX + (size_t)cbase * d.plane + h;
+#pragma unroll
+        for (int j = 0; j < kFPer; ++j) {
+          if (cbase + j < d.n_cls) {
+            const float xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+            const float ts[4] = {tv[j].x, tv[j].y, tv[j].z, tv[j].w};
+            float gv[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) distill_elem_fast<kAlphaHalf, true, true>(xs[v], ts[v], keep[v], kk[v], fc, acc, gv[v]);
+            if (args.dbg & 2u) *reinterpret_cast<float4*>(out + (size_t)j * d.plane) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+            else __stcs(reinterpret_cast<float4*>(out + (size_t)j * d.plane), make_float4(gv[0], gv[1], gv[2], gv[3]));
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[rs.stage]);
+      rs.advance<kFStages>();
+    }
+    if (cur_level >= 0) {
+      const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
+      if (tid == 0) lvl_sum[cur_level] = s;
+    }
+  }
+
+  // ================= last CTA: per-level loss from the per-CTA partials, fixed order, fp64 =================
+  if (stamp) args.stamps[blockIdx.x * 5 + 3] = gtimer();
+  if (publish_and_ticket<SAD_MAX_LEVELS>(lvl_sum, args.p2_partials, &args.ctrl[1], &is_last)) {
+    __threadfence();
+    for (int k = warp; k < args.n_levels; k += kFThreads / 32) {
+      const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane);
+      // the fast path accumulates twice the summand
+      if (lane == 0) args.lv[k].loss[0] = (float)(0.5 * s / (double)Np) * args.scale;
+    }
+    if (tid == 0) {
+      args.ctrl[0] = 0u;
+      args.ctrl[1] = 0u;
+    }
+    if (stamp) args.stamps[blockIdx.x * 5 + 4] = gtimer();
+  }
+}
+
+static size_t fused_units(const sad_distill_level* levels, int n_levels, int num_classes, uint64_t* p1_units) {
+  uint64_t t = 0, p1 = 0;
+  const uint32_t C = (uint32_t)num_classes, cg = (C + kFCT - 1) / kFCT;
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_distill_level& L = levels[l];
+    const uint64_t HW = (uint64_t)L.H * L.W, NA = (uint64_t)L.N * ((uint32_t)L.D / C);
+    t += NA * ((HW + kFHW - 1) / kFHW) * cg;
+    p1 += ((uint64_t)L.N * L.D * HW + kF1Chunk - 1) / kF1Chunk;
+  }
+  if (p1_units) *p1_units = p1;
+  return (size_t)t;
+}
+
+// layout of the fused workspace: [0,256) ctrl | phase-1 partials | phase-2 partials | debug stamps
+static size_t fused_ws_bytes(size_t) {
+  return 256 + 2 * (size_t)kMaxRingCtas * SAD_MAX_LEVELS * sizeof(float) + (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long);
+}
+
+bool distill_fused_supported(const sad_distill_level* levels, int n_levels, const sad_distill_params* p, float power) {
+  if (!(p->gamma == 2.0f && p->beta == 0.0f)) return false;
+  if (!distill_ring_supported(levels, n_levels, p->num_classes)) return false;
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_distill_level& L = levels[l];
+    if (!L.loss || !L.d_logits) return false;
+    const uint64_t n = (uint64_t)L.N * L.D * L.H * L.W;
+    if (n == 0 || n > 0xfffffff0ull) return false;
+  }
+  uint64_t p1 = 0;
+  const size_t units = fused_units(levels, n_levels, p->num_classes, &p1);
+  return units > 0 && units < 0x3fffffffull && p1 < 0x3fffffffull && power == power;
+}
+
+int launch_distill_fused(const sad_distill_level* levels, int n_levels, float power, float* norm_out, const sad_distill_params* p,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  FusedArgs a{};
+  const uint32_t C = (uint32_t)p->num_classes, cg = (C + kFCT - 1) / kFCT;
+  uint64_t t = 0, p1 = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_distill_level& L = levels[l];
+    const uint64_t HW = (uint64_t)L.H * L.W, NA = (uint64_t)L.N * ((uint32_t)L.D / C);
+    const uint64_t tiles = (HW + kFHW - 1) / kFHW;
+    FusedLevel& D = a.lv[l];
+    D.X = L.logits;
+    D.T = L.teacher_prob;
+    D.G = L.labels;
+    D.dX = L.d_logits;
+    D.loss = L.loss;
+    D.d_loss = L.d_loss;
+    D.HW = (uint32_t)HW;
+    D.hw_tiles = (uint32_t)tiles;
+    D.unit_begin = (uint32_t)t;
+    t += NA * tiles * cg;
+    D.unit_end = (uint32_t)t;
+    D.elems = (uint32_t)((uint64_t)L.N * L.D * HW);
+    D.p1_begin = (uint32_t)p1;
+    p1 += ((uint64_t)D.elems + kF1Chunk - 1) / kF1Chunk;
+    D.p1_end = (uint32_t)p1;
+  }
+  a.n_levels = n_levels;
+  a.num_classes = p->num_classes;
+  a.class_groups = (int32_t)cg;
+  a.ignored_label = p->ignored_label;
+  a.total_units = (uint32_t)t;
+  a.p1_total = (uint32_t)p1;
+  a.alpha = p->alpha;
+  a.scale = p->scale;
+  a.power = power;
+  a.norm_out = norm_out;
+  if (const char* e = getenv("SAD_FUSED_DEBUG")) a.dbg = (uint32_t)atoi(e);
+  if (!workspace || workspace_bytes < fused_ws_bytes((size_t)t) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return set_error(SAD_ERR_WORKSPACE, "distill fused: workspace must be 256-byte aligned and >= sad_distill_fused_workspace_bytes()");
+  a.ctrl = static_cast<unsigned int*>(workspace);
+  a.p1_partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  a.p2_partials = a.p1_partials + (size_t)kMaxRingCtas * SAD_MAX_LEVELS;
+  a.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + fused_ws_bytes((size_t)t) -
+                                                   (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long));
+
+  int dev = 0, sms = 0, rc;
+  if ((rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) != SAD_OK) return rc;
+  if ((rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) != SAD_OK) return rc;
+  const bool half = p->alpha == 0.5f;
+  const bool accurate = power == floorf(power) || !(power > 0.f);  // integer / non-positive exponents: full powf semantics
+  const void* kern = half ? (accurate ? (const void*)distill_fused_kernel<true, true> : (const void*)distill_fused_kernel<true, false>)
+                          : (accurate ? (const void*)distill_fused_kernel<false, true> : (const void*)distill_fused_kernel<false, false>);
+  if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes), "cudaFuncSetAttribute")) != SAD_OK)
+    return rc;
+  int per_sm = 0;
+  if ((rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFThreads, kFusedSmemBytes), "occupancy query")) != SAD_OK) return rc;
+  if (per_sm < 1) return set_error(SAD_ERR_CUDA, "distill fused: the kernel does not fit on an SM");
+  if (per_sm > 2) per_sm = 2;
+  uint32_t grid = (uint32_t)(sms * per_sm);   // every CTA must be resident: the kernel contains a grid-wide barrier
+  if (grid > (uint32_t)kMaxRingCtas) grid = kMaxRingCtas;
+  void* params[] = {&a};
+  rc = check_cuda(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFThreads), params, kFusedSmemBytes, st), "distill fused launch");
+  if (rc != SAD_OK) return rc;
+  count_launch(1);
+  return SAD_OK;
+}
+
+size_t distill_fused_workspace_bytes(const sad_distill_level* levels, int n_levels, int num_classes) {
+  return fused_ws_bytes(fused_units(levels, n_levels, num_classes, nullptr));
+}
+
+}  // namespace sad
+
+using namespace sad;
+
+extern "C" {
+
+SAD_EXPORT size_t sad_distill_fused_workspace_bytes(const sad_distill_level* levels, int n_levels, int num_classes) {
+  if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || num_classes < 1) return 0;
+  int64_t sizes[SAD_MAX_LEVELS];
+  for (int l = 0; l < n_levels; ++l) {
+    if (levels[l].N < 0 || levels[l].D < 0 || levels[l].H < 0 || levels[l].W < 0 || levels[l].D % num_classes) return 0;
+    sizes[l] = (int64_t)levels[l].N * levels[l].D * levels[l].H * levels[l].W;
+  }
+  size_t need = distill_fused_workspace_bytes(levels, n_levels, num_classes);
+  const size_t a = sad_pow_sum_workspace_bytes(sizes, n_levels), b = sad_distill_workspace_bytes(levels, n_levels);
+  if (a > need) need = a;
+  if (b > need) need = b;
+  return need;
+}
+
+SAD_EXPORT int sad_distill_fused_f32(const sad_distill_level* levels, int n_levels, float power, float* normalizer_out,
+                                     const sad_distill_params* params, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!levels || !params || !normalizer_out || n_levels < 1 || n_levels > SAD_MAX_LEVELS)
+    return set_error(SAD_ERR_INVALID, "distill fused: bad argument");
+  if (params->num_classes < 1) return set_error(SAD_ERR_INVALID, "distill fused: num_classes must be >= 1");
+  if (!(params->scale >= 0.f)) return set_error(SAD_ERR_INVALID, "distill fused: scale must be >= 0");
+  bool dims_ok = true;
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_distill_level& L = levels[l];
+    if (L.N < 0 || L.D < 0 || L.H < 0 || L.W < 0 || L.D % params->num_classes) dims_ok = false;
+    else if ((uint64_t)L.N * L.D * L.H * L.W && (!L.logits || !L.teacher_prob || !L.labels)) dims_ok = false;
+  }
+  if (!dims_ok) return set_error(SAD_ERR_INVALID, "distill fused: bad level (negative size, D % num_classes != 0 or null tensor)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (distill_fused_supported(levels, n_levels, params, power))
+    return launch_distill_fused(levels, n_levels, power, normalizer_out, params, workspace, workspace_bytes, st);
+  // general arguments / shapes: the same contract as two launches sharing the workspace one after the other
+  const float* ins[SAD_MAX_LEVELS];
+  int64_t sizes[SAD_MAX_LEVELS];
+  for (int l = 0; l < n_levels; ++l) {
+    ins[l] = levels[l].teacher_prob;
+    sizes[l] = (int64_t)levels[l].N * levels[l].D * levels[l].H * levels[l].W;
+  }
+  int rc = sad_pow_sum_f32(ins, sizes, n_levels, power, normalizer_out, workspace, workspace_bytes, stream);
+  if (rc != SAD_OK) return rc;
+  return sad_distill_f32(levels, n_levels, normalizer_out, params, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

@@ -228,11 +228,21 @@ __device__ __forceinline__ bool publish_and_ticket(const float* vals_smem, float
   return *is_last_smem;
 }
 
-// fp64 sum over CTAs of slot k, executed by one full warp; result valid in every lane
+// fp64 sum over CTAs of slot k, executed by one full warp; result valid in every lane.  The loads of up to 384 CTAs'
+// partials are issued together (one L2 round trip instead of one per 32 CTAs); the additions keep a fixed order.
 template <int kSlots>
 __device__ __forceinline__ double warp_sum_partials(const float* partials, int k, int lane) {
+  constexpr int kBatch = 12;
+  float v[kBatch];
+#pragma unroll
+  for (int i = 0; i < kBatch; ++i) {
+    const uint32_t b = (uint32_t)lane + 32u * i;
+    v[i] = b < gridDim.x ? __ldcg(partials + (size_t)b * kSlots + k) : 0.f;
+  }
   double s = 0.0;
-  for (uint32_t b = lane; b < gridDim.x; b += 32) s += (double)__ldcg(partials + (size_t)b * kSlots + k);
+#pragma unroll
+  for (int i = 0; i < kBatch; ++i) s += (double)v[i];
+  for (uint32_t b = (uint32_t)lane + 32u * kBatch; b < gridDim.x; b += 32) s += (double)__ldcg(partials + (size_t)b * kSlots + k);
   return warp_sum(s);
 }
 

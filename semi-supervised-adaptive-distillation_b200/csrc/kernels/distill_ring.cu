@@ -86,8 +86,10 @@ __global__ void __launch_bounds__(kRThreads, 2) distill_ring_kernel(const __grid
   __shared__ bool is_last;
 
   const int tid = threadIdx.x;
-  const uint32_t u0 = (uint32_t)((uint64_t)blockIdx.x * args.total_units / gridDim.x);
-  const uint32_t u1 = (uint32_t)((uint64_t)(blockIdx.x + 1) * args.total_units / gridDim.x);
+  // units are dealt round-robin (CTA c takes c, c + grid, ...): the small units of the coarse FPN levels, which sit at
+  // the end of the unit list, are spread over all CTAs instead of giving the last CTAs almost nothing to do, and at
+  // any instant the grid works on consecutive units
+  const uint32_t u0 = blockIdx.x, u1 = args.total_units, ustep = gridDim.x;
 
   if (tid == 0) {
 #pragma unroll
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kRThreads, 2) distill_ring_kernel(const __grid
       float kg = 0.f;
       int kg_level = -1;
 #pragma unroll 1
-      for (uint32_t u = u0; u < u1; ++u) {
+      for (uint32_t u = u0; u < u1; u += ustep) {
         while (u >= args.lv[l].unit_end) ++l;
         const RingLevel& L = args.lv[l];
         if (kGrad && kg_level != l) {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kRThreads, 2) distill_ring_kernel(const __grid
     int cur_level = -1;
     RingState rs;
 #pragma unroll 1
-    for (uint32_t u = u0; u < u1; ++u) {
+    for (uint32_t u = u0; u < u1; u += ustep) {
       mbar_wait(&full_bar[rs.stage], rs.phase);
       const UnitDesc d = desc[rs.stage];
       const RingStage& st = stages[rs.stage];

@@ -91,6 +91,10 @@ def lib():
         l.sad_distill_workspace_bytes.argtypes = [C.POINTER(DistillLevel), C.c_int]
         l.sad_distill_f32.argtypes = [C.POINTER(DistillLevel), C.c_int, C.c_void_p, C.POINTER(DistillParams),
                                       C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_distill_fused_workspace_bytes.restype = C.c_size_t
+        l.sad_distill_fused_workspace_bytes.argtypes = [C.POINTER(DistillLevel), C.c_int, C.c_int]
+        l.sad_distill_fused_f32.argtypes = [C.POINTER(DistillLevel), C.c_int, C.c_float, C.c_void_p, C.POINTER(DistillParams),
+                                            C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.sad_ctx_destroy.argtypes = [C.c_void_p]
         l.sad_ctx_destroy.restype = None

@@ -109,6 +109,21 @@ def distill(levels, normalizer, want_loss=True, want_grad=True, d_loss=None, wor
     return losses, grads
 
 
+def distill_step(levels, power=1.8, workspace=None, d_loss=None, **args):
+    """PowSum over the levels' teacher probabilities + loss + gradient of every level through the single-launch entry
+    point sad_distill_fused_f32.  Returns (normalizer, losses, d_logits)."""
+    levels = list(levels)
+    params = default_params(**args)
+    arr, losses, grads = _levels_struct(levels, True, True, d_loss)
+    dev = levels[0][0].device
+    norm = torch.empty((), dtype=torch.float32, device=dev)
+    if workspace is None:
+        workspace = Workspace(lib().sad_distill_fused_workspace_bytes(arr, len(levels), params.num_classes), dev)
+    check(lib().sad_distill_fused_f32(arr, len(levels), float(power), C.c_void_p(norm.data_ptr()), C.byref(params),
+                                      workspace.ptr, workspace.nbytes, _stream()))
+    return norm, losses, grads
+
+
 class DistillPlan:
     """Pre-bound PowSum + fused multi-level loss+grad for fixed device tensors: the launch
     descriptors are built once so the timed loop only enqueues two kernels."""
@@ -127,8 +142,15 @@ class DistillPlan:
         self._ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in self.teacher])
         self._sizes = (C.c_int64 * n)(*[t.numel() for t in self.teacher])
         self.n = n
+        self.ws_fused = Workspace(lib().sad_distill_fused_workspace_bytes(self.arr, n, self.params.num_classes), dev)
 
     def run(self):
+        """The whole loss step in one launch (sad_distill_fused_f32)."""
+        check(lib().sad_distill_fused_f32(self.arr, self.n, self.power, C.c_void_p(self.normalizer.data_ptr()),
+                                          C.byref(self.params), self.ws_fused.ptr, self.ws_fused.nbytes, _stream()))
+
+    def run_two_launches(self):
+        """PowSum, then the fused multi-level loss + gradient: the operator-by-operator form."""
         st = _stream()
         l = lib()
         check(l.sad_pow_sum_f32(self._ptrs, self._sizes, self.n, self.power, C.c_void_p(self.normalizer.data_ptr()),

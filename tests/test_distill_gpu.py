@@ -276,3 +276,80 @@ def test_host_step_end_to_end(ops, oracle):
         assert_loss_close(losses[i], oracle.distill_loss(*l, wp, **HEAD), "level %d" % i)
         assert_grad_close(outs[i].numpy(), oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)
     step.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole loss step in one cooperative launch (sad_distill_fused_f32): PowSum -> grid barrier -> loss + gradient
+# ---------------------------------------------------------------------------------------------
+def _pyr(n, shapes, seed, stress=False):
+    from sad_b200 import synthetic
+    return [synthetic.make_level(np.random.default_rng(seed + i), n, h, w, stress=stress) for i, (h, w) in enumerate(shapes)]
+
+
+@pytest.mark.parametrize("alpha", [0.5, 0.25])
+@pytest.mark.parametrize("stress", [False, True])
+def test_fused_step_matches_oracle(ops, oracle, alpha, stress):
+    host = _pyr(2, [(8, 16), (4, 8), (2, 6), (1, 4)], 50, stress)
+    args = dict(HEAD, alpha=alpha)
+    wp = oracle.pow_sum([l[1] for l in host], 1.8)
+    norm, losses, grads = ops.distill_step([_dev(l) for l in host], power=1.8, **args)
+    torch.cuda.synchronize()
+    assert_loss_close(norm.item(), wp, "normaliser")
+    for i, l in enumerate(host):
+        assert_loss_close(losses[i].item(), oracle.distill_loss(*l, wp, **args), "loss level %d" % i)
+        assert_grad_close(grads[i].cpu().numpy(), oracle.distill_grad(*l, wp, d_loss=1.0, **args), "grad level %d" % i)
+
+
+def test_fused_step_equals_two_launch_path_at_config2_size(ops):
+    # BASELINE.json configs[1]: bs = 2, 600 px, 5 levels.  Same arithmetic per element -> gradients bit-equal given the
+    # same normaliser; the normaliser / losses are sums over a different partition -> equal to rounding.
+    from sad_b200 import synthetic
+    host = synthetic.make_pyramid(1234, 2, 600)
+    dev = [_dev(l) for l in host]
+    plan = ops.DistillPlan(dev, power=1.8, **HEAD)
+    plan.run_two_launches()
+    torch.cuda.synchronize()
+    n2, l2, g2 = plan.normalizer.item(), [l.item() for l in plan.losses], [g.clone() for g in plan.grads]
+    for g in plan.grads:
+        g.zero_()
+    runs = []
+    for _ in range(3):
+        plan.run()
+        torch.cuda.synchronize()
+        runs.append((plan.normalizer.item(), [l.item() for l in plan.losses]))
+    n1, l1 = runs[0]
+    assert runs[1] == runs[0] and runs[2] == runs[0], "the fused step must be bit-identical run to run (dynamic schedule)"
+    assert abs(n1 - n2) <= 2e-6 * abs(n2)
+    for a, b in zip(l1, l2):
+        assert abs(a - b) <= 1e-5 * abs(b)
+    # gradients: same element arithmetic, normaliser equal to ~1e-7 relative
+    for a, b in zip(plan.grads, g2):
+        assert torch.allclose(a, b, rtol=1e-5, atol=0)
+    # exactness of the normaliser against the fp64 sum of x^1.8
+    exact = sum(float((torch.from_numpy(l[1]).double() ** 1.8).sum()) for l in host)
+    assert abs(n1 - exact) <= 2e-5 * exact
+
+
+def test_fused_entry_point_general_arguments_take_the_two_launch_path(ops, oracle):
+    # gamma != 2, beta != 0, integer power, ragged H*W: same contract through the fallback
+    host = _pyr(1, [(5, 7), (3, 3)], 80)
+    args = dict(gamma=1.5, alpha=0.25, beta=0.5, scale=0.7, num_classes=80, ignored_label=-1)
+    wp = oracle.pow_sum([l[1] for l in host], 2.0)
+    norm, losses, grads = ops.distill_step([_dev(l) for l in host], power=2.0, **args)
+    assert_loss_close(norm.item(), wp, "normaliser")
+    for i, l in enumerate(host):
+        assert_loss_close(losses[i].item(), oracle.distill_loss(*l, wp, **args), "loss level %d" % i)
+        assert_grad_close(grads[i].cpu().numpy(), oracle.distill_grad(*l, wp, d_loss=1.0, **args), "grad level %d" % i)
+
+
+def test_fused_step_integer_power_and_nan_teacher(ops, oracle):
+    # power = 1 (kPowAccurate instantiation); a teacher probability of exactly 1 makes that element NaN in the
+    # reference even with beta = 0 (...loss_op.cu:59,93) and therefore the level's loss NaN
+    host = _pyr(1, [(4, 8), (2, 4)], 90)
+    host[1][1][0, 3, 1, 2] = 1.0
+    wp = oracle.pow_sum([l[1] for l in host], 1.0)
+    norm, losses, grads = ops.distill_step([_dev(l) for l in host], power=1.0, **HEAD)
+    assert_loss_close(norm.item(), wp, "normaliser")
+    assert_loss_close(losses[0].item(), oracle.distill_loss(*host[0], wp, **HEAD))
+    assert np.isnan(losses[1].item()) and np.isnan(oracle.distill_loss(*host[1], wp, **HEAD))
+    assert_grad_close(grads[1].cpu().numpy(), oracle.distill_grad(*host[1], wp, d_loss=1.0, **HEAD))
