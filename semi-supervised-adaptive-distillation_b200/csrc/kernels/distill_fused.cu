@@ -11,8 +11,10 @@
 // loads and streaming stores, so phase 2 finds T still in the 126 MB L2 (ncu: 172 MB read from DRAM per launch instead of
 // 236 MB; with evict-first in phase 1 it is 208 MB).
 // Work units are dealt round-robin (static): a dynamic hand-out through an atomic counter with per-unit loss slots was
-// measured too (globaltimer stamps per CTA): it narrows the spread of the CTAs' finish times from 5.3 to 3 us but its
-// per-unit overhead delays all of them by 4 us, and its fixed-order final reduction over 5220 slots costs another 7 us.
+// measured too (globaltimer stamps per CTA, SAD_FUSED_DEBUG=8 + scripts/fused_stamps.py): it narrows the spread of the
+// CTAs' finish times (static: up to 11 us apart) to 3 us but its per-unit overhead delays all of them by 4 us and the
+// fixed-order reduction over the unit slots lengthens the tail; a hybrid (first 50-85 % static, rest dynamic) was
+// slower than the static deal at every split (68.4-74.3 us vs 66.3 us).  16 instead of 8 consumer warps: no change.
 //
 // Determinism: static unit assignment, per-CTA partial sums, fixed-order fp64 finish: bit-identical run to run.
 //
