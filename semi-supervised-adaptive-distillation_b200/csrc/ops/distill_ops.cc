@@ -214,6 +214,65 @@ bool SigmoidAdaptiveDistillLossMultiLevelOp<float, CUDAContext>::RunOnDevice() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// SigmoidAdaptiveDistillStep: the PowSum that produces the normaliser folded into the multi-level op — the whole
+// add_distill_loss sub-graph (retinanet_heads.py:313-352) plus its gradient ops as ONE cooperative launch
+// (sad_distill_fused_f32).  Produced by FuseAdaptiveDistillOps when the group's normaliser blob is the output of a
+// PowSum over exactly the group's teacher-probability blobs, in the same order.
+// Inputs : X_0, T_0, G_0, ..., X_{L-1}, T_{L-1}, G_{L-1}                        (3L)
+// Outputs: loss_0 .. loss_{L-1}, dX_0 .. dX_{L-1}, normalizer                   (2L + 1)
+// Args   : those of SigmoidAdaptiveDistillLoss + "d_loss" + "power" (PowSum's argument, default 1.0)
+template <typename T, class Context>
+class SigmoidAdaptiveDistillStepOp final : public Operator<Context> {
+ public:
+  SigmoidAdaptiveDistillStepOp(const OperatorDef& def, Workspace* ws)
+      : Operator<Context>(def, ws), params_(ReadDistillParams(this)),
+        d_loss_(OperatorBase::GetSingleArgument<float>("d_loss", 1.f)),
+        power_(OperatorBase::GetSingleArgument<float>("power", 1.f)) {
+    CAFFE_ENFORCE(InputSize() % 3 == 0 && InputSize() >= 3, "expected 3*L inputs");
+    levels_ = InputSize() / 3;
+    CAFFE_ENFORCE(levels_ <= SAD_MAX_LEVELS, "at most ", SAD_MAX_LEVELS, " levels");
+    CAFFE_ENFORCE_EQ(OutputSize(), 2 * levels_ + 1, "expected L losses, L gradients and the normaliser");
+  }
+  USE_OPERATOR_CONTEXT_FUNCTIONS;
+  bool RunOnDevice() override { CAFFE_NOT_IMPLEMENTED; }
+
+ protected:
+  sad_distill_params params_;
+  float d_loss_, power_;
+  int levels_;
+  KernelWorkspace scratch_;
+  Tensor<CUDAContext> d_loss_dev_;
+};
+
+template <>
+bool SigmoidAdaptiveDistillStepOp<float, CUDAContext>::RunOnDevice() {
+  sad_distill_level L[SAD_MAX_LEVELS];
+  if (d_loss_ != 1.f && d_loss_dev_.size() != 1) {
+    d_loss_dev_.Resize(vector<TIndex>());
+    CUDA_ENFORCE(cudaMemcpyAsync(d_loss_dev_.mutable_data<float>(), &d_loss_, sizeof(float), cudaMemcpyHostToDevice,
+                                 context_.cuda_stream()));
+  }
+  for (int l = 0; l < levels_; ++l) {
+    const auto& X = Input(3 * l);
+    FillLevel(&L[l], X, Input(3 * l + 1), Input(3 * l + 2), params_.num_classes);
+    auto* loss = Output(l);
+    loss->Resize(vector<TIndex>());
+    L[l].loss = loss->mutable_data<float>();
+    auto* dX = Output(levels_ + l);
+    dX->ResizeLike(X);
+    L[l].d_logits = dX->mutable_data<float>();
+    L[l].d_loss = d_loss_ != 1.f ? d_loss_dev_.data<float>() : nullptr;
+  }
+  auto* norm = Output(2 * levels_);
+  norm->Resize(vector<TIndex>());   // PowSum's output is a scalar (pow_sum_op.cu:31)
+  void* ws = scratch_.Ensure(sad_distill_fused_workspace_bytes(L, levels_, params_.num_classes), &context_);
+  EnforceSad(sad_distill_fused_f32(L, levels_, power_, norm->mutable_data<float>(), &params_, ws, scratch_.bytes(),
+                                   context_.cuda_stream()),
+             "sad_distill_fused_f32");
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // ConstantFill (subset): output shaped like input 0 (or arg "shape"), filled with float "value".
 // Only here so NetDefs dumped by Detectron (loss-gradient seeds, utils/blob.py:166-172) run
 // unmodified through the executor; reference: caffe2/caffe2/operators/filler_op.h.
@@ -263,6 +322,7 @@ REGISTER_CPU_OPERATOR(SigmoidAdaptiveDistillLossGradient, SigmoidAdaptiveDistill
 REGISTER_CUDA_OPERATOR(SigmoidAdaptiveDistillLoss, SigmoidAdaptiveDistillLossOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(SigmoidAdaptiveDistillLossGradient, SigmoidAdaptiveDistillLossGradientOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(SigmoidAdaptiveDistillLossMultiLevel, SigmoidAdaptiveDistillLossMultiLevelOp<float, CUDAContext>);
+REGISTER_CUDA_OPERATOR(SigmoidAdaptiveDistillStep, SigmoidAdaptiveDistillStepOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(ConstantFill, ConstantFillOp<CUDAContext>);
 
 OPERATOR_SCHEMA(SigmoidAdaptiveDistillLoss)
@@ -296,6 +356,14 @@ OPERATOR_SCHEMA(SigmoidAdaptiveDistillLossMultiLevel)
     .NumInputs(4, 3 * SAD_MAX_LEVELS + 1)
     .NumOutputs(2, 2 * SAD_MAX_LEVELS)
     .SetDoc("All FPN levels of SigmoidAdaptiveDistillLoss and its gradient in one kernel launch.")
+    .Arg("d_loss", "(float) default 1.0; constant upstream gradient of every level's loss.");
+
+OPERATOR_SCHEMA(SigmoidAdaptiveDistillStep)
+    .NumInputs(3, 3 * SAD_MAX_LEVELS)
+    .NumOutputs(3, 2 * SAD_MAX_LEVELS + 1)
+    .SetDoc("PowSum over the levels' teacher probabilities, then every level's SigmoidAdaptiveDistillLoss and gradient, "
+            "in one cooperative kernel launch.")
+    .Arg("power", "(float) default 1.0; PowSum's exponent.")
     .Arg("d_loss", "(float) default 1.0; constant upstream gradient of every level's loss.");
 
 OPERATOR_SCHEMA(ConstantFill).NumInputs(0, 1).NumOutputs(1).AllowInplace({{0, 0}});
@@ -376,18 +444,54 @@ int FuseAdaptiveDistillOps(NetDef* net) {
       result.push_back(first);
       continue;
     }
+    // the normaliser: if it is the output of a PowSum (already emitted, same device) over exactly this group's
+    // teacher-probability blobs in this order, and nothing between that PowSum and here rewrites them, the PowSum is
+    // folded in too (retinanet_heads.py:320-328 builds it right before the loss ops)
+    size_t pow_at = result.size();
+    for (size_t r = 0; r < result.size(); ++r) {
+      const OperatorDef& c = result[r];
+      if (c.type() == "PowSum" && c.output_size() == 1 && c.output(0) == first.input(3) &&
+          c.device_option().device_type() == CUDA && c.device_option().cuda_gpu_id() == first.device_option().cuda_gpu_id() &&
+          c.input_size() == (int)fwd.size()) {
+        bool same = true;
+        for (size_t k = 0; k < fwd.size(); ++k) same = same && c.input((int)k) == ops[fwd[k]].input(1);
+        if (same) pow_at = r;
+      }
+    }
+    if (pow_at != result.size()) {
+      const string& nb = first.input(3);
+      for (size_t r = pow_at + 1; r < result.size(); ++r) {       // ops emitted after the PowSum
+        for (const auto& in : result[r].input())
+          if (in == nb) pow_at = result.size();                    // someone else already reads the normaliser
+        for (const auto& out : result[r].output())
+          for (size_t f : fwd)
+            if (out == ops[f].input(1) || out == nb) pow_at = result.size();
+        if (pow_at == result.size()) break;
+      }
+    }
     OperatorDef fused;
-    fused.set_type("SigmoidAdaptiveDistillLossMultiLevel");
     fused.set_name(first.name());
     for (size_t f : fwd)
       for (int k = 0; k < 3; ++k) fused.add_input(ops[f].input(k));
-    fused.add_input(first.input(3));
-    for (size_t f : fwd) fused.add_output(ops[f].output(0));
-    for (size_t g : grad) fused.add_output(ops[g].output(0));
     for (const auto& a : first.arg()) *fused.add_arg() = a;
     Argument* dl = fused.add_arg();
     dl->set_name("d_loss");
     dl->set_f(d_loss_value);
+    if (pow_at != result.size()) {
+      fused.set_type("SigmoidAdaptiveDistillStep");
+      Argument* pw = fused.add_arg();
+      pw->set_name("power");
+      pw->set_f(ArgumentHelper::GetSingleArgument<OperatorDef, float>(result[pow_at], "power", 1.f));
+      for (size_t f : fwd) fused.add_output(ops[f].output(0));
+      for (size_t g : grad) fused.add_output(ops[g].output(0));
+      fused.add_output(first.input(3));
+      result.erase(result.begin() + pow_at);
+    } else {
+      fused.set_type("SigmoidAdaptiveDistillLossMultiLevel");
+      fused.add_input(first.input(3));
+      for (size_t f : fwd) fused.add_output(ops[f].output(0));
+      for (size_t g : grad) fused.add_output(ops[g].output(0));
+    }
     *fused.mutable_device_option() = first.device_option();
     result.push_back(fused);
     for (size_t f : fwd) consumed[f] = true;

@@ -18,6 +18,7 @@ def test_operators_registered_under_reference_names(oplib):
         for name in ("PowSum", "SigmoidAdaptiveDistillLoss", "SigmoidAdaptiveDistillLossGradient"):
             assert oplib.HasOperator(name, dev), (name, dev)
     assert oplib.HasOperator("SigmoidAdaptiveDistillLossMultiLevel", c2.CUDA)
+    assert oplib.HasOperator("SigmoidAdaptiveDistillStep", c2.CUDA)
 
 
 def test_schema_arity_matches_reference(oplib):
@@ -123,14 +124,16 @@ def test_fusion_pass_groups_levels(oplib):
     net, losses, grads = retinanet_heads.add_distill_loss(gpu_id=1, num_gpus=8)
     fused, n = oplib.FuseAdaptiveDistillOps(net.to_text())
     assert n == 1
-    assert fused.count('type: "SigmoidAdaptiveDistillLossMultiLevel"') == 1
+    # the adaptive normaliser is a PowSum over exactly the group's teacher blobs (retinanet_heads.py:320-328): it is
+    # folded in too -> ONE op (one cooperative launch) for PowSum + 5 losses + 5 gradients
+    assert fused.count('type: "SigmoidAdaptiveDistillStep"') == 1
     assert fused.count('type: "SigmoidAdaptiveDistillLoss"') == 0
     assert fused.count('type: "SigmoidAdaptiveDistillLossGradient"') == 0
-    assert fused.count('type: "PowSum"') == 1 and fused.count('type: "ConstantFill"') == 5
-    for b in losses + grads:  # blob names preserved
+    assert fused.count('type: "PowSum"') == 0 and fused.count('type: "ConstantFill"') == 5
+    for b in losses + grads + ["gpu_1/distill_normalizer"]:  # blob names preserved, the normaliser is still produced
         assert 'output: "%s"' % b in fused
-    # PowSum still precedes the fused op, which precedes the ConstantFills
-    assert fused.index("PowSum") < fused.index("MultiLevel") < fused.index("ConstantFill")
+    assert 'name: "power"' in fused and ('f: 1.8' in fused or 'f: 1.79999995' in fused)
+    assert fused.count("input:") == 15 + 5          # 3 per level + the ConstantFills' inputs
     # different arguments -> not fusable
     net.op[2].arg["alpha"] = 0.25
     fused2, n2 = oplib.FuseAdaptiveDistillOps(net.to_text())
@@ -139,6 +142,20 @@ def test_fusion_pass_groups_levels(oplib):
     net3, _, _ = retinanet_heads.add_distill_loss(with_gradients=False)
     fused3, n3 = oplib.FuseAdaptiveDistillOps(net3.to_text())
     assert n3 == 0 and fused3.count('type: "SigmoidAdaptiveDistillLoss"') == 5
+
+
+def test_fusion_pass_keeps_a_foreign_normaliser(oplib):
+    # ADAPTIVE_NORMALIZER off: the normaliser is retnet_fg_num, produced elsewhere -> the multi-level op with a normaliser input
+    net, losses, grads = retinanet_heads.add_distill_loss(cfg=dict(ADAPTIVE_NORMALIZER=False))
+    fused, n = oplib.FuseAdaptiveDistillOps(net.to_text())
+    assert n == 1 and fused.count('type: "SigmoidAdaptiveDistillLossMultiLevel"') == 1
+    assert 'input: "gpu_0/retnet_fg_num"' in fused
+    # a PowSum over OTHER blobs (or in another order) is not folded
+    net, _, _ = retinanet_heads.add_distill_loss()
+    net.op[0].input = list(reversed(net.op[0].input))
+    fused, n = oplib.FuseAdaptiveDistillOps(net.to_text())
+    assert n == 1 and fused.count('type: "PowSum"') == 1 and fused.count('type: "SigmoidAdaptiveDistillLossMultiLevel"') == 1
+    assert fused.index("PowSum") < fused.index("MultiLevel")
 
 
 # ---------------------------------------------------------------------------------------------

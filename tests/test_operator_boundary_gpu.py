@@ -88,14 +88,18 @@ def test_reference_graph_unfused_and_fused(oplib, oracle):
     lu, gu, nu = _run_net(oplib, host, fuse=False)
     lf, gf, nf = _run_net(oplib, host, fuse=True)
     assert_loss_close(nu, wp)
-    assert nu == nf
+    # the pass folds PowSum + 5 losses + 5 gradients into ONE SigmoidAdaptiveDistillStep op (one cooperative launch).
+    # It does not change results beyond summation order: the normaliser and the losses are sums whose partition over
+    # CTAs differs (last-bit differences); the gradients use the same element arithmetic and inherit the normaliser's
+    # last-bit difference as a common factor
+    assert abs(float(nu) - float(nf)) <= 2e-6 * abs(float(nu))
     for i, l in enumerate(host):
         assert_loss_close(lu[i], oracle.distill_loss(*l, wp, **HEAD), "level %d" % i)
         assert_grad_close(gu[i], oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)
-        # the pass does not change results: gradients are element-wise (bit-equal); the loss is a sum whose
-        # partition over CTAs differs between the one-level and the all-levels launch (last-bit differences)
-        assert np.array_equal(gu[i], gf[i])
-        assert abs(float(lu[i]) - float(lf[i])) <= 1e-6 * abs(float(lu[i]))
+        assert_loss_close(lf[i], oracle.distill_loss(*l, wp, **HEAD), "fused level %d" % i)
+        assert_grad_close(gf[i], oracle.distill_grad(*l, wp, **HEAD), "fused level %d" % i)
+        np.testing.assert_allclose(gf[i], gu[i], rtol=1e-5, atol=0)
+        assert abs(float(lu[i]) - float(lf[i])) <= 1e-5 * abs(float(lu[i]))
 
 
 def test_against_unmodified_reference_cuda_ops(oplib, reflib, oracle):
