@@ -236,6 +236,53 @@ def run_head_step(args, rank, world, barrier, native):
     }
 
 
+def run_full_step(args, rank, world, barrier, native):
+    """BASELINE.json configs[3] geometry (configs[2] per GPU): R-50-FPN student <- R-101-FPN teacher, full distillation
+    training step at bs = 2 per GPU, 600 px, one allreduce of the flat [head | body] gradient buffer.  The heads, the
+    distillation loss and the exchange are this repository's kernels; the ResNet/FPN bodies, focal / box losses and the
+    optimiser are PyTorch/cuDNN scaffolding (full_step.py)."""
+    import torch
+    import torch.distributed as dist
+    from sad_b200.full_step import FullDistillStep
+
+    K = args.full_steps or min(args.steps, 20)
+    st = FullDistillStep(n_images=2, scale_px=600, world=world, rank=rank)
+    for _ in range(3):
+        st.step()
+    barrier()
+    n0 = native.lib().sad_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev0.record()
+    for i in range(K):
+        st.forward_backward()
+        ar[i][0].record()
+        st.allreduce()
+        ar[i][1].record()
+        st.sgd()
+    ev1.record()
+    barrier()
+    launches = int(native.lib().sad_launch_count() - n0)
+    t = torch.tensor([ev0.elapsed_time(ev1) / K, sum(a.elapsed_time(b) for a, b in ar) / K], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0].item()), float(t[1].item())
+    losses = st.losses()
+    assert all(v == v for v in [losses["bbox"], losses["normalizer"]] + losses["distill"] + losses["focal"]), ("non-finite loss", losses)
+    return {
+        "metric": "RetinaNet-R50 distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms,
+        "steps": K, "images_per_gpu": st.images, "scaling": "weak",
+        "workload": "R-50-FPN student <- R-101-FPN teacher (random init), 3x640x1024 synthetic images, bs=2/GPU: teacher fwd, student "
+                    "fwd+bwd, focal + box + adaptive distillation losses, ONE allreduce of %d gradient bytes, momentum SGD" % st.exchange.nbytes,
+        "native": "both RetinaNet heads (tcgen05 tf32), PowSum + distillation loss/gradient (one cooperative launch), SigmoidFocalLoss + "
+                  "gradient accumulated into the same d(logits), gradient exchange",
+        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32), teacher Sigmoid, dense smooth-L1, SGD in PyTorch (SURVEY.md 8f next rows)",
+        "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
+        "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
+        "params": st.param_count(), "gpu_launches": launches, "losses": losses,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,6 +292,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head-steps", type=int, default=0, help="head distillation steps (0 = min(steps, 100); -1 = skip)")
+    ap.add_argument("--full-steps", type=int, default=0, help="full R-50 <- R-101 distillation steps (0 = min(steps, 20); -1 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -269,7 +317,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
-    from sad_b200 import native, ops, synthetic
+    from sad_b200 import native, ops, parallel, synthetic
+    numa = parallel.bind_to_gpu_numa_node(local_rank)  # before any pinned host allocation (the e2e path streams host buffers)
 
     # ---- inputs: this rank's shard (2 images), NSETS rotating copies so no step finds its inputs in L2
     NSETS = 3
@@ -353,6 +402,10 @@ def main():
     if args.head_steps >= 0:
         head_line = run_head_step(args, rank, world, barrier, native)
 
+    full_line = None
+    if args.full_steps >= 0:
+        full_line = run_full_step(args, rank, world, barrier, native)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -367,7 +420,7 @@ def main():
         "config": {"workload": WORKLOAD, "anchors_per_gpu_step": anchors, "elements_per_gpu_step": elements,
                    "args": HEAD, "power": POWER,
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2; one step touches 236 MB" % (NSETS, NSETS * 3 * elements * 4 / 1e6),
-                   "parallelism": "image-sharded x%d, no data-path collective" % world},
+                   "parallelism": "image-sharded x%d, no data-path collective" % world, "host_binding": numa},
         "roofline": {"bound": "hbm", "kernel": "distill_fused_kernel<alpha=.5> (cooperative persistent TMA-ring: PowSum, grid barrier, 5-level loss+grad)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic_per_launch(), "algorithmic_bytes_per_launch": BYTES_PER_ELEMENT * elements,
@@ -382,6 +435,9 @@ def main():
     }
     if head_line:
         line["head_step"] = head_line
+    if full_line:
+        line["full_step"] = full_line
+        line["gpu_launches"] += full_line["gpu_launches"]
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_oracle
         sample = host  # the full configs[1] batch, one pass (about 10-30 s of CPU work spread over the cores)

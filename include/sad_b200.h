@@ -94,6 +94,27 @@ int sad_distill_f32(const sad_distill_level* levels, int n_levels, const float* 
                     const sad_distill_params* params, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SigmoidFocalLoss (+Gradient) — replaces
+ *   SigmoidFocalLossOp<float, CUDAContext>::RunOnDevice          (caffe2/modules/detectron/sigmoid_focal_loss_op.cu:112-144)
+ *   SigmoidFocalLossGradientOp<float, CUDAContext>::RunOnDevice  (caffe2/modules/detectron/sigmoid_focal_loss_op.cu:147-173)
+ * and their kernels (:26-66, :68-109): the classification loss on the SAME logits and labels as the distillation loss
+ * (retinanet_heads.py:277-293).  loss and/or d_logits in one pass; accumulate_grad != 0 adds the gradient into d_logits
+ * (the autograd Sum of the two consumers of the logits, core.py:695,792-842).  The ignore label is the literal -1 as in
+ * the reference (:42).  fg_num: device fp32, element 0 (retnet_fg_num).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sad_focal_params {
+  float gamma;         /* arg "gamma", default 1.0 */
+  float alpha;         /* arg "alpha", default 0.25 */
+  float scale;         /* arg "scale", default 1.0, must be >= 0 */
+  int32_t num_classes; /* arg "num_classes", default 80 */
+} sad_focal_params;
+void sad_focal_default_params(sad_focal_params* p);
+size_t sad_focal_workspace_bytes(void); /* needed when loss != NULL; 256-byte aligned, sad_workspace_init once */
+int sad_sigmoid_focal_loss_f32(const float* logits, const int32_t* labels, const float* fg_num, int N, int D, int H, int W,
+                               const sad_focal_params* params, float* loss /* or NULL */, const float* d_loss /* NULL = 1.0 */,
+                               float* d_logits /* or NULL */, int accumulate_grad, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole loss step of add_distill_loss (detectron/lib/modeling/retinanet_heads.py:313-352) in ONE launch:
  *   normalizer_out[0] = PowSum(levels[0..n).teacher_prob, power)           (pow_sum_op.cu:25-43)
  *   levels[l].loss, levels[l].d_logits = SigmoidAdaptiveDistillLoss(+Gradient)(..., normalizer_out)  for every level

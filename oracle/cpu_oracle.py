@@ -62,6 +62,10 @@ def lib():
         l.oracle_conv2d_bwd.argtypes = [_f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9
         l.oracle_relu.argtypes = [_f32p, _f32p, C.c_int64]
         l.oracle_relu_grad.argtypes = [_f32p, _f32p, _f32p, C.c_int64]
+        l.oracle_focal_loss.restype = C.c_float
+        l.oracle_focal_loss.argtypes = [C.c_int] * 4 + [_f32p, _i32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, _f32p]
+        l.oracle_focal_grad.restype = None
+        l.oracle_focal_grad.argtypes = [C.c_int] * 4 + [_f32p, _i32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, _f32p, _f32p]
         _lib = l
     return _lib
 
@@ -109,6 +113,33 @@ def distill_grad(logits, teacher_prob, labels, normalizer, d_loss=1.0, gamma=1.0
     dX = np.empty(max(1, x.size), dtype=np.float32)
     lib().oracle_distill_grad(N, D, H, W, int(ignored_label), x.reshape(-1), t.reshape(-1), g.reshape(-1), wp,
                               float(gamma), float(alpha), float(beta), int(num_classes), float(scale), dl, dX)
+    return dX[:x.size].reshape(x.shape)
+
+
+def focal_loss(logits, labels, fg_num, gamma=1.0, alpha=0.25, scale=1.0, num_classes=80, return_elements=False):
+    """SigmoidFocalLoss (sigmoid_focal_loss_op.cu:26-66,112-144): scalar loss in the reference's summation order."""
+    x = np.ascontiguousarray(logits, dtype=np.float32)
+    g = np.ascontiguousarray(labels, dtype=np.int32)
+    wp = np.asarray([fg_num], dtype=np.float32).reshape(1)
+    N, D, H, W = x.shape
+    losses = np.empty(max(1, x.size), dtype=np.float32)
+    val = lib().oracle_focal_loss(N, D, H, W, x.reshape(-1), g.reshape(-1), wp, float(gamma), float(alpha), int(num_classes),
+                                  float(scale), losses)
+    if return_elements:
+        return np.float32(val), losses[:x.size].reshape(x.shape)
+    return np.float32(val)
+
+
+def focal_grad(logits, labels, fg_num, d_loss=1.0, gamma=1.0, alpha=0.25, scale=1.0, num_classes=80):
+    """SigmoidFocalLossGradient (sigmoid_focal_loss_op.cu:68-109,147-173)."""
+    x = np.ascontiguousarray(logits, dtype=np.float32)
+    g = np.ascontiguousarray(labels, dtype=np.int32)
+    wp = np.asarray([fg_num], dtype=np.float32).reshape(1)
+    dl = np.asarray([d_loss], dtype=np.float32).reshape(1)
+    N, D, H, W = x.shape
+    dX = np.empty(max(1, x.size), dtype=np.float32)
+    lib().oracle_focal_grad(N, D, H, W, x.reshape(-1), g.reshape(-1), wp, float(gamma), float(alpha), int(num_classes),
+                            float(scale), dl, dX)
     return dX[:x.size].reshape(x.shape)
 
 

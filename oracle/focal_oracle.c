@@ -1,0 +1,95 @@
+/* TEST INFRASTRUCTURE — CPU oracle for SigmoidFocalLoss / SigmoidFocalLossGradient (the classification loss that
+ * shares logits and labels with the distillation loss).  Same rules as distill_oracle.c:
+ * only tests/, smoke() and bench.py's CPU-baseline legs may load it.
+ *
+ * One C function per reference function, every implicit float<->double promotion of the device expressions written
+ * out as an explicit cast:
+ *   oracle_focal_loss_elem  <- caffe2/modules/detectron/sigmoid_focal_loss_op.cu:26-66   (SigmoidFocalLossKernel)
+ *   oracle_focal_grad_elem  <- caffe2/modules/detectron/sigmoid_focal_loss_op.cu:68-109  (SigmoidFocalLossGradientKernel)
+ *   oracle_focal_loss       <- ...:112-144 (kernel, math::Sum without scratch, math::Scale)
+ *   oracle_focal_grad       <- ...:147-173 (kernel, math::Scale over the tensor)
+ * Pinned against the reference itself: the unmodified sigmoid_focal_loss_op.{cc,cu} are part of oracle/_ref/libref_ops.so
+ * and are run side by side on the GPU (tests/test_focal_gpu.py), and their outputs are committed as golden vectors.
+ */
+#include <float.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+extern float oracle_ref_order_sum(const float* x, int64_t n); /* distill_oracle.c: math_gpu.cu:1021-1058 */
+
+/* label of element i of an (N, D, H, W) tensor and its class index d (sigmoid_focal_loss_op.cu:32-40) */
+static inline int focal_target(const int32_t* targets, int64_t i, int D, int H, int W, int num_classes, int* d_out) {
+  int x = (int)(i % W);
+  int y = (int)((i / W) % H);
+  int c = (int)((i / ((int64_t)W * H)) % D);
+  int n = (int)(i / ((int64_t)W * H * D));
+  int A = D / num_classes;
+  int a = c / num_classes;
+  *d_out = c % num_classes;
+  return targets[(int64_t)n * (H * W * A) + (int64_t)a * (H * W) + y * W + x];
+}
+
+ORACLE_API float oracle_focal_loss_elem(float logit, int t, int d, float weight_pos, float gamma, float alpha) {
+  float c1 = (float)(t == (d + 1));
+  float c2 = (float)((t != -1) & (t != (d + 1)));
+  float Np = (float)fmax((double)weight_pos, 1.0);
+  float zn = (float)((1.0 - (double)alpha) / (double)Np);
+  float zp = alpha / Np;
+  float p = (float)(1. / (1. + (double)expf(-logit)));
+  float term1 = powf((float)(1. - (double)p), gamma) * logf(fmaxf(p, FLT_MIN));
+  int ge = logit >= 0;
+  float term2 = (float)((double)powf(p, gamma) *
+                        (-1. * (double)logit * (double)ge - (double)logf((float)(1. + (double)expf((float)((double)logit - 2. * (double)logit * (double)ge))))));
+  float loss = (float)0.0;
+  loss += -c1 * term1 * zp;
+  loss += -c2 * term2 * zn;
+  return loss;
+}
+
+ORACLE_API float oracle_focal_grad_elem(float logit, int t, int d, float weight_pos, float gamma, float alpha, float a_loss) {
+  float Np = (float)fmax((double)weight_pos, 1.0);
+  float zn = (float)((1.0 - (double)alpha) / (double)Np);
+  float zp = alpha / Np;
+  float c1 = (float)(t == (d + 1));
+  float c2 = (float)((t != -1) & (t != (d + 1)));
+  float p = (float)(1. / (1. + (double)expf(-logit)));
+  float term1 = (float)((double)powf((float)(1. - (double)p), gamma) * (1. - (double)p - (double)(p * gamma * logf(fmaxf(p, FLT_MIN)))));
+  int ge = logit >= 0;
+  float term2 = (float)((double)powf(p, gamma) *
+                        ((-1. * (double)logit * (double)ge - (double)logf((float)(1. + (double)expf((float)((double)logit - 2. * (double)logit * (double)ge))))) *
+                             (1. - (double)p) * (double)gamma -
+                         (double)p));
+  float dx = (float)0.0;
+  dx += -c1 * zp * term1;
+  dx += -c2 * zn * term2;
+  dx = dx * a_loss;
+  return dx;
+}
+
+ORACLE_API float oracle_focal_loss(int N, int D, int H, int W, const float* logits, const int32_t* targets, const float* weight_pos,
+                                   float gamma, float alpha, int num_classes, float scale, float* losses) {
+  const int64_t n = (int64_t)N * D * H * W;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    int d;
+    int t = focal_target(targets, i, D, H, W, num_classes, &d);
+    losses[i] = oracle_focal_loss_elem(logits[i], t, d, weight_pos[0], gamma, alpha);
+  }
+  float s = oracle_ref_order_sum(losses, n);
+  return s * scale; /* math::Scale(1, scale_, avg_loss, avg_loss) */
+}
+
+ORACLE_API void oracle_focal_grad(int N, int D, int H, int W, const float* logits, const int32_t* targets, const float* weight_pos,
+                                  float gamma, float alpha, int num_classes, float scale, const float* d_loss, float* dX) {
+  const int64_t n = (int64_t)N * D * H * W;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    int d;
+    int t = focal_target(targets, i, D, H, W, num_classes, &d);
+    float g = oracle_focal_grad_elem(logits[i], t, d, weight_pos[0], gamma, alpha, d_loss[0]);
+    dX[i] = g * scale; /* math::Scale(n, scale_, dX, dX): a separate rounding */
+  }
+}

@@ -1,0 +1,247 @@
+"""The full RetinaNet distillation training step of BASELINE.json configs[2..4] on one GPU's image shard:
+
+    teacher  (frozen, forward only): ResNet-101 + FPN body -> RetinaNet head -> Sigmoid           model_builder.py:379-393
+    student  (trained)             : ResNet-50  + FPN body -> RetinaNet head                      model_builder.py:395-400
+    losses   : SigmoidFocalLoss + SelectSmoothL1Loss (retinanet_heads.py:248-311) and the adaptive distillation loss
+               PowSum + SigmoidAdaptiveDistillLoss (retinanet_heads.py:313-352)                   model_builder.py:402-406
+    backward : head (ConvGradient / ReluGradient / Sum) -> FPN -> ResNet body (res2 and below frozen, ResNet.py:88-104)
+    exchange : ONE allreduce over the flat gradient buffer [head | body]                          optimizer.py:72-92
+    update   : momentum SGD with weight decay                                                     optimizer.py:95-130
+
+What runs where.  ON the hot path and therefore on this repository's kernels: both RetinaNet heads
+(tcgen05 convolutions, `sad_head_*`), PowSum + distillation loss + gradient (one cooperative launch), SigmoidFocalLoss +
+gradient (native kernel, accumulated into the same d(logits)) and the gradient exchange.  OFF the hot path (§8f "next" rows, ranks 1-4) and therefore SCAFFOLDING in plain PyTorch / cuDNN, there only so
+that the step is complete and its imgs/s can be measured: the ResNet + FPN bodies (random init, AffineChannel = frozen
+per-channel scale/bias, affine_channel_op.cc:70-78), the teacher Sigmoid, a dense masked smooth-L1
+stand-in for SelectSmoothL1Loss (its sparse location lists come from the data loader, which is out of scope), and the
+optimiser.  Synthetic images, labels and box targets (there is no dataset in this environment).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, parallel, synthetic
+from .head import RetinaNetHead
+
+
+# ------------------------------------------------------------------------------------------------------------
+# scaffolding: ResNet-C4..C5 + FPN in PyTorch (detectron/lib/modeling/ResNet.py:88-278, FPN.py:94-249)
+# ------------------------------------------------------------------------------------------------------------
+class AffineChannel(nn.Module):
+    """Frozen batch-norm stand-in: y = x * scale + bias per channel, parameters not trained."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.register_buffer("scale", torch.ones(1, c, 1, 1))
+        self.register_buffer("bias", torch.zeros(1, c, 1, 1))
+
+    def forward(self, x):
+        return torch.addcmul(self.bias, x, self.scale)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, cin, cout, cmid, stride, groups=1):
+        super().__init__()
+        # stride on the first 1x1 (RESNETS.STRIDE_1X1 = True for the R-50 / R-101 configs)
+        self.c1, self.a1 = nn.Conv2d(cin, cmid, 1, stride=stride, bias=False), AffineChannel(cmid)
+        self.c2, self.a2 = nn.Conv2d(cmid, cmid, 3, padding=1, groups=groups, bias=False), AffineChannel(cmid)
+        self.c3, self.a3 = nn.Conv2d(cmid, cout, 1, bias=False), AffineChannel(cout)
+        self.short = None
+        if cin != cout or stride != 1:
+            self.short = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), AffineChannel(cout))
+
+    def forward(self, x):
+        y = F.relu(self.a1(self.c1(x)), inplace=True)
+        y = F.relu(self.a2(self.c2(y)), inplace=True)
+        y = self.a3(self.c3(y))
+        return F.relu(y + (x if self.short is None else self.short(x)), inplace=True)
+
+
+class ResNetFPN(nn.Module):
+    """C3..C5 -> P3..P7 (FPN.DIM = 256; P6, P7 by stride-2 3x3 convolutions: FPN.EXTRA_CONV_LEVELS, FPN.py:199-219)."""
+
+    def __init__(self, blocks=(3, 4, 6, 3), dim=256):
+        super().__init__()
+        self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), AffineChannel(64), nn.ReLU(inplace=True),
+                                  nn.MaxPool2d(3, stride=2, padding=1))
+        stages, cin = [], 64
+        for i, n in enumerate(blocks):
+            cout, cmid = 256 * 2 ** i, 64 * 2 ** i
+            stages.append(nn.Sequential(*[Bottleneck(cin if j == 0 else cout, cout, cmid, (1 if i == 0 else 2) if j == 0 else 1)
+                                          for j in range(n)]))
+            cin = cout
+        self.res2, self.res3, self.res4, self.res5 = stages
+        self.lat = nn.ModuleList([nn.Conv2d(c, dim, 1) for c in (512, 1024, 2048)])
+        self.out = nn.ModuleList([nn.Conv2d(dim, dim, 3, padding=1) for _ in range(3)])
+        self.p6 = nn.Conv2d(2048, dim, 3, stride=2, padding=1)
+        self.p7 = nn.Conv2d(dim, dim, 3, stride=2, padding=1)
+        for p in list(self.stem.parameters()) + list(self.res2.parameters()):   # TRAIN.FREEZE_AT = 2
+            p.requires_grad_(False)
+
+    def forward(self, x):
+        with torch.no_grad():
+            c2 = self.res2(self.stem(x))
+        c3 = self.res3(c2)
+        c4 = self.res4(c3)
+        c5 = self.res5(c4)
+        p5 = self.lat[2](c5)
+        p4 = self.lat[1](c4) + F.interpolate(p5, scale_factor=2, mode="nearest")
+        p3 = self.lat[0](c3) + F.interpolate(p4, scale_factor=2, mode="nearest")
+        p6 = self.p6(c5)
+        p7 = self.p7(F.relu(p6))
+        return [self.out[0](p3), self.out[1](p4), self.out[2](p5), p6, p7]
+
+
+def sigmoid_focal_loss(logits, labels, fg_num, gamma=2.0, alpha=0.25, scale=1.0, num_classes=80):
+    """SigmoidFocalLoss (sigmoid_focal_loss_op.cu:26-66) in plain PyTorch (scaffolding)."""
+    n, d, h, w = logits.shape
+    x = logits.view(n, d // num_classes, num_classes, h, w)
+    t = labels.view(n, d // num_classes, 1, h, w)
+    cls = torch.arange(1, num_classes + 1, device=logits.device, dtype=labels.dtype).view(1, 1, num_classes, 1, 1)
+    c1 = t == cls
+    c2 = (t != -1) & ~c1
+    p = torch.sigmoid(x)
+    term1 = (1 - p) ** gamma * F.logsigmoid(x)
+    term2 = p ** gamma * F.logsigmoid(-x)
+    np_ = torch.clamp(fg_num, min=1.0)
+    return -(torch.where(c1, term1 * alpha, torch.zeros_like(x)) + torch.where(c2, term2 * (1 - alpha), torch.zeros_like(x))).sum() / np_ * scale
+
+
+def masked_smooth_l1(box, targets, labels, fg_num, beta=0.11, scale=1.0):
+    """Dense stand-in for SelectSmoothL1Loss (select_smooth_l1_loss_op.cu:23-54): smooth-L1 over the 4 deltas of every
+    foreground anchor, / max(fg_num, 1)."""
+    n, d, h, w = box.shape
+    v = (box - targets).view(n, d // 4, 4, h, w)
+    a = v.abs()
+    l = torch.where(a < beta, 0.5 * v * v / beta, a - 0.5 * beta)
+    return (l * (labels > 0).view(n, d // 4, 1, h, w)).sum() / torch.clamp(fg_num, min=1.0) * scale
+
+
+class _StudentHead(torch.autograd.Function):
+    """The student's RetinaNet head (this repository's kernels) inside PyTorch's autograd graph."""
+
+    @staticmethod
+    def forward(ctx, step, *fpn):
+        ctx.step = step
+        fpn = [f.contiguous() for f in fpn]
+        step.head.forward(fpn, training=True, out=(step.cls, step.box))
+        return tuple(t.detach() for t in (*step.cls, *step.box))   # fresh tensor objects over the persistent output buffers
+
+    @staticmethod
+    def backward(ctx, *g):
+        st = ctx.step
+        L = len(st.cls)
+        # d(logits) = distillation gradient (fused kernel) + focal-loss gradient (native kernel, accumulated in place): the
+        # autograd Sum of the two consumers of retnet_cls_pred_fpnL (core.py:695,792-842); nothing in PyTorch consumes
+        # the logits, so g[l] is normally None
+        d_cls = [st.plan.grads[l] if g[l] is None else st.plan.grads[l].add_(g[l]) for l in range(L)]
+        d_box = [g[L + l].contiguous() if g[L + l] is not None else torch.zeros_like(st.box[l]) for l in range(L)]
+        d_fpn = st.head.backward(d_cls, d_box, want_d_fpn=True, d_fpn=st.d_fpn)
+        return (None, *d_fpn)
+
+
+class FullDistillStep:
+    def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
+                 temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4):
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.world, self.rank, self.images = int(world), int(rank), int(n_images)
+        self.lr, self.mom, self.wd = lr, momentum, weight_decay
+        shapes = synthetic.level_shapes(scale_px)
+        H, W = shapes[0][0] * 8, shapes[0][1] * 8
+        torch.backends.cudnn.allow_tf32 = True          # the bodies run on cuDNN's TF32 tensor-core path (scaffolding)
+        torch.backends.cudnn.benchmark = True
+        torch.manual_seed(seed)                         # same weights on every rank
+        self.student = ResNetFPN(student_blocks).to(self.device).to(memory_format=torch.channels_last)
+        self.teacher = ResNetFPN(teacher_blocks).to(self.device).to(memory_format=torch.channels_last).eval()
+        for p in self.teacher.parameters():
+            p.requires_grad_(False)
+        self.body_params = [p for p in self.student.parameters() if p.requires_grad]
+        n_body = sum(p.numel() for p in self.body_params)
+        # ONE flat gradient buffer [head | body]: the head writes its slice, autograd accumulates into views of the rest
+        probe = RetinaNetHead(n_images, shapes, device=self.device, seed=seed)
+        n_head = probe.flat_grads.numel()
+        probe.close()
+        self.flat_grads = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
+        self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head])
+        self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1)
+        off = n_head
+        for p in self.body_params:
+            p.grad = self.flat_grads[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.n_head, self.n_body = n_head, n_body
+        self.exchange = parallel.GradientExchange(self.flat_grads, world=self.world)
+        self.body_momentum = [torch.zeros_like(p) for p in self.body_params]
+        self.head_momentum = torch.zeros_like(self.head.flat_params)
+        # this rank's synthetic shard
+        g = torch.Generator(device=self.device).manual_seed(seed + 7919 * (rank + 1))
+        N, A = n_images, synthetic.NUM_ANCHORS
+        self.images_t = torch.randn(N, 3, H, W, device=self.device, generator=g).contiguous(memory_format=torch.channels_last)
+        self.labels, self.box_targets = [], []
+        for h, w in shapes:
+            u = torch.rand(N, A, h, w, device=self.device, generator=g)
+            lab = torch.zeros(N, A, h, w, dtype=torch.int32, device=self.device)
+            lab[u < 0.005] = -1
+            fg = (u >= 0.005) & (u < 0.006)
+            lab[fg] = torch.randint(1, synthetic.NUM_CLASSES + 1, (int(fg.sum()),), device=self.device, generator=g, dtype=torch.int32)
+            self.labels.append(lab)
+            self.box_targets.append(torch.randn(N, A * 4, h, w, device=self.device, generator=g) * 0.2)
+        self.fg_num = torch.stack([(l > 0).sum() for l in self.labels]).sum().float().reshape(1)
+        self.focal_ws = [ops.focal_workspace(self.device) for _ in shapes]
+        self.focal_losses = [torch.zeros((), device=self.device) for _ in shapes]
+        self.cls, self.box = self.head.alloc_outputs()
+        self.t_cls, self.t_box = self.teacher_head.alloc_outputs()
+        self.t_prob = [torch.empty_like(c) for c in self.t_cls]
+        self.d_fpn = [torch.empty(N, 256, h, w, device=self.device) for h, w in shapes]
+        self.loss_scale = 1.0 / self.world                       # detector.py:650-655
+        self.plan = ops.DistillPlan(list(zip(self.cls, self.t_prob, self.labels)), power=power, gamma=distill_gamma,
+                                    alpha=distill_alpha, beta=0.0, scale=parallel.distill_loss_scale(temperature, self.world),
+                                    num_classes=synthetic.NUM_CLASSES, ignored_label=-1)
+        self.last = {}
+
+    def forward_backward(self):
+        with torch.no_grad():                                            # teacher: forward only (model.train = False)
+            t_fpn = [f.contiguous() for f in self.teacher(self.images_t)]
+            self.teacher_head.forward(t_fpn, training=False, out=(self.t_cls, self.t_box))
+            for p, c in zip(self.t_prob, self.t_cls):
+                torch.sigmoid(c, out=p)                                  # retinanet_heads.py:153-163 (scaffolding)
+        self.flat_grads[self.n_head:].zero_()
+        fpn = self.student(self.images_t)
+        outs = _StudentHead.apply(self, *fpn)
+        L = len(self.cls)
+        cls, box = outs[:L], outs[L:]
+        self.plan.run()                                                  # PowSum + distillation loss + d(logits), one launch
+        for l in range(L):                                               # SigmoidFocalLoss + gradient, added into d(logits)
+            ops.sigmoid_focal_loss(self.cls[l], self.labels[l], self.fg_num, accumulate_into=self.plan.grads[l], workspace=self.focal_ws[l],
+                                   loss_out=self.focal_losses[l], gamma=2.0, alpha=0.25, scale=self.loss_scale,
+                                   num_classes=synthetic.NUM_CLASSES)
+        loss = sum(masked_smooth_l1(b, t, l, self.fg_num, scale=self.loss_scale) for b, t, l in zip(box, self.box_targets, self.labels))
+        loss.backward()
+        self.last = {"bbox": loss.detach(), "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
+                     "normalizer": self.plan.normalizer}
+
+    def allreduce(self):
+        return self.exchange.allreduce()
+
+    @torch.no_grad()
+    def sgd(self):
+        """MomentumSGDUpdate with weight decay (optimizer.py:95-130; scaffolding: torch foreach ops)."""
+        grads = [p.grad for p in self.body_params]
+        torch._foreach_add_(grads, self.body_params, alpha=self.wd)
+        torch._foreach_mul_(self.body_momentum, self.mom)
+        torch._foreach_add_(self.body_momentum, grads, alpha=self.lr)
+        torch._foreach_sub_(self.body_params, self.body_momentum)
+        hg = self.head.flat_grads.add(self.head.flat_params, alpha=self.wd)
+        self.head_momentum.mul_(self.mom).add_(hg, alpha=self.lr)
+        self.head.flat_params.sub_(self.head_momentum)
+
+    def step(self):
+        self.forward_backward()
+        self.allreduce()
+        self.sgd()
+
+    def losses(self):
+        return {"bbox": float(self.last["bbox"]), "focal": [float(x) for x in self.last["focal"]],
+                "distill": [float(x) for x in self.last["distill"]], "normalizer": float(self.last["normalizer"])}
+
+    def param_count(self):
+        return {"head": self.n_head, "body_trainable": self.n_body}

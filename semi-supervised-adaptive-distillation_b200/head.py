@@ -31,7 +31,7 @@ def param_names(num_convs=4, k_min=K_MIN):
 
 class RetinaNetHead:
     def __init__(self, n_images, level_shapes, dim=256, num_convs=4, num_anchors=9, num_classes=80, prior_prob=0.01,
-                 device="cuda", seed=0):
+                 device="cuda", seed=0, grad_buffer=None):
         self.N, self.level_shapes = int(n_images), [tuple(s) for s in level_shapes]
         self.dim, self.num_convs = int(dim), int(num_convs)
         self.cls_out, self.bbox_out = num_anchors * num_classes, num_anchors * 4
@@ -54,7 +54,13 @@ class RetinaNetHead:
         self.shapes = shapes
         total = sum(math.prod(s) for s in shapes.values())
         self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.flat_grads = torch.zeros(total, dtype=torch.float32, device=self.device)
+        if grad_buffer is None:
+            grad_buffer = torch.zeros(total, dtype=torch.float32, device=self.device)
+        # a caller-owned slice lets the head's gradients live inside a larger flat buffer (one allreduce for the whole model)
+        if not (grad_buffer.is_cuda and grad_buffer.dtype == torch.float32 and grad_buffer.is_contiguous() and grad_buffer.numel() == total
+                and grad_buffer.data_ptr() % 16 == 0):
+            raise ValueError("grad_buffer must be a contiguous 16-byte aligned CUDA fp32 tensor of %d elements" % total)
+        self.flat_grads = grad_buffer
         self.params, self.grads, off = {}, {}, 0
         for n in self.names:
             k = math.prod(shapes[n])

@@ -30,6 +30,10 @@ class DistillParams(C.Structure):
                 ("num_classes", C.c_int32), ("ignored_label", C.c_int32)]
 
 
+class FocalParams(C.Structure):
+    _fields_ = [("gamma", C.c_float), ("alpha", C.c_float), ("scale", C.c_float), ("num_classes", C.c_int32)]
+
+
 class ConvLevel(C.Structure):
     _fields_ = [("x_nhwc", C.c_void_p), ("y_nchw", C.c_void_p), ("y_nhwc", C.c_void_p),
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu_mask_nhwc", C.c_void_p),
@@ -95,6 +99,12 @@ def lib():
         l.sad_distill_fused_workspace_bytes.argtypes = [C.POINTER(DistillLevel), C.c_int, C.c_int]
         l.sad_distill_fused_f32.argtypes = [C.POINTER(DistillLevel), C.c_int, C.c_float, C.c_void_p, C.POINTER(DistillParams),
                                             C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_focal_default_params.argtypes = [C.POINTER(FocalParams)]
+        l.sad_focal_default_params.restype = None
+        l.sad_focal_workspace_bytes.restype = C.c_size_t
+        l.sad_sigmoid_focal_loss_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.POINTER(FocalParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_size_t, C.c_void_p]
         l.sad_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.sad_ctx_destroy.argtypes = [C.c_void_p]
         l.sad_ctx_destroy.restype = None

@@ -109,6 +109,35 @@ def distill(levels, normalizer, want_loss=True, want_grad=True, d_loss=None, wor
     return losses, grads
 
 
+def focal_workspace(device):
+    return Workspace(lib().sad_focal_workspace_bytes(), device)
+
+
+def sigmoid_focal_loss(logits, labels, fg_num, want_loss=True, want_grad=True, d_loss=None, accumulate_into=None, workspace=None,
+                       loss_out=None, gamma=1.0, alpha=0.25, scale=1.0, num_classes=80):
+    """SigmoidFocalLoss and/or its gradient for one level.  Returns (loss or None, d_logits or None).
+    accumulate_into: an existing d_logits tensor the gradient is ADDED to (the autograd Sum with the distillation gradient)."""
+    _require_cuda(logits, torch.float32, "logits")
+    _require_cuda(labels, torch.int32, "labels")
+    _require_cuda(fg_num, torch.float32, "fg_num")
+    n, d, h, w = logits.shape
+    p = native.FocalParams()
+    lib().sad_focal_default_params(C.byref(p))
+    p.gamma, p.alpha, p.scale, p.num_classes = float(gamma), float(alpha), float(scale), int(num_classes)
+    loss = (loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=logits.device)) if want_loss else None
+    grad = None
+    if want_grad:
+        grad = accumulate_into if accumulate_into is not None else torch.empty_like(logits)
+    if want_loss and workspace is None:
+        workspace = Workspace(lib().sad_focal_workspace_bytes(), logits.device)
+    check(lib().sad_sigmoid_focal_loss_f32(
+        C.c_void_p(logits.data_ptr()), C.c_void_p(labels.data_ptr()), C.c_void_p(fg_num.data_ptr()), n, d, h, w, C.byref(p),
+        C.c_void_p(loss.data_ptr()) if loss is not None else None, C.c_void_p(d_loss.data_ptr()) if d_loss is not None else None,
+        C.c_void_p(grad.data_ptr()) if grad is not None else None, 1 if accumulate_into is not None else 0,
+        workspace.ptr if workspace is not None else None, workspace.nbytes if workspace is not None else 0, _stream()))
+    return loss, grad
+
+
 def distill_step(levels, power=1.8, workspace=None, d_loss=None, **args):
     """PowSum over the levels' teacher probabilities + loss + gradient of every level through the single-launch entry
     point sad_distill_fused_f32.  Returns (normalizer, losses, d_logits)."""

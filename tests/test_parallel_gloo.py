@@ -72,3 +72,12 @@ def test_loss_scale_and_single_process_exchange():
     with pytest.raises(ValueError):
         parallel.GradientExchange(torch.zeros(4, dtype=torch.float64), world=1)
     assert parallel.GradientExchange(torch.zeros(1024), world=8).bus_bytes() == 2 * 7 / 8 * 4096
+
+
+def test_cpulist_parser_and_numa_binding_is_harmless_without_a_gpu():
+    from sad_b200 import parallel
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    msg = parallel.bind_to_gpu_numa_node(0)       # no CUDA device here: must report, not raise, and change nothing
+    assert isinstance(msg, str) and os.sched_getaffinity(0) == before
