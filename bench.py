@@ -249,20 +249,25 @@ def run_full_step(args, rank, world, barrier, native):
     st = FullDistillStep(n_images=2, scale_px=600, world=world, rank=rank)
     for _ in range(3):
         st.step()
-    barrier()
     n0 = native.lib().sad_launch_count()
+    st.forward_backward()
+    per_step = int(native.lib().sad_launch_count() - n0)
+    graphed = st.capture()
+    for _ in range(2):
+        st.step()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ev0.record()
     for i in range(K):
-        st.forward_backward()
+        st.run()
         ar[i][0].record()
         st.allreduce()
         ar[i][1].record()
         st.sgd()
     ev1.record()
     barrier()
-    launches = int(native.lib().sad_launch_count() - n0)
+    launches = per_step * K
     t = torch.tensor([ev0.elapsed_time(ev1) / K, sum(a.elapsed_time(b) for a, b in ar) / K], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -279,7 +284,8 @@ def run_full_step(args, rank, world, barrier, native):
         "scaffolding": "ResNet/FPN bodies on cuDNN (TF32), teacher Sigmoid, dense smooth-L1, SGD in PyTorch (SURVEY.md 8f next rows)",
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
-        "params": st.param_count(), "gpu_launches": launches, "losses": losses,
+        "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),
+        "cuda_graph_error": getattr(st, "capture_error", None), "losses": losses,
     }
 
 

@@ -219,6 +219,34 @@ class FullDistillStep:
         self.last = {"bbox": loss.detach(), "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
                      "normalizer": self.plan.normalizer}
 
+    def capture(self, warmup=3):
+        """Capture forward_backward() (teacher forward, student forward + backward, all losses: several hundred launches,
+        cuDNN and this repository's kernels alike) into ONE CUDA graph.  Returns True when the graph was built; on any
+        capture error the step stays eager."""
+        try:
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self.forward_backward()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward_backward()
+            self.graph = g
+            return True
+        except Exception as e:  # leave a usable eager step behind
+            self.graph, self.capture_error = None, "%s: %s" % (type(e).__name__, str(e)[:200])
+            torch.cuda.synchronize()
+            return False
+
+    def run(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+        else:
+            self.forward_backward()
+
     def allreduce(self):
         return self.exchange.allreduce()
 
@@ -235,7 +263,7 @@ class FullDistillStep:
         self.head.flat_params.sub_(self.head_momentum)
 
     def step(self):
-        self.forward_backward()
+        self.run()
         self.allreduce()
         self.sgd()
 
