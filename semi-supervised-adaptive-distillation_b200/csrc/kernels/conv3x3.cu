@@ -57,12 +57,14 @@ constexpr int kCvCols = 32;
 constexpr int kCvN = kCvRows * kCvCols;  // 256
 constexpr int kCvKC = 32;
 constexpr int kCvStages = 4;
+constexpr int kCvStagesPair = 6;   // CTA-pair kernel: 32 KB stages
 constexpr int kCvABytes = kCvM * kCvKC * 4;            // 16 KB
 constexpr int kCvBBytes = kCvN * kCvKC * 4;            // 32 KB
 constexpr int kCvStageBytes = kCvABytes + kCvBBytes;   // 48 KB
 constexpr int kCvThreads = 192;                        // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
 constexpr int kCvTmemCols = 512;                       // 2 accumulator buffers x 256 columns
 constexpr size_t kCvSmemBytes = (size_t)kCvStages * kCvStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static_assert((2 * 6 + 4 + 6) * 8 + 4 <= 256, "barrier block");
 
 struct ConvLevel {
   float* y_nchw;            // may be null
@@ -76,7 +78,8 @@ struct ConvLevel {
 };
 struct alignas(64) ConvArgs {
   CUtensorMap tmap_w;
-  CUtensorMap tmap_x[SAD_MAX_LEVELS];
+  CUtensorMap tmap_x[SAD_MAX_LEVELS];    // box {32 ci, 32 x, 8 y, 1 n}: a whole pixel tile
+  CUtensorMap tmap_xh[SAD_MAX_LEVELS];   // box {32 ci, 32 x, 4 y, 1 n}: half a pixel tile (CTA-pair kernel)
   ConvLevel lv[SAD_MAX_LEVELS];
   const float* bias;
   int32_t n_levels, cin, cout, relu;
@@ -105,76 +108,126 @@ __device__ __forceinline__ ConvTile conv_decode_tile(const ConvArgs& a, uint32_t
   return t;
 }
 
+// kC2: launched as clusters of 2 CTAs (the two SMs of one TPC) that execute ONE 256-channel x 256-pixel MMA per step
+// (tcgen05.mma.cta_group::2, SASS UTCHMMA.2CTA): each CTA stages its own 128-channel weight tile (16 KB) and HALF of the
+// pixel tile (4 of the 8 rows, 16 KB) per stage — 32 instead of 48 KB of TMA traffic per CTA and stage, 6 instead of 4
+// stages in the same shared memory — the leader CTA's MMA thread issues for both, and each CTA's 128 x 256 fp32
+// accumulator sits in its own TMEM.  m_tiles then counts PAIRS of 128-channel tiles; both CTAs walk the same tile sequence.
+// Measured on B200 (bs = 16, 256 -> 256 / 720 channels): 737 / 744 TF/s against 739 / 695 TF/s for one-CTA tiles; whole head
+// step 14.99 vs 15.60 ms at bs = 16 and 2.131 vs 2.152 ms at bs = 2.  Cycle counters in the MMA thread (12 tiles of 288
+// MMAs per CTA): 78 % of its time it is blocked issuing into a busy tensor pipe (128 cycles per MMA, the rate
+// scripts/probe/mma_probe.cu measures for both forms), 22 % waiting for operands.
+// Dead ends measured on the way: stream-K scheduling (-10..-17 %), multicasting the activation tile to two
+// independent one-CTA MMAs (+-0), L2 prefetch of the next tile (+-0), and `mbarrier.arrive.release.cluster` for the
+// cross-CTA hand-over, which costs ~1400 cycles per call and halved the throughput until replaced by the default form.
+//   barriers   full[s]      one per CTA: its own copies (32 KB)
+//              peer_full[s] in the LEADER: the partner's relay thread arrives when the partner's full[s] completed (letting the
+//                           partner's copies signal the leader's barrier directly — the cta_group::2 form of the TMA load — was
+//                           measured 2x slower: 1650 instead of 780 cycles per stage)
+//              empty[s]     one per CTA: the leader's commit multicasts "stage read" to both producers
+//              tmem_full[b] one per CTA: the leader's commit multicasts "accumulator complete" to both epilogues
+//              tmem_empty[b] lives in the LEADER: 256 arrivals, both CTAs' epilogue threads (the partner's remotely)
+template <bool kC2>
 __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __grid_constant__ ConvArgs args) {
+  constexpr int kStages = kC2 ? kCvStagesPair : kCvStages;
+  constexpr int kBBytes = kC2 ? kCvBBytes / 2 : kCvBBytes;
+  constexpr int kStageBytes = kCvABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (128B-swizzle atoms are 1024 B), barriers behind it
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kCvStages * kCvStageBytes);
-  uint64_t* full_bar = bars;                    // [kCvStages] TMA -> MMA
-  uint64_t* empty_bar = bars + kCvStages;       // [kCvStages] MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * kCvStages;   // [2] MMA -> epilogue
-  uint64_t* tmem_empty = tmem_full + 2;         // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;       // [kStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;   // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;       // [2] epilogue -> MMA
+  uint64_t* peer_full = tmem_empty + 2;       // [kStages] pair only: partner's stage landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = kC2 ? cluster_ctarank() : 0u;            // which 128-channel half of the pair
+  const uint32_t wstream = kC2 ? blockIdx.x >> 1 : blockIdx.x;    // work stream (both CTAs of a pair walk the same one)
+  const uint32_t nstreams = kC2 ? gridDim.x >> 1 : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.tmap_w);
     for (int l = 0; l < args.n_levels; ++l)
-      tma_prefetch_desc(&args.tmap_x[l]);
+      tma_prefetch_desc(kC2 ? &args.tmap_xh[l] : &args.tmap_x[l]);
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kCvStages; ++s) {
+      for (int s = 0; s < kStages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
+        mbar_init(&peer_full[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full[b], 1);
-        mbar_init(&tmem_empty[b], 128);
+        mbar_init(&tmem_empty[b], kC2 ? 256 : 128);
       }
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc<kCvTmemCols>(tmem_slot);
+    if (kC2) tmem_alloc_2sm<kCvTmemCols>(tmem_slot);
+    else tmem_alloc<kCvTmemCols>(tmem_slot);
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (kC2) cluster_sync_all();   // the partner's mbarriers exist before anything of ours can signal them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t k_blocks = args.k_blocks;  // ceil(Cin / 32)
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs of a pair) =====================
     if (lane == 0) {
       RingState rs;
       int l_hint = 0;
-      for (uint32_t tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-        const ConvTile t = conv_decode_tile(args, tile, l_hint);
-        const CUtensorMap* mx = &args.tmap_x[t.l];
+      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
+        ConvTile t = conv_decode_tile(args, tile, l_hint);
+        if (kC2) t.m0 = (2 * (t.m0 / kCvM) + (int)crank) * kCvM;
+        const CUtensorMap* mx = kC2 ? &args.tmap_xh[t.l] : &args.tmap_x[t.l];
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           for (uint32_t kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
-            uint8_t* sa = smem + (size_t)rs.stage * kCvStageBytes;
+            uint8_t* sa = smem + (size_t)rs.stage * kStageBytes;
             uint8_t* sb = sa + kCvABytes;
-            mbar_arrive_expect_tx(&full_bar[rs.stage], kCvStageBytes);
-            tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kCvKC, t.m0, tap);
-            tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kCvKC, t.x0 + dx, t.y0 + dy, t.n);
-            rs.advance<kCvStages>();
+            if (kC2) {
+              mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
+              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kCvKC, t.m0, tap);
+              // my half of the pixel tile: rows y0 + 4 * rank .. + 3 (= accumulator columns 128 * rank .. + 127)
+              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kCvKC, t.x0 + dx, t.y0 + (int)crank * (kCvRows / 2) + dy, t.n);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
+              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kCvKC, t.m0, tap);
+              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kCvKC, t.x0 + dx, t.y0 + dy, t.n);
+            }
+            rs.advance<kStages>();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
+    // ===================== MMA issuer (one thread; pair: of the leader CTA only) =====================
+    if (kC2 && lane == 0 && crank != 0) {
+      // partner CTA: relay "my stage landed" to the leader's MMA thread
+      RingState rs;
+      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
+        const uint32_t n_kb = 9u * k_blocks;
+        for (uint32_t kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full_bar[rs.stage], rs.phase);
+          mbar_arrive_cluster(map_to_cta(&peer_full[rs.stage], 0));
+          rs.advance<kStages>();
+        }
+      }
+    }
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
       RingState rs;
       uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++it) {
+      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
         const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(&tmem_empty[buf], aphase ^ 1u);
         tc_fence_after_sync();
@@ -182,8 +235,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
         const uint32_t n_kb = 9u * k_blocks;
         for (uint32_t kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full_bar[rs.stage], rs.phase);
+          if (kC2) mbar_wait_cluster(&peer_full[rs.stage], rs.phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kCvStageBytes);
+          const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kStageBytes);
           const uint32_t b_addr = a_addr + kCvABytes;
 #pragma unroll
           for (int k = 0; k < kCvKC / 8; ++k) {
@@ -191,12 +245,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             // one K step of 8 = +32 B inside the swizzled row
             const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+            if (kC2) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+            else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
           }
-          umma_commit(&empty_bar[rs.stage]);  // frees the smem stage when these MMAs have read it
-          rs.advance<kCvStages>();
+          // frees the smem stage when these MMAs have read it (pair: in both CTAs)
+          if (kC2) umma_commit_2sm(&empty_bar[rs.stage], (uint16_t)0x3);
+          else umma_commit(&empty_bar[rs.stage]);
+          rs.advance<kStages>();
         }
-        umma_commit(&tmem_full[buf]);  // accumulator complete
+        // accumulator complete (pair: both CTAs' halves)
+        if (kC2) umma_commit_2sm(&tmem_full[buf], (uint16_t)0x3);
+        else umma_commit(&tmem_full[buf]);
       }
     }
   } else {
@@ -205,9 +264,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
     const int row = q * 32 + lane;
     uint32_t it = 0;
     int l_hint = 0;
-    for (uint32_t tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
       const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
-      const ConvTile t = conv_decode_tile(args, tile, l_hint);
+      ConvTile t = conv_decode_tile(args, tile, l_hint);
+      if (kC2) t.m0 = (2 * (t.m0 / kCvM) + (int)crank) * kCvM;
       const ConvLevel& L = args.lv[t.l];
       const int co = t.m0 + row;
       const bool co_ok = co < args.cout;
@@ -289,14 +349,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(&tmem_empty[buf]);
+      if (kC2) mbar_arrive_cluster(map_to_cta(&tmem_empty[buf], 0));   // the leader's MMA thread owns the accumulator hand-over
+      else mbar_arrive(&tmem_empty[buf]);
     }
   }
 
   __syncthreads();
+  if (kC2) cluster_sync_all();   // nothing of the partner's (copies, barrier arrivals, MMA reads of my tiles) may still be in flight
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc<kCvTmemCols>(tmem_base);
+    if (kC2) tmem_dealloc_2sm<kCvTmemCols>(tmem_base);
+    else tmem_dealloc<kCvTmemCols>(tmem_base);
   }
 }
 
@@ -513,7 +576,10 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ConvArgs a{};
   uint64_t tiles = 0;
-  const uint32_t m_tiles = (uint32_t)((cout + kCvM - 1) / kCvM);
+  // two or more 128-channel tiles: CTA pairs (clusters of 2) share each pixel tile's activations; m_tiles then counts pairs
+  const uint32_t m_single = (uint32_t)((cout + kCvM - 1) / kCvM);
+  const bool pair = m_single >= 2;
+  const uint32_t m_tiles = pair ? (m_single + 1) / 2 : m_single;
   bool tma_ok = (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(packed) & 15) == 0);
   int rc;
   for (int l = 0; l < n_levels; ++l) {
@@ -569,9 +635,12 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     const sad_conv_level& L = levels[l];
     if ((uint64_t)L.N * L.H * L.W == 0) {  // empty level: a valid dummy map (never used, no tiles)
       a.tmap_x[l] = a.tmap_w;
+      a.tmap_xh[l] = a.tmap_w;
       continue;
     }
     if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows, "activations {C,W,H,N}")) != SAD_OK) return rc;
+    if ((rc = encode_nhwc_map(&a.tmap_xh[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows / 2, "activations {C,W,H,N}, half tile")) != SAD_OK)
+      return rc;
   }
   a.bias = bias;
   a.n_levels = n_levels;
@@ -584,11 +653,35 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
 
   int sms = 0;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
-  if ((rc = check_cuda(cudaFuncSetAttribute(conv3x3_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
-                       "cudaFuncSetAttribute(conv3x3)")) != SAD_OK)
-    return rc;
-  const uint32_t grid = a.total_tiles < (uint32_t)sms ? a.total_tiles : (uint32_t)sms;
-  conv3x3_tf32_kernel<<<grid, kCvThreads, kCvSmemBytes, st>>>(a);
+  if (pair) {
+    auto kern = conv3x3_tf32_kernel<true>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
+                         "cudaFuncSetAttribute(conv3x3 pair)")) != SAD_OK)
+      return rc;
+    uint32_t pairs = (uint32_t)sms / 2;
+    if (pairs > a.total_tiles) pairs = a.total_tiles;
+    if (pairs < 1) pairs = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kCvThreads);
+    cfg.dynamicSmemBytes = kCvSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if ((rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "conv3x3 pair launch")) != SAD_OK) return rc;
+  } else {
+    auto kern = conv3x3_tf32_kernel<false>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
+                         "cudaFuncSetAttribute(conv3x3)")) != SAD_OK)
+      return rc;
+    const uint32_t grid = a.total_tiles < (uint32_t)sms ? a.total_tiles : (uint32_t)sms;
+    kern<<<grid, kCvThreads, kCvSmemBytes, st>>>(a);
+  }
   count_launch(1);
   return check_cuda(cudaGetLastError(), "conv3x3 launch");
 }
