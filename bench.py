@@ -273,15 +273,15 @@ def run_full_step(args, rank, world, barrier, native):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ar_ms = float(t[0].item()), float(t[1].item())
     losses = st.losses()
-    assert all(v == v for v in [losses["bbox"], losses["normalizer"]] + losses["distill"] + losses["focal"]), ("non-finite loss", losses)
+    assert all(v == v for v in [losses["normalizer"]] + losses["bbox"] + losses["distill"] + losses["focal"]), ("non-finite loss", losses)
     return {
         "metric": "RetinaNet-R50 distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms,
         "steps": K, "images_per_gpu": st.images, "scaling": "weak",
         "workload": "R-50-FPN student <- R-101-FPN teacher (random init), 3x640x1024 synthetic images, bs=2/GPU: teacher fwd, student "
                     "fwd+bwd, focal + box + adaptive distillation losses, ONE allreduce of %d gradient bytes, momentum SGD" % st.exchange.nbytes,
-        "native": "both RetinaNet heads (tcgen05 tf32), PowSum + distillation loss/gradient (one cooperative launch), SigmoidFocalLoss + "
-                  "gradient accumulated into the same d(logits), gradient exchange",
-        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32), teacher Sigmoid, dense smooth-L1, SGD in PyTorch (SURVEY.md 8f next rows)",
+        "native": "both RetinaNet heads forward + backward (tcgen05 tf32), PowSum + distillation loss/gradient (one cooperative launch), "
+                  "SigmoidFocalLoss + gradient accumulated into the same d(logits), SelectSmoothL1Loss + gradient, gradient exchange",
+        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32) under autograd, teacher Sigmoid, SGD in PyTorch (SURVEY.md 8f ranks 2-4)",
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
         "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),

@@ -115,6 +115,15 @@ int sad_sigmoid_focal_loss_f32(const float* logits, const int32_t* labels, const
                                const sad_focal_params* params, float* loss /* or NULL */, const float* d_loss /* NULL = 1.0 */,
                                float* d_logits /* or NULL */, int accumulate_grad, void* workspace, size_t workspace_bytes, void* stream);
 
+/* SelectSmoothL1Loss (+Gradient) — replaces SelectSmoothL1LossOp / SelectSmoothL1LossGradientOp<float, CUDAContext>::RunOnDevice
+ * (caffe2/modules/detectron/select_smooth_l1_loss_op.cu:90-143, 145-181; kernels :23-54, :57-86): smooth-L1 over the 4 deltas of the
+ * M foreground anchors listed in `locs` (M x 4 FLOAT rows {n, first channel, y, x}) against `y` (M x 4), / max(fg_num, 1), x scale.
+ * loss and/or d_y_hat (zero-filled, then the 4*M entries scattered, scaled by d_loss (NULL = 1) and scale).  M = 0: loss 0. */
+size_t sad_smooth_l1_workspace_bytes(void); /* needed when loss != NULL */
+int sad_select_smooth_l1_loss_f32(const float* y_hat, const float* y, const float* locs, const float* fg_num, int N, int D, int H, int W,
+                                  int M, float beta, float scale, float* loss /* or NULL */, const float* d_loss /* NULL = 1.0 */,
+                                  float* d_y_hat /* or NULL */, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole loss step of add_distill_loss (detectron/lib/modeling/retinanet_heads.py:313-352) in ONE launch:
  *   normalizer_out[0] = PowSum(levels[0..n).teacher_prob, power)           (pow_sum_op.cu:25-43)
  *   levels[l].loss, levels[l].d_logits = SigmoidAdaptiveDistillLoss(+Gradient)(..., normalizer_out)  for every level

@@ -64,6 +64,10 @@ def lib():
         l.oracle_relu_grad.argtypes = [_f32p, _f32p, _f32p, C.c_int64]
         l.oracle_focal_loss.restype = C.c_float
         l.oracle_focal_loss.argtypes = [C.c_int] * 4 + [_f32p, _i32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, _f32p]
+        l.oracle_select_smooth_l1_loss.restype = C.c_float
+        l.oracle_select_smooth_l1_loss.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p]
+        l.oracle_select_smooth_l1_grad.restype = None
+        l.oracle_select_smooth_l1_grad.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p, _f32p]
         l.oracle_focal_grad.restype = None
         l.oracle_focal_grad.argtypes = [C.c_int] * 4 + [_f32p, _i32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, _f32p, _f32p]
         _lib = l
@@ -141,6 +145,24 @@ def focal_grad(logits, labels, fg_num, d_loss=1.0, gamma=1.0, alpha=0.25, scale=
     lib().oracle_focal_grad(N, D, H, W, x.reshape(-1), g.reshape(-1), wp, float(gamma), float(alpha), int(num_classes),
                             float(scale), dl, dX)
     return dX[:x.size].reshape(x.shape)
+
+
+def select_smooth_l1(y_hat, y, locs, fg_num, beta=1.0, scale=1.0, d_loss=1.0):
+    """(loss, d_y_hat) of SelectSmoothL1Loss / Gradient (select_smooth_l1_loss_op.cu:23-86, 90-181)."""
+    yh = np.ascontiguousarray(y_hat, dtype=np.float32)
+    N, D, H, W = yh.shape
+    y = np.ascontiguousarray(y, dtype=np.float32).reshape(-1, 4)
+    locs = np.ascontiguousarray(locs, dtype=np.float32).reshape(-1, 4)
+    M = y.shape[0]
+    S = np.asarray([fg_num], dtype=np.float32)
+    dl = np.asarray([d_loss], dtype=np.float32)
+    buff = np.empty(max(1, yh.size), dtype=np.float32)
+    grad = np.empty(max(1, yh.size), dtype=np.float32)
+    yy = y.reshape(-1) if M else np.zeros(4, np.float32)
+    ll = locs.reshape(-1) if M else np.zeros(4, np.float32)
+    loss = lib().oracle_select_smooth_l1_loss(N, D, H, W, M, yh.reshape(-1), yy, ll, S, float(beta), float(scale), buff)
+    lib().oracle_select_smooth_l1_grad(N, D, H, W, M, yh.reshape(-1), yy, ll, S, float(beta), float(scale), dl, grad)
+    return np.float32(loss), grad[:yh.size].reshape(yh.shape)
 
 
 def distill_elem_f64(x, pt, keep=1, wp=1.0, gamma=2.0, alpha=0.5, beta=0.0, d_loss=1.0, scale=1.0):

@@ -93,3 +93,39 @@ ORACLE_API void oracle_focal_grad(int N, int D, int H, int W, const float* logit
     dX[i] = g * scale; /* math::Scale(n, scale_, dX, dX): a separate rounding */
   }
 }
+
+/* SelectSmoothL1Loss / Gradient: caffe2/modules/detectron/select_smooth_l1_loss_op.cu:23-54 (kernel), :90-143 (zero-filled buffer as
+ * large as Y_hat, kernel, math::Sum over the WHOLE buffer, math::Scale), :57-86 and :145-181 (gradient: zero fill + scatter). */
+ORACLE_API float oracle_select_smooth_l1_loss(int N, int D, int H, int W, int M, const float* Y_hat, const float* Y, const float* L,
+                                              const float* S, float beta, float scale, float* buff) {
+  const int64_t total = (int64_t)N * D * H * W;
+  if (M == 0) return 0.f;
+  for (int64_t i = 0; i < total; ++i) buff[i] = 0.f;
+  for (int i = 0; i < M; ++i) {
+    int n = (int)L[i * 4], c = (int)L[i * 4 + 1], y = (int)L[i * 4 + 2], x = (int)L[i * 4 + 3];
+    for (int j = 0; j < 4; ++j) {
+      int ind = n * (D * H * W) + (c + j) * (H * W) + y * W + x;
+      float val = Y_hat[ind] - Y[i * 4 + j];
+      float abs_val = fabsf(val);
+      if (abs_val < beta) buff[ind] = (float)((0.5 * (double)val * (double)val / (double)beta) / fmax((double)S[0], 1.0));
+      else buff[ind] = (float)(((double)abs_val - 0.5 * (double)beta) / fmax((double)S[0], 1.0));
+    }
+  }
+  return oracle_ref_order_sum(buff, total) * scale;
+}
+
+ORACLE_API void oracle_select_smooth_l1_grad(int N, int D, int H, int W, int M, const float* Y_hat, const float* Y, const float* L,
+                                             const float* S, float beta, float scale, const float* d_loss, float* out) {
+  const int64_t total = (int64_t)N * D * H * W;
+  for (int64_t i = 0; i < total; ++i) out[i] = 0.f;
+  for (int i = 0; i < M; ++i) {
+    int n = (int)L[i * 4], c = (int)L[i * 4 + 1], y = (int)L[i * 4 + 2], x = (int)L[i * 4 + 3];
+    for (int j = 0; j < 4; ++j) {
+      int ind = n * (D * H * W) + (c + j) * (H * W) + y * W + x;
+      float val = Y_hat[ind] - Y[i * 4 + j];
+      float abs_val = fabsf(val);
+      if (abs_val < beta) out[ind] = (float)((double)(scale * d_loss[0] * val / beta) / fmax((double)S[0], 1.0));
+      else out[ind] = (float)((double)(scale * d_loss[0] * (float)((0.f < val) - (val < 0.f))) / fmax((double)S[0], 1.0));
+    }
+  }
+}

@@ -8,13 +8,13 @@
     exchange : ONE allreduce over the flat gradient buffer [head | body]                          optimizer.py:72-92
     update   : momentum SGD with weight decay                                                     optimizer.py:95-130
 
-What runs where.  ON the hot path and therefore on this repository's kernels: both RetinaNet heads
-(tcgen05 convolutions, `sad_head_*`), PowSum + distillation loss + gradient (one cooperative launch), SigmoidFocalLoss +
-gradient (native kernel, accumulated into the same d(logits)) and the gradient exchange.  OFF the hot path (§8f "next" rows, ranks 1-4) and therefore SCAFFOLDING in plain PyTorch / cuDNN, there only so
-that the step is complete and its imgs/s can be measured: the ResNet + FPN bodies (random init, AffineChannel = frozen
-per-channel scale/bias, affine_channel_op.cc:70-78), the teacher Sigmoid, a dense masked smooth-L1
-stand-in for SelectSmoothL1Loss (its sparse location lists come from the data loader, which is out of scope), and the
-optimiser.  Synthetic images, labels and box targets (there is no dataset in this environment).
+What runs where.  On this repository's kernels: both RetinaNet heads (tcgen05 convolutions,
+`sad_head_*`), PowSum + distillation loss + gradient (one cooperative launch), SigmoidFocalLoss + gradient (accumulated into
+the same d(logits)), SelectSmoothL1Loss + gradient, and the gradient exchange — every loss and the whole head, forward and
+backward.  SCAFFOLDING in plain PyTorch / cuDNN (§8f ranks 2-4), there only so that the step is complete and its imgs/s can
+be measured: the ResNet + FPN bodies (random init, AffineChannel = frozen per-channel scale/bias,
+affine_channel_op.cc:70-78; autograd carries d(fpn_L) from the head's backward into them), the teacher Sigmoid and the
+optimiser.  Synthetic images, labels, foreground locations and box targets (there is no dataset in this environment).
 """
 import torch
 import torch.nn as nn
@@ -92,54 +92,6 @@ class ResNetFPN(nn.Module):
         return [self.out[0](p3), self.out[1](p4), self.out[2](p5), p6, p7]
 
 
-def sigmoid_focal_loss(logits, labels, fg_num, gamma=2.0, alpha=0.25, scale=1.0, num_classes=80):
-    """SigmoidFocalLoss (sigmoid_focal_loss_op.cu:26-66) in plain PyTorch (scaffolding)."""
-    n, d, h, w = logits.shape
-    x = logits.view(n, d // num_classes, num_classes, h, w)
-    t = labels.view(n, d // num_classes, 1, h, w)
-    cls = torch.arange(1, num_classes + 1, device=logits.device, dtype=labels.dtype).view(1, 1, num_classes, 1, 1)
-    c1 = t == cls
-    c2 = (t != -1) & ~c1
-    p = torch.sigmoid(x)
-    term1 = (1 - p) ** gamma * F.logsigmoid(x)
-    term2 = p ** gamma * F.logsigmoid(-x)
-    np_ = torch.clamp(fg_num, min=1.0)
-    return -(torch.where(c1, term1 * alpha, torch.zeros_like(x)) + torch.where(c2, term2 * (1 - alpha), torch.zeros_like(x))).sum() / np_ * scale
-
-
-def masked_smooth_l1(box, targets, labels, fg_num, beta=0.11, scale=1.0):
-    """Dense stand-in for SelectSmoothL1Loss (select_smooth_l1_loss_op.cu:23-54): smooth-L1 over the 4 deltas of every
-    foreground anchor, / max(fg_num, 1)."""
-    n, d, h, w = box.shape
-    v = (box - targets).view(n, d // 4, 4, h, w)
-    a = v.abs()
-    l = torch.where(a < beta, 0.5 * v * v / beta, a - 0.5 * beta)
-    return (l * (labels > 0).view(n, d // 4, 1, h, w)).sum() / torch.clamp(fg_num, min=1.0) * scale
-
-
-class _StudentHead(torch.autograd.Function):
-    """The student's RetinaNet head (this repository's kernels) inside PyTorch's autograd graph."""
-
-    @staticmethod
-    def forward(ctx, step, *fpn):
-        ctx.step = step
-        fpn = [f.contiguous() for f in fpn]
-        step.head.forward(fpn, training=True, out=(step.cls, step.box))
-        return tuple(t.detach() for t in (*step.cls, *step.box))   # fresh tensor objects over the persistent output buffers
-
-    @staticmethod
-    def backward(ctx, *g):
-        st = ctx.step
-        L = len(st.cls)
-        # d(logits) = distillation gradient (fused kernel) + focal-loss gradient (native kernel, accumulated in place): the
-        # autograd Sum of the two consumers of retnet_cls_pred_fpnL (core.py:695,792-842); nothing in PyTorch consumes
-        # the logits, so g[l] is normally None
-        d_cls = [st.plan.grads[l] if g[l] is None else st.plan.grads[l].add_(g[l]) for l in range(L)]
-        d_box = [g[L + l].contiguous() if g[L + l] is not None else torch.zeros_like(st.box[l]) for l in range(L)]
-        d_fpn = st.head.backward(d_cls, d_box, want_d_fpn=True, d_fpn=st.d_fpn)
-        return (None, *d_fpn)
-
-
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
                  temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4):
@@ -176,7 +128,7 @@ class FullDistillStep:
         g = torch.Generator(device=self.device).manual_seed(seed + 7919 * (rank + 1))
         N, A = n_images, synthetic.NUM_ANCHORS
         self.images_t = torch.randn(N, 3, H, W, device=self.device, generator=g).contiguous(memory_format=torch.channels_last)
-        self.labels, self.box_targets = [], []
+        self.labels = []
         for h, w in shapes:
             u = torch.rand(N, A, h, w, device=self.device, generator=g)
             lab = torch.zeros(N, A, h, w, dtype=torch.int32, device=self.device)
@@ -184,14 +136,24 @@ class FullDistillStep:
             fg = (u >= 0.005) & (u < 0.006)
             lab[fg] = torch.randint(1, synthetic.NUM_CLASSES + 1, (int(fg.sum()),), device=self.device, generator=g, dtype=torch.int32)
             self.labels.append(lab)
-            self.box_targets.append(torch.randn(N, A * 4, h, w, device=self.device, generator=g) * 0.2)
         self.fg_num = torch.stack([(l > 0).sum() for l in self.labels]).sum().float().reshape(1)
+        # foreground anchors as SelectSmoothL1Loss takes them (roi_data/retinanet.py:178-195): rows {image, 4 * anchor, y, x} as floats
+        # and an (M, 4) target per level
+        self.box_locs, self.box_targets = [], []
+        for lab in self.labels:
+            idx = (lab > 0).nonzero()
+            locs = torch.stack([idx[:, 0], idx[:, 1] * 4, idx[:, 2], idx[:, 3]], dim=1).float().contiguous()
+            self.box_locs.append(locs)
+            self.box_targets.append((torch.randn(locs.shape[0], 4, device=self.device, generator=g) * 0.2).contiguous())
+        self.box_ws = [ops.focal_workspace(self.device) for _ in shapes]
+        self.box_losses = [torch.zeros((), device=self.device) for _ in shapes]
         self.focal_ws = [ops.focal_workspace(self.device) for _ in shapes]
         self.focal_losses = [torch.zeros((), device=self.device) for _ in shapes]
         self.cls, self.box = self.head.alloc_outputs()
         self.t_cls, self.t_box = self.teacher_head.alloc_outputs()
         self.t_prob = [torch.empty_like(c) for c in self.t_cls]
         self.d_fpn = [torch.empty(N, 256, h, w, device=self.device) for h, w in shapes]
+        self.d_box = [torch.empty_like(b) for b in self.box]
         self.loss_scale = 1.0 / self.world                       # detector.py:650-655
         self.plan = ops.DistillPlan(list(zip(self.cls, self.t_prob, self.labels)), power=power, gamma=distill_gamma,
                                     alpha=distill_alpha, beta=0.0, scale=parallel.distill_loss_scale(temperature, self.world),
@@ -205,18 +167,23 @@ class FullDistillStep:
             for p, c in zip(self.t_prob, self.t_cls):
                 torch.sigmoid(c, out=p)                                  # retinanet_heads.py:153-163 (scaffolding)
         self.flat_grads[self.n_head:].zero_()
-        fpn = self.student(self.images_t)
-        outs = _StudentHead.apply(self, *fpn)
+        fpn = self.student(self.images_t)                                # PyTorch graph ends here ...
+        fpn_c = [f.detach().contiguous() for f in fpn]
         L = len(self.cls)
-        cls, box = outs[:L], outs[L:]
+        self.head.forward(fpn_c, training=True, out=(self.cls, self.box))
         self.plan.run()                                                  # PowSum + distillation loss + d(logits), one launch
-        for l in range(L):                                               # SigmoidFocalLoss + gradient, added into d(logits)
+        for l in range(L):
+            # SigmoidFocalLoss + gradient, added into the distillation gradient (the autograd Sum of the two consumers of
+            # retnet_cls_pred_fpnL, core.py:695,792-842)
             ops.sigmoid_focal_loss(self.cls[l], self.labels[l], self.fg_num, accumulate_into=self.plan.grads[l], workspace=self.focal_ws[l],
                                    loss_out=self.focal_losses[l], gamma=2.0, alpha=0.25, scale=self.loss_scale,
                                    num_classes=synthetic.NUM_CLASSES)
-        loss = sum(masked_smooth_l1(b, t, l, self.fg_num, scale=self.loss_scale) for b, t, l in zip(box, self.box_targets, self.labels))
-        loss.backward()
-        self.last = {"bbox": loss.detach(), "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
+            # SelectSmoothL1Loss + gradient (RETINANET.BBOX_REG_BETA = 0.11)
+            ops.select_smooth_l1_loss(self.box[l], self.box_targets[l], self.box_locs[l], self.fg_num, beta=0.11, scale=self.loss_scale,
+                                      workspace=self.box_ws[l], loss_out=self.box_losses[l], grad_out=self.d_box[l])
+        d_fpn = self.head.backward(self.plan.grads, self.d_box, want_d_fpn=True, d_fpn=self.d_fpn)
+        torch.autograd.backward(fpn, d_fpn)                              # ... and resumes here: FPN and ResNet body backward
+        self.last = {"bbox": self.box_losses, "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
                      "normalizer": self.plan.normalizer}
 
     def capture(self, warmup=3):
@@ -268,7 +235,7 @@ class FullDistillStep:
         self.sgd()
 
     def losses(self):
-        return {"bbox": float(self.last["bbox"]), "focal": [float(x) for x in self.last["focal"]],
+        return {"bbox": [float(x) for x in self.last["bbox"]], "focal": [float(x) for x in self.last["focal"]],
                 "distill": [float(x) for x in self.last["distill"]], "normalizer": float(self.last["normalizer"])}
 
     def param_count(self):

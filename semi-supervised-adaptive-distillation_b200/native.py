@@ -105,6 +105,9 @@ def lib():
         l.sad_sigmoid_focal_loss_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.POINTER(FocalParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                  C.c_size_t, C.c_void_p]
+        l.sad_smooth_l1_workspace_bytes.restype = C.c_size_t
+        l.sad_select_smooth_l1_loss_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.sad_ctx_destroy.argtypes = [C.c_void_p]
         l.sad_ctx_destroy.restype = None

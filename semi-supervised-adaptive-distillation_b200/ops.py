@@ -138,6 +138,28 @@ def sigmoid_focal_loss(logits, labels, fg_num, want_loss=True, want_grad=True, d
     return loss, grad
 
 
+def select_smooth_l1_loss(y_hat, y, locs, fg_num, beta=1.0, scale=1.0, want_loss=True, want_grad=True, d_loss=None, workspace=None,
+                          loss_out=None, grad_out=None):
+    """SelectSmoothL1Loss and/or its gradient for one level: y_hat (N, A*4, H, W), y (M, 4), locs (M, 4) float {n, c, y, x}."""
+    _require_cuda(y_hat, torch.float32, "y_hat")
+    m = int(y.shape[0]) if y.numel() else 0
+    if m:
+        _require_cuda(y, torch.float32, "y")
+        _require_cuda(locs, torch.float32, "locs")
+    n, d, h, w = y_hat.shape
+    loss = (loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=y_hat.device)) if want_loss else None
+    grad = (grad_out if grad_out is not None else torch.empty_like(y_hat)) if want_grad else None
+    if want_loss and workspace is None:
+        workspace = Workspace(lib().sad_smooth_l1_workspace_bytes(), y_hat.device)
+    check(lib().sad_select_smooth_l1_loss_f32(
+        C.c_void_p(y_hat.data_ptr()), C.c_void_p(y.data_ptr()) if m else None, C.c_void_p(locs.data_ptr()) if m else None,
+        C.c_void_p(fg_num.data_ptr()), n, d, h, w, m, float(beta), float(scale),
+        C.c_void_p(loss.data_ptr()) if loss is not None else None, C.c_void_p(d_loss.data_ptr()) if d_loss is not None else None,
+        C.c_void_p(grad.data_ptr()) if grad is not None else None,
+        workspace.ptr if workspace is not None else None, workspace.nbytes if workspace is not None else 0, _stream()))
+    return loss, grad
+
+
 def distill_step(levels, power=1.8, workspace=None, d_loss=None, **args):
     """PowSum over the levels' teacher probabilities + loss + gradient of every level through the single-launch entry
     point sad_distill_fused_f32.  Returns (normalizer, losses, d_logits)."""
