@@ -280,8 +280,9 @@ def run_full_step(args, rank, world, barrier, native):
         "workload": "R-50-FPN student <- R-101-FPN teacher (random init), 3x640x1024 synthetic images, bs=2/GPU: teacher fwd, student "
                     "fwd+bwd, focal + box + adaptive distillation losses, ONE allreduce of %d gradient bytes, momentum SGD" % st.exchange.nbytes,
         "native": "both RetinaNet heads forward + backward (tcgen05 tf32), PowSum + distillation loss/gradient (one cooperative launch), "
-                  "SigmoidFocalLoss + gradient accumulated into the same d(logits), SelectSmoothL1Loss + gradient, gradient exchange",
-        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32) under autograd, teacher Sigmoid, SGD in PyTorch (SURVEY.md 8f ranks 2-4)",
+                  "SigmoidFocalLoss + gradient accumulated into the same d(logits), SelectSmoothL1Loss + gradient, teacher Sigmoid fused into its "
+                  "prediction convolution, gradient exchange",
+        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32) under autograd, SGD in PyTorch (SURVEY.md 8f ranks 3-4)",
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
         "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),

@@ -212,7 +212,8 @@ typedef struct sad_pack_item {
   int32_t cin, cout, mode;
 } sad_pack_item;
 int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, void* stream);
-/* y = conv3x3(x, packed) + bias (bias may be NULL), optionally followed by ReLU (relu != 0).
+/* y = conv3x3(x, packed) + bias (bias may be NULL), followed by the activation `relu`: 0 none, 1 ReLU (relu_op.cu:22-28),
+ * 2 Sigmoid (caffe2/caffe2/operators/sigmoid_op.cu:24-29 — the teacher's retnet_cls_prob_fpnL, retinanet_heads.py:153-163).
  * `cin`/`cout` are the K/M of `packed` (for the data gradient pass cin = Cout_of_forward, cout = Cin_of_forward). */
 int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                         int cout, int relu, void* stream);
@@ -263,6 +264,9 @@ typedef struct sad_head_config {
   int32_t num_convs;            /* RETINANET.NUM_CONVS = 4 */
   int32_t cls_out;              /* A * (NUM_CLASSES - 1) = 720 */
   int32_t bbox_out;             /* A * 4 = 36 */
+  int32_t cls_output_sigmoid;   /* 0: cls output = logits (retnet_cls_pred_fpnL, the student).  1: = Sigmoid(logits)
+                                   (retnet_cls_prob_fpnL: what the graph adds when model.train is False, i.e. for the
+                                   teacher, retinanet_heads.py:153-163) fused into the prediction convolution's epilogue */
 } sad_head_config;
 typedef struct sad_head_weights {
   const float* cls_tower_w[SAD_HEAD_MAX_CONVS];  /* (dim, dim, 3, 3) */

@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             v[i] += b;
-            if (args.relu) v[i] = fmaxf(v[i], 0.f);
+            if (args.relu == 1) v[i] = fmaxf(v[i], 0.f);
+            else if (args.relu == 2) v[i] = __frcp_rn(1.f + __expf(-v[i]));   // Sigmoid (sigmoid_op.cu:24-29): the teacher's class probabilities
           }
           if (L.bits_in) {
             // ReluGradient (relu_op.cu:29-35: dX = Y > 0 ? dY : 0) from the sign bits the forward pass left: 1 word per row
@@ -427,7 +428,8 @@ __global__ void conv3x3_simt_kernel(const float* __restrict__ xt, const float* _
       const float* xp = xt + (((size_t)n * H + sy) * W + sx) * cin;
       for (int ci = 0; ci < cin; ++ci) acc = fmaf(wrow[ci], xp[ci], acc);
     }
-    if (relu) acc = fmaxf(acc, 0.f);
+    if (relu == 1) acc = fmaxf(acc, 0.f);
+    else if (relu == 2) acc = __frcp_rn(1.f + __expf(-acc));
     if (mask_nhwc && !(mask_nhwc[i] > 0.f)) acc = 0.f;
     const size_t word = (((size_t)n * H + yy) * ((W + 31) / 32) + (xx >> 5)) * cout + co;
     if (bits_in && !((bits_in[word] >> (xx & 31)) & 1u)) acc = 0.f;

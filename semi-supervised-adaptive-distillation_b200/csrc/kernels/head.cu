@@ -277,7 +277,8 @@ SAD_EXPORT int sad_head_forward(sad_head* h, const sad_head_weights* w, const fl
       in = h->act[t][i];
     }
     float* const* out = t == 0 ? cls_logits_nchw : bbox_pred_nchw;
-    if ((rc = conv_levels(h, in, out, nullptr, nullptr, nullptr, 0, h->packed[0][t][nc], pred_b(w, t), dim, pred_out(h->cfg, t), 0, s)) != SAD_OK)
+    const int act = (t == 0 && h->cfg.cls_output_sigmoid) ? 2 : 0;
+    if ((rc = conv_levels(h, in, out, nullptr, nullptr, nullptr, 0, h->packed[0][t][nc], pred_b(w, t), dim, pred_out(h->cfg, t), act, s)) != SAD_OK)
       return rc;
   }
   if ((rc = check_cuda(cudaEventRecord(h->ev_join, h->s_side), "cudaEventRecord")) != SAD_OK) return rc;
@@ -289,6 +290,8 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
                                  int accumulate, void* stream) {
   if (!h || !grads) return set_error(SAD_ERR_INVALID, "sad_head_backward: null argument");
   if (!d_cls_logits_nchw && !d_bbox_pred_nchw) return set_error(SAD_ERR_INVALID, "sad_head_backward: no output gradient given");
+  if (h->cfg.cls_output_sigmoid)
+    return set_error(SAD_ERR_UNSUPPORTED, "sad_head_backward: a head whose classification output is Sigmoid(logits) is forward-only (the teacher)");
   if (!h->packed_bwd_valid)
     return set_error(SAD_ERR_INVALID, "sad_head_backward: call sad_head_forward(training = 1) first (it keeps the activations and packs the weights)");
   int rc;

@@ -13,8 +13,8 @@ What runs where.  On this repository's kernels (SURVEY.md §8a-e and §8f rank 1
 the same d(logits)), SelectSmoothL1Loss + gradient, and the gradient exchange — every loss and the whole head, forward and
 backward.  SCAFFOLDING in plain PyTorch / cuDNN (§8f ranks 2-4), there only so that the step is complete and its imgs/s can
 be measured: the ResNet + FPN bodies (random init, AffineChannel = frozen per-channel scale/bias,
-affine_channel_op.cc:70-78; autograd carries d(fpn_L) from the head's backward into them), the teacher Sigmoid and the
-optimiser.  Synthetic images, labels, foreground locations and box targets (there is no dataset in this environment).
+affine_channel_op.cc:70-78; autograd carries d(fpn_L) from the head's backward into them) and the optimiser.  The teacher's
+Sigmoid is fused into its prediction convolution (§8f rank 2).  Synthetic images, labels, foreground locations and box targets (there is no dataset in this environment).
 """
 import torch
 import torch.nn as nn
@@ -115,7 +115,7 @@ class FullDistillStep:
         probe.close()
         self.flat_grads = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
         self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head])
-        self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1)
+        self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1, cls_output_sigmoid=True)
         off = n_head
         for p in self.body_params:
             p.grad = self.flat_grads[off:off + p.numel()].view_as(p)
@@ -150,8 +150,7 @@ class FullDistillStep:
         self.focal_ws = [ops.focal_workspace(self.device) for _ in shapes]
         self.focal_losses = [torch.zeros((), device=self.device) for _ in shapes]
         self.cls, self.box = self.head.alloc_outputs()
-        self.t_cls, self.t_box = self.teacher_head.alloc_outputs()
-        self.t_prob = [torch.empty_like(c) for c in self.t_cls]
+        self.t_prob, self.t_box = self.teacher_head.alloc_outputs()
         self.d_fpn = [torch.empty(N, 256, h, w, device=self.device) for h, w in shapes]
         self.d_box = [torch.empty_like(b) for b in self.box]
         self.loss_scale = 1.0 / self.world                       # detector.py:650-655
@@ -163,9 +162,8 @@ class FullDistillStep:
     def forward_backward(self):
         with torch.no_grad():                                            # teacher: forward only (model.train = False)
             t_fpn = [f.contiguous() for f in self.teacher(self.images_t)]
-            self.teacher_head.forward(t_fpn, training=False, out=(self.t_cls, self.t_box))
-            for p, c in zip(self.t_prob, self.t_cls):
-                torch.sigmoid(c, out=p)                                  # retinanet_heads.py:153-163 (scaffolding)
+            # teacher/retnet_cls_prob_fpnL: the Sigmoid of retinanet_heads.py:153-163 runs in the prediction convolution's epilogue
+            self.teacher_head.forward(t_fpn, training=False, out=(self.t_prob, self.t_box))
         self.flat_grads[self.n_head:].zero_()
         fpn = self.student(self.images_t)                                # PyTorch graph ends here ...
         fpn_c = [f.detach().contiguous() for f in fpn]

@@ -53,7 +53,8 @@ SAD_HEAD_MAX_CONVS = 8
 
 class HeadConfig(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("N", C.c_int32), ("H", C.c_int32 * SAD_MAX_LEVELS), ("W", C.c_int32 * SAD_MAX_LEVELS),
-                ("dim", C.c_int32), ("num_convs", C.c_int32), ("cls_out", C.c_int32), ("bbox_out", C.c_int32)]
+                ("dim", C.c_int32), ("num_convs", C.c_int32), ("cls_out", C.c_int32), ("bbox_out", C.c_int32),
+                ("cls_output_sigmoid", C.c_int32)]
 
 
 class HeadTensors(C.Structure):

@@ -227,3 +227,27 @@ def test_head_errors():
         head.backward(d_cls, None)      # backward before a training forward
     with pytest.raises(ValueError):
         head.forward([torch.zeros(1, 32, 4, 9, device="cuda")])
+
+
+def test_teacher_head_emits_class_probabilities():
+    # model.train = False adds Sigmoid -> retnet_cls_prob_fpnL (retinanet_heads.py:153-163); here it is the prediction convolution's epilogue
+    from sad_b200 import native
+    from sad_b200.head import RetinaNetHead
+    shapes = [(8, 32), (4, 16)]
+    student = RetinaNetHead(2, shapes, dim=64, num_convs=2, num_anchors=3, num_classes=8, seed=5)
+    teacher = RetinaNetHead(2, shapes, dim=64, num_convs=2, num_anchors=3, num_classes=8, seed=5, cls_output_sigmoid=True)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for p in student.params.values():
+        p.normal_(0.0, 0.2, generator=g)
+    teacher.flat_params.copy_(student.flat_params)
+    fpn = [torch.randn(2, 64, h, w, device="cuda", generator=g) for h, w in shapes]
+    logits, box_s = student.forward(fpn, training=False)
+    prob, box_t = teacher.forward(fpn, training=False)
+    torch.cuda.synchronize()
+    for l in range(len(shapes)):
+        assert torch.equal(box_s[l], box_t[l])
+        ref = torch.sigmoid(logits[l].double())
+        assert float((prob[l].double() - ref).abs().max()) <= 2e-6      # fast exp + reciprocal vs exact sigmoid, values in (0, 1)
+        assert float(prob[l].min()) >= 0.0 and float(prob[l].max()) <= 1.0
+    with pytest.raises(native.SadError, match="forward-only"):
+        teacher.backward([torch.zeros_like(p) for p in prob], None)
