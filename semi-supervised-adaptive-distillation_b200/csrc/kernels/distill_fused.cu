@@ -14,7 +14,8 @@
 // measured too (globaltimer stamps per CTA, SAD_FUSED_DEBUG=8 + scripts/fused_stamps.py): it narrows the spread of the
 // CTAs' finish times (static: up to 11 us apart) to 3 us but its per-unit overhead delays all of them by 4 us and the
 // fixed-order reduction over the unit slots lengthens the tail; a hybrid (first 50-85 % static, rest dynamic) was
-// slower than the static deal at every split (68.4-74.3 us vs 66.3 us).  16 instead of 8 consumer warps: no change.
+// slower than the static deal at every split (68.4-74.3 us vs 66.3 us).  16 instead of 8 consumer warps: no change;
+// 3 CTAs per SM with 2-stage rings (72 registers, no spills): 69.5 us.
 //
 // Determinism: static unit assignment, per-CTA partial sums, fixed-order fp64 finish: bit-identical run to run.
 //
