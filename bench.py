@@ -178,7 +178,7 @@ def _tensor_peak():
 def run_head_step(args, rank, world, barrier, native):
     """the widened path on every rank's own 2-image shard — student head forward, PowSum, fused
     distillation loss + gradient, head backward (device work replayed from ONE CUDA graph), then the step's only
-    collective (SUM-allreduce of the 25.9 MB flat head-gradient buffer) and the momentum-SGD update."""
+    collective (SUM-allreduce of the 25.9 MB flat head-gradient buffer) and the momentum-SGD update (one launch)."""
     import torch
     import torch.distributed as dist
     from sad_b200.step import DistillHeadStep
@@ -281,8 +281,8 @@ def run_full_step(args, rank, world, barrier, native):
                     "fwd+bwd, focal + box + adaptive distillation losses, ONE allreduce of %d gradient bytes, momentum SGD" % st.exchange.nbytes,
         "native": "both RetinaNet heads forward + backward (tcgen05 tf32), PowSum + distillation loss/gradient (one cooperative launch), "
                   "SigmoidFocalLoss + gradient accumulated into the same d(logits), SelectSmoothL1Loss + gradient, teacher Sigmoid fused into its "
-                  "prediction convolution, gradient exchange",
-        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32) under autograd, SGD in PyTorch (SURVEY.md 8f ranks 3-4)",
+                  "prediction convolution, gradient exchange, momentum-SGD update (one launch over the flat buffers)",
+        "scaffolding": "ResNet/FPN bodies on cuDNN (TF32) under autograd (SURVEY.md 8f rank 3)",
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
         "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),

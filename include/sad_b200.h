@@ -124,6 +124,22 @@ int sad_select_smooth_l1_loss_f32(const float* y_hat, const float* y, const floa
                                   int M, float beta, float scale, float* loss /* or NULL */, const float* d_loss /* NULL = 1.0 */,
                                   float* d_y_hat /* or NULL */, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Momentum SGD over one flat parameter buffer — replaces, per parameter blob, the Scale(2.0) of bias gradients, the
+ * WeightedSum weight decay and MomentumSGDUpdate (detectron/lib/modeling/optimizer.py:95-130;
+ * caffe2/caffe2/sgd/momentum_sgd_op_gpu.cu:23-54) with ONE launch.  param, grad, momentum_buf: flat fp32 buffers of
+ * sum(count) elements, 16-byte aligned, updated in place exactly like the op's outputs {grad, momentum, param}.
+ * Consecutive `segments` tile the buffer; per element  g' = grad_multiplier * g + weight_decay * p,
+ * then  adjusted = lr * g' + momentum * m;  m = g = adjusted;  p -= adjusted   (nesterov != 0: the :44-51 form).
+ * lr: device fp32 scalar (the blob `lr`). */
+#define SAD_MAX_SGD_SEGMENTS 8
+typedef struct sad_sgd_segment {
+  int64_t count;         /* elements */
+  float grad_multiplier; /* 1 for weights, 2 for biases (optimizer.py:115-121) */
+  float weight_decay;    /* SOLVER.WEIGHT_DECAY for weights, 0 for biases */
+} sad_sgd_segment;
+int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
+                         const float* lr, float momentum, int nesterov, void* stream);
+
 /* The whole loss step of add_distill_loss (detectron/lib/modeling/retinanet_heads.py:313-352) in ONE launch:
  *   normalizer_out[0] = PowSum(levels[0..n).teacher_prob, power)           (pow_sum_op.cu:25-43)
  *   levels[l].loss, levels[l].d_logits = SigmoidAdaptiveDistillLoss(+Gradient)(..., normalizer_out)  for every level

@@ -68,6 +68,8 @@ def lib():
         l.oracle_select_smooth_l1_loss.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p]
         l.oracle_select_smooth_l1_grad.restype = None
         l.oracle_select_smooth_l1_grad.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p, _f32p]
+        l.oracle_momentum_sgd.restype = None
+        l.oracle_momentum_sgd.argtypes = [C.c_int64, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float]
         l.oracle_focal_grad.restype = None
         l.oracle_focal_grad.argtypes = [C.c_int] * 4 + [_f32p, _i32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, _f32p, _f32p]
         _lib = l
@@ -163,6 +165,13 @@ def select_smooth_l1(y_hat, y, locs, fg_num, beta=1.0, scale=1.0, d_loss=1.0):
     loss = lib().oracle_select_smooth_l1_loss(N, D, H, W, M, yh.reshape(-1), yy, ll, S, float(beta), float(scale), buff)
     lib().oracle_select_smooth_l1_grad(N, D, H, W, M, yh.reshape(-1), yy, ll, S, float(beta), float(scale), dl, grad)
     return np.float32(loss), grad[:yh.size].reshape(yh.shape)
+
+
+def momentum_sgd(param, grad, mom, lr, momentum=0.9, nesterov=False, grad_mult=1.0, wd=0.0):
+    """Returns updated copies (param, grad, momentum) — optimizer.py:115-130 + momentum_sgd_op_gpu.cu:23-54."""
+    p, g, m = (np.array(a, dtype=np.float32, copy=True).reshape(-1) for a in (param, grad, mom))
+    lib().oracle_momentum_sgd(p.size, p, g, m, float(lr), float(momentum), 1 if nesterov else 0, float(grad_mult), float(wd))
+    return p, g, m
 
 
 def distill_elem_f64(x, pt, keep=1, wp=1.0, gamma=2.0, alpha=0.5, beta=0.0, d_loss=1.0, scale=1.0):

@@ -129,3 +129,26 @@ ORACLE_API void oracle_select_smooth_l1_grad(int N, int D, int H, int W, int M, 
     }
   }
 }
+
+/* MomentumSGDUpdate with Detectron's preamble per parameter (detectron/lib/modeling/optimizer.py:115-130):
+ * bias: Scale(grad, 2.0); weight: WeightedSum(grad, 1, param, wd); then MomentumSGDKernel (momentum_sgd_op_gpu.cu:23-54). */
+ORACLE_API void oracle_momentum_sgd(int64_t n, float* param, float* grad, float* mom, float lr, float momentum, int nesterov,
+                                    float grad_mult, float wd) {
+  for (int64_t i = 0; i < n; ++i) {
+    float g = grad[i];
+    if (grad_mult != 1.f) g = g * grad_mult;              /* Scale */
+    if (wd != 0.f) g = g * 1.f + param[i] * wd;           /* WeightedSum: sum of w_k * x_k */
+    if (!nesterov) {
+      const float adjusted_gradient = lr * g + momentum * mom[i];
+      mom[i] = adjusted_gradient;
+      grad[i] = adjusted_gradient;
+      param[i] -= adjusted_gradient;
+    } else {
+      const float mi = mom[i];
+      const float mi_new = momentum * mi + lr * g;
+      mom[i] = mi_new;
+      grad[i] = (1 + momentum) * mi_new - momentum * mi;
+      param[i] -= grad[i];
+    }
+  }
+}

@@ -1,0 +1,124 @@
+// MomentumSGDUpdate with Detectron's per-parameter preamble, one launch for a whole flat parameter buffer
+// (SURVEY.md §8f rank 4).  Replaces, per parameter blob of detectron/lib/modeling/optimizer.py:95-130,
+//   Scale(param_grad, 2.0)                                  for biases            (optimizer.py:115-121)
+//   WeightedSum([param_grad, one, param, wd], param_grad)   for weights           (optimizer.py:122-124)
+//   MomentumSGDUpdate([grad, momentum, lr, param])          caffe2/caffe2/sgd/momentum_sgd_op_gpu.cu:23-54
+// i.e. ~3 launches per blob and 60 for the head alone.  The flat buffer is described by up to SAD_MAX_SGD_SEGMENTS
+// ranges, each with its gradient multiplier (2 for biases) and weight decay (0 for biases).  HBM-bound: reads g, m, p
+// and writes g, m, p = 24 B/parameter (the reference's three ops move 8 + 12..16 + 24 B).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sad_b200.h"
+#include "sad_internal.h"
+
+namespace sad {
+
+struct SgdArgs {
+  float* param;
+  float* grad;
+  float* mom;
+  const float* lr;
+  int64_t seg_end[SAD_MAX_SGD_SEGMENTS];
+  float grad_mult[SAD_MAX_SGD_SEGMENTS];
+  float weight_decay[SAD_MAX_SGD_SEGMENTS];
+  int32_t n_segs, nesterov;
+  int64_t total;
+  float momentum;
+};
+
+__device__ __forceinline__ void sgd_elem(float& p, float& g, float& m, float LR, float momentum, float mult, float wd, bool nesterov) {
+  const float gi = mult * g + wd * p;                      // Scale(2.0) for biases / WeightedSum(grad, 1, param, wd) for weights
+  if (!nesterov) {
+    const float adjusted = LR * gi + momentum * m;         // momentum_sgd_op_gpu.cu:35-41
+    m = adjusted;
+    g = adjusted;
+    p -= adjusted;
+  } else {
+    const float mi_new = momentum * m + LR * gi;           // :44-51
+    g = (1.f + momentum) * mi_new - momentum * m;
+    m = mi_new;
+    p -= g;
+  }
+}
+
+__global__ void __launch_bounds__(256) momentum_sgd_kernel(const SgdArgs a) {
+  const float LR = __ldg(a.lr);
+  const int64_t n4 = a.total >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const bool nest = a.nesterov != 0;
+  for (int64_t q = tid; q < n4; q += stride) {
+    const int64_t i = q << 2;
+    float4 p = reinterpret_cast<float4*>(a.param)[q], g = reinterpret_cast<float4*>(a.grad)[q], m = reinterpret_cast<float4*>(a.mom)[q];
+    int s = 0;
+    while (s + 1 < a.n_segs && i >= a.seg_end[s]) ++s;
+    if (i + 3 < a.seg_end[s]) {   // the whole quad lies in one segment (the common case)
+      const float mult = a.grad_mult[s], wd = a.weight_decay[s];
+      sgd_elem(p.x, g.x, m.x, LR, a.momentum, mult, wd, nest);
+      sgd_elem(p.y, g.y, m.y, LR, a.momentum, mult, wd, nest);
+      sgd_elem(p.z, g.z, m.z, LR, a.momentum, mult, wd, nest);
+      sgd_elem(p.w, g.w, m.w, LR, a.momentum, mult, wd, nest);
+    } else {
+      float* pp = &p.x;
+      float* gp = &g.x;
+      float* mp = &m.x;
+      for (int k = 0; k < 4; ++k) {
+        int sk = s;
+        while (sk + 1 < a.n_segs && i + k >= a.seg_end[sk]) ++sk;
+        sgd_elem(pp[k], gp[k], mp[k], LR, a.momentum, a.grad_mult[sk], a.weight_decay[sk], nest);
+      }
+    }
+    reinterpret_cast<float4*>(a.param)[q] = p;
+    reinterpret_cast<float4*>(a.grad)[q] = g;
+    reinterpret_cast<float4*>(a.mom)[q] = m;
+  }
+  for (int64_t i = (n4 << 2) + tid; i < a.total; i += stride) {
+    int s = 0;
+    while (s + 1 < a.n_segs && i >= a.seg_end[s]) ++s;
+    sgd_elem(a.param[i], a.grad[i], a.mom[i], LR, a.momentum, a.grad_mult[s], a.weight_decay[s], nest);
+  }
+}
+
+}  // namespace sad
+
+using namespace sad;
+
+extern "C" {
+
+SAD_EXPORT int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
+                                    const float* lr, float momentum, int nesterov, void* stream) {
+  if (!segments || n_segments < 1 || n_segments > SAD_MAX_SGD_SEGMENTS)
+    return set_error(SAD_ERR_INVALID, "momentum sgd: n_segments must be in [1, SAD_MAX_SGD_SEGMENTS]");
+  if (!lr) return set_error(SAD_ERR_INVALID, "momentum sgd: null learning rate");
+  SgdArgs a{};
+  int64_t end = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    if (segments[s].count < 0) return set_error(SAD_ERR_INVALID, "momentum sgd: negative segment length");
+    end += segments[s].count;
+    a.seg_end[s] = end;
+    a.grad_mult[s] = segments[s].grad_multiplier;
+    a.weight_decay[s] = segments[s].weight_decay;
+  }
+  if (end == 0) return SAD_OK;
+  if (!param || !grad || !momentum_buf) return set_error(SAD_ERR_INVALID, "momentum sgd: null buffer");
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf)) & 15)
+    return set_error(SAD_ERR_INVALID, "momentum sgd: buffers must be 16-byte aligned");
+  a.param = param;
+  a.grad = grad;
+  a.mom = momentum_buf;
+  a.lr = lr;
+  a.n_segs = n_segments;
+  a.nesterov = nesterov;
+  a.total = end;
+  a.momentum = momentum;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (end / 4 + 255) / 256;
+  const int64_t cap = (int64_t)sms * 8;
+  const unsigned blocks = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+  momentum_sgd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "momentum sgd launch");
+}
+
+}  // extern "C"

@@ -6,15 +6,15 @@
                PowSum + SigmoidAdaptiveDistillLoss (retinanet_heads.py:313-352)                   model_builder.py:402-406
     backward : head (ConvGradient / ReluGradient / Sum) -> FPN -> ResNet body (res2 and below frozen, ResNet.py:88-104)
     exchange : ONE allreduce over the flat gradient buffer [head | body]                          optimizer.py:72-92
-    update   : momentum SGD with weight decay                                                     optimizer.py:95-130
+    update   : momentum SGD, bias 2x / weight decay preamble, ONE launch over the flat buffers    optimizer.py:95-130
 
 What runs where.  On this repository's kernels: both RetinaNet heads (tcgen05 convolutions,
 `sad_head_*`), PowSum + distillation loss + gradient (one cooperative launch), SigmoidFocalLoss + gradient (accumulated into
 the same d(logits)), SelectSmoothL1Loss + gradient, and the gradient exchange — every loss and the whole head, forward and
 backward.  SCAFFOLDING in plain PyTorch / cuDNN (§8f ranks 2-4), there only so that the step is complete and its imgs/s can
 be measured: the ResNet + FPN bodies (random init, AffineChannel = frozen per-channel scale/bias,
-affine_channel_op.cc:70-78; autograd carries d(fpn_L) from the head's backward into them) and the optimiser.  The teacher's
-Sigmoid is fused into its prediction convolution (§8f rank 2).  Synthetic images, labels, foreground locations and box targets (there is no dataset in this environment).
+affine_channel_op.cc:70-78; autograd carries d(fpn_L) from the head's backward into them).  The teacher's Sigmoid is fused
+into its prediction convolution (§8f rank 2) and the optimiser step is one native launch over the flat buffers (§8f rank 4).  Synthetic images, labels, foreground locations and box targets (there is no dataset in this environment).
 """
 import torch
 import torch.nn as nn
@@ -107,23 +107,33 @@ class FullDistillStep:
         self.teacher = ResNetFPN(teacher_blocks).to(self.device).to(memory_format=torch.channels_last).eval()
         for p in self.teacher.parameters():
             p.requires_grad_(False)
-        self.body_params = [p for p in self.student.parameters() if p.requires_grad]
+        # ONE flat parameter buffer and ONE flat gradient buffer laid out [head weights | head biases | body weights | body biases]:
+        # the head writes its gradient slice, autograd accumulates into views of the body slice; one allreduce, one SGD launch
+        body = [p for p in self.student.parameters() if p.requires_grad]
+        self.body_params = [p for p in body if p.dim() > 1] + [p for p in body if p.dim() == 1]
+        n_body_w = sum(p.numel() for p in self.body_params if p.dim() > 1)
         n_body = sum(p.numel() for p in self.body_params)
-        # ONE flat gradient buffer [head | body]: the head writes its slice, autograd accumulates into views of the rest
         probe = RetinaNetHead(n_images, shapes, device=self.device, seed=seed)
         n_head = probe.flat_grads.numel()
         probe.close()
         self.flat_grads = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
-        self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head])
+        self.flat_params = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
+        self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head],
+                                  param_buffer=self.flat_params[:n_head])
         self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1, cls_output_sigmoid=True)
         off = n_head
         for p in self.body_params:
-            p.grad = self.flat_grads[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            k = p.numel()
+            self.flat_params[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_params[off:off + k].view(p.shape)
+            p.grad = self.flat_grads[off:off + k].view(p.shape)
+            off += k
         self.n_head, self.n_body = n_head, n_body
         self.exchange = parallel.GradientExchange(self.flat_grads, world=self.world)
-        self.body_momentum = [torch.zeros_like(p) for p in self.body_params]
-        self.head_momentum = torch.zeros_like(self.head.flat_params)
+        self.momentum = torch.zeros_like(self.flat_params)
+        self.lr_dev = torch.tensor(lr, dtype=torch.float32, device=self.device)
+        hw, hb = self.head.sgd_segments(weight_decay)
+        self.sgd_segments = [hw, hb, (n_body_w, 1.0, weight_decay), (n_body - n_body_w, 2.0, 0.0)]
         # this rank's synthetic shard
         g = torch.Generator(device=self.device).manual_seed(seed + 7919 * (rank + 1))
         N, A = n_images, synthetic.NUM_ANCHORS
@@ -217,15 +227,9 @@ class FullDistillStep:
 
     @torch.no_grad()
     def sgd(self):
-        """MomentumSGDUpdate with weight decay (optimizer.py:95-130; scaffolding: torch foreach ops)."""
-        grads = [p.grad for p in self.body_params]
-        torch._foreach_add_(grads, self.body_params, alpha=self.wd)
-        torch._foreach_mul_(self.body_momentum, self.mom)
-        torch._foreach_add_(self.body_momentum, grads, alpha=self.lr)
-        torch._foreach_sub_(self.body_params, self.body_momentum)
-        hg = self.head.flat_grads.add(self.head.flat_params, alpha=self.wd)
-        self.head_momentum.mul_(self.mom).add_(hg, alpha=self.lr)
-        self.head.flat_params.sub_(self.head_momentum)
+        """Scale(2x bias gradients) + WeightedSum weight decay + MomentumSGDUpdate of every trainable blob (optimizer.py:95-130)
+        in ONE launch over the flat [head | body] buffers."""
+        ops.momentum_sgd(self.flat_params, self.flat_grads, self.momentum, self.sgd_segments, self.lr_dev, momentum=self.mom)
 
     def step(self):
         self.run()

@@ -20,18 +20,21 @@ K_MIN = 3  # cfg.FPN.RPN_MIN_LEVEL
 
 
 def param_names(num_convs=4, k_min=K_MIN):
-    """Blob names in the order the flat parameter / gradient buffers are laid out."""
+    """Blob names in the order the flat parameter / gradient buffers are laid out: every weight first, then every bias, so
+    that the optimiser's two parameter classes (weights: weight decay; biases: 2x gradient, no decay — optimizer.py:115-124)
+    are two contiguous segments of the flat buffer (one sad_momentum_sgd_f32 launch)."""
     names = []
-    for tower in ("cls", "bbox"):
-        for i in range(num_convs):
-            names += ["retnet_%s_conv_n%d_fpn%d_w" % (tower, i, k_min), "retnet_%s_conv_n%d_fpn%d_b" % (tower, i, k_min)]
-        names += ["retnet_%s_pred_fpn%d_w" % (tower, k_min), "retnet_%s_pred_fpn%d_b" % (tower, k_min)]
+    for suffix in ("_w", "_b"):
+        for tower in ("cls", "bbox"):
+            for i in range(num_convs):
+                names.append("retnet_%s_conv_n%d_fpn%d%s" % (tower, i, k_min, suffix))
+            names.append("retnet_%s_pred_fpn%d%s" % (tower, k_min, suffix))
     return names
 
 
 class RetinaNetHead:
     def __init__(self, n_images, level_shapes, dim=256, num_convs=4, num_anchors=9, num_classes=80, prior_prob=0.01,
-                 device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False):
+                 device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False, param_buffer=None):
         self.N, self.level_shapes = int(n_images), [tuple(s) for s in level_shapes]
         self.dim, self.num_convs = int(dim), int(num_convs)
         self.cls_out, self.bbox_out = num_anchors * num_classes, num_anchors * 4
@@ -55,7 +58,13 @@ class RetinaNetHead:
             shapes[n] = (out, self.dim, 3, 3) if n.endswith("_w") else (out,)
         self.shapes = shapes
         total = sum(math.prod(s) for s in shapes.values())
-        self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
+        if param_buffer is None:
+            param_buffer = torch.zeros(total, dtype=torch.float32, device=self.device)
+        if not (param_buffer.is_cuda and param_buffer.dtype == torch.float32 and param_buffer.is_contiguous() and param_buffer.numel() == total
+                and param_buffer.data_ptr() % 16 == 0):
+            raise ValueError("param_buffer must be a contiguous 16-byte aligned CUDA fp32 tensor of %d elements" % total)
+        self.flat_params = param_buffer.zero_()
+        self.n_weights = sum(math.prod(s) for n, s in shapes.items() if n.endswith("_w"))
         if grad_buffer is None:
             grad_buffer = torch.zeros(total, dtype=torch.float32, device=self.device)
         # a caller-owned slice lets the head's gradients live inside a larger flat buffer (one allreduce for the whole model)
@@ -87,6 +96,10 @@ class RetinaNetHead:
         t.cls_pred_w, t.cls_pred_b = d["retnet_cls_pred_fpn3_w"].data_ptr(), d["retnet_cls_pred_fpn3_b"].data_ptr()
         t.bbox_pred_w, t.bbox_pred_b = d["retnet_bbox_pred_fpn3_w"].data_ptr(), d["retnet_bbox_pred_fpn3_b"].data_ptr()
         return t
+
+    def sgd_segments(self, weight_decay):
+        """[(count, gradient multiplier, weight decay)] of the flat buffers for ops.momentum_sgd (optimizer.py:115-124)."""
+        return [(self.n_weights, 1.0, weight_decay), (self.flat_params.numel() - self.n_weights, 2.0, 0.0)]
 
     def close(self):
         if getattr(self, "handle", None):

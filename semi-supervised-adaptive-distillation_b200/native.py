@@ -34,6 +34,10 @@ class FocalParams(C.Structure):
     _fields_ = [("gamma", C.c_float), ("alpha", C.c_float), ("scale", C.c_float), ("num_classes", C.c_int32)]
 
 
+class SgdSegment(C.Structure):
+    _fields_ = [("count", C.c_int64), ("grad_multiplier", C.c_float), ("weight_decay", C.c_float)]
+
+
 class ConvLevel(C.Structure):
     _fields_ = [("x_nhwc", C.c_void_p), ("y_nchw", C.c_void_p), ("y_nhwc", C.c_void_p),
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu_mask_nhwc", C.c_void_p),
@@ -109,6 +113,8 @@ def lib():
         l.sad_smooth_l1_workspace_bytes.restype = C.c_size_t
         l.sad_select_smooth_l1_loss_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_momentum_sgd_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SgdSegment), C.c_int, C.c_void_p, C.c_float, C.c_int,
+                                           C.c_void_p]
         l.sad_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.sad_ctx_destroy.argtypes = [C.c_void_p]
         l.sad_ctx_destroy.restype = None

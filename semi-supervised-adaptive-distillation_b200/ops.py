@@ -160,6 +160,21 @@ def select_smooth_l1_loss(y_hat, y, locs, fg_num, beta=1.0, scale=1.0, want_loss
     return loss, grad
 
 
+def momentum_sgd(param, grad, momentum_buf, segments, lr, momentum=0.9, nesterov=False):
+    """In-place momentum SGD over flat buffers.  segments: [(count, grad_multiplier, weight_decay)] tiling the buffers;
+    lr: CUDA fp32 scalar tensor (the `lr` blob, updated by the learning-rate policy between steps)."""
+    for name, t in (("param", param), ("grad", grad), ("momentum", momentum_buf)):
+        _require_cuda(t, torch.float32, name)
+    _require_cuda(lr, torch.float32, "lr")
+    arr = (native.SgdSegment * len(segments))()
+    for i, (cnt, mult, wd) in enumerate(segments):
+        arr[i].count, arr[i].grad_multiplier, arr[i].weight_decay = int(cnt), float(mult), float(wd)
+    if sum(int(c) for c, _, _ in segments) != param.numel() or grad.numel() != param.numel() or momentum_buf.numel() != param.numel():
+        raise ValueError("the segments must tile the flat buffers exactly")
+    check(lib().sad_momentum_sgd_f32(C.c_void_p(param.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(momentum_buf.data_ptr()),
+                                     arr, len(segments), C.c_void_p(lr.data_ptr()), float(momentum), 1 if nesterov else 0, _stream()))
+
+
 def distill_step(levels, power=1.8, workspace=None, d_loss=None, **args):
     """PowSum over the levels' teacher probabilities + loss + gradient of every level through the single-launch entry
     point sad_distill_fused_f32.  Returns (normalizer, losses, d_logits)."""

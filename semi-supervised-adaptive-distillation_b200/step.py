@@ -4,7 +4,7 @@
     ->  SigmoidAdaptiveDistillLoss + Gradient per level (:331-348, fused, one launch)
     ->  head backward (ConvGradient / ReluGradient / Sum, core.py:695-842)
     ->  ONE allreduce of the flat head-gradient buffer (optimizer.py:72-92 issues one per parameter blob)
-    ->  MomentumSGDUpdate (optimizer.py:95-130)  [plain torch foreach ops: an SURVEY.md §8f "next" row]
+    ->  MomentumSGDUpdate with the bias / weight-decay preamble (optimizer.py:95-130): one launch over the flat buffers
 
 The path shards by image (optimizer.py:62-69 builds the ops per GPU scope; the normaliser is per GPU), so the
 only exchange is the gradient allreduce; the loss is pre-scaled by 1 / world (detector.py:650-655) so the SUM is the mean.
@@ -47,6 +47,7 @@ class DistillHeadStep:
                                     scale=parallel.distill_loss_scale(temperature, self.world), num_classes=Cc, ignored_label=-1)
         self.exchange = parallel.GradientExchange(self.head.flat_grads, world=self.world)
         self.momentum = torch.zeros_like(self.head.flat_params)
+        self.lr = torch.tensor(0.01, dtype=torch.float32, device=self.device)
         self.graph = None
         self.images = N
         self.anchors = int(sum(l.numel() for l in self.labels))
@@ -81,12 +82,11 @@ class DistillHeadStep:
         """The step's only collective: SUM of the flat head-gradient buffer over the ranks."""
         return self.exchange.allreduce()
 
-    def sgd(self, lr=0.01, momentum=0.9, weight_decay=1e-4):
-        """MomentumSGDUpdate with weight decay folded in (optimizer.py:95-130; biases get lr x2 and no decay there —
-        kept simple here: this update is not on the measured hot path)."""
-        g = self.head.flat_grads.add(self.head.flat_params, alpha=weight_decay)
-        self.momentum.mul_(momentum).add_(g, alpha=lr)
-        self.head.flat_params.sub_(self.momentum)
+    def sgd(self, momentum=0.9, weight_decay=1e-4):
+        """Scale(2x bias gradients) + WeightedSum weight decay + MomentumSGDUpdate of all 20 head blobs (optimizer.py:95-130)
+        in ONE launch over the flat buffers; the learning rate is the device scalar self.lr (the `lr` blob)."""
+        ops.momentum_sgd(self.head.flat_params, self.head.flat_grads, self.momentum, self.head.sgd_segments(weight_decay), self.lr,
+                         momentum=momentum)
 
     def losses(self):
         return [l.item() for l in self.plan.losses]
