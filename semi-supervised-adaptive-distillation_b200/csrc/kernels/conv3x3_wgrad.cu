@@ -48,7 +48,8 @@ constexpr int kWgChunkBytes = kWgKP * 128;               // one {32 ch x 32 px} 
 constexpr int kWgABytes = (kWgM / 32) * kWgChunkBytes;   // 16 KB
 constexpr int kWgBBytes = (kWgN / 32) * kWgChunkBytes;   // 32 KB
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;     // 48 KB
-constexpr int kWgThreads = 192;                          // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
+constexpr int kWgEpiWarps = 8;                           // two warps per TMEM lane quarter, each draining 4 of the 8 column blocks
+constexpr int kWgThreads = 64 + 32 * kWgEpiWarps;        // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
 constexpr int kWgTmemCols = 512;                         // 2 accumulator buffers x 256 columns
 constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageBytes + 1024 + 256;
 constexpr int kWgMaxSplits = 64;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full[b], 1);
-        mbar_init(&tmem_empty[b], 128);
+        mbar_init(&tmem_empty[b], 32 * kWgEpiWarps);
       }
       mbar_fence_init();
     }
@@ -223,7 +224,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
     }
   } else {
     // ===================== epilogue: TMEM -> partial[split][tap][co][ci] =====================
-    const int q = warp & 3;
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int jhalf = (warp - 2) >> 2;   // which half of the accumulator's column blocks this warp drains
     const int row = q * 32 + lane;
     uint32_t itn = 0;
     for (uint32_t item = blockIdx.x; item < args.total_items; item += gridDim.x, ++itn) {
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
       float* dst = args.partial + (((size_t)it.split * 9 + it.tap) * args.cout + (co_ok ? co : 0)) * args.cin + it.n0;
       const bool empty = it.kb_end == it.kb_begin;  // a split with no pixel blocks: the accumulator was never written
 #pragma unroll 1
-      for (int j = 0; j < kWgN / 32; ++j) {
+      for (int j = jhalf * (kWgN / 64); j < (jhalf + 1) * (kWgN / 64); ++j) {
         float v[32];
         tmem_ld_32x32(taddr + j * 32, v);
         if (co_ok) {
