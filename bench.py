@@ -236,17 +236,19 @@ def run_head_step(args, rank, world, barrier, native):
     }
 
 
-def run_full_step(args, rank, world, barrier, native):
-    """BASELINE.json configs[3] geometry (configs[2] per GPU): R-50-FPN student <- R-101-FPN teacher, full distillation
-    training step at bs = 2 per GPU, 600 px, one allreduce of the flat [head | body] gradient buffer.  The heads, the
-    distillation loss and the exchange are this repository's kernels; the ResNet/FPN bodies, focal / box losses and the
-    optimiser are PyTorch/cuDNN scaffolding (full_step.py)."""
+def run_full_step(args, rank, world, barrier, native, n_images=2):
+    """BASELINE.json configs[3] geometry (n_images = 2 per GPU) or configs[2] (n_images = 16 on one GPU): R-50-FPN student <-
+    R-101-FPN teacher, full distillation training step, 600 px, one allreduce of the flat [head | body] gradient buffer.
+    Heads, every loss, the exchange and the optimiser step are this repository's kernels; the ResNet/FPN bodies are
+    PyTorch/cuDNN scaffolding (full_step.py)."""
     import torch
     import torch.distributed as dist
     from sad_b200.full_step import FullDistillStep
 
     K = args.full_steps or min(args.steps, 20)
-    st = FullDistillStep(n_images=2, scale_px=600, world=world, rank=rank)
+    if n_images > 2:
+        K = min(K, 10)
+    st = FullDistillStep(n_images=n_images, scale_px=600, world=world, rank=rank)
     for _ in range(3):
         st.step()
     n0 = native.lib().sad_launch_count()
@@ -277,8 +279,9 @@ def run_full_step(args, rank, world, barrier, native):
     return {
         "metric": "RetinaNet-R50 distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms,
         "steps": K, "images_per_gpu": st.images, "scaling": "weak",
-        "workload": "R-50-FPN student <- R-101-FPN teacher (random init), 3x640x1024 synthetic images, bs=2/GPU: teacher fwd, student "
+        "workload": "R-50-FPN student <- R-101-FPN teacher (random init), 3x640x1024 synthetic images, bs=%d/GPU: teacher fwd, student " % n_images +
                     "fwd+bwd, focal + box + adaptive distillation losses, ONE allreduce of %d gradient bytes, momentum SGD" % st.exchange.nbytes,
+        "baseline_config": "configs[3] (bs=2 per GPU)" if n_images == 2 else "configs[2] (bs=%d on one GPU)" % n_images,
         "native": "both RetinaNet heads forward + backward (tcgen05 tf32), PowSum + distillation loss/gradient (one cooperative launch), "
                   "SigmoidFocalLoss + gradient accumulated into the same d(logits), SelectSmoothL1Loss + gradient, teacher Sigmoid fused into its "
                   "prediction convolution, gradient exchange, momentum-SGD update (one launch over the flat buffers)",
@@ -409,9 +412,14 @@ def main():
     if args.head_steps >= 0:
         head_line = run_head_step(args, rank, world, barrier, native)
 
-    full_line = None
+    full_line = full16_line = None
     if args.full_steps >= 0:
         full_line = run_full_step(args, rank, world, barrier, native)
+        if world == 1:   # BASELINE.json configs[2]: the same step at bs = 16 on one GPU
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            full16_line = run_full_step(args, rank, world, barrier, native, n_images=16)
 
     if rank != 0:
         if world > 1:
@@ -445,6 +453,9 @@ def main():
     if full_line:
         line["full_step"] = full_line
         line["gpu_launches"] += full_line["gpu_launches"]
+    if full16_line:
+        line["full_step_bs16"] = full16_line
+        line["gpu_launches"] += full16_line["gpu_launches"]
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_oracle
         sample = host  # the full configs[1] batch, one pass (about 10-30 s of CPU work spread over the cores)
