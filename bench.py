@@ -407,6 +407,22 @@ def main():
     for a, b in zip(e2e_losses, plans[0].losses):
         assert abs(a - b.item()) <= 1e-5 * abs(b.item()), ("e2e/device loss mismatch", a, b.item())
     step.close()
+    # the same call with the gradients LEFT ON THE DEVICE (d_logits = NULL: what a training step does — ConvGradient consumes
+    # them there); only the losses and the normaliser are read back
+    step2 = ops.HostStep(local_rank)
+    step2.bind(cpu, None, power=POWER, **HEAD)
+    for _ in range(3):
+        step2.run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step2.run()
+    torch.cuda.synchronize()
+    e2e_dt2 = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_dt2, op=dist.ReduceOp.MAX)
+    e2e_value2 = world * anchors / float(e2e_dt2.item()) / 1e6
+    step2.close()
 
     head_line = None
     if args.head_steps >= 0:
@@ -444,7 +460,10 @@ def main():
                      "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
-                "api": "sad_distill_step_host (pinned host buffers in, losses + normaliser + gradients out)"},
+                "api": "sad_distill_step_host (pinned host buffers in, losses + normaliser + gradients out)",
+                "gradients_on_device": {"value": e2e_value2, "unit": UNIT, "ms_per_step": float(e2e_dt2.item()) * 1e3,
+                                        "d2h_bytes_per_step": 4 * (len(host) * 2 + 1),
+                                        "note": "same call with d_logits = NULL: gradients stay in HBM for ConvGradient, only losses + normaliser return"}},
         "gpu_launches": int(launches) + (head_line["gpu_launches"] if head_line else 0),
         "clocks": sampler.result(),
     }
