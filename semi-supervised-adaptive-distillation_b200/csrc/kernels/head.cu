@@ -14,7 +14,7 @@
 //             bias + ReLU fused, activations kept channels-last for the next layer and for backward)
 //   backward: 2 layout passes + per conv {1 weight-gradient launch + bias partials + finish, 1 data-gradient
 //             launch with ReluGradient fused (from 1-bit sign planes the forward pass leaves)}; the two towers
-//             run on two streams.
+//             run on two streams, and each tower's weight gradients on a further stream behind its data-gradient chain.
 // Boundary tensors keep the operator contract: fpn_L, logits, box deltas and their gradients are NCHW
 // fp32; weights (Cout, Cin, 3, 3); gradients in the weights' layouts.
 #include <cuda_runtime.h>
@@ -39,15 +39,22 @@ struct sad_head {
   float* act[2][SAD_HEAD_MAX_CONVS][SAD_MAX_LEVELS] = {};
   // sign bits of act (1 bit per element): what the fused ReluGradient of the backward pass reads
   uint32_t* bits[2][SAD_HEAD_MAX_CONVS][SAD_MAX_LEVELS] = {};
-  // channels-last gradients: gpred[t] = d(prediction) (Cout = pred_out[t]); g[t][2] ping-pong (dim)
+  // channels-last gradients: gpred[t] = d(prediction) (Cout = pred_out[t]); g[t][i] = d(output of tower conv i) (dim).
+  // One buffer per layer (no ping-pong): the weight-gradient stream may still read g[t][i] while the data-gradient
+  // stream is two layers further down
   float* gpred[2][SAD_MAX_LEVELS] = {};
-  float* g[2][2][SAD_MAX_LEVELS] = {};
+  float* g[2][SAD_HEAD_MAX_CONVS][SAD_MAX_LEVELS] = {};
   // packed weights [mode][tower][conv], conv index num_convs = prediction conv
   float* packed[2][2][SAD_HEAD_MAX_CONVS + 1] = {};
   void* wg_ws[2] = {};
   size_t wg_ws_bytes = 0;
   cudaStream_t s_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_main = nullptr;
+  // backward: per tower the weight gradients (wgrad + bias partials + finish) run on their own stream behind the
+  // data-gradient chain, so their small tail kernels and the ragged last wave of the data-gradient kernels fill each other
+  cudaStream_t s_wg[2] = {};
+  cudaEvent_t ev_dy[2][SAD_HEAD_MAX_CONVS + 1] = {};   // "the gradient of conv i's output is ready"
+  cudaEvent_t ev_wg_done[2] = {};
   bool packed_bwd_valid = false;
 };
 
@@ -206,7 +213,7 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
         slot(reinterpret_cast<float**>(&h->bits[t][i][l]), sad_conv3x3_sign_bits_bytes(cfg->N, dim, cfg->H[l], cfg->W[l]) / sizeof(float));
       }
       slot(&h->gpred[t][l], h->pixels[l] * pred_out(*cfg, t));
-      for (int k = 0; k < 2; ++k) slot(&h->g[t][k][l], h->pixels[l] * dim);
+      for (int k = 0; k < nc; ++k) slot(&h->g[t][k][l], h->pixels[l] * dim);
     }
   }
   for (int mode = 0; mode < 2; ++mode)
@@ -228,6 +235,16 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
     sad_head_destroy(h);
     return rc;
   }
+  for (int t = 0; t < 2; ++t) {
+    rc = check_cuda(cudaStreamCreateWithFlags(&h->s_wg[t], cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc == SAD_OK) rc = check_cuda(cudaEventCreateWithFlags(&h->ev_wg_done[t], cudaEventDisableTiming), "cudaEventCreate");
+    for (int i = 0; i <= nc && rc == SAD_OK; ++i)
+      rc = check_cuda(cudaEventCreateWithFlags(&h->ev_dy[t][i], cudaEventDisableTiming), "cudaEventCreate");
+    if (rc != SAD_OK) {
+      sad_head_destroy(h);
+      return rc;
+    }
+  }
   *out = h;
   return SAD_OK;
 }
@@ -238,6 +255,12 @@ SAD_EXPORT void sad_head_destroy(sad_head* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
+  for (int t = 0; t < 2; ++t) {
+    if (h->s_wg[t]) cudaStreamDestroy(h->s_wg[t]);
+    if (h->ev_wg_done[t]) cudaEventDestroy(h->ev_wg_done[t]);
+    for (int i = 0; i <= SAD_HEAD_MAX_CONVS; ++i)
+      if (h->ev_dy[t][i]) cudaEventDestroy(h->ev_dy[t][i]);
+  }
   if (h->arena) cudaFree(h->arena);
   delete h;
 }
@@ -314,15 +337,23 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
     float* dwp = t == 0 ? grads->cls_pred_w : grads->bbox_pred_w;
     float* dbp = t == 0 ? grads->cls_pred_b : grads->bbox_pred_b;
     if (!dwp) return set_error(SAD_ERR_INVALID, "sad_head_backward: null prediction weight gradient");
+    cudaStream_t sw = h->s_wg[t];   // weight gradients of this tower
+    // hand a finished output gradient to the weight-gradient stream
+    auto dy_ready = [&](int i) -> int {
+      int r = check_cuda(cudaEventRecord(h->ev_dy[t][i], s), "cudaEventRecord");
+      if (r != SAD_OK) return r;
+      return check_cuda(cudaStreamWaitEvent(sw, h->ev_dy[t][i], 0), "cudaStreamWaitEvent");
+    };
     if ((rc = layout_levels(h, dpred, h->gpred[t], po, s)) != SAD_OK) return rc;
-    if ((rc = wgrad_levels(h, pred_in, h->gpred[t], dim, po, dwp, dbp, accumulate, ws, s)) != SAD_OK) return rc;
+    if ((rc = dy_ready(nc)) != SAD_OK) return rc;
+    if ((rc = wgrad_levels(h, pred_in, h->gpred[t], dim, po, dwp, dbp, accumulate, ws, sw)) != SAD_OK) return rc;
     // data gradient of the prediction conv; its input is the last tower activation (post-ReLU) -> ReluGradient fused
     float* const* dy = h->gpred[t];
     int dy_c = po;
     for (int i = nc; i >= 0; --i) {
       const bool last = i == 0;  // this pass produces d(fpn_L)
       if (last && !d_fpn_nchw) break;
-      float* const* out_cl = last ? nullptr : h->g[t][i & 1];
+      float* const* out_cl = last ? nullptr : h->g[t][i - 1];
       uint32_t* const* mask = last ? nullptr : h->bits[t][i - 1];
       int acc = 0;
       if (last) {
@@ -338,15 +369,19 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
         if (t == 0 && two && (rc = check_cuda(cudaEventRecord(h->ev_main, s), "cudaEventRecord")) != SAD_OK) return rc;
         break;
       }
-      // tower conv i-1: weight gradient from its input and the gradient just produced
+      // tower conv i-1: weight gradient from its input and the gradient just produced, on the weight-gradient stream
       float* const* in = i - 1 > 0 ? h->act[t][i - 2] : h->x0;
       float* dwt = t == 0 ? grads->cls_tower_w[i - 1] : grads->bbox_tower_w[i - 1];
       float* dbt = t == 0 ? grads->cls_tower_b[i - 1] : grads->bbox_tower_b[i - 1];
       if (!dwt) return set_error(SAD_ERR_INVALID, "sad_head_backward: null tower weight gradient");
-      if ((rc = wgrad_levels(h, in, out_cl, dim, dim, dwt, dbt, accumulate, ws, s)) != SAD_OK) return rc;
+      if ((rc = dy_ready(i - 1)) != SAD_OK) return rc;
+      if ((rc = wgrad_levels(h, in, out_cl, dim, dim, dwt, dbt, accumulate, ws, sw)) != SAD_OK) return rc;
       dy = out_cl;
       dy_c = dim;
     }
+    // join the weight-gradient stream into the caller's stream
+    if ((rc = check_cuda(cudaEventRecord(h->ev_wg_done[t], sw), "cudaEventRecord")) != SAD_OK) return rc;
+    if ((rc = check_cuda(cudaStreamWaitEvent(st, h->ev_wg_done[t], 0), "cudaStreamWaitEvent")) != SAD_OK) return rc;
   }
   if (two) {
     if ((rc = check_cuda(cudaEventRecord(h->ev_join, h->s_side), "cudaEventRecord")) != SAD_OK) return rc;
