@@ -13,11 +13,9 @@ echo "== bench" ; timeout 900 python bench.py 2>&1 | tail -3 | tee $OUT/bench_${
 echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee $OUT/bench_ref_${TAG}.json
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv \
-    python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/ncu_list_${TAG}.log 2>&1
-echo "== ncu full (distill)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:distill_kernel -s 3 -c 2 -o $OUT/prof_distill_${TAG} -f \
-    python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_${TAG}.log 2>&1
-echo "== ncu full (pow_sum)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pow_sum_kernel -s 3 -c 2 -o $OUT/prof_powsum_${TAG} -f \
-    python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_ps_${TAG}.log 2>&1
+    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --head-steps 2 --full-steps -1 > $OUT/ncu_list_${TAG}.log 2>&1
+echo "== ncu full (the dominant kernel: PowSum + loss + gradient in one cooperative launch)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:distill_fused_kernel -s 5 -c 2 -o $OUT/prof_fused_${TAG} -f \
+    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --head-steps -1 --full-steps -1 --e2e-steps 1 > $OUT/ncu_full_${TAG}.log 2>&1
+echo "== head kernels: see scripts/gpu_prof_head.sh"
 ls -la $OUT
