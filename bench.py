@@ -120,6 +120,35 @@ def cpu_reference_pass(levels, cpu_oracle):
     return wp, out
 
 
+def operator_net_ms(lib_path, host_levels, fuse=False, runs=5):
+    """the reference's OWN CUDA operators (pow_sum_op.cu and
+    sigmoid_adaptive_distillation_loss_op.cu compiled unmodified into oracle/_ref/libref_ops.so,
+    with its single-block math::Sum, temp buffers and extra Scale passes) run as the reference
+    graph builds them (PowSum, 5 x loss, 5 x gradient) on the same inputs on this GPU.  Wall time
+    around RunNet with a device synchronise on both sides (the reference ops synchronise
+    themselves).  The same NetDef is also run through the product's operator library
+    (lib_path=None), as built and after its FuseAdaptiveDistillOps graph pass."""
+    import torch
+    from sad_b200 import c2, retinanet_heads
+    lib = c2.OperatorLibrary(lib_path) if lib_path else c2.OperatorLibrary()
+    net, _, _ = retinanet_heads.add_distill_loss(gpu_id=0, num_gpus=1)
+    text = net.to_text()
+    if fuse:
+        text, _ = lib.FuseAdaptiveDistillOps(text)
+    ws = lib.Workspace()
+    dev = [tuple(torch.from_numpy(a).cuda() for a in l) for l in host_levels]
+    retinanet_heads.feed_level_blobs(ws, 0, dev)
+    ws.CreateNet(text)
+    for _ in range(2):
+        ws.RunNet(net.name)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(runs):
+        ws.RunNet(net.name)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / runs * 1e3
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -488,6 +517,30 @@ def main():
         line["cpu_baseline"] = {"value": anchors / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d passes over the full configs[1] batch (245520 anchors each): PowSum + loss fwd + grad, %.2f s per "
                                           "pass, %.1f core-seconds in total" % (passes, dt, dt * passes * cores)}
+        # one thread, on a bounded sample (levels P5..P7), as SURVEY.md 8(d) asks
+        cpu_oracle.set_num_threads(1)
+        small = sample[2:]
+        t0 = time.perf_counter()
+        cpu_reference_pass(small, cpu_oracle)
+        line["cpu_baseline"]["single_thread_value"] = synthetic.anchors_in(small) / (time.perf_counter() - t0) / 1e6
+        cpu_oracle.set_num_threads(cores)
+        # the reference's own CUDA operators on this GPU, same inputs (checker library, timed beside the product)
+        try:
+            if os.path.exists(cpu_oracle.REF_GPU_LIB):
+                ref_ms = operator_net_ms(cpu_oracle.REF_GPU_LIB, host)
+                line["cpu_baseline"]["reference_cuda_on_this_gpu"] = {
+                    "value": anchors / (ref_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ref_ms,
+                    "what": "oracle/_ref/libref_ops.so: the reference's unmodified pow_sum_op.cu + "
+                            "sigmoid_adaptive_distillation_loss_op.cu run as the PowSum + 5 x (loss, gradient) operator net, "
+                            "wall time per RunNet"}
+            own_ms, own_fused_ms = operator_net_ms(None, host), operator_net_ms(None, host, fuse=True)
+            line["operator_net"] = {
+                "value": anchors / (own_fused_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": own_fused_ms,
+                "unfused_ms_per_step": own_ms,
+                "what": "the same NetDef through libcaffe2_detectron_ops_gpu.so (the drop-in operators), wall time per RunNet: "
+                        "as built (11 operators) and after the FuseAdaptiveDistillOps graph pass (one operator)"}
+        except Exception as e:  # a checker failure must not take the bench line down
+            line["cpu_baseline"]["reference_cuda_error"] = str(e)[:200]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

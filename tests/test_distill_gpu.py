@@ -353,3 +353,25 @@ def test_fused_step_integer_power_and_nan_teacher(ops, oracle):
     assert_loss_close(losses[0].item(), oracle.distill_loss(*host[0], wp, **HEAD))
     assert np.isnan(losses[1].item()) and np.isnan(oracle.distill_loss(*host[1], wp, **HEAD))
     assert_grad_close(grads[1].cpu().numpy(), oracle.distill_grad(*host[1], wp, d_loss=1.0, **HEAD))
+
+
+def test_config5_geometry_one_image_500px(ops, oracle):
+    # BASELINE.json configs[4]: 500 px scale (3 x 512 x 896 -> 64x112 ... 4x7), one image per GPU.  Level sizes are not
+    # multiples of the kernels' 8 KB units here (P7: 4 * 7 * 720 = 20 160 floats), so unit tails are on the path.
+    from sad_b200 import synthetic
+    host = synthetic.make_pyramid(4321, 1, 500)
+    assert synthetic.anchors_in(host) == 85932
+    wp = oracle.pow_sum([l[1] for l in host], 1.8)
+    norm, losses, grads = ops.distill_step([_dev(l) for l in host], power=1.8, **HEAD)
+    torch.cuda.synchronize()
+    assert_loss_close(norm.item(), wp, "normaliser")
+    n = _scalar(wp)
+    l2, g2 = ops.distill([_dev(l) for l in host], n, **HEAD)
+    for i, l in enumerate(host):
+        ref_loss, elems = oracle.distill_loss(*l, wp, return_elements=True, **HEAD)
+        exact_loss = float(elems.astype(np.float64).sum()) * HEAD["scale"]
+        assert_reduced_close(l2[i].item(), ref_loss, exact_loss, "loss level %d" % i)
+        assert_grad_close(g2[i].cpu().numpy(), oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)
+        # the one-launch step computes its own normaliser (<= 1e-4 from the reference-order one)
+        assert abs(losses[i].item() - exact_loss) <= 3e-4 * abs(exact_loss)
+        assert torch.allclose(grads[i], g2[i], rtol=3e-4, atol=1e-12)

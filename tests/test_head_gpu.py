@@ -251,3 +251,15 @@ def test_teacher_head_emits_class_probabilities():
         assert float(prob[l].min()) >= 0.0 and float(prob[l].max()) <= 1.0
     with pytest.raises(native.SadError, match="forward-only"):
         teacher.backward([torch.zeros_like(p) for p in prob], None)
+
+
+def test_head_config5_geometry_one_image_500px():
+    # BASELINE.json configs[4] geometry: 3 x 512 x 896 -> 64x112, 32x56, 16x28, 8x14, 4x7, one image per GPU
+    # (rows of 112 / 56 / 28 / 14 / 7 pixels: every pixel tile has a ragged tail, TMA zero fill on both borders)
+    shapes = [(64, 112), (32, 56), (16, 28), (8, 14), (4, 7)]
+    head, fpn, d_cls, d_box = _make(1, shapes, 256, 4, 9, 80, seed=21)
+    cls, box = head.forward(fpn)
+    d_fpn = head.backward(d_cls, d_box)
+    torch.cuda.synchronize()
+    check_against(head, cls, box, d_fpn, staged_reference(head, fpn, d_cls, d_box, TorchF64Backend(), product_acts=True),
+                  tight=(3e-3, 1e-3))
