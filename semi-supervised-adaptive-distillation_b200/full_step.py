@@ -39,6 +39,56 @@ class AffineChannel(nn.Module):
         return torch.addcmul(self.bias, x, self.scale)
 
 
+class _ConvAffine(torch.autograd.Function):
+    """act(conv(x, w) * scale + bias (+ z)) as ONE cuDNN call: the frozen AffineChannel is folded into the weights
+    (conv(x, w) * s = conv(x, w * s)) and bias, residual add and ReLU ride in the convolution's epilogue
+    (cudnnConvolutionBiasActivationForward).  Unfused, every convolution of the bodies is followed by 2-3 elementwise
+    passes over its output, which cost more than the convolutions themselves (measured: 4.7 of 13.5 ms at bs = 2).
+    Backward: ReluGradient from the saved output (one pass), cuDNN data / weight gradients of the folded convolution,
+    dW = dW_folded * s."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale, bias, z, stride, padding, relu):
+        w_eff = w if scale is None else w * scale.view(-1, 1, 1, 1)
+        s, p, d = (stride, stride), (padding, padding), (1, 1)
+        if z is not None:
+            out = torch.cudnn_convolution_add_relu(x, w_eff, z, 1.0, bias, s, p, d, 1)
+        elif relu:
+            out = torch.cudnn_convolution_relu(x, w_eff, bias, s, p, d, 1)
+        else:
+            out = F.conv2d(x, w_eff, bias, stride, padding)
+        ctx.conv = (s, p, d)
+        ctx.masked = relu or z is not None
+        ctx.has_z = z is not None
+        ctx.save_for_backward(x, w_eff, scale, out if ctx.masked else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_eff, scale, out = ctx.saved_tensors
+        s, p, d = ctx.conv
+        g = torch.ops.aten.threshold_backward(dy, out, 0) if ctx.masked else dy
+        dx, dw, _ = torch.ops.aten.convolution_backward(g, x, w_eff, None, s, p, d, False, [0, 0], 1,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        if dw is not None and scale is not None:
+            dw = dw * scale.view(-1, 1, 1, 1)
+        dz = g if (ctx.has_z and ctx.needs_input_grad[4]) else None
+        return dx, dw, None, None, dz, None, None, None
+
+
+def conv_affine(conv, aff, x, z=None, relu=True):
+    """Fused conv -> AffineChannel (-> + z) (-> ReLU).  Frozen convolutions (the teacher, res2 and below) fold once."""
+    stride, padding = conv.stride[0], conv.padding[0]
+    if not conv.weight.requires_grad:
+        folded = getattr(conv, "_folded", None)
+        if folded is None:
+            with torch.no_grad():
+                folded = (conv.weight * aff.scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+            conv._folded = folded
+        return _ConvAffine.apply(x, folded, None, aff.bias.view(-1), z, stride, padding, relu)
+    return _ConvAffine.apply(x, conv.weight, aff.scale, aff.bias.view(-1), z, stride, padding, relu)
+
+
 class Bottleneck(nn.Module):
     def __init__(self, cin, cout, cmid, stride, groups=1):
         super().__init__()
@@ -47,10 +97,16 @@ class Bottleneck(nn.Module):
         self.c2, self.a2 = nn.Conv2d(cmid, cmid, 3, padding=1, groups=groups, bias=False), AffineChannel(cmid)
         self.c3, self.a3 = nn.Conv2d(cmid, cout, 1, bias=False), AffineChannel(cout)
         self.short = None
+        self.fused = groups == 1
         if cin != cout or stride != 1:
             self.short = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), AffineChannel(cout))
 
     def forward(self, x):
+        if self.fused:
+            y = conv_affine(self.c1, self.a1, x)
+            y = conv_affine(self.c2, self.a2, y)
+            z = x if self.short is None else conv_affine(self.short[0], self.short[1], x, relu=False)
+            return conv_affine(self.c3, self.a3, y, z=z)
         y = F.relu(self.a1(self.c1(x)), inplace=True)
         y = F.relu(self.a2(self.c2(y)), inplace=True)
         y = self.a3(self.c3(y))
@@ -60,8 +116,9 @@ class Bottleneck(nn.Module):
 class ResNetFPN(nn.Module):
     """C3..C5 -> P3..P7 (FPN.DIM = 256; P6, P7 by stride-2 3x3 convolutions: FPN.EXTRA_CONV_LEVELS, FPN.py:199-219)."""
 
-    def __init__(self, blocks=(3, 4, 6, 3), dim=256):
+    def __init__(self, blocks=(3, 4, 6, 3), dim=256, fused=True):
         super().__init__()
+        self.fused = fused
         self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), AffineChannel(64), nn.ReLU(inplace=True),
                                   nn.MaxPool2d(3, stride=2, padding=1))
         stages, cin = [], 64
@@ -77,10 +134,16 @@ class ResNetFPN(nn.Module):
         self.p7 = nn.Conv2d(dim, dim, 3, stride=2, padding=1)
         for p in list(self.stem.parameters()) + list(self.res2.parameters()):   # TRAIN.FREEZE_AT = 2
             p.requires_grad_(False)
+        for m in self.modules():
+            if isinstance(m, Bottleneck):
+                m.fused = m.fused and fused
 
     def forward(self, x):
         with torch.no_grad():
-            c2 = self.res2(self.stem(x))
+            if self.fused:
+                c2 = self.res2(self.stem[3](conv_affine(self.stem[0], self.stem[1], x)))
+            else:
+                c2 = self.res2(self.stem(x))
         c3 = self.res3(c2)
         c4 = self.res4(c3)
         c5 = self.res5(c4)
@@ -94,7 +157,8 @@ class ResNetFPN(nn.Module):
 
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
-                 temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4):
+                 temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4,
+                 fused_body=True):
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world, self.rank, self.images = int(world), int(rank), int(n_images)
         self.lr, self.mom, self.wd = lr, momentum, weight_decay
@@ -103,8 +167,8 @@ class FullDistillStep:
         torch.backends.cudnn.allow_tf32 = True          # the bodies run on cuDNN's TF32 tensor-core path (scaffolding)
         torch.backends.cudnn.benchmark = True
         torch.manual_seed(seed)                         # same weights on every rank
-        self.student = ResNetFPN(student_blocks).to(self.device).to(memory_format=torch.channels_last)
-        self.teacher = ResNetFPN(teacher_blocks).to(self.device).to(memory_format=torch.channels_last).eval()
+        self.student = ResNetFPN(student_blocks, fused=fused_body).to(self.device).to(memory_format=torch.channels_last)
+        self.teacher = ResNetFPN(teacher_blocks, fused=fused_body).to(self.device).to(memory_format=torch.channels_last).eval()
         for p in self.teacher.parameters():
             p.requires_grad_(False)
         # ONE flat parameter buffer and ONE flat gradient buffer laid out [head weights | head biases | body weights | body biases]:

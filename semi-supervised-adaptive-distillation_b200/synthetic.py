@@ -12,8 +12,12 @@ CLS_BIAS = -4.59511985013459  # -log((1 - pi) / pi), pi = 0.01 (retinanet_heads.
 
 
 def level_shapes(scale_px=600):
-    """[(H, W)] for FPN levels 3..7."""
-    if scale_px == 600:
+    """[(H, W)] for FPN levels 3..7.  scale_px: 600, 500, or a padded (height, width) in multiples of 128."""
+    if isinstance(scale_px, (tuple, list)):
+        h, w = int(scale_px[0]), int(scale_px[1])
+        if h <= 0 or w <= 0 or h % 128 or w % 128:
+            raise ValueError("padded image size must be positive multiples of COARSEST_STRIDE = 128")
+    elif scale_px == 600:
         h, w = 640, 1024
     elif scale_px == 500:
         h, w = 512, 896

@@ -1,0 +1,103 @@
+"""The full distillation step (BASELINE.json configs[2..4]) at a small geometry: the scaffolding bodies' fused
+conv + AffineChannel (+ residual) + ReLU path against the plain module graph, and the step's bookkeeping
+(flat [head | body] buffers, CUDA graph == eager, one SGD launch moves every trainable parameter)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fp32_cudnn():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def _randomise_affine(net, seed):
+    from sad_b200.full_step import AffineChannel
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, AffineChannel):
+            m.scale.copy_(0.5 + torch.rand(m.scale.shape, device="cuda", generator=g))
+            m.bias.copy_(0.2 * torch.randn(m.bias.shape, device="cuda", generator=g))
+
+
+def test_fused_body_matches_module_graph(fp32_cudnn):
+    from sad_b200.full_step import ResNetFPN
+    torch.manual_seed(3)
+    plain = ResNetFPN((1, 2, 1, 1), fused=False).cuda().to(memory_format=torch.channels_last)
+    fused = ResNetFPN((1, 2, 1, 1), fused=True).cuda().to(memory_format=torch.channels_last)
+    fused.load_state_dict(plain.state_dict())
+    _randomise_affine(plain, 5)
+    fused.load_state_dict(plain.state_dict())
+    x = torch.randn(2, 3, 128, 256, device="cuda").contiguous(memory_format=torch.channels_last)
+    outs_p, outs_f = plain(x), fused(x)
+    d = [torch.randn_like(o) for o in outs_p]
+    torch.autograd.backward(outs_p, d)
+    torch.autograd.backward(outs_f, d)
+    torch.cuda.synchronize()
+    for a, b in zip(outs_p, outs_f):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 2e-4 * float(a.abs().max())
+    n_grads = 0
+    for (name, p), (_, q) in zip(plain.named_parameters(), fused.named_parameters()):
+        assert (p.grad is None) == (q.grad is None), name
+        if p.grad is not None:
+            n_grads += 1
+            assert float((p.grad - q.grad).abs().max()) <= 5e-4 * float(p.grad.abs().max()) + 1e-7, name
+    assert n_grads > 20
+    # frozen below res3 (TRAIN.FREEZE_AT = 2) in both forms
+    assert all(p.grad is None for p in fused.res2.parameters()) and all(p.grad is None for p in fused.stem.parameters())
+
+
+def test_full_step_small_geometry():
+    from sad_b200.full_step import FullDistillStep
+    step = FullDistillStep(n_images=1, scale_px=(128, 256), student_blocks=(1, 1, 1, 1), teacher_blocks=(1, 1, 2, 1), seed=11)
+    n = step.param_count()
+    assert step.flat_grads.numel() == n["head"] + n["body_trainable"] == step.flat_params.numel()
+    # body parameters and their gradients are views of the flat buffers (one allreduce, one SGD launch)
+    lo, hi = step.flat_params.data_ptr(), step.flat_params.data_ptr() + 4 * step.flat_params.numel()
+    assert all(lo <= p.data_ptr() < hi for p in step.body_params)
+    step.forward_backward()
+    torch.cuda.synchronize()
+    eager = step.losses()
+    g_eager = step.flat_grads.clone()
+    for k in ("bbox", "focal", "distill"):
+        assert len(eager[k]) == 5 and all(np.isfinite(v) and v >= 0.0 for v in eager[k]), (k, eager[k])
+    assert eager["normalizer"] > 0.0
+    assert float(g_eager[:n["head"]].abs().sum()) > 0.0 and float(g_eager[n["head"]:].abs().sum()) > 0.0
+    assert bool(torch.isfinite(g_eager).all())
+    # the captured graph replays the same step (same inputs, same weights)
+    assert step.capture(), getattr(step, "capture_error", None)
+    step.run()
+    torch.cuda.synchronize()
+    again = step.losses()
+    for k in ("bbox", "focal", "distill"):
+        assert np.allclose(again[k], eager[k], rtol=1e-4, atol=1e-7), k
+    assert float((step.flat_grads - g_eager).abs().max()) <= 2e-3 * float(g_eager.abs().max())
+    # one optimiser launch moves every trainable blob: head and body
+    before = step.flat_params.clone()
+    step.allreduce()
+    step.sgd()
+    torch.cuda.synchronize()
+    moved = (step.flat_params != before)
+    assert bool(moved[:n["head"]].any()) and bool(moved[n["head"]:].any())
+    assert float(moved.float().mean()) > 0.5
+    # the teacher is frozen and forward-only
+    assert all(not p.requires_grad for p in step.teacher.parameters())
+
+
+def test_fused_and_plain_bodies_give_the_same_step_losses():
+    from sad_b200.full_step import FullDistillStep
+    kw = dict(n_images=1, scale_px=(128, 256), student_blocks=(1, 1, 1, 1), teacher_blocks=(1, 1, 1, 1), seed=5)
+    a, b = FullDistillStep(fused_body=True, **kw), FullDistillStep(fused_body=False, **kw)
+    a.forward_backward()
+    b.forward_backward()
+    torch.cuda.synchronize()
+    la, lb = a.losses(), b.losses()
+    for k in ("bbox", "focal", "distill"):
+        assert np.allclose(la[k], lb[k], rtol=5e-3, atol=1e-6), (k, la[k], lb[k])    # both on TF32 tensor cores, different cuDNN engines
+    assert abs(la["normalizer"] - lb["normalizer"]) <= 5e-3 * lb["normalizer"]
