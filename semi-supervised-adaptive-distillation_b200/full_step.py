@@ -158,9 +158,11 @@ class ResNetFPN(nn.Module):
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
                  temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4,
-                 fused_body=True):
+                 fused_body=True, overlap_teacher=True):
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world, self.rank, self.images = int(world), int(rank), int(n_images)
+        self.overlap_teacher = bool(overlap_teacher)
+        self.teacher_stream = torch.cuda.Stream(device=self.device)
         self.lr, self.mom, self.wd = lr, momentum, weight_decay
         shapes = synthetic.level_shapes(scale_px)
         H, W = shapes[0][0] * 8, shapes[0][1] * 8
@@ -234,7 +236,13 @@ class FullDistillStep:
         self.last = {}
 
     def forward_backward(self):
-        with torch.no_grad():                                            # teacher: forward only (model.train = False)
+        # The teacher does not depend on the student until the distillation loss: it runs on its own stream beside the
+        # student's forward pass (at bs = 2 the res4 / res5 convolutions of either body fill well under 148 SMs on their own).
+        main = torch.cuda.current_stream()
+        if self.overlap_teacher:
+            self.teacher_stream.wait_stream(main)
+        with torch.cuda.stream(self.teacher_stream if self.overlap_teacher else main), torch.no_grad():
+            # teacher: forward only (model.train = False)
             t_fpn = [f.contiguous() for f in self.teacher(self.images_t)]
             # teacher/retnet_cls_prob_fpnL: the Sigmoid of retinanet_heads.py:153-163 runs in the prediction convolution's epilogue
             self.teacher_head.forward(t_fpn, training=False, out=(self.t_prob, self.t_box))
@@ -243,6 +251,8 @@ class FullDistillStep:
         fpn_c = [f.detach().contiguous() for f in fpn]
         L = len(self.cls)
         self.head.forward(fpn_c, training=True, out=(self.cls, self.box))
+        if self.overlap_teacher:
+            main.wait_stream(self.teacher_stream)
         self.plan.run()                                                  # PowSum + distillation loss + d(logits), one launch
         for l in range(L):
             # SigmoidFocalLoss + gradient, added into the distillation gradient (the autograd Sum of the two consumers of
