@@ -239,6 +239,9 @@ int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float*
  * dx == dy), as the towers use them (retinanet_heads.py:124,209). */
 int sad_relu_f32(const float* x, float* y, int64_t n, void* stream);
 int sad_relu_grad_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+/* Sigmoid (caffe2/caffe2/operators/sigmoid_op.cu:24-29): y = 1 / (1 + exp(-x)), in place allowed.  The teacher graph's
+ * retnet_cls_pred_fpnL -> retnet_cls_prob_fpnL (retinanet_heads.py:153-163) as a stand-alone operator. */
+int sad_sigmoid_f32(const float* x, float* y, int64_t n, void* stream);
 
 /* Weight and bias gradient — replaces the filter/bias half of CudnnConvGradientOp::DoRunWithType
  *   (caffe2/caffe2/operators/conv_op_cudnn.cc:1011-1040: cudnnConvolutionBackwardBias / BackwardFilter)

@@ -48,6 +48,26 @@ __global__ void __launch_bounds__(256) relu_grad_kernel(const float* __restrict_
   }
 }
 
+// Sigmoid as a stand-alone operator (caffe2/caffe2/operators/sigmoid_op.cu:24-29: Y = 1 / (1 + exp(-X))): what the teacher's
+// graph appends to retnet_cls_pred_fpnL when model.train is False (retinanet_heads.py:153-163).  8 B/element, HBM-bound.
+// The fused head object never launches it: there the Sigmoid is the prediction convolution's epilogue.
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
+__global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int vec) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const size_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 v = x4[i];
+      y4[i] = make_float4(sigmoid_ref(v.x), sigmoid_ref(v.y), sigmoid_ref(v.z), sigmoid_ref(v.w));
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) y[i] = sigmoid_ref(x[i]);
+  } else {
+    for (size_t i = tid; i < n; i += stride) y[i] = sigmoid_ref(x[i]);
+  }
+}
+
 static unsigned ew_grid(size_t n) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -69,6 +89,15 @@ SAD_EXPORT int sad_relu_f32(const float* x, float* y, int64_t n, void* stream) {
   relu_kernel<<<ew_grid((size_t)n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, (size_t)n, vec);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "relu launch");
+}
+
+SAD_EXPORT int sad_sigmoid_f32(const float* x, float* y, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !y))) return set_error(SAD_ERR_INVALID, "sigmoid: bad argument");
+  if (n == 0) return SAD_OK;
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  sigmoid_kernel<<<ew_grid((size_t)n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, (size_t)n, vec);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "sigmoid launch");
 }
 
 SAD_EXPORT int sad_relu_grad_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream) {

@@ -209,6 +209,23 @@ bool HeadReluOp<float, CUDAContext>::RunOnDevice() {
   return true;
 }
 
+// Sigmoid (sigmoid_op.cu:24-29) for the teacher graph's class probabilities (retinanet_heads.py:153-163)
+template <typename T, class Context>
+class HeadSigmoidOp final : public Operator<Context> {
+ public:
+  USE_SIMPLE_CTOR_DTOR(HeadSigmoidOp);
+  USE_OPERATOR_CONTEXT_FUNCTIONS;
+  bool RunOnDevice() override { CAFFE_NOT_IMPLEMENTED; }
+};
+template <>
+bool HeadSigmoidOp<float, CUDAContext>::RunOnDevice() {
+  const auto& X = Input(0);
+  auto* Y = Output(0);
+  Y->ResizeLike(X);
+  EnforceSadConv(sad_sigmoid_f32(X.data<float>(), Y->mutable_data<float>(), X.size(), context_.cuda_stream()), "sad_sigmoid_f32");
+  return true;
+}
+
 template <typename T, class Context>
 class HeadReluGradientOp final : public Operator<Context> {
  public:
@@ -235,6 +252,7 @@ REGISTER_CUDNN_OPERATOR(Conv, HeadConvOp<float, CUDAContext>);                  
 REGISTER_CUDNN_OPERATOR(ConvGradient, HeadConvGradientOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(Relu, HeadReluOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(ReluGradient, HeadReluGradientOp<float, CUDAContext>);
+REGISTER_CUDA_OPERATOR(Sigmoid, HeadSigmoidOp<float, CUDAContext>);
 
 OPERATOR_SCHEMA(Conv)
     .NumInputs(2, 3)
@@ -248,6 +266,7 @@ OPERATOR_SCHEMA(Conv)
 OPERATOR_SCHEMA(ConvGradient).NumInputs(2, 3).NumOutputs(1, 3);
 OPERATOR_SCHEMA(Relu).NumInputs(1).NumOutputs(1).AllowInplace({{0, 0}}).IdenticalTypeAndShape();
 OPERATOR_SCHEMA(ReluGradient).NumInputs(2).NumOutputs(1).AllowInplace({{1, 0}});
+OPERATOR_SCHEMA(Sigmoid).NumInputs(1).NumOutputs(1).AllowInplace({{0, 0}}).IdenticalTypeAndShape();  // sigmoid_op.cc
 
 // caffe2/caffe2/operators/conv_gradient_op.cc:35-77
 class GetConvGradient : public GradientMakerBase {

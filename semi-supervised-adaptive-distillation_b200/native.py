@@ -145,6 +145,7 @@ def lib():
                                         C.POINTER(HeadTensors), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         l.sad_head_copy_activation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.sad_relu_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        l.sad_sigmoid_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.sad_relu_grad_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.sad_conv3x3_sign_bits_bytes.restype = C.c_size_t
         l.sad_conv3x3_sign_bits_bytes.argtypes = [C.c_int] * 4

@@ -1,5 +1,6 @@
-"""Host mirror of the graph wiring on the path: detectron/lib/modeling/retinanet_heads.py:313-352
-(`add_distill_loss`) plus what Caffe2 autograd appends for it (loss-gradient ConstantFill from
+"""Host mirror of the graph wiring on the path: detectron/lib/modeling/retinanet_heads.py:63-245
+(`add_fpn_retinanet_outputs`, the head), :248-311 (`add_fpn_retinanet_losses`) and :313-352
+(`add_distill_loss`) plus what Caffe2 autograd appends for the latter (loss-gradient ConstantFill from
 detectron/lib/utils/blob.py:166-172 and the gradient ops from the C++ gradient maker).
 
 The reference emits OperatorDefs by name into the NetDef; this module emits the same ops with the
@@ -14,6 +15,100 @@ DISTILLATION = dict(LOSS_ALPHA=0.5, LOSS_GAMMA=2.0, LOSS_BETA=0.0, IGNORED_LABEL
                     ADAPTIVE_NORMALIZER=True, LOGITS_POWER=1.8)
 RPN_MIN_LEVEL, RPN_MAX_LEVEL = 3, 7
 NUM_CLASSES = 81  # cfg.MODEL.NUM_CLASSES incl. background; the op gets NUM_CLASSES - 1
+# detectron/lib/core/config.py RETINANET.*: 3 aspect ratios x 3 scales per octave, 4 tower convolutions, separate towers,
+# per-class sigmoid, prior 0.01, focal gamma 2 / alpha 0.25, box beta 0.11 / weight 1
+RETINANET = dict(NUM_CONVS=4, ASPECT_RATIOS=3, SCALES_PER_OCTAVE=3, SHARE_CLS_BBOX_TOWER=False, PRIOR_PROB=0.01,
+                 LOSS_GAMMA=2.0, LOSS_ALPHA=0.25, BBOX_REG_BETA=0.11, BBOX_REG_WEIGHT=1.0, CLASS_SPECIFIC_BBOX=False)
+FPN_DIM = 256
+
+
+def get_retinanet_bias_init(cfg=None):
+    """retinanet_heads.py:29-60, per-class sigmoid case: ('ConstantFill', value = -log((1 - pi) / pi))."""
+    import math
+    pi = dict(RETINANET, **(cfg or {}))["PRIOR_PROB"]
+    return ("ConstantFill", {"value": -math.log((1.0 - pi) / pi)})
+
+
+def add_fpn_retinanet_outputs(blobs_in, gpu_id=0, train=True, dim_in=FPN_DIM, cfg=None, scope="",
+                              k_min=RPN_MIN_LEVEL, k_max=RPN_MAX_LEVEL):
+    """The RetinaNet head as the reference emits it (retinanet_heads.py:63-245): per level two towers of NUM_CONVS
+    Conv3x3 + in-place Relu, then the class-logit and box convolutions; level k_min creates the parameters, the other levels
+    reuse them (ConvShared = a Conv reading level k_min's `_w` / `_b` blobs); `train=False` (the teacher,
+    model_builder.py:379-393) appends Sigmoid -> retnet_cls_prob_fpnL.  `blobs_in` is in the reference's reversed order
+    (coarsest level first), `scope` is e.g. "teacher/".
+
+    Returns (NetDef, params, cls_outputs, bbox_outputs): params = [(blob, shape, (fill_op, fill_args))] in creation order —
+    the same blob names as head.param_names(), which lays them out weights first, biases second."""
+    cfg = dict(RETINANET, **(cfg or {}))
+    assert len(blobs_in) == k_max - k_min + 1
+    A = cfg["ASPECT_RATIOS"] * cfg["SCALES_PER_OCTAVE"]
+    cls_dim = (NUM_CLASSES - 1) * A
+    box_dim = (4 * (NUM_CLASSES - 1) if cfg["CLASS_SPECIFIC_BBOX"] else 4) * A
+    pre = "gpu_%d/%s" % (gpu_id, scope)
+    dev = c2.DeviceOption(c2.CUDA, gpu_id)
+    gauss, zero = ("GaussianFill", {"std": 0.01}), ("ConstantFill", {"value": 0.0})
+    ops, params = [], []
+
+    def conv(bl_in, name, cout, lvl, bias_init=zero):
+        # model.Conv / model.ConvShared (cnn.py): Conv with engine CUDNN, order NCHW; the parameter blobs belong to level k_min
+        owner = name.replace("fpn%d" % lvl, "fpn%d" % k_min)
+        if lvl == k_min:
+            params.append((pre + name + "_w", (cout, dim_in, 3, 3), gauss))
+            params.append((pre + name + "_b", (cout,), bias_init))
+        ops.append(c2.CreateOperator("Conv", [bl_in, pre + owner + "_w", pre + owner + "_b"], [pre + name], device_option=dev,
+                                     engine="CUDNN", kernel=3, pad=1, stride=1, order="NCHW"))
+        return pre + name
+
+    def tower(kind, lvl):
+        bl = blobs_in[k_max - lvl]
+        for n in range(cfg["NUM_CONVS"]):
+            bl = conv(bl, "retnet_%s_conv_n%d_fpn%d" % (kind, n, lvl), dim_in, lvl)
+            ops.append(c2.CreateOperator("Relu", [bl], [bl], device_option=dev))      # model.Relu(bl_out, bl_out)
+        return bl
+
+    cls_out, bbox_feat = [], []
+    for lvl in range(k_min, k_max + 1):
+        feat = tower("cls", lvl)
+        pred = conv(feat, "retnet_cls_pred_fpn%d" % lvl, cls_dim, lvl, bias_init=get_retinanet_bias_init(cfg))
+        if not train:
+            prob = pre + "retnet_cls_prob_fpn%d" % lvl
+            ops.append(c2.CreateOperator("Sigmoid", [pred], [prob], device_option=dev))
+            pred = prob
+        cls_out.append(pred)
+        if cfg["SHARE_CLS_BBOX_TOWER"]:
+            bbox_feat.append(feat)
+    if not cfg["SHARE_CLS_BBOX_TOWER"]:
+        for lvl in range(k_min, k_max + 1):
+            bbox_feat.append(tower("bbox", lvl))
+    box_out = [conv(bbox_feat[i], "retnet_bbox_pred_fpn%d" % lvl, box_dim, lvl) for i, lvl in enumerate(range(k_min, k_max + 1))]
+    return c2.NetDef("retinanet_head_gpu%d%s" % (gpu_id, "_" + scope.strip("/") if scope else ""), ops), params, cls_out, box_out
+
+
+def add_fpn_retinanet_losses(gpu_id=0, num_gpus=1, cfg=None, k_min=RPN_MIN_LEVEL, k_max=RPN_MAX_LEVEL):
+    """retinanet_heads.py:248-311: SelectSmoothL1Loss per level, then SigmoidFocalLoss per level, loss scale 1 / NUM_GPUS
+    (model.GetLossScale, detector.py:650-655).  Returns (NetDef, loss blob names)."""
+    cfg = dict(RETINANET, **(cfg or {}))
+    pre = "gpu_%d/" % gpu_id
+    dev = c2.DeviceOption(c2.CUDA, gpu_id)
+    scale = 1.0 / num_gpus
+    ops, losses = [], []
+    for lvl in range(k_min, k_max + 1):
+        sfx = "fpn%d" % lvl
+        ops.append(c2.CreateOperator(
+            "SelectSmoothL1Loss",
+            [pre + "retnet_bbox_pred_" + sfx, pre + "retnet_roi_bbox_targets_" + sfx, pre + "retnet_roi_fg_bbox_locs_" + sfx,
+             pre + "retnet_fg_num"],
+            [pre + "retnet_loss_bbox_" + sfx], device_option=dev, beta=float(cfg["BBOX_REG_BETA"]),
+            scale=scale * float(cfg["BBOX_REG_WEIGHT"])))
+        losses.append(pre + "retnet_loss_bbox_" + sfx)
+    for lvl in range(k_min, k_max + 1):
+        sfx = "fpn%d" % lvl
+        ops.append(c2.CreateOperator(
+            "SigmoidFocalLoss", [pre + "retnet_cls_pred_" + sfx, pre + "retnet_cls_labels_" + sfx, pre + "retnet_fg_num"],
+            [pre + "fl_" + sfx], device_option=dev, gamma=float(cfg["LOSS_GAMMA"]), alpha=float(cfg["LOSS_ALPHA"]), scale=scale,
+            num_classes=NUM_CLASSES - 1))
+        losses.append(pre + "fl_" + sfx)
+    return c2.NetDef("retinanet_losses_gpu%d" % gpu_id, ops), losses
 
 
 def add_distill_loss(gpu_id=0, num_gpus=1, cfg=None, with_gradients=True, k_min=RPN_MIN_LEVEL, k_max=RPN_MAX_LEVEL):

@@ -201,3 +201,67 @@ def test_relu_gradient_maker_uses_the_output(oplib):
     op = c2.CreateOperator("Relu", ["t"], ["t"], device_option=c2.DeviceOption(c2.CUDA, 0))
     types, ins, outs, gin = _grad_fields(oplib.GetGradientDefs(op, ["t_grad"]))
     assert types == ["ReluGradient"] and ins == ["t", "t_grad"] and outs == ["t_grad"]
+
+
+# ---------------------------------------------------------------------------------------------
+# head graph (retinanet_heads.py:63-245) and its losses (:248-311) as NetDefs
+# ---------------------------------------------------------------------------------------------
+def test_head_graph_wiring_matches_reference(oplib):
+    from sad_b200 import head
+    blobs_in = ["gpu_0/fpn_%d" % l for l in (7, 6, 5, 4, 3)]                 # coarsest first, like FPN.add_fpn returns them
+    net, params, cls_out, box_out = retinanet_heads.add_fpn_retinanet_outputs(blobs_in, gpu_id=0, train=True)
+    # per level: 2 towers x 4 x (Conv + in-place Relu) + 2 prediction convolutions
+    assert len(net.op) == 5 * (2 * 4 * 2 + 2)
+    assert [o.type for o in net.op[:9]] == ["Conv", "Relu"] * 4 + ["Conv"]
+    first = net.op[0]
+    assert first.input == ["gpu_0/fpn_3", "gpu_0/retnet_cls_conv_n0_fpn3_w", "gpu_0/retnet_cls_conv_n0_fpn3_b"]
+    assert first.output == ["gpu_0/retnet_cls_conv_n0_fpn3"] and first.engine == "CUDNN"
+    assert first.arg == dict(kernel=3, pad=1, stride=1, order="NCHW")
+    assert net.op[1].input == net.op[1].output == first.output               # model.Relu(bl_out, bl_out)
+    # levels 4..7 are ConvShared: their convolutions read level 3's parameter blobs
+    lvl5 = [o for o in net.op if o.type == "Conv" and o.output[0].endswith("_fpn5")]
+    assert len(lvl5) == 10 and all(o.input[1].endswith("_fpn3_w") and o.input[2].endswith("_fpn3_b") for o in lvl5)
+    assert [o.input[0] for o in net.op if o.output == ["gpu_0/retnet_cls_conv_n0_fpn7"] and o.type == "Conv"] == ["gpu_0/fpn_7"]
+    assert cls_out == ["gpu_0/retnet_cls_pred_fpn%d" % l for l in range(3, 8)]
+    assert box_out == ["gpu_0/retnet_bbox_pred_fpn%d" % l for l in range(3, 8)]
+    # parameters: created once (level 3), same names as the fused head object's flat buffer
+    names = [n for n, _, _ in params]
+    assert len(names) == 20 and sorted(names) == sorted("gpu_0/" + n for n in head.param_names())
+    shapes = {n: s for n, s, _ in params}
+    assert shapes["gpu_0/retnet_cls_pred_fpn3_w"] == (720, 256, 3, 3) and shapes["gpu_0/retnet_bbox_pred_fpn3_w"] == (36, 256, 3, 3)
+    assert shapes["gpu_0/retnet_bbox_conv_n3_fpn3_b"] == (256,)
+    fills = {n: f for n, _, f in params}
+    assert fills["gpu_0/retnet_cls_conv_n0_fpn3_w"] == ("GaussianFill", {"std": 0.01})
+    kind, args = fills["gpu_0/retnet_cls_pred_fpn3_b"]
+    assert kind == "ConstantFill" and abs(args["value"] - (-4.59511985013459)) < 1e-12       # -log((1 - pi) / pi), pi = 0.01
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 6463220
+    # every op resolves in the registry and the text survives the parser
+    assert all(oplib.HasOperator(o.type, c2.CUDA) for o in net.op)
+    assert oplib.NormalizeNetText(net.to_text()).count("op {") == len(net.op)
+    # the teacher's graph (model.train = False, name scope teacher/): Sigmoid -> retnet_cls_prob_fpnL
+    tnet, tparams, tcls, _ = retinanet_heads.add_fpn_retinanet_outputs(["gpu_1/teacher/fpn_%d" % l for l in (7, 6, 5, 4, 3)],
+                                                                       gpu_id=1, train=False, scope="teacher/")
+    assert len(tnet.op) == len(net.op) + 5 and oplib.HasOperator("Sigmoid", c2.CUDA)
+    sig = [o for o in tnet.op if o.type == "Sigmoid"]
+    assert [o.input[0] for o in sig] == ["gpu_1/teacher/retnet_cls_pred_fpn%d" % l for l in range(3, 8)]
+    assert tcls == ["gpu_1/teacher/retnet_cls_prob_fpn%d" % l for l in range(3, 8)]
+    # ... which are exactly PowSum's inputs in add_distill_loss
+    assert retinanet_heads.add_distill_loss(gpu_id=1, num_gpus=8)[0].op[0].input == tcls
+    # a shared tower feeds the box predictions from the class tower
+    snet, sparams, _, _ = retinanet_heads.add_fpn_retinanet_outputs(blobs_in, cfg=dict(SHARE_CLS_BBOX_TOWER=True))
+    assert len(snet.op) == 5 * (4 * 2 + 2) and len(sparams) == 12
+    assert [o.input[0] for o in snet.op if o.output == ["gpu_0/retnet_bbox_pred_fpn4"]] == ["gpu_0/retnet_cls_conv_n3_fpn4"]
+
+
+def test_head_loss_wiring_matches_reference(oplib):
+    net, losses = retinanet_heads.add_fpn_retinanet_losses(gpu_id=2, num_gpus=8)
+    assert [o.type for o in net.op] == ["SelectSmoothL1Loss"] * 5 + ["SigmoidFocalLoss"] * 5
+    box = net.op[0]
+    assert box.input == ["gpu_2/retnet_bbox_pred_fpn3", "gpu_2/retnet_roi_bbox_targets_fpn3", "gpu_2/retnet_roi_fg_bbox_locs_fpn3",
+                         "gpu_2/retnet_fg_num"]
+    assert box.arg == dict(beta=0.11, scale=0.125)
+    fl = net.op[5]
+    assert fl.input == ["gpu_2/retnet_cls_pred_fpn3", "gpu_2/retnet_cls_labels_fpn3", "gpu_2/retnet_fg_num"]
+    assert fl.arg == dict(gamma=2.0, alpha=0.25, scale=0.125, num_classes=80)
+    assert losses == ["gpu_2/retnet_loss_bbox_fpn%d" % l for l in range(3, 8)] + ["gpu_2/fl_fpn%d" % l for l in range(3, 8)]
+    assert all(oplib.HasOperator(o.type, c2.CUDA) for o in net.op)

@@ -197,3 +197,86 @@ def test_head_conv_op_rejects_shapes_outside_its_class(oplib):
     ws.FeedBlob("w5", torch.zeros(8, 4, 3, 3, device="cuda"))
     with pytest.raises(c2.EnforceNotMet, match="channels"):
         ws.RunOperatorOnce(c2.CreateOperator("Conv", ["x", "w5"], ["y"], device_option=dev, kernel=3, pad=1, stride=1))
+
+
+def test_head_netdef_through_the_operators_equals_the_fused_head_object(oplib):
+    # retinanet_heads.py:63-245 emitted op by op (90 Conv / Relu operators, ConvShared levels reading level 3's blobs) against
+    # sad_head_forward, which runs the same graph as 10 launches.  Same kernels, same packed tf32 weights, same rounding points
+    # (activations are rounded when their channels-last copy is written), so the results agree to fp32 round-off.
+    from sad_b200 import c2, retinanet_heads
+    from sad_b200.head import RetinaNetHead
+    shapes, n, dim = [(16, 24), (8, 12), (4, 6), (2, 3), (1, 2)], 2, 32
+    student = RetinaNetHead(n, shapes, dim=dim, seed=9)
+    teacher = RetinaNetHead(n, shapes, dim=dim, seed=9, cls_output_sigmoid=True)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for name, p in student.params.items():
+        p.normal_(0.0, 0.08 if name.endswith("_w") else 0.1, generator=g)
+    teacher.flat_params.copy_(student.flat_params)
+    fpn = [torch.randn(n, dim, h, w, device="cuda", generator=g).clamp_(min=0) for h, w in shapes]
+    cls, box = student.forward(fpn, training=False)
+    prob, _ = teacher.forward(fpn, training=False)
+    blobs_in = ["gpu_0/fpn_%d" % l for l in (7, 6, 5, 4, 3)]
+    for train, scope, ref_cls in ((True, "", cls), (False, "teacher/", prob)):
+        net, params, cls_out, box_out = retinanet_heads.add_fpn_retinanet_outputs(
+            [b.replace("gpu_0/", "gpu_0/" + scope) for b in blobs_in], train=train, dim_in=dim, scope=scope)
+        ws = oplib.Workspace()
+        for l, f in zip((3, 4, 5, 6, 7), fpn):
+            ws.FeedBlob("gpu_0/%sfpn_%d" % (scope, l), f)
+        for name, shape, _ in params:
+            p = student.params[name.split("/")[-1]]
+            assert tuple(p.shape) == shape
+            ws.FeedBlob(name, p)
+        ws.CreateNet(net.to_text())
+        ws.RunNet(net.name)
+        for l in range(5):
+            got_cls, got_box = ws.FetchBlob(cls_out[l]), ws.FetchBlob(box_out[l])
+            assert got_cls.shape == tuple(ref_cls[l].shape) and got_box.shape == tuple(box[l].shape)
+            assert np.abs(got_cls - ref_cls[l].cpu().numpy()).max() <= 2e-5 * max(1.0, float(ref_cls[l].abs().max()))
+            assert np.abs(got_box - box[l].cpu().numpy()).max() <= 2e-5 * max(1.0, float(box[l].abs().max()))
+        if not train:
+            assert float(ws.FetchBlob(cls_out[0]).min()) > 0.0 and float(ws.FetchBlob(cls_out[0]).max()) < 1.0
+
+
+def test_sigmoid_operator(oplib):
+    from sad_b200 import c2
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    ws = oplib.Workspace()
+    x = torch.linspace(-30.0, 30.0, 4099, device="cuda")          # odd length: the scalar tail runs too
+    ws.FeedBlob("x", x)
+    ws.RunOperatorOnce(c2.CreateOperator("Sigmoid", ["x"], ["y"], device_option=dev))
+    ref = 1.0 / (1.0 + np.exp(-x.double().cpu().numpy()))
+    assert np.abs(ws.FetchBlob("y") - ref).max() <= 1e-6
+    ws.RunOperatorOnce(c2.CreateOperator("Sigmoid", ["x"], ["x"], device_option=dev))   # in place (AllowInplace {0, 0})
+    assert np.abs(ws.FetchBlob("x") - ref).max() <= 1e-6
+
+
+def test_head_loss_netdef_runs_through_the_operators(oplib, oracle):
+    from sad_b200 import c2, retinanet_heads
+    rng = np.random.default_rng(12)
+    net, losses = retinanet_heads.add_fpn_retinanet_losses(gpu_id=0, num_gpus=2)
+    ws = oplib.Workspace()
+    shapes = [(8, 12), (4, 6), (2, 3), (1, 2), (1, 1)]
+    host, fg_total = [], 0
+    for l, (h, w) in zip(range(3, 8), shapes):
+        logits = rng.normal(-2.0, 2.0, (2, 720, h, w)).astype(np.float32)
+        labels = rng.integers(-1, 81, (2, 9, h, w)).astype(np.int32)
+        labels[rng.random(labels.shape) < 0.9] = 0
+        box = rng.normal(0, 1, (2, 36, h, w)).astype(np.float32)
+        fg = np.argwhere(labels > 0)
+        locs = np.stack([fg[:, 0], fg[:, 1] * 4, fg[:, 2], fg[:, 3]], axis=1).astype(np.float32).reshape(-1, 4)
+        tgt = rng.normal(0, 0.3, (locs.shape[0], 4)).astype(np.float32)
+        fg_total += locs.shape[0]
+        host.append((logits, labels, box, locs, tgt))
+    fg_num = np.array([float(max(fg_total, 1))], dtype=np.float32)
+    ws.FeedBlob("gpu_0/retnet_fg_num", torch.from_numpy(fg_num).cuda())
+    for l, (logits, labels, box, locs, tgt) in zip(range(3, 8), host):
+        for name, a in (("retnet_cls_pred", logits), ("retnet_cls_labels", labels), ("retnet_bbox_pred", box),
+                        ("retnet_roi_fg_bbox_locs", locs), ("retnet_roi_bbox_targets", tgt)):
+            ws.FeedBlob("gpu_0/%s_fpn%d" % (name, l), torch.from_numpy(a).cuda())
+    ws.CreateNet(net.to_text())
+    ws.RunNet(net.name)
+    for i, (logits, labels, box, locs, tgt) in enumerate(host):
+        ref_fl = oracle.focal_loss(logits, labels, float(fg_num[0]), gamma=2.0, alpha=0.25, scale=0.5, num_classes=80)
+        assert_loss_close(ws.FetchBlob(losses[5 + i]), ref_fl, "focal level %d" % i)
+        ref_box = oracle.select_smooth_l1(box, tgt, locs, float(fg_num[0]), beta=0.11, scale=0.5)[0]
+        assert_loss_close(ws.FetchBlob(losses[i]), ref_box, "box level %d" % i)
