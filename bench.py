@@ -265,7 +265,7 @@ def run_head_step(args, rank, world, barrier, native):
     }
 
 
-def run_full_step(args, rank, world, barrier, native, n_images=2):
+def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False):
     """BASELINE.json configs[3] geometry (n_images = 2 per GPU) or configs[2] (n_images = 16 on one GPU): R-50-FPN student <-
     R-101-FPN teacher, full distillation training step, 600 px, one allreduce of the flat [head | body] gradient buffer.
     Heads, every loss, the exchange and the optimiser step are this repository's kernels; the ResNet/FPN bodies are
@@ -277,7 +277,11 @@ def run_full_step(args, rank, world, barrier, native, n_images=2):
     K = args.full_steps or min(args.steps, 20)
     if n_images > 2:
         K = min(K, 10)
-    st = FullDistillStep(n_images=n_images, scale_px=600, world=world, rank=rank)
+    if config5:   # configs[4]: R-101 student <- ResNeXt-101-64x4d teacher, 500 px, one image per GPU
+        st = FullDistillStep(n_images=n_images, scale_px=500, world=world, rank=rank, student_blocks=(3, 4, 23, 3),
+                             teacher_blocks=(3, 4, 23, 3), teacher_body=dict(groups=64, width_per_group=4, stride_1x1=False))
+    else:
+        st = FullDistillStep(n_images=n_images, scale_px=600, world=world, rank=rank)
     for _ in range(3):
         st.step()
     n0 = native.lib().sad_launch_count()
@@ -305,7 +309,7 @@ def run_full_step(args, rank, world, barrier, native, n_images=2):
     ms, ar_ms = float(t[0].item()), float(t[1].item())
     losses = st.losses()
     assert all(v == v for v in [losses["normalizer"]] + losses["bbox"] + losses["distill"] + losses["focal"]), ("non-finite loss", losses)
-    return {
+    line = {
         "metric": "RetinaNet-R50 distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms,
         "steps": K, "images_per_gpu": st.images, "scaling": "weak",
         "workload": "R-50-FPN student <- R-101-FPN teacher (random init), 3x640x1024 synthetic images, bs=%d/GPU: teacher fwd, student " % n_images +
@@ -320,6 +324,17 @@ def run_full_step(args, rank, world, barrier, native, n_images=2):
         "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),
         "cuda_graph_error": getattr(st, "capture_error", None), "losses": losses,
     }
+    if config5:
+        line["metric"] = "RetinaNet-R101 distill-step imgs/sec"
+        line["workload"] = ("R-101-FPN student <- ResNeXt-101-64x4d-FPN teacher (random init), 3x512x896 synthetic images (500 px scale), "
+                            "bs=%d/GPU: teacher fwd, student fwd+bwd, focal + box + adaptive distillation losses, ONE allreduce of %d "
+                            "gradient bytes, momentum SGD" % (n_images, st.exchange.nbytes))
+        line["baseline_config"] = "configs[4] geometry and models (bs=1 per GPU); computed in tf32 / fp32, i.e. at higher precision than the fp16 the config names"
+    st.head.close()
+    st.teacher_head.close()
+    del st
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -457,9 +472,13 @@ def main():
     if args.head_steps >= 0:
         head_line = run_head_step(args, rank, world, barrier, native)
 
-    full_line = full16_line = None
+    full_line = full16_line = full5_line = None
     if args.full_steps >= 0:
         full_line = run_full_step(args, rank, world, barrier, native)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        full5_line = run_full_step(args, rank, world, barrier, native, n_images=1, config5=True)
         if world == 1:   # BASELINE.json configs[2]: the same step at bs = 16 on one GPU
             import gc
             gc.collect()
@@ -504,6 +523,9 @@ def main():
     if full16_line:
         line["full_step_bs16"] = full16_line
         line["gpu_launches"] += full16_line["gpu_launches"]
+    if full5_line:
+        line["full_step_config5"] = full5_line
+        line["gpu_launches"] += full5_line["gpu_launches"]
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_oracle
         sample = host  # the full configs[1] batch; passes are repeated until >= 10 core-seconds of CPU work were timed

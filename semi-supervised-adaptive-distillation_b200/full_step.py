@@ -48,16 +48,16 @@ class _ConvAffine(torch.autograd.Function):
     dW = dW_folded * s."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, bias, z, stride, padding, relu):
+    def forward(ctx, x, w, scale, bias, z, stride, padding, relu, groups=1):
         w_eff = w if scale is None else w * scale.view(-1, 1, 1, 1)
         s, p, d = (stride, stride), (padding, padding), (1, 1)
         if z is not None:
-            out = torch.cudnn_convolution_add_relu(x, w_eff, z, 1.0, bias, s, p, d, 1)
+            out = torch.cudnn_convolution_add_relu(x, w_eff, z, 1.0, bias, s, p, d, groups)
         elif relu:
-            out = torch.cudnn_convolution_relu(x, w_eff, bias, s, p, d, 1)
+            out = torch.cudnn_convolution_relu(x, w_eff, bias, s, p, d, groups)
         else:
-            out = F.conv2d(x, w_eff, bias, stride, padding)
-        ctx.conv = (s, p, d)
+            out = F.conv2d(x, w_eff, bias, stride, padding, 1, groups)
+        ctx.conv = (s, p, d, groups)
         ctx.masked = relu or z is not None
         ctx.has_z = z is not None
         ctx.save_for_backward(x, w_eff, scale, out if ctx.masked else None)
@@ -66,14 +66,14 @@ class _ConvAffine(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w_eff, scale, out = ctx.saved_tensors
-        s, p, d = ctx.conv
+        s, p, d, groups = ctx.conv
         g = torch.ops.aten.threshold_backward(dy, out, 0) if ctx.masked else dy
-        dx, dw, _ = torch.ops.aten.convolution_backward(g, x, w_eff, None, s, p, d, False, [0, 0], 1,
+        dx, dw, _ = torch.ops.aten.convolution_backward(g, x, w_eff, None, s, p, d, False, [0, 0], groups,
                                                         [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         if dw is not None and scale is not None:
             dw = dw * scale.view(-1, 1, 1, 1)
         dz = g if (ctx.has_z and ctx.needs_input_grad[4]) else None
-        return dx, dw, None, None, dz, None, None, None
+        return dx, dw, None, None, dz, None, None, None, None
 
 
 def conv_affine(conv, aff, x, z=None, relu=True):
@@ -85,19 +85,21 @@ def conv_affine(conv, aff, x, z=None, relu=True):
             with torch.no_grad():
                 folded = (conv.weight * aff.scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
             conv._folded = folded
-        return _ConvAffine.apply(x, folded, None, aff.bias.view(-1), z, stride, padding, relu)
-    return _ConvAffine.apply(x, conv.weight, aff.scale, aff.bias.view(-1), z, stride, padding, relu)
+        return _ConvAffine.apply(x, folded, None, aff.bias.view(-1), z, stride, padding, relu, conv.groups)
+    return _ConvAffine.apply(x, conv.weight, aff.scale, aff.bias.view(-1), z, stride, padding, relu, conv.groups)
 
 
 class Bottleneck(nn.Module):
-    def __init__(self, cin, cout, cmid, stride, groups=1):
+    def __init__(self, cin, cout, cmid, stride, groups=1, stride_1x1=True):
         super().__init__()
-        # stride on the first 1x1 (RESNETS.STRIDE_1X1 = True for the R-50 / R-101 configs)
-        self.c1, self.a1 = nn.Conv2d(cin, cmid, 1, stride=stride, bias=False), AffineChannel(cmid)
-        self.c2, self.a2 = nn.Conv2d(cmid, cmid, 3, padding=1, groups=groups, bias=False), AffineChannel(cmid)
+        # stride on the first 1x1 (RESNETS.STRIDE_1X1 = True for the R-50 / R-101 configs) or on the 3x3 (False: the ResNeXt
+        # teacher, configs/focal_distillation/retinanet_X-101-64x4d-FPN_1x_teacher.yaml:20-24; ResNet.py:236-278)
+        s1, s3 = (stride, 1) if stride_1x1 else (1, stride)
+        self.c1, self.a1 = nn.Conv2d(cin, cmid, 1, stride=s1, bias=False), AffineChannel(cmid)
+        self.c2, self.a2 = nn.Conv2d(cmid, cmid, 3, stride=s3, padding=1, groups=groups, bias=False), AffineChannel(cmid)
         self.c3, self.a3 = nn.Conv2d(cmid, cout, 1, bias=False), AffineChannel(cout)
         self.short = None
-        self.fused = groups == 1
+        self.fused = True
         if cin != cout or stride != 1:
             self.short = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), AffineChannel(cout))
 
@@ -116,16 +118,18 @@ class Bottleneck(nn.Module):
 class ResNetFPN(nn.Module):
     """C3..C5 -> P3..P7 (FPN.DIM = 256; P6, P7 by stride-2 3x3 convolutions: FPN.EXTRA_CONV_LEVELS, FPN.py:199-219)."""
 
-    def __init__(self, blocks=(3, 4, 6, 3), dim=256, fused=True):
+    def __init__(self, blocks=(3, 4, 6, 3), dim=256, fused=True, groups=1, width_per_group=64, stride_1x1=True):
+        """groups / width_per_group: RESNETS.NUM_GROUPS / WIDTH_PER_GROUP (1 / 64 = ResNet, 64 / 4 = ResNeXt-101-64x4d: the
+        bottleneck width is groups * width_per_group * 2^stage, ResNet.py:94-97)."""
         super().__init__()
         self.fused = fused
         self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), AffineChannel(64), nn.ReLU(inplace=True),
                                   nn.MaxPool2d(3, stride=2, padding=1))
         stages, cin = [], 64
         for i, n in enumerate(blocks):
-            cout, cmid = 256 * 2 ** i, 64 * 2 ** i
-            stages.append(nn.Sequential(*[Bottleneck(cin if j == 0 else cout, cout, cmid, (1 if i == 0 else 2) if j == 0 else 1)
-                                          for j in range(n)]))
+            cout, cmid = 256 * 2 ** i, groups * width_per_group * 2 ** i
+            stages.append(nn.Sequential(*[Bottleneck(cin if j == 0 else cout, cout, cmid, (1 if i == 0 else 2) if j == 0 else 1,
+                                                     groups=groups, stride_1x1=stride_1x1) for j in range(n)]))
             cin = cout
         self.res2, self.res3, self.res4, self.res5 = stages
         self.lat = nn.ModuleList([nn.Conv2d(c, dim, 1) for c in (512, 1024, 2048)])
@@ -158,7 +162,9 @@ class ResNetFPN(nn.Module):
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
                  temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4,
-                 fused_body=True, overlap_teacher=True):
+                 fused_body=True, overlap_teacher=True, teacher_body=None):
+        """teacher_body: extra ResNetFPN arguments of the teacher, e.g. dict(groups=64, width_per_group=4, stride_1x1=False)
+        for the ResNeXt-101-64x4d teacher of BASELINE.json configs[4]."""
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world, self.rank, self.images = int(world), int(rank), int(n_images)
         self.overlap_teacher = bool(overlap_teacher)
@@ -170,7 +176,7 @@ class FullDistillStep:
         torch.backends.cudnn.benchmark = True
         torch.manual_seed(seed)                         # same weights on every rank
         self.student = ResNetFPN(student_blocks, fused=fused_body).to(self.device).to(memory_format=torch.channels_last)
-        self.teacher = ResNetFPN(teacher_blocks, fused=fused_body).to(self.device).to(memory_format=torch.channels_last).eval()
+        self.teacher = ResNetFPN(teacher_blocks, fused=fused_body, **(teacher_body or {})).to(self.device).to(memory_format=torch.channels_last).eval()
         for p in self.teacher.parameters():
             p.requires_grad_(False)
         # ONE flat parameter buffer and ONE flat gradient buffer laid out [head weights | head biases | body weights | body biases]:

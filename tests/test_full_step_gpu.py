@@ -25,11 +25,12 @@ def _randomise_affine(net, seed):
             m.bias.copy_(0.2 * torch.randn(m.bias.shape, device="cuda", generator=g))
 
 
-def test_fused_body_matches_module_graph(fp32_cudnn):
+@pytest.mark.parametrize("body", [dict(), dict(groups=8, width_per_group=4, stride_1x1=False)], ids=["resnet", "resnext"])
+def test_fused_body_matches_module_graph(fp32_cudnn, body):
     from sad_b200.full_step import ResNetFPN
     torch.manual_seed(3)
-    plain = ResNetFPN((1, 2, 1, 1), fused=False).cuda().to(memory_format=torch.channels_last)
-    fused = ResNetFPN((1, 2, 1, 1), fused=True).cuda().to(memory_format=torch.channels_last)
+    plain = ResNetFPN((1, 2, 1, 1), fused=False, **body).cuda().to(memory_format=torch.channels_last)
+    fused = ResNetFPN((1, 2, 1, 1), fused=True, **body).cuda().to(memory_format=torch.channels_last)
     fused.load_state_dict(plain.state_dict())
     _randomise_affine(plain, 5)
     fused.load_state_dict(plain.state_dict())
@@ -41,13 +42,17 @@ def test_fused_body_matches_module_graph(fp32_cudnn):
     torch.cuda.synchronize()
     for a, b in zip(outs_p, outs_f):
         assert a.shape == b.shape
-        assert float((a - b).abs().max()) <= 2e-4 * float(a.abs().max())
+        assert float((a - b).detach().abs().max()) <= 2e-4 * float(a.detach().abs().max())
     n_grads = 0
     for (name, p), (_, q) in zip(plain.named_parameters(), fused.named_parameters()):
         assert (p.grad is None) == (q.grad is None), name
         if p.grad is not None:
             n_grads += 1
-            assert float((p.grad - q.grad).abs().max()) <= 5e-4 * float(p.grad.abs().max()) + 1e-7, name
+            # conv(x, w * s) + b and conv(x, w) * s + b differ in the last bits, so a pre-activation within round-off of zero can
+            # fall on the other side of the ReLU in the two graphs: single gradient entries may move (max gate), the tensor not (L2 gate)
+            diff = (p.grad - q.grad).double()
+            assert float(diff.abs().max()) <= 1e-2 * float(p.grad.abs().max()) + 1e-7, name
+            assert float(diff.norm()) <= 2e-3 * float(p.grad.double().norm()) + 1e-9, name
     assert n_grads > 20
     # frozen below res3 (TRAIN.FREEZE_AT = 2) in both forms
     assert all(p.grad is None for p in fused.res2.parameters()) and all(p.grad is None for p in fused.stem.parameters())
