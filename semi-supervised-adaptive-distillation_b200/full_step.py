@@ -45,11 +45,15 @@ class _ConvAffine(torch.autograd.Function):
     (cudnnConvolutionBiasActivationForward).  Unfused, every convolution of the bodies is followed by 2-3 elementwise
     passes over its output, which cost more than the convolutions themselves (measured: 4.7 of 13.5 ms at bs = 2).
     Backward: ReluGradient from the saved output (one pass), cuDNN data / weight gradients of the folded convolution,
-    dW = dW_folded * s."""
+    dW = dW_folded * s.  `prefolded`: w * s computed by the caller for every convolution at once (FullDistillStep: one
+    multi-tensor launch per step instead of one per convolution); the weight gradient then comes back UNSCALED and the
+    caller multiplies the whole gradient buffer by s once after the backward pass."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, bias, z, stride, padding, relu, groups=1):
-        w_eff = w if scale is None else w * scale.view(-1, 1, 1, 1)
+    def forward(ctx, x, w, scale, bias, z, stride, padding, relu, groups=1, prefolded=None):
+        w_eff = prefolded if prefolded is not None else (w if scale is None else w * scale.view(-1, 1, 1, 1))
+        if prefolded is not None:
+            scale = None
         s, p, d = (stride, stride), (padding, padding), (1, 1)
         if z is not None:
             out = torch.cudnn_convolution_add_relu(x, w_eff, z, 1.0, bias, s, p, d, groups)
@@ -73,7 +77,7 @@ class _ConvAffine(torch.autograd.Function):
         if dw is not None and scale is not None:
             dw = dw * scale.view(-1, 1, 1, 1)
         dz = g if (ctx.has_z and ctx.needs_input_grad[4]) else None
-        return dx, dw, None, None, dz, None, None, None, None
+        return dx, dw, None, None, dz, None, None, None, None, None
 
 
 def conv_affine(conv, aff, x, z=None, relu=True):
@@ -86,7 +90,8 @@ def conv_affine(conv, aff, x, z=None, relu=True):
                 folded = (conv.weight * aff.scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
             conv._folded = folded
         return _ConvAffine.apply(x, folded, None, aff.bias.view(-1), z, stride, padding, relu, conv.groups)
-    return _ConvAffine.apply(x, conv.weight, aff.scale, aff.bias.view(-1), z, stride, padding, relu, conv.groups)
+    return _ConvAffine.apply(x, conv.weight, aff.scale, aff.bias.view(-1), z, stride, padding, relu, conv.groups,
+                             getattr(conv, "_prefolded", None))
 
 
 class Bottleneck(nn.Module):
@@ -196,10 +201,25 @@ class FullDistillStep:
         off = n_head
         for p in self.body_params:
             k = p.numel()
-            self.flat_params[off:off + k].copy_(p.detach().reshape(-1))
-            p.data = self.flat_params[off:off + k].view(p.shape)
-            p.grad = self.flat_grads[off:off + k].view(p.shape)
+            if p.dim() == 4:   # stored channels-last inside the flat buffers: cuDNN takes the views as they are (no per-step copies)
+                co, ci, kh, kw = p.shape
+                view = lambda flat: flat[off:off + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                view = lambda flat: flat[off:off + k].view(p.shape)
+            view(self.flat_params).copy_(p.detach())
+            p.data = view(self.flat_params)
+            p.grad = view(self.flat_grads)
             off += k
+        # AffineChannel folding of every trainable fused convolution in ONE multi-tensor launch per step (see _ConvAffine)
+        self._fold = []
+        if fused_body:
+            for m in self.student.modules():
+                if isinstance(m, Bottleneck) and m.fused:
+                    pairs = [(m.c1, m.a1), (m.c2, m.a2), (m.c3, m.a3)] + ([(m.short[0], m.short[1])] if m.short is not None else [])
+                    self._fold += [(c, a) for c, a in pairs if c.weight.requires_grad]
+        self._fold_w = [c.weight.detach() for c, _ in self._fold]
+        self._fold_g = [c.weight.grad for c, _ in self._fold]
+        self.refold()
         self.n_head, self.n_body = n_head, n_body
         self.exchange = parallel.GradientExchange(self.flat_grads, world=self.world)
         self.momentum = torch.zeros_like(self.flat_params)
@@ -241,6 +261,15 @@ class FullDistillStep:
                                     num_classes=synthetic.NUM_CLASSES, ignored_label=-1)
         self.last = {}
 
+    def refold(self):
+        """(Re)build what depends on the frozen AffineChannel values: the per-weight expanded scales of the student and the
+        folded weights of the frozen convolutions.  Call after loading AffineChannel parameters."""
+        self._fold_s = [torch.empty_like(w).copy_(a.scale.view(-1, 1, 1, 1).expand_as(w)) for w, (_, a) in zip(self._fold_w, self._fold)]
+        for net in (self.student, self.teacher):
+            for m in net.modules():
+                if isinstance(m, nn.Conv2d) and hasattr(m, "_folded"):
+                    del m._folded
+
     def forward_backward(self):
         # The teacher does not depend on the student until the distillation loss: it runs on its own stream beside the
         # student's forward pass (at bs = 2 the res4 / res5 convolutions of either body fill well under 148 SMs on their own).
@@ -253,6 +282,10 @@ class FullDistillStep:
             # teacher/retnet_cls_prob_fpnL: the Sigmoid of retinanet_heads.py:153-163 runs in the prediction convolution's epilogue
             self.teacher_head.forward(t_fpn, training=False, out=(self.t_prob, self.t_box))
         self.flat_grads[self.n_head:].zero_()
+        if self._fold:
+            with torch.no_grad():
+                for (conv, _), w_eff in zip(self._fold, torch._foreach_mul(self._fold_w, self._fold_s)):
+                    conv._prefolded = w_eff
         fpn = self.student(self.images_t)                                # PyTorch graph ends here ...
         fpn_c = [f.detach().contiguous() for f in fpn]
         L = len(self.cls)
@@ -271,6 +304,8 @@ class FullDistillStep:
                                       workspace=self.box_ws[l], loss_out=self.box_losses[l], grad_out=self.d_box[l])
         d_fpn = self.head.backward(self.plan.grads, self.d_box, want_d_fpn=True, d_fpn=self.d_fpn)
         torch.autograd.backward(fpn, d_fpn)                              # ... and resumes here: FPN and ResNet body backward
+        if self._fold:
+            torch._foreach_mul_(self._fold_g, self._fold_s)              # dW = dW_folded * s, deferred from _ConvAffine.backward
         self.last = {"bbox": self.box_losses, "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
                      "normalizer": self.plan.normalizer}
 
