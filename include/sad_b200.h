@@ -243,6 +243,21 @@ int sad_relu_grad_f32(const float* y, const float* dy, float* dx, int64_t n, voi
  * retnet_cls_pred_fpnL -> retnet_cls_prob_fpnL (retinanet_heads.py:153-163) as a stand-alone operator. */
 int sad_sigmoid_f32(const float* x, float* y, int64_t n, void* stream);
 
+/* AffineChannel / AffineChannelGradient — replace AffineChannelOp / AffineChannelGradientOp<float, CUDAContext>::RunOnDevice
+ * (caffe2/modules/detectron/affine_channel_op.cu:52-98; kernels :22-48): the frozen batch-norm of every ResNet / FPN body
+ * convolution (detectron/lib/modeling/ResNet.py:219-278).  x: (N, C, H, W) viewed as N*C rows of HW elements;
+ * y = x * scale[c] + bias[c] (one fused multiply-add, as the reference's expression compiles).  bias == NULL is the gradient
+ * form dx = dy * scale[c] (x = dy, y = dx).  In place allowed (schema AllowInplace, affine_channel_op.cc:29,56). */
+int sad_affine_channel_f32(const float* x, const float* scale, const float* bias /* or NULL */, float* y, int N, int C, int64_t HW,
+                           void* stream);
+/* UpsampleNearest / UpsampleNearestGradient — replace UpsampleNearestOp / UpsampleNearestGradientOp<float, CUDAContext>::
+ * RunOnDevice (caffe2/modules/detectron/upsample_nearest_op.cu:116-158, 162-211; kernels :62-113): FPN's top-down path
+ * (detectron/lib/modeling/FPN.py:230-249).  x: (outer, H, W) with outer = product of the leading dimensions (N*C for 4-D,
+ * C for 3-D tensors); y: (outer, H*scale, W*scale), y[o][Y][X] = x[o][Y/scale][X/scale].  The gradient sums each
+ * scale x scale block of dy in the reference's order (x offset outer, y offset inner) and is therefore bit-identical to it. */
+int sad_upsample_nearest_f32(const float* x, float* y, int64_t outer, int H, int W, int scale, void* stream);
+int sad_upsample_nearest_grad_f32(const float* dy, float* dx, int64_t outer, int H, int W, int scale, void* stream);
+
 /* Weight and bias gradient — replaces the filter/bias half of CudnnConvGradientOp::DoRunWithType
  *   (caffe2/caffe2/operators/conv_op_cudnn.cc:1011-1040: cudnnConvolutionBackwardBias / BackwardFilter)
  * and the autograd Sum over the FPN levels that share the weight (caffe2/caffe2/python/core.py:695,706-842):

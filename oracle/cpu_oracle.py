@@ -70,6 +70,12 @@ def lib():
         l.oracle_select_smooth_l1_grad.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p, _f32p]
         l.oracle_momentum_sgd.restype = None
         l.oracle_momentum_sgd.argtypes = [C.c_int64, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float]
+        l.oracle_affine_channel.restype = None
+        l.oracle_affine_channel.argtypes = [C.c_int64, C.c_int, C.c_int64, _f32p, _f32p, C.c_void_p, _f32p]
+        l.oracle_upsample_nearest.restype = None
+        l.oracle_upsample_nearest.argtypes = [_f32p, _f32p, C.c_int64] + [C.c_int] * 4
+        l.oracle_upsample_nearest_grad.restype = None
+        l.oracle_upsample_nearest_grad.argtypes = [_f32p, _f32p, C.c_int64] + [C.c_int] * 4
         l.oracle_focal_grad.restype = None
         l.oracle_focal_grad.argtypes = [C.c_int] * 4 + [_f32p, _i32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, _f32p, _f32p]
         _lib = l
@@ -223,3 +229,35 @@ def relu_grad(Y, dY):
     dX = np.empty_like(Y)
     lib().oracle_relu_grad(Y.reshape(-1), dY.reshape(-1), dX.reshape(-1), Y.size)
     return dX
+
+
+def affine_channel(x, scale, bias=None):
+    """AffineChannel (bias given) / AffineChannelGradient (bias None) — affine_channel_op.cu:22-48."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    scale = np.ascontiguousarray(scale, dtype=np.float32)
+    N, Cc, H, W = x.shape
+    out = np.empty_like(x)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    lib().oracle_affine_channel(x.size, Cc, H * W, x.reshape(-1), scale, None if b is None else b.ctypes.data, out.reshape(-1))
+    return out
+
+
+def _d123(shape):
+    """(d1, d2, d3) as upsample_nearest_op.cu:129-138 takes them from a 3-D or 4-D shape."""
+    return tuple(shape[-3:])
+
+
+def upsample_nearest(x, scale=2):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.shape[:-2] + (x.shape[-2] * scale, x.shape[-1] * scale), dtype=np.float32)
+    d1, d2, d3 = _d123(out.shape)
+    lib().oracle_upsample_nearest(x.reshape(-1), out.reshape(-1), out.size, scale, d1, d2, d3)
+    return out
+
+
+def upsample_nearest_grad(x_shape, dy, scale=2):
+    dy = np.ascontiguousarray(dy, dtype=np.float32)
+    dx = np.empty(tuple(x_shape), dtype=np.float32)
+    d1, d2, d3 = _d123(dx.shape)
+    lib().oracle_upsample_nearest_grad(dx.reshape(-1), dy.reshape(-1), dx.size, scale, d1, d2, d3)
+    return dx

@@ -85,6 +85,17 @@ class EnforceNotMet : public std::exception {
 #define CAFFE_ENFORCE_GE(x, y, ...) CAFFE_ENFORCE_BINARY_OP_(>=, x, y, __VA_ARGS__)
 #define CAFFE_ENFORCE_GT(x, y, ...) CAFFE_ENFORCE_BINARY_OP_(>, x, y, __VA_ARGS__)
 
+// glog's debug-only checks (caffe2/caffe2/core/logging_is_not_google_glog.h:121-146): compiled out in release builds,
+// which is how Detectron's operators are built; the operands are not evaluated.
+#define SAD_SHIM_DCHECK_(x, y) \
+  while (false) (void)((x), (y))
+#define DCHECK_EQ(x, y) SAD_SHIM_DCHECK_(x, y)
+#define DCHECK_NE(x, y) SAD_SHIM_DCHECK_(x, y)
+#define DCHECK_LE(x, y) SAD_SHIM_DCHECK_(x, y)
+#define DCHECK_LT(x, y) SAD_SHIM_DCHECK_(x, y)
+#define DCHECK_GE(x, y) SAD_SHIM_DCHECK_(x, y)
+#define DCHECK_GT(x, y) SAD_SHIM_DCHECK_(x, y)
+
 // CUDA_ENFORCE lives in common_gpu.h
 }  // namespace caffe2
 #endif

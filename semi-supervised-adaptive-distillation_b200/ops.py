@@ -393,3 +393,57 @@ def conv3x3_wgrad(xs_nhwc, dys_nhwc, want_bias=True, accumulate_into=None, works
                                       1 if accumulate_into is not None else 0,
                                       C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
     return dw, db
+
+
+def affine_channel(x, scale, bias, out=None):
+    """AffineChannel (affine_channel_op.cu:52-75): y = x * scale[c] + bias[c] over (N, C, H, W); out may be x (in place)."""
+    _require_cuda(x, torch.float32, "x")
+    _require_cuda(scale, torch.float32, "scale")
+    _require_cuda(bias, torch.float32, "bias")
+    if x.dim() != 4 or scale.numel() != x.shape[1] or bias.numel() != x.shape[1]:
+        raise ValueError("x must be (N, C, H, W) and scale / bias must have C elements")
+    y = torch.empty_like(x) if out is None else out
+    check(lib().sad_affine_channel_f32(C.c_void_p(x.data_ptr()), C.c_void_p(scale.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                       C.c_void_p(y.data_ptr()), x.shape[0], x.shape[1], x.shape[2] * x.shape[3], _stream()))
+    return y
+
+
+def affine_channel_grad(scale, dy, out=None):
+    """AffineChannelGradient (affine_channel_op.cu:77-98): dx = dy * scale[c]; out may be dy (in place)."""
+    _require_cuda(dy, torch.float32, "dy")
+    _require_cuda(scale, torch.float32, "scale")
+    if dy.dim() != 4 or scale.numel() != dy.shape[1]:
+        raise ValueError("dy must be (N, C, H, W) and scale must have C elements")
+    dx = torch.empty_like(dy) if out is None else out
+    check(lib().sad_affine_channel_f32(C.c_void_p(dy.data_ptr()), C.c_void_p(scale.data_ptr()), None, C.c_void_p(dx.data_ptr()),
+                                       dy.shape[0], dy.shape[1], dy.shape[2] * dy.shape[3], _stream()))
+    return dx
+
+
+def _outer_hw(t):
+    if t.dim() not in (3, 4):
+        raise ValueError("UpsampleNearest takes a 3-D or 4-D tensor")
+    outer = 1
+    for d in t.shape[:-2]:
+        outer *= d
+    return outer, t.shape[-2], t.shape[-1]
+
+
+def upsample_nearest(x, scale=2):
+    """UpsampleNearest (upsample_nearest_op.cu:116-158): nearest-neighbour upsampling of the last two dimensions."""
+    _require_cuda(x, torch.float32, "x")
+    outer, h, w = _outer_hw(x)
+    y = torch.empty(tuple(x.shape[:-2]) + (h * scale, w * scale), dtype=torch.float32, device=x.device)
+    check(lib().sad_upsample_nearest_f32(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), outer, h, w, int(scale), _stream()))
+    return y
+
+
+def upsample_nearest_grad(x, dy, scale=2):
+    """UpsampleNearestGradient (upsample_nearest_op.cu:162-211): dx like x, each element the sum of its scale x scale block of dy."""
+    _require_cuda(dy, torch.float32, "dy")
+    outer, h, w = _outer_hw(x)
+    if dy.numel() != x.numel() * scale * scale:
+        raise ValueError("dy must be the upsampled shape of x")
+    dx = torch.empty(tuple(x.shape), dtype=torch.float32, device=dy.device)
+    check(lib().sad_upsample_nearest_grad_f32(C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()), outer, h, w, int(scale), _stream()))
+    return dx
