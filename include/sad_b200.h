@@ -243,6 +243,11 @@ int sad_relu_grad_f32(const float* y, const float* dy, float* dx, int64_t n, voi
  * retnet_cls_pred_fpnL -> retnet_cls_prob_fpnL (retinanet_heads.py:153-163) as a stand-alone operator. */
 int sad_sigmoid_f32(const float* x, float* y, int64_t n, void* stream);
 
+/* Scale (caffe2/caffe2/operators/scale_op.h:31-50, math::Scale caffe2/caffe2/utils/math_gpu.cu:1293-1302): y = x * alpha, in place
+ * allowed.  The momentum correction of a learning-rate change (detectron/lib/modeling/detector.py:628-648) over the flat
+ * momentum buffer in one launch. */
+int sad_scale_f32(const float* x, float* y, int64_t n, float alpha, void* stream);
+
 /* AffineChannel / AffineChannelGradient — replace AffineChannelOp / AffineChannelGradientOp<float, CUDAContext>::RunOnDevice
  * (caffe2/modules/detectron/affine_channel_op.cu:52-98; kernels :22-48): the frozen batch-norm of every ResNet / FPN body
  * convolution (detectron/lib/modeling/ResNet.py:219-278).  x: (N, C, H, W) viewed as N*C rows of HW elements;

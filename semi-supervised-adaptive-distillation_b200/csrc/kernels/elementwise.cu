@@ -68,6 +68,25 @@ __global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ 
   }
 }
 
+// Scale (caffe2/caffe2/operators/scale_op.h:31-50 -> math::Scale, caffe2/caffe2/utils/math_gpu.cu:1264-1302: y = x * alpha): what
+// _CorrectMomentum runs over every `<param>_momentum` blob when the learning rate changes (detectron/lib/modeling/detector.py:
+// 628-648); over the flat momentum buffer it is one launch instead of one per parameter.  8 B/element, HBM-bound.
+__global__ void __launch_bounds__(256) scale_kernel(const float* x, float* y, float alpha, size_t n, int vec) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const size_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 v = x4[i];
+      y4[i] = make_float4(v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha);
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) y[i] = x[i] * alpha;
+  } else {
+    for (size_t i = tid; i < n; i += stride) y[i] = x[i] * alpha;
+  }
+}
+
 static unsigned ew_grid(size_t n) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -98,6 +117,15 @@ SAD_EXPORT int sad_sigmoid_f32(const float* x, float* y, int64_t n, void* stream
   sigmoid_kernel<<<ew_grid((size_t)n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, (size_t)n, vec);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "sigmoid launch");
+}
+
+SAD_EXPORT int sad_scale_f32(const float* x, float* y, int64_t n, float alpha, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !y))) return set_error(SAD_ERR_INVALID, "scale: bad argument");
+  if (n == 0) return SAD_OK;
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  scale_kernel<<<ew_grid((size_t)n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, alpha, (size_t)n, vec);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "scale launch");
 }
 
 SAD_EXPORT int sad_relu_grad_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream) {

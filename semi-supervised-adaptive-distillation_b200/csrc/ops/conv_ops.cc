@@ -245,7 +245,29 @@ bool HeadReluGradientOp<float, CUDAContext>::RunOnDevice() {
   return true;
 }
 
+// Scale (caffe2/caffe2/operators/scale_op.h:31-50): the operator _CorrectMomentum creates per momentum blob (detector.py:643-647)
+template <typename T, class Context>
+class HeadScaleOp final : public Operator<Context> {
+ public:
+  HeadScaleOp(const OperatorDef& def, Workspace* ws)
+      : Operator<Context>(def, ws), scale_(OperatorBase::GetSingleArgument<float>("scale", 1.0f)) {}
+  USE_OPERATOR_CONTEXT_FUNCTIONS;
+  bool RunOnDevice() override { CAFFE_NOT_IMPLEMENTED; }
+
+ protected:
+  float scale_;
+};
+template <>
+bool HeadScaleOp<float, CUDAContext>::RunOnDevice() {
+  const auto& X = Input(0);
+  auto* Y = Output(0);
+  Y->ResizeLike(X);
+  EnforceSadConv(sad_scale_f32(X.data<float>(), Y->mutable_data<float>(), X.size(), scale_, context_.cuda_stream()), "sad_scale_f32");
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
+REGISTER_CUDA_OPERATOR(Scale, HeadScaleOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(Conv, HeadConvOp<float, CUDAContext>);
 REGISTER_CUDA_OPERATOR(ConvGradient, HeadConvGradientOp<float, CUDAContext>);
 REGISTER_CUDNN_OPERATOR(Conv, HeadConvOp<float, CUDAContext>);                  // conv_op_cudnn.cc:1130-1131
@@ -266,6 +288,7 @@ OPERATOR_SCHEMA(Conv)
 OPERATOR_SCHEMA(ConvGradient).NumInputs(2, 3).NumOutputs(1, 3);
 OPERATOR_SCHEMA(Relu).NumInputs(1).NumOutputs(1).AllowInplace({{0, 0}}).IdenticalTypeAndShape();
 OPERATOR_SCHEMA(ReluGradient).NumInputs(2).NumOutputs(1).AllowInplace({{1, 0}});
+OPERATOR_SCHEMA(Scale).NumInputs(1).NumOutputs(1).AllowInplace({{0, 0}}).IdenticalTypeAndShape().Arg("scale", "(float, default 1.0)");  // scale_op.cc
 OPERATOR_SCHEMA(Sigmoid).NumInputs(1).NumOutputs(1).AllowInplace({{0, 0}}).IdenticalTypeAndShape();  // sigmoid_op.cc
 
 // caffe2/caffe2/operators/conv_gradient_op.cc:35-77
@@ -299,5 +322,14 @@ class GetReluGradient : public GradientMakerBase {
   }
 };
 REGISTER_GRADIENT(Relu, GetReluGradient);
+
+// caffe2/caffe2/operators/scale_op.cc:33-41: the gradient of Scale is Scale with the copied argument
+class GetScaleGradient : public GradientMakerBase {
+  using GradientMakerBase::GradientMakerBase;
+  vector<OperatorDef> GetGradientDefs() override {
+    return SingleGradientDef("Scale", "", vector<string>{GO(0)}, vector<string>{GI(0)});
+  }
+};
+REGISTER_GRADIENT(Scale, GetScaleGradient);
 
 }  // namespace caffe2

@@ -97,6 +97,18 @@ class RetinaNetHead:
         t.bbox_pred_w, t.bbox_pred_b = d["retnet_bbox_pred_fpn3_w"].data_ptr(), d["retnet_bbox_pred_fpn3_b"].data_ptr()
         return t
 
+    def views(self, flat_buffer):
+        """{blob name: view} over another flat buffer laid out like flat_params (e.g. the momentum buffer: the reference's
+        `<name>_momentum` blobs, optimizer.py:103-107) — what weights_io loads and saves by name."""
+        if flat_buffer.numel() != self.flat_params.numel():
+            raise ValueError("flat buffer must have %d elements" % self.flat_params.numel())
+        out, off = {}, 0
+        for n in self.names:
+            k = math.prod(self.shapes[n])
+            out[n] = flat_buffer[off:off + k].view(self.shapes[n])
+            off += k
+        return out
+
     def sgd_segments(self, weight_decay):
         """[(count, gradient multiplier, weight decay)] of the flat buffers for ops.momentum_sgd (optimizer.py:115-124)."""
         return [(self.n_weights, 1.0, weight_decay), (self.flat_params.numel() - self.n_weights, 2.0, 0.0)]

@@ -147,6 +147,7 @@ def lib():
         l.sad_relu_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.sad_sigmoid_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.sad_relu_grad_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        l.sad_scale_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
         l.sad_affine_channel_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
         l.sad_upsample_nearest_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.sad_upsample_nearest_grad_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]

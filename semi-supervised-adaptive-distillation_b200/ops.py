@@ -447,3 +447,10 @@ def upsample_nearest_grad(x, dy, scale=2):
     dx = torch.empty(tuple(x.shape), dtype=torch.float32, device=dy.device)
     check(lib().sad_upsample_nearest_grad_f32(C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()), outer, h, w, int(scale), _stream()))
     return dx
+
+
+def scale_(x, alpha):
+    """Scale in place (scale_op.h:31-50): x *= alpha — the momentum correction of a learning-rate change (detector.py:628-648)."""
+    _require_cuda(x, torch.float32, "x")
+    check(lib().sad_scale_f32(C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), x.numel(), float(alpha), _stream()))
+    return x

@@ -107,3 +107,36 @@ def test_body_ops_reject_bad_arguments():
         ops.upsample_nearest(x, 0)
     with pytest.raises(ValueError):
         ops.affine_channel(x, torch.ones(3, device="cuda"), torch.ones(3, device="cuda"))
+
+
+def test_scale_and_learning_rate_update_with_momentum_correction():
+    """Scale (scale_op.h:31-50) bit-exact against the product x * alpha, and UpdateWorkspaceLr (detector.py:598-648) over the
+    device `lr` blob and a flat momentum buffer: no correction during warm-up-sized changes, one Scale launch per decay step."""
+    from sad_b200 import c2, ops, solver
+    x = torch.randn(100003, device="cuda")
+    want = x * 0.1
+    y = ops.scale_(x.clone(), 0.1)
+    assert torch.equal(y, want)
+    view = x[1:].clone()          # unaligned start: scalar path
+    assert torch.equal(ops.scale_(x[1:], 0.1), view * 0.1)
+    # the operator _CorrectMomentum creates (detector.py:643-647), in place on a momentum blob
+    lib = c2.OperatorLibrary()
+    ws = lib.Workspace()
+    m = torch.randn(4, 4, 3, 3, device="cuda")
+    ws.FeedBlob("w_momentum", m.clone())
+    ws.RunOperatorOnce(c2.CreateOperator("Scale", ["w_momentum"], ["w_momentum"], device_option=c2.DeviceOption(c2.CUDA, 0), scale=0.1))
+    assert np.array_equal(np.asarray(ws.FetchBlob("w_momentum")), (m * 0.1).cpu().numpy())
+
+    cfg = solver.SolverConfig(BASE_LR=0.01, LR_POLICY="steps_with_decay", STEPS=[0, 20, 30], MAX_ITER=40, WARM_UP_ITERS=10)
+    lr_blob = torch.zeros((), device="cuda")                 # optimizer.py:58-60: the lr blob starts at 0
+    mom = torch.ones(1000, device="cuda")
+    lr = solver.LearningRate(cfg, lr_blob, [mom])
+    for it in range(40):
+        new = lr.update(it)
+        assert np.float32(lr_blob.item()) == new == solver.get_lr_at_iter(cfg, it)
+    assert lr.corrections == 2
+    # 0.01 -> 0.001 -> 0.0001 in float32: the buffer was multiplied by new/old twice
+    f = np.float32(1.0)
+    for a, b in ((solver.get_lr_at_iter(cfg, 19), solver.get_lr_at_iter(cfg, 20)), (solver.get_lr_at_iter(cfg, 29), solver.get_lr_at_iter(cfg, 30))):
+        f = np.float32(f * np.float32(b / a))
+    assert torch.all(mom == float(f))
