@@ -26,10 +26,11 @@ logger = logging.getLogger(__name__)
 
 
 def unscope_name(name):
-    """utils/c2.py:95-102: 'gpu_0/foo' -> 'foo'; names that do not start with 'gpu' pass through ('teacher/foo' stays)."""
+    """utils/c2.py:95-102: 'gpu_0/foo' -> 'foo'.  This fork cuts at the FIRST separator (stock Detectron: the last) and passes names
+    that do not start with 'gpu' through, so 'gpu_0/teacher/foo' -> 'teacher/foo' and 'teacher/foo' stays."""
     if name[:3] != "gpu":
         return name
-    return name[name.rfind("/") + 1:]
+    return name[name.find("/") + 1:]
 
 
 def load_blobs(weights_file):

@@ -75,7 +75,7 @@ def _params():
 
 def test_unscope_name():
     assert W.unscope_name("gpu_0/conv1_w") == "conv1_w"
-    assert W.unscope_name("gpu_3/teacher/conv1_w") == "conv1_w"   # utils/c2.py:95-102 takes everything after the LAST slash
+    assert W.unscope_name("gpu_3/teacher/conv1_w") == "teacher/conv1_w"   # utils/c2.py:101-102: cut at the FIRST separator
     assert W.unscope_name("teacher/conv1_w") == "teacher/conv1_w"
     assert W.unscope_name("conv1_w") == "conv1_w"
 
