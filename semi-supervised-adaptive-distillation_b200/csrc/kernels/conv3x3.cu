@@ -37,6 +37,7 @@
 //
 // Channel counts that are not a multiple of 4 (TMA needs 16-byte strides) take conv3x3_simt_kernel.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -129,8 +130,13 @@ __device__ __forceinline__ ConvTile conv_decode_tile(const ConvArgs& a, uint32_t
 //              empty[s]     one per CTA: the leader's commit multicasts "stage read" to both producers
 //              tmem_full[b] one per CTA: the leader's commit multicasts "accumulator complete" to both epilogues
 //              tmem_empty[b] lives in the LEADER: 256 arrivals, both CTAs' epilogue threads (the partner's remotely)
-template <bool kC2, bool kSigmoid>
+// kF16: fp16 operands (tcgen05.mma kind::f16, K = 16 per instruction): the channels-last input, the packed weights and the
+// channels-last output are fp16; a stage still holds 128-byte rows, i.e. 64 instead of 32 input channels, so a tile takes
+// half as many stages and MMAs.  Accumulation, bias, activation and the NCHW output stay fp32 (BASELINE.json configs[4]:
+// "mixed fp16 compute / fp32 loss accumulate").  fp16 keeps the 10-bit mantissa of tf32; values beyond 65504 become inf.
+template <bool kC2, bool kSigmoid, bool kF16 = false>
 __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __grid_constant__ ConvArgs args) {
+  constexpr int kKCe = kF16 ? 2 * kCvKC : kCvKC;   // input channels per stage (one 128-byte row)
   constexpr int kStages = kC2 ? kCvStagesPair : kCvStages;
   constexpr int kBBytes = kC2 ? kCvBBytes / 2 : kCvBBytes;
   constexpr int kStageBytes = kCvABytes + kBBytes;
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t k_blocks = args.k_blocks;  // ceil(Cin / 32)
+  const uint32_t k_blocks = args.k_blocks;  // ceil(Cin / kKCe)
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
@@ -198,13 +204,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             uint8_t* sb = sa + kCvABytes;
             if (kC2) {
               mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
-              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kCvKC, t.m0, tap);
+              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kKCe, t.m0, tap);
               // my half of the pixel tile: rows y0 + 4 * rank .. + 3 (= accumulator columns 128 * rank .. + 127)
-              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kCvKC, t.x0 + dx, t.y0 + (int)crank * (kCvRows / 2) + dy, t.n);
+              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kKCe, t.x0 + dx, t.y0 + (int)crank * (kCvRows / 2) + dy, t.n);
             } else {
               mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
-              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kCvKC, t.m0, tap);
-              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kCvKC, t.x0 + dx, t.y0 + dy, t.n);
+              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kKCe, t.m0, tap);
+              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kKCe, t.x0 + dx, t.y0 + dy, t.n);
             }
             rs.advance<kStages>();
           }
@@ -226,7 +232,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
       }
     }
     if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
+      constexpr uint32_t idesc = kF16 ? umma_idesc_f16(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0)
+                                      : umma_idesc_tf32(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
       RingState rs;
       uint32_t it = 0;
       for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
@@ -243,12 +250,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
           const uint32_t b_addr = a_addr + kCvABytes;
 #pragma unroll
           for (int k = 0; k < kCvKC / 8; ++k) {
-            // both operands K-major: rows of 128 B (32 tf32), 8-row groups 1024 B apart (SBO);
-            // one K step of 8 = +32 B inside the swizzled row
+            // both operands K-major: rows of 128 B (32 tf32 or 64 fp16), 8-row groups 1024 B apart (SBO);
+            // one K step (8 tf32 or 16 fp16) = +32 B inside the swizzled row
             const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            if (kC2) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
-            else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+            if (kF16) {
+              if (kC2) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+              else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+            } else {
+              if (kC2) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+              else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+            }
           }
           // frees the smem stage when these MMAs have read it (pair: in both CTAs)
           if (kC2) umma_commit_2sm(&empty_bar[rs.stage], (uint16_t)0x3);
@@ -347,11 +359,19 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             }
           }
           if (ycl) {
-            // channels-last: for a fixed pixel the warp's 32 lanes (consecutive co) write one 128 B line
-            float* dst = ycl + ((size_t)y * L.W + t.x0) * args.cout;
+            if (kF16) {
+              // fp16 channels-last: the same element offsets in 2-byte elements (the warp's 32 lanes write one 64 B line)
+              __half* dst = reinterpret_cast<__half*>(L.y_nhwc) + (size_t)t.n * HW * args.cout + co + ((size_t)y * L.W + t.x0) * args.cout;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (t.x0 + i < L.W) dst[(size_t)i * args.cout] = to_tf32_rna(v[i]);
+              for (int i = 0; i < 32; ++i)
+                if (t.x0 + i < L.W) dst[(size_t)i * args.cout] = __float2half_rn(v[i]);
+            } else {
+              // channels-last: for a fixed pixel the warp's 32 lanes (consecutive co) write one 128 B line
+              float* dst = ycl + ((size_t)y * L.W + t.x0) * args.cout;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (t.x0 + i < L.W) dst[(size_t)i * args.cout] = to_tf32_rna(v[i]);
+            }
           }
         }
       }
@@ -387,17 +407,21 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+__device__ __forceinline__ void store_operand(float* p, float v) { *p = to_tf32_rna(v); }
+__device__ __forceinline__ void store_operand(__half* p, float v) { *p = __float2half_rn(v); }
+
 struct PackMulti {
   const float* src[SAD_MAX_PACK_ITEMS];
-  float* dst[SAD_MAX_PACK_ITEMS];
+  float* dst[SAD_MAX_PACK_ITEMS];   // fp16 instantiation: __half storage
   int32_t cin[SAD_MAX_PACK_ITEMS], cout[SAD_MAX_PACK_ITEMS], mode[SAD_MAX_PACK_ITEMS];
 };
 // every weight tensor of the head in one launch: blockIdx.y selects the tensor; one thread per (row m, column k)
 // of the packed planes moves the 9 taps (writes coalesced along k in each tap plane)
+template <typename OutT>
 __global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
   const int k_ = blockIdx.y;
   const float* __restrict__ w = p.src[k_];
-  float* __restrict__ out = p.dst[k_];
+  OutT* __restrict__ out = reinterpret_cast<OutT*>(p.dst[k_]);
   const int cout = p.cout[k_], cin = p.cin[k_], mode = p.mode[k_];
   const uint32_t M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
   const uint32_t plane = M * K;
@@ -408,7 +432,7 @@ __global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) v[tap] = __ldg(src + tap);
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) out[(size_t)tap * plane + i] = to_tf32_rna(mode == 0 ? v[tap] : v[8 - tap]);
+    for (int tap = 0; tap < 9; ++tap) store_operand(out + (size_t)tap * plane + i, mode == 0 ? v[tap] : v[8 - tap]);
   }
 }
 
@@ -462,6 +486,7 @@ struct LayoutArgs {
   int32_t n_levels, C;
   uint32_t tiles_c, total_tiles;
 };
+template <typename OutT>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant__ LayoutArgs a) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -476,7 +501,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
     const uint32_t n = r / a.tiles_c;
     const uint32_t hw0 = th * 32, c0 = tc * 32;
     const float* src = L.src + (size_t)n * a.C * L.HW;
-    float* dst = L.dst + (size_t)n * a.C * L.HW;
+    OutT* dst = reinterpret_cast<OutT*>(L.dst) + (size_t)n * a.C * L.HW;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t c = c0 + ty + k * 8, hw = hw0 + tx;
@@ -486,7 +511,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t hw = hw0 + ty + k * 8, c = c0 + tx;
-      if (c < (uint32_t)a.C && hw < L.HW) dst[(size_t)hw * a.C + c] = to_tf32_rna(tile[tx][ty + k * 8]);
+      if (c < (uint32_t)a.C && hw < L.HW) store_operand(dst + (size_t)hw * a.C + c, tile[tx][ty + k * 8]);
     }
     __syncthreads();
   }
@@ -522,7 +547,7 @@ SAD_EXPORT int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int co
   return check_cuda(cudaGetLastError(), "conv3x3 pack launch");
 }
 
-SAD_EXPORT int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, void* stream) {
+static int pack_weights_multi_impl(const sad_pack_item* items, int n_items, void* stream, bool f16) {
   if (!items || n_items < 1 || n_items > SAD_MAX_PACK_ITEMS) return set_error(SAD_ERR_INVALID, "conv3x3 pack multi: n_items must be in [1, 32]");
   PackMulti p{};
   size_t most = 0;
@@ -539,12 +564,13 @@ SAD_EXPORT int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, in
     if (total > most) most = total;
   }
   const unsigned bx = (unsigned)((most + 255) / 256 < 1024 ? (most + 255) / 256 : 1024);
-  conv3x3_pack_multi_kernel<<<dim3(bx, (unsigned)n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (f16) conv3x3_pack_multi_kernel<__half><<<dim3(bx, (unsigned)n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else conv3x3_pack_multi_kernel<float><<<dim3(bx, (unsigned)n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "conv3x3 pack multi launch");
 }
 
-SAD_EXPORT int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
+static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int channels, void* stream, bool f16) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || channels < 1) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: bad argument");
   LayoutArgs a{};
   a.n_levels = n_levels;
@@ -570,15 +596,16 @@ SAD_EXPORT int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels
   int sms = 0, rc;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   const uint32_t grid = a.total_tiles < (uint32_t)sms * 8u ? a.total_tiles : (uint32_t)sms * 8u;
-  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (f16) nchw_to_nhwc_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else nchw_to_nhwc_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
 }
 
 // `packed` has layout [tap][cout][cin] (sad_conv3x3_pack_weights_f32 mode 0 for the forward operator,
 // mode 1 — with cin/cout swapped by the caller — for the data gradient).
-SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
-                                   int cout, int relu, void* stream) {
+static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
+                            int cout, int relu, void* stream, bool f16) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3: n_levels must be in [1, 8]");
   if (!packed || cin < 1 || cout < 1) return set_error(SAD_ERR_INVALID, "conv3x3: bad weights/channels");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -588,7 +615,7 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
   const uint32_t m_single = (uint32_t)((cout + kCvM - 1) / kCvM);
   const bool pair = m_single >= 2;
   const uint32_t m_tiles = pair ? (m_single + 1) / 2 : m_single;
-  bool tma_ok = (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(packed) & 15) == 0);
+  bool tma_ok = (cin % (f16 ? 8 : 4) == 0) && ((reinterpret_cast<uintptr_t>(packed) & 15) == 0);   // 16-byte tensor-map strides
   int rc;
   for (int l = 0; l < n_levels; ++l) {
     const sad_conv_level& L = levels[l];
@@ -614,6 +641,13 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     if (tiles > 0x7fffffffull) return set_error(SAD_ERR_INVALID, "conv3x3: too many tiles");
   }
   if (tiles == 0) return SAD_OK;
+  if (!tma_ok && f16)
+    return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 fp16: needs Cin % 8 == 0 and 16-byte aligned tensors (there is no SIMT fp16 path)");
+  if (f16) {
+    for (int l = 0; l < n_levels; ++l)
+      if (levels[l].relu_mask_nhwc || levels[l].relu_bits_in || levels[l].relu_bits_out || levels[l].accumulate_nchw)
+        return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 fp16: forward only (no ReLU masks / sign bits / accumulation)");
+  }
   if (!tma_ok) {  // channel count / alignment the TMA path cannot address
     for (int l = 0; l < n_levels; ++l) {
       const sad_conv_level& L = levels[l];
@@ -634,16 +668,26 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     return SAD_OK;
   }
   {
+    const cuuint64_t esz = f16 ? 2 : 4;
     const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
-    const cuuint64_t str[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cin * cout * 4};
-    const cuuint32_t box[3] = {kCvKC, kCvM, 1};
-    if ((rc = encode_map(&a.tmap_w, packed, 3, dims, str, box, "packed weights")) != SAD_OK) return rc;
+    const cuuint64_t str[2] = {(cuuint64_t)cin * esz, (cuuint64_t)cin * cout * esz};
+    const cuuint32_t box[3] = {(cuuint32_t)(f16 ? 2 * kCvKC : kCvKC), kCvM, 1};
+    if ((rc = encode_map(&a.tmap_w, packed, 3, dims, str, box, "packed weights", CU_TENSOR_MAP_SWIZZLE_128B,
+                         f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) != SAD_OK)
+      return rc;
   }
   for (int l = 0; l < n_levels; ++l) {
     const sad_conv_level& L = levels[l];
     if ((uint64_t)L.N * L.H * L.W == 0) {  // empty level: a valid dummy map (never used, no tiles)
       a.tmap_x[l] = a.tmap_w;
       a.tmap_xh[l] = a.tmap_w;
+      continue;
+    }
+    if (f16) {
+      if ((rc = encode_nhwc_map_f16(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows, "fp16 activations {C,W,H,N}")) != SAD_OK) return rc;
+      if ((rc = encode_nhwc_map_f16(&a.tmap_xh[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows / 2, "fp16 activations {C,W,H,N}, half tile")) !=
+          SAD_OK)
+        return rc;
       continue;
     }
     if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows, "activations {C,W,H,N}")) != SAD_OK) return rc;
@@ -656,13 +700,15 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
   a.cout = cout;
   a.relu = relu;
   a.m_tiles = m_tiles;
-  a.k_blocks = (uint32_t)((cin + kCvKC - 1) / kCvKC);
+  const int kc = f16 ? 2 * kCvKC : kCvKC;
+  a.k_blocks = (uint32_t)((cin + kc - 1) / kc);
   a.total_tiles = (uint32_t)tiles;
 
   int sms = 0;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   if (pair) {
-    auto kern = relu == 2 ? conv3x3_tf32_kernel<true, true> : conv3x3_tf32_kernel<true, false>;
+    auto kern = f16 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true> : conv3x3_tf32_kernel<true, false, true>)
+                    : (relu == 2 ? conv3x3_tf32_kernel<true, true, false> : conv3x3_tf32_kernel<true, false, false>);
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
                          "cudaFuncSetAttribute(conv3x3 pair)")) != SAD_OK)
       return rc;
@@ -683,7 +729,8 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
     cfg.numAttrs = 1;
     if ((rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "conv3x3 pair launch")) != SAD_OK) return rc;
   } else {
-    auto kern = relu == 2 ? conv3x3_tf32_kernel<false, true> : conv3x3_tf32_kernel<false, false>;
+    auto kern = f16 ? (relu == 2 ? conv3x3_tf32_kernel<false, true, true> : conv3x3_tf32_kernel<false, false, true>)
+                    : (relu == 2 ? conv3x3_tf32_kernel<false, true, false> : conv3x3_tf32_kernel<false, false, false>);
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
                          "cudaFuncSetAttribute(conv3x3)")) != SAD_OK)
       return rc;
@@ -692,6 +739,27 @@ SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, c
   }
   count_launch(1);
   return check_cuda(cudaGetLastError(), "conv3x3 launch");
+}
+
+SAD_EXPORT int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, void* stream) {
+  return pack_weights_multi_impl(items, n_items, stream, false);
+}
+SAD_EXPORT int sad_conv3x3_pack_weights_multi_f16(const sad_pack_item* items, int n_items, void* stream) {
+  return pack_weights_multi_impl(items, n_items, stream, true);
+}
+SAD_EXPORT int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
+  return nchw_to_nhwc_impl(levels, n_levels, channels, stream, false);
+}
+SAD_EXPORT int sad_nchw_to_nhwc_f16(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
+  return nchw_to_nhwc_impl(levels, n_levels, channels, stream, true);
+}
+SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
+                                   int cout, int relu, void* stream) {
+  return conv3x3_fwd_impl(levels, n_levels, packed, bias, cin, cout, relu, stream, false);
+}
+SAD_EXPORT int sad_conv3x3_fwd_f16(const sad_conv_level* levels, int n_levels, const void* packed_f16, const float* bias, int cin,
+                                   int cout, int relu, void* stream) {
+  return conv3x3_fwd_impl(levels, n_levels, static_cast<const float*>(packed_f16), bias, cin, cout, relu, stream, true);
 }
 
 }  // extern "C"

@@ -33,11 +33,12 @@ inline EncodeTiledFn encode_fn() {
 
 // fp32 tensor map with 128-byte swizzle; out-of-bounds elements read as zero
 inline int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const char* what, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                      const cuuint32_t* box, const char* what, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(SAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(SAD_ERR_CUDA, std::string("cuTensorMapEncodeTiled(") + what + ") failed: CUresult " + std::to_string((int)r));
@@ -51,6 +52,13 @@ inline int encode_nhwc_map(CUtensorMap* m, const float* xt, int N, int C, int H,
   const cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
   const cuuint32_t box[4] = {32, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   return encode_map(m, xt, 4, dims, str, box, what, swizzle);
+}
+// the same for fp16 activations: box {64 channels, box_x, box_y, 1} = the same 128-byte rows
+inline int encode_nhwc_map_f16(CUtensorMap* m, const void* xt, int N, int C, int H, int W, int box_x, int box_y, const char* what) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+  return encode_map(m, xt, 4, dims, str, box, what, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
 }
 
 inline int sm_count(int* sms) {

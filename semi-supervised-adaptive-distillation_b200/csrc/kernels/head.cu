@@ -95,7 +95,7 @@ int pack_all(sad_head* h, const sad_head_weights* w, bool with_bwd, cudaStream_t
         it.mode = mode;
       }
   h->packed_bwd_valid = with_bwd;
-  return sad_conv3x3_pack_weights_multi_f32(items, n, st);
+  return h->cfg.compute_f16 ? sad_conv3x3_pack_weights_multi_f16(items, n, st) : sad_conv3x3_pack_weights_multi_f32(items, n, st);
 }
 
 int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float* const* y_nhwc, uint32_t* const* bits_out,
@@ -114,6 +114,8 @@ int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float*
     lv[l].relu_bits_in = bits_in ? bits_in[l] : nullptr;
     lv[l].accumulate_nchw = accumulate;
   }
+  // fp16 head: the arena's channels-last / packed buffers hold fp16 elements (half of each fp32-sized slot is used)
+  if (h->cfg.compute_f16) return sad_conv3x3_fwd_f16(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
   return sad_conv3x3_fwd_f32(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
 }
 
@@ -126,7 +128,7 @@ int layout_levels(const sad_head* h, const float* const* src, float* const* dst,
     lv[l].H = h->cfg.H[l];
     lv[l].W = h->cfg.W[l];
   }
-  return sad_nchw_to_nhwc_f32(lv, h->cfg.n_levels, channels, st);
+  return h->cfg.compute_f16 ? sad_nchw_to_nhwc_f16(lv, h->cfg.n_levels, channels, st) : sad_nchw_to_nhwc_f32(lv, h->cfg.n_levels, channels, st);
 }
 
 int wgrad_levels(const sad_head* h, float* const* x, float* const* dy, int cin, int cout, float* dw, float* db, int accumulate, void* ws,
@@ -270,6 +272,7 @@ SAD_EXPORT size_t sad_head_device_bytes(const sad_head* h) { return h ? h->arena
 SAD_EXPORT int sad_head_copy_activation(const sad_head* h, int tower, int conv, int level, float* dst_nhwc, void* stream) {
   if (!h || !dst_nhwc || tower < 0 || tower > 1 || level < 0 || level >= h->cfg.n_levels || conv < -1 || conv >= h->cfg.num_convs)
     return set_error(SAD_ERR_INVALID, "sad_head_copy_activation: bad argument");
+  if (h->cfg.compute_f16) return set_error(SAD_ERR_UNSUPPORTED, "sad_head_copy_activation: an fp16 head keeps fp16 activations");
   const float* src = conv < 0 ? h->x0[level] : h->act[tower][conv][level];
   const size_t bytes = h->pixels[level] * h->cfg.dim * sizeof(float);
   if (bytes == 0) return SAD_OK;
@@ -282,6 +285,8 @@ SAD_EXPORT int sad_head_forward(sad_head* h, const sad_head_weights* w, const fl
   if (!h || !fpn_nchw || !cls_logits_nchw || !bbox_pred_nchw) return set_error(SAD_ERR_INVALID, "sad_head_forward: null argument");
   int rc;
   if ((rc = validate_weights(h, w, "sad_head_forward")) != SAD_OK) return rc;
+  if (h->cfg.compute_f16 && training)
+    return set_error(SAD_ERR_UNSUPPORTED, "sad_head_forward: an fp16 head is forward-only (the teacher); the gradient kernels are tf32");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = h->cfg.num_convs, dim = h->cfg.dim;
   if ((rc = layout_levels(h, fpn_nchw, h->x0, dim, st)) != SAD_OK) return rc;
@@ -315,6 +320,7 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
   if (!d_cls_logits_nchw && !d_bbox_pred_nchw) return set_error(SAD_ERR_INVALID, "sad_head_backward: no output gradient given");
   if (h->cfg.cls_output_sigmoid)
     return set_error(SAD_ERR_UNSUPPORTED, "sad_head_backward: a head whose classification output is Sigmoid(logits) is forward-only (the teacher)");
+  if (h->cfg.compute_f16) return set_error(SAD_ERR_UNSUPPORTED, "sad_head_backward: an fp16 head is forward-only (the teacher)");
   if (!h->packed_bwd_valid)
     return set_error(SAD_ERR_INVALID, "sad_head_backward: call sad_head_forward(training = 1) first (it keeps the activations and packs the weights)");
   int rc;

@@ -454,3 +454,63 @@ def scale_(x, alpha):
     _require_cuda(x, torch.float32, "x")
     check(lib().sad_scale_f32(C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), x.numel(), float(alpha), _stream()))
     return x
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16-operand forward convolution (BASELINE.json configs[4]: mixed fp16 compute, fp32 accumulate) — forward only
+# ---------------------------------------------------------------------------------------------
+def conv3x3_pack_f16(weight):
+    """(Cout, Cin, 3, 3) fp32 -> [tap][Cout][Cin] fp16 (round to nearest) for sad_conv3x3_fwd_f16."""
+    _require_cuda(weight, torch.float32, "weight")
+    cout, cin = weight.shape[0], weight.shape[1]
+    if tuple(weight.shape[2:]) != (3, 3):
+        raise ValueError("weight must be (Cout, Cin, 3, 3)")
+    packed = torch.empty(9 * cin * cout, dtype=torch.float16, device=weight.device)
+    item = (native.PackItem * 1)()
+    item[0].weight, item[0].packed, item[0].cin, item[0].cout, item[0].mode = weight.data_ptr(), packed.data_ptr(), cin, cout, 0
+    check(lib().sad_conv3x3_pack_weights_multi_f16(item, 1, _stream()))
+    return packed
+
+
+def to_nhwc_f16(xs):
+    """NCHW fp32 -> channels-last (N, H, W, C) fp16, every level in one launch."""
+    xs = list(xs)
+    arr = (native.LayoutLevel * len(xs))()
+    outs = []
+    for i, x in enumerate(xs):
+        _require_cuda(x, torch.float32, "x[%d]" % i)
+        if x.shape[1] != xs[0].shape[1]:
+            raise ValueError("all levels must have the same channel count")
+        n, c, h, w = x.shape
+        outs.append(torch.empty((n, h, w, c), dtype=torch.float16, device=x.device))
+        arr[i].src_nchw, arr[i].dst_nhwc = x.data_ptr(), outs[-1].data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = n, h, w
+    check(lib().sad_nchw_to_nhwc_f16(arr, len(xs), xs[0].shape[1], _stream()))
+    return outs
+
+
+def conv3x3_forward_f16(xs_nhwc_f16, packed_f16, cout, bias=None, relu=0, want_nchw=True, want_nhwc=False):
+    """Conv (+bias, + activation: 0 none, 1 ReLU, 2 Sigmoid) of every level in one launch with fp16 operands.
+    xs_nhwc_f16: channels-last fp16 inputs (to_nhwc_f16 or a previous call's fp16 output).  Returns (ys_nchw fp32, ys_nhwc fp16)."""
+    arr = (ConvLevel * len(xs_nhwc_f16))()
+    ys, yts = [], []
+    cin = xs_nhwc_f16[0].shape[3]
+    for i, xt in enumerate(xs_nhwc_f16):
+        _require_cuda(xt, torch.float16, "x_nhwc[%d]" % i)
+        n, h, w, c = xt.shape
+        if c != cin:
+            raise ValueError("all levels must have the same channel count")
+        arr[i].x_nhwc = xt.data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = n, h, w
+        if want_nchw:
+            ys.append(torch.empty((n, cout, h, w), dtype=torch.float32, device=xt.device))
+            arr[i].y_nchw = ys[-1].data_ptr()
+        if want_nhwc:
+            yts.append(torch.empty((n, h, w, cout), dtype=torch.float16, device=xt.device))
+            arr[i].y_nhwc = yts[-1].data_ptr()
+    _require_cuda(packed_f16, torch.float16, "packed")
+    if packed_f16.numel() != 9 * cin * cout:
+        raise ValueError("packed weights must hold 9 * Cin * Cout fp16 elements")
+    b = C.c_void_p(bias.data_ptr()) if bias is not None else None
+    check(lib().sad_conv3x3_fwd_f16(arr, len(xs_nhwc_f16), C.c_void_p(packed_f16.data_ptr()), b, cin, cout, int(relu), _stream()))
+    return ys, yts

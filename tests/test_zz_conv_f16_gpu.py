@@ -1,0 +1,120 @@
+"""GPU parity of the fp16-operand forward convolution (tcgen05 kind::f16; BASELINE.json configs[4]: "mixed fp16 compute / fp32 loss
+accumulate") and of the forward-only fp16 head (the teacher) against the CPU oracle (oracle/conv_oracle.c restating
+conv_op_impl.h:31-180).
+
+Two gates, both written here:
+  * against the oracle run on the SAME fp16-rounded operands (numpy float16 round trip of activations and weights): only the
+    accumulation order differs (fp32 in TMEM vs fp32 in the oracle's GEMM): max|d| <= 2e-5 * max|ref|;
+  * against the oracle on the unrounded fp32 operands: fp16 keeps tf32's 10-bit mantissa, so the tf32 gate of
+    tests/test_conv_gpu.py applies unchanged: max|d| <= 3e-3 * max|ref|, rms(d) <= 1e-3 * rms(ref).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, max_tol, rms_tol, what):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert np.isfinite(got).all(), what + ": non-finite output"
+    m, d = np.abs(ref).max(), np.abs(got - ref)
+    assert d.max() <= max_tol * m, "%s: max|d| %.3g > %.1e * max|ref| %.3g (at %s)" % (what, d.max(), max_tol, m,
+                                                                                    np.unravel_index(d.argmax(), d.shape))
+    rms = np.sqrt((d ** 2).mean()) / max(np.sqrt((ref ** 2).mean()), 1e-30)
+    assert rms <= rms_tol, "%s: relative rms %.3g" % (what, rms)
+
+
+def _h(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+CASES = [
+    # (N, Cin, Cout, H, W)
+    ((1, 64, 128, 8, 32), "one tile, one k-block per tap"),
+    ((2, 128, 128, 16, 64), "2x2 pixel tiles, two k-blocks"),
+    ((1, 256, 256, 20, 32), "head tower shape, CTA pair, ragged rows (P5)"),
+    ((2, 256, 256, 5, 8), "P7, CTA pair"),
+    ((1, 96, 36, 12, 20), "K tail (Cin = 96 = 64 + 32), M tail (Cout = 36), ragged columns"),
+    ((1, 64, 720, 8, 40), "cls_pred Cout = 720: 3 pairs of M tiles, last partial"),
+    ((1, 64, 64, 7, 14), "W % 4 != 0: scalar NCHW stores"),
+]
+
+
+@pytest.mark.parametrize("shape,name", CASES, ids=[c[1] for c in CASES])
+def test_f16_forward_matches_oracle(oracle, shape, name):
+    from sad_b200 import ops
+    N, Cin, Cout, H, W = shape
+    rng = np.random.default_rng(N * 1000 + Cin + Cout + H)
+    x = np.maximum(rng.standard_normal((N, Cin, H, W)), 0).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal((Cout,)).astype(np.float32)
+    xd, wd, bd = (torch.from_numpy(a).cuda() for a in (x, w, b))
+    xh = ops.to_nhwc_f16([xd])
+    assert xh[0].dtype == torch.float16 and np.array_equal(xh[0].permute(0, 3, 1, 2).float().cpu().numpy(), _h(x)), "layout pass rounds to fp16"
+    packed = ops.conv3x3_pack_f16(wd)
+    assert np.array_equal(packed.view(9, Cout, Cin).float().cpu().numpy(), _h(w).reshape(Cout, Cin, 9).transpose(2, 0, 1)), "pack rounds to fp16"
+    (y,), (ycl,) = ops.conv3x3_forward_f16(xh, packed, Cout, bd, relu=1, want_nhwc=True)
+    torch.cuda.synchronize()
+    same_operands = oracle.relu(oracle.conv2d_fwd(_h(x), _h(w), b))
+    _close(y.cpu().numpy(), same_operands, 2e-5, 1e-5, "fp16 conv+relu vs oracle on fp16-rounded operands: " + name)
+    _close(y.cpu().numpy(), oracle.relu(oracle.conv2d_fwd(x, w, b)), 3e-3, 1e-3, "fp16 conv+relu vs fp32 oracle: " + name)
+    # the channels-last fp16 copy is the fp32 result rounded once more
+    assert ycl.dtype == torch.float16
+    assert torch.equal(ycl.permute(0, 3, 1, 2), y.half()), "channels-last fp16 output = fp16(fp32 output)"
+    (y0,), _ = ops.conv3x3_forward_f16(xh, packed, Cout, None, relu=0)
+    _close(y0.cpu().numpy(), oracle.conv2d_fwd(_h(x), _h(w), None), 2e-5, 1e-5, "fp16 conv (no bias) " + name)
+    (ys,), _ = ops.conv3x3_forward_f16(xh, packed, Cout, bd, relu=2)
+    ref_s = 1.0 / (1.0 + np.exp(-oracle.conv2d_fwd(_h(x), _h(w), b).astype(np.float64)))
+    _close(ys.cpu().numpy(), ref_s, 1e-5, 1e-5, "fp16 conv + Sigmoid " + name)
+
+
+def test_f16_all_levels_in_one_launch(oracle):
+    """The five FPN levels of a 320 px image in one launch (weights shared across levels, retinanet_heads.py:90-152)."""
+    from sad_b200 import ops
+    rng = np.random.default_rng(7)
+    shapes = [(40, 64), (20, 32), (10, 16), (5, 8), (3, 4)]
+    w = (rng.standard_normal((256, 256, 3, 3)) / 48.0).astype(np.float32)
+    b = rng.standard_normal((256,)).astype(np.float32)
+    xs = [np.maximum(rng.standard_normal((2, 256, h, ww)), 0).astype(np.float32) for h, ww in shapes]
+    xh = ops.to_nhwc_f16([torch.from_numpy(x).cuda() for x in xs])
+    ys, _ = ops.conv3x3_forward_f16(xh, ops.conv3x3_pack_f16(torch.from_numpy(w).cuda()), 256, torch.from_numpy(b).cuda(), relu=1)
+    torch.cuda.synchronize()
+    for x, y in zip(xs, ys):
+        _close(y.cpu().numpy(), oracle.relu(oracle.conv2d_fwd(_h(x), _h(w), b)), 2e-5, 1e-5, "level %s" % (x.shape,))
+
+
+def test_f16_rejects_what_it_cannot_do():
+    from sad_b200 import native, ops
+    x = torch.zeros(1, 4, 4, 36, dtype=torch.float16, device="cuda")       # Cin % 8 != 0
+    with pytest.raises(native.SadError, match="fp16"):
+        ops.conv3x3_forward_f16([x], torch.zeros(9 * 36 * 8, dtype=torch.float16, device="cuda"), 8)
+
+
+def test_f16_teacher_head_matches_tf32_head():
+    """The forward-only teacher head (cls output = Sigmoid(logits), retinanet_heads.py:153-163) with fp16 operands against the
+    tf32 head on the same weights and inputs.  Both carry 10-bit-mantissa operands and fp32 accumulation; they differ in where
+    the rounding falls (tf32 truncation inside the MMA vs fp16 round-to-nearest when stored), measured through 5 layers."""
+    from sad_b200 import head, native
+    shapes = [(20, 32), (10, 16), (5, 8)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    fpn = [torch.randn(2, 256, h, w, device="cuda", generator=g).clamp_(min=0) * 0.5 for h, w in shapes]
+    ref = head.RetinaNetHead(2, shapes, cls_output_sigmoid=True, seed=5)
+    f16 = head.RetinaNetHead(2, shapes, cls_output_sigmoid=True, seed=5, compute_f16=True)
+    # sigma = 0.01 initialisation leaves every logit at the bias; scale the weights up so the towers matter
+    for h_ in (ref, f16):
+        for n in h_.names:
+            if n.endswith("_w"):
+                h_.params[n].mul_(4.0)
+    assert torch.equal(ref.flat_params, f16.flat_params)
+    p_ref, b_ref = ref.forward(fpn, training=False)
+    p_f16, b_f16 = f16.forward(fpn, training=False)
+    torch.cuda.synchronize()
+    for a, b in zip(p_ref + b_ref, p_f16 + b_f16):
+        assert torch.isfinite(b).all()
+        d = (a - b).abs().max().item()
+        assert d <= 3e-3 * a.abs().max().item(), "fp16 head vs tf32 head: max|d| %.3g of max %.3g" % (d, a.abs().max().item())
+    assert (p_ref[0].std() > 1e-4).item(), "the comparison must not be between constant outputs"
+    with pytest.raises(native.SadError, match="forward-only"):
+        f16.forward(fpn, training=True)
