@@ -173,9 +173,10 @@ class ResNetFPN(nn.Module):
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
                  temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4,
-                 fused_body=True, overlap_teacher=True, teacher_body=None):
+                 fused_body=True, overlap_teacher=True, teacher_body=None, teacher_head_f16=False):
         """teacher_body: extra ResNetFPN arguments of the teacher, e.g. dict(groups=64, width_per_group=4, stride_1x1=False)
-        for the ResNeXt-101-64x4d teacher of BASELINE.json configs[4]."""
+        for the ResNeXt-101-64x4d teacher of BASELINE.json configs[4].  teacher_head_f16: the forward-only teacher head on fp16
+        operands (tcgen05 kind::f16, fp32 accumulation; configs[4]: "mixed fp16 compute / fp32 loss accumulate")."""
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world, self.rank, self.images = int(world), int(rank), int(n_images)
         self.overlap_teacher = bool(overlap_teacher)
@@ -203,7 +204,8 @@ class FullDistillStep:
         self.flat_params = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
         self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head],
                                   param_buffer=self.flat_params[:n_head])
-        self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1, cls_output_sigmoid=True)
+        self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1, cls_output_sigmoid=True,
+                                          compute_f16=teacher_head_f16)
         off = n_head
         for p in self.body_params:
             k = p.numel()

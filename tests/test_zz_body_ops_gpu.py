@@ -111,7 +111,7 @@ def test_body_ops_reject_bad_arguments():
 
 def test_scale_and_learning_rate_update_with_momentum_correction():
     """Scale (scale_op.h:31-50) bit-exact against the product x * alpha, and UpdateWorkspaceLr (detector.py:598-648) over the
-    device `lr` blob and a flat momentum buffer: no correction during warm-up-sized changes, one Scale launch per decay step."""
+    device `lr` blob and a flat momentum buffer: no correction on the first iteration (the blob starts at 0), one Scale launch per decay step."""
     from sad_b200 import c2, ops, solver
     x = torch.randn(100003, device="cuda")
     want = x * 0.1
@@ -127,7 +127,9 @@ def test_scale_and_learning_rate_update_with_momentum_correction():
     ws.RunOperatorOnce(c2.CreateOperator("Scale", ["w_momentum"], ["w_momentum"], device_option=c2.DeviceOption(c2.CUDA, 0), scale=0.1))
     assert np.array_equal(np.asarray(ws.FetchBlob("w_momentum")), (m * 0.1).cpu().numpy())
 
-    cfg = solver.SolverConfig(BASE_LR=0.01, LR_POLICY="steps_with_decay", STEPS=[0, 20, 30], MAX_ITER=40, WARM_UP_ITERS=10)
+    # no warm-up here: over 10 iterations its per-iteration ratios (1.2, 1.17, ...) would exceed SCALE_MOMENTUM_THRESHOLD, unlike the
+    # reference's 500-1000 iteration warm-ups (ratio <= 1.002; covered on CPU by tests/test_solver_weights.py)
+    cfg = solver.SolverConfig(BASE_LR=0.01, LR_POLICY="steps_with_decay", STEPS=[0, 20, 30], MAX_ITER=40, WARM_UP_ITERS=0)
     lr_blob = torch.zeros((), device="cuda")                 # optimizer.py:58-60: the lr blob starts at 0
     mom = torch.ones(1000, device="cuda")
     lr = solver.LearningRate(cfg, lr_blob, [mom])
