@@ -65,3 +65,26 @@ def test_operator_library_exports_handle_api():
     for name in ["c2_workspace_create", "c2_feed_external", "c2_run_operator_once", "c2_create_net", "c2_run_net",
                  "c2_fetch", "c2_gradient_defs", "c2_has_operator", "c2_fuse_adaptive_distill_ops"]:
         assert hasattr(lib, name), name
+
+
+def test_new_entry_points_validate_arguments_without_device():
+    """AffineChannel / UpsampleNearest / Scale / fp16 convolution: bad arguments are refused before any CUDA call."""
+    from sad_b200 import native
+    lib = native.lib()
+    p = C.c_void_p(256)
+    assert lib.sad_affine_channel_f32(p, p, p, p, 1, 0, 4, None) == -1 and b"bad shape" in lib.sad_last_error()
+    assert lib.sad_affine_channel_f32(None, p, p, p, 1, 2, 4, None) == -1 and b"null" in lib.sad_last_error()
+    assert lib.sad_affine_channel_f32(p, p, p, p, 0, 2, 4, None) == 0                      # empty tensor: nothing to do
+    assert lib.sad_affine_channel_f32(p, p, p, p, 1 << 15, 1 << 10, 1 << 10, None) == -4   # 2^35 elements: int indexing refused
+    assert lib.sad_upsample_nearest_f32(p, p, 1, 2, 2, 0, None) == -1 and b"scale" in lib.sad_last_error()
+    assert lib.sad_upsample_nearest_f32(p, p, 0, 2, 2, 2, None) == 0
+    assert lib.sad_upsample_nearest_grad_f32(None, p, 1, 2, 2, 2, None) == -1
+    assert lib.sad_scale_f32(None, p, 4, 1.0, None) == -1 and lib.sad_scale_f32(p, p, 0, 1.0, None) == 0
+    lv = (native.ConvLevel * 1)()
+    assert lib.sad_conv3x3_fwd_f16(lv, 0, p, None, 64, 64, 0, None) == -1
+    assert lib.sad_conv3x3_fwd_f16(lv, 1, None, None, 64, 64, 0, None) == -1
+    lv[0].N, lv[0].H, lv[0].W = 1, 4, 4
+    lv[0].x_nhwc, lv[0].y_nchw = 256, 256
+    assert lib.sad_conv3x3_fwd_f16(lv, 1, p, None, 36, 64, 0, None) == -4 and b"Cin % 8" in lib.sad_last_error()
+    lv[0].accumulate_nchw = 1
+    assert lib.sad_conv3x3_fwd_f16(lv, 1, p, None, 64, 64, 0, None) == -4 and b"forward only" in lib.sad_last_error()
