@@ -357,7 +357,17 @@ class FullDistillStep:
         in ONE launch over the flat [head | body] buffers."""
         ops.momentum_sgd(self.flat_params, self.flat_grads, self.momentum, self.sgd_segments, self.lr_dev, momentum=self.mom)
 
-    def step(self):
+    def update_lr(self, cur_iter, solver_cfg):
+        """model.UpdateWorkspaceLr(cur_iter, lr_policy.get_lr_at_iter(cur_iter)) (utils/train.py loop, detector.py:598-648): sets the
+        device `lr` scalar the optimiser launch reads and rescales the flat update history when the rate jumps."""
+        from . import solver
+        if getattr(self, "_lr_state", None) is None or self._lr_state.solver is not solver_cfg:
+            self._lr_state = solver.LearningRate(solver_cfg, self.lr_dev, [self.momentum])
+        return self._lr_state.update(cur_iter)
+
+    def step(self, cur_iter=None, solver_cfg=None):
+        if solver_cfg is not None:
+            self.update_lr(cur_iter, solver_cfg)
         self.run()
         self.allreduce()
         self.sgd()
