@@ -173,6 +173,10 @@ void sad_ctx_destroy(sad_ctx* ctx);
 /* losses_out: host, n_levels floats.  normalizer_out: host, 1 float (may be NULL). */
 int sad_distill_step_host(sad_ctx* ctx, const sad_host_level* levels, int n_levels, float power,
                           const sad_distill_params* params, float* losses_out, float* normalizer_out);
+/* Pipeline granularity of sad_distill_step_host: a chunk is a run of whole anchors of one image of one level, capped at `bytes`
+ * of logits (0 = default: environment SAD_HOST_CHUNK_BYTES, else 4 MB).  Smaller chunks shorten the un-overlapped head of the
+ * pipeline (the first logits copy after the teacher probabilities) at the price of more launches. */
+int sad_ctx_set_host_chunk_bytes(sad_ctx* ctx, size_t bytes);
 /* device address of level i's gradient from the last sad_distill_step_host call */
 float* sad_ctx_device_d_logits(sad_ctx* ctx, int level);
 

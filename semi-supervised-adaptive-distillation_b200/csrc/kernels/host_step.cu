@@ -6,12 +6,17 @@
 //   compute  stream :               PowSum        | loss+grad 0 | loss+grad 1 | ...
 //   copy-out stream :                                           | dX chunk 0  | dX chunk 1 ... | losses
 //
-// A chunk is one image of one level (NCHW images are contiguous), ordered largest first so the
-// un-overlapped D2H tail is the smallest chunk.  The normaliser needs every teacher probability
-// (PowSum runs over all levels, reference retinanet_heads.py:320-328), hence T goes first.
+// A chunk is a run of whole ANCHORS of one image of one level: the (A*C, H, W) block of an image is contiguous and the
+// kernel's label indexing (loss_op.cu:35-42: t = gt[n*H*W*A + a*H*W + y*W + x]) only needs the label base moved by
+// a0*H*W, so anchors [a0, a0 + k) of image n are a valid (N = 1, D = k*C, H, W) level of their own.  Chunks are capped at
+// ~4 MB (SAD_HOST_CHUNK_BYTES) and ordered largest first so the un-overlapped D2H tail is the smallest chunk.
+// The normaliser needs every teacher probability (PowSum runs over all levels, reference retinanet_heads.py:320-328),
+// hence T goes first and the critical path is  H2D(T) + H2D(first X chunk) + kernel + D2H(all dX):  with whole images as
+// chunks the middle term was a 29.5 MB copy (0.54 ms of 3.65 ms per step at configs[1], measured r01j/r01k).
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -34,6 +39,7 @@ struct sad_ctx {
   Buf ws_pow, ws_dist, scalars;  // scalars: [0] normaliser, [1..] per-chunk losses
   float* h_scalars = nullptr;    // pinned mirror of `scalars`
   size_t h_scalars_cap = 0;
+  size_t chunk_bytes = 0;        // 0 = default (SAD_HOST_CHUNK_BYTES or 4 MB)
 };
 
 namespace {
@@ -49,9 +55,17 @@ int grow(sad_ctx::Buf& b, size_t bytes, bool is_workspace, cudaStream_t st) {
   return SAD_OK;
 }
 struct Chunk {
-  int level, n;
-  size_t elems;
+  int level, n, a0, k;   // anchors [a0, a0 + k) of image n of `level`
+  size_t elems;          // k * num_classes * H * W
 };
+size_t host_chunk_bytes() {
+  static const size_t v = [] {
+    const char* e = std::getenv("SAD_HOST_CHUNK_BYTES");
+    const long long x = e ? std::atoll(e) : 0;
+    return x > 0 ? (size_t)x : (size_t)4 << 20;
+  }();
+  return v;
+}
 }  // namespace
 
 extern "C" {
@@ -94,6 +108,12 @@ SAD_EXPORT void sad_ctx_destroy(sad_ctx* c) {
   delete c;
 }
 
+SAD_EXPORT int sad_ctx_set_host_chunk_bytes(sad_ctx* c, size_t bytes) {
+  if (!c) return set_error(SAD_ERR_INVALID, "sad_ctx_set_host_chunk_bytes: null context");
+  c->chunk_bytes = bytes;
+  return SAD_OK;
+}
+
 SAD_EXPORT float* sad_ctx_device_d_logits(sad_ctx* c, int level) {
   if (!c || level < 0 || level >= SAD_MAX_LEVELS) return nullptr;
   return static_cast<float*>(c->dX[level].p);
@@ -124,8 +144,19 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
       return rc;
     sizes[l] = (int64_t)elems;
     t_dev[l] = static_cast<const float*>(c->T[l].p);
-    for (int n = 0; n < L.N; ++n)
-      if (per_img) chunks.push_back({l, n, per_img});
+    const int A = L.D / params->num_classes;
+    const size_t per_anchor = (size_t)params->num_classes * L.H * L.W;
+    if (per_img) {
+      // anchors per chunk: as many as fit the byte cap, spread evenly (9 anchors, cap 2 -> 2,2,2,2,1 becomes 5 chunks of <= 2)
+      int k_cap = (int)std::max<size_t>(1, (c->chunk_bytes ? c->chunk_bytes : host_chunk_bytes()) / (per_anchor * 4));
+      if (k_cap > A) k_cap = A;
+      const int pieces = (A + k_cap - 1) / k_cap;
+      for (int n = 0; n < L.N; ++n)
+        for (int pc = 0; pc < pieces; ++pc) {
+          const int a0 = (int)(((int64_t)A * pc) / pieces), a1 = (int)(((int64_t)A * (pc + 1)) / pieces);
+          if (a1 > a0) chunks.push_back({l, n, a0, a1 - a0, (size_t)(a1 - a0) * per_anchor});
+        }
+    }
   }
   std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.elems > b.elems; });
   const size_t n_chunks = chunks.size();
@@ -147,11 +178,11 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
   float* d_loss = d_norm + 1;
   if ((rc = grow(c->ws_pow, sad_pow_sum_workspace_bytes(sizes, n_levels), true, c->s_k)) != SAD_OK) return rc;
   {
-    // largest single-image chunk bounds the distill workspace
+    // the largest chunk bounds the distill workspace
     size_t need = 256;
     for (const Chunk& ch : chunks) {
       sad_distill_level one{};
-      one.N = 1; one.D = levels[ch.level].D; one.H = levels[ch.level].H; one.W = levels[ch.level].W;
+      one.N = 1; one.D = ch.k * params->num_classes; one.H = levels[ch.level].H; one.W = levels[ch.level].W;
       need = std::max(need, sad_distill_workspace_bytes(&one, 1));
     }
     if ((rc = grow(c->ws_dist, need, true, c->s_k)) != SAD_OK) return rc;
@@ -169,12 +200,14 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
   for (size_t i = 0; i < n_chunks; ++i) {
     const Chunk& ch = chunks[i];
     const sad_host_level& L = levels[ch.level];
-    const size_t xoff = (size_t)ch.n * ch.elems;
-    const size_t lab_per_img = (size_t)(L.D / params->num_classes) * L.H * L.W;
-    const size_t goff = (size_t)ch.n * lab_per_img;
+    const size_t hw = (size_t)L.H * L.W;
+    const size_t xoff = ((size_t)ch.n * L.D + (size_t)ch.a0 * params->num_classes) * hw;
+    const size_t lab_per_img = (size_t)(L.D / params->num_classes) * hw;
+    const size_t goff = (size_t)ch.n * lab_per_img + (size_t)ch.a0 * hw;
+    const size_t lab_elems = (size_t)ch.k * hw;
     float* dXd = static_cast<float*>(c->dX[ch.level].p) + xoff;
     if ((rc = check_cuda(cudaMemcpyAsync(static_cast<float*>(c->X[ch.level].p) + xoff, L.logits + xoff, ch.elems * 4, cudaMemcpyHostToDevice, c->s_in), "H2D X")) != SAD_OK ||
-        (rc = check_cuda(cudaMemcpyAsync(static_cast<int32_t*>(c->G[ch.level].p) + goff, L.labels + goff, lab_per_img * 4, cudaMemcpyHostToDevice, c->s_in), "H2D G")) != SAD_OK)
+        (rc = check_cuda(cudaMemcpyAsync(static_cast<int32_t*>(c->G[ch.level].p) + goff, L.labels + goff, lab_elems * 4, cudaMemcpyHostToDevice, c->s_in), "H2D G")) != SAD_OK)
       return rc;
     cudaEventRecord(c->ev_in[i], c->s_in);
     cudaStreamWaitEvent(c->s_k, c->ev_in[i], 0);
@@ -185,7 +218,7 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
     one.d_logits = dXd;
     one.loss = d_loss + i;
     one.d_loss = nullptr;
-    one.N = 1; one.D = L.D; one.H = L.H; one.W = L.W;
+    one.N = 1; one.D = ch.k * params->num_classes; one.H = L.H; one.W = L.W;
     if ((rc = sad_distill_f32(&one, 1, d_norm, params, c->ws_dist.p, c->ws_dist.cap, c->s_k)) != SAD_OK) return rc;
     cudaEventRecord(c->ev_k[i], c->s_k);
     if (L.d_logits) {
@@ -201,7 +234,7 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
   if ((rc = check_cuda(cudaStreamSynchronize(c->s_in), "sync")) != SAD_OK) return rc;
 
   for (int l = 0; l < n_levels; ++l) losses_out[l] = 0.f;
-  for (size_t i = 0; i < n_chunks; ++i) losses_out[chunks[i].level] += c->h_scalars[1 + i];  // images in order n = 0, 1, ...
+  for (size_t i = 0; i < n_chunks; ++i) losses_out[chunks[i].level] += c->h_scalars[1 + i];  // fixed order: (image, anchor run) ascending per level
   if (normalizer_out) *normalizer_out = c->h_scalars[0];
   return SAD_OK;
 }

@@ -124,6 +124,7 @@ def lib():
         l.sad_ctx_destroy.restype = None
         l.sad_distill_step_host.argtypes = [C.c_void_p, C.POINTER(HostLevel), C.c_int, C.c_float,
                                             C.POINTER(DistillParams), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        l.sad_ctx_set_host_chunk_bytes.argtypes = [C.c_void_p, C.c_size_t]
         l.sad_ctx_device_d_logits.restype = C.c_void_p
         l.sad_ctx_device_d_logits.argtypes = [C.c_void_p, C.c_int]
         l.sad_nchw_to_nhwc_f32.argtypes = [C.POINTER(LayoutLevel), C.c_int, C.c_int, C.c_void_p]

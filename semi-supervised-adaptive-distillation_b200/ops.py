@@ -240,6 +240,10 @@ class HostStep:
         self.handle = C.c_void_p()
         check(lib().sad_ctx_create(int(device), C.byref(self.handle)))
 
+    def set_chunk_bytes(self, nbytes):
+        """Pipeline granularity (sad_ctx_set_host_chunk_bytes): logits bytes per chunk of whole anchors; 0 = default (4 MB)."""
+        check(lib().sad_ctx_set_host_chunk_bytes(self.handle, int(nbytes)))
+
     def close(self):
         if self.handle:
             lib().sad_ctx_destroy(self.handle)

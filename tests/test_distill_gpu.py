@@ -278,6 +278,33 @@ def test_host_step_end_to_end(ops, oracle):
     step.close()
 
 
+@pytest.mark.parametrize("chunk_bytes", [1, 120_000, 450_000])
+def test_host_step_anchor_run_chunks(ops, oracle, chunk_bytes):
+    """The host pipeline cuts every image into runs of whole anchors (label base moved by a0 * H * W, loss_op.cu:35-42).  One anchor
+    per chunk (cap 1 byte), uneven runs (9 anchors in pieces of <= 2: 1 + 2 + 2 + 2 + 2 at P5) and whole images must all give the
+    oracle's losses and, element for element, the SAME gradient bits as the whole-image pipeline."""
+    from sad_b200 import synthetic
+    shapes = [(20, 32), (10, 16), (5, 8)]      # 204.8 / 51.2 / 12.8 KB of logits per anchor
+    host = [synthetic.make_level(np.random.default_rng(190 + i), 2, h, w) for i, (h, w) in enumerate(shapes)]
+    cpu = [tuple(torch.from_numpy(a).pin_memory() for a in l) for l in host]
+    wp = oracle.pow_sum([l[1] for l in host], 1.8)
+    results = {}
+    for cap in (1 << 40, chunk_bytes):
+        outs = [torch.zeros_like(l[0]).pin_memory() for l in cpu]
+        step = ops.HostStep(0)
+        step.set_chunk_bytes(cap)
+        step.bind(cpu, outs, power=1.8, **HEAD)
+        losses, norm = step.run()
+        step.close()
+        assert_loss_close(norm, wp)
+        for i, l in enumerate(host):
+            assert_loss_close(losses[i], oracle.distill_loss(*l, wp, **HEAD), "level %d (chunk cap %d)" % (i, cap))
+            assert_grad_close(outs[i].numpy(), oracle.distill_grad(*l, wp, **HEAD), "level %d (chunk cap %d)" % (i, cap))
+        results[cap] = [o.clone() for o in outs]
+    for a_, b_ in zip(results[1 << 40], results[chunk_bytes]):
+        assert torch.equal(a_, b_), "chunking must not change a single gradient bit"
+
+
 # ---------------------------------------------------------------------------------------------
 # the whole loss step in one cooperative launch (sad_distill_fused_f32): PowSum -> grid barrier -> loss + gradient
 # ---------------------------------------------------------------------------------------------
