@@ -174,8 +174,9 @@ void sad_ctx_destroy(sad_ctx* ctx);
 int sad_distill_step_host(sad_ctx* ctx, const sad_host_level* levels, int n_levels, float power,
                           const sad_distill_params* params, float* losses_out, float* normalizer_out);
 /* Pipeline granularity of sad_distill_step_host: a chunk is a run of whole anchors of one image of one level, capped at `bytes`
- * of logits (0 = default: environment SAD_HOST_CHUNK_BYTES, else 4 MB).  Smaller chunks shorten the un-overlapped head of the
- * pipeline (the first logits copy after the teacher probabilities) at the price of more launches. */
+ * of logits (0 = default: environment SAD_HOST_CHUNK_BYTES, else 16 MB).  Smaller chunks shorten the un-overlapped head of the
+ * pipeline (the first logits copy after the teacher probabilities) at the price of more launches; measured sweep in
+ * profiles/r01l_e2e_chunk_sweep.json. */
 int sad_ctx_set_host_chunk_bytes(sad_ctx* ctx, size_t bytes);
 /* device address of level i's gradient from the last sad_distill_step_host call */
 float* sad_ctx_device_d_logits(sad_ctx* ctx, int level);
@@ -296,6 +297,14 @@ size_t sad_conv3x3_wgrad_workspace_bytes(const sad_wgrad_level* levels, int n_le
 /* d_weight: (Cout, Cin, 3, 3) fp32; d_bias: (Cout) fp32 or NULL; workspace: 256-byte aligned device memory */
 int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
                           int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* Weight (+ bias) gradient with fp16 operands: x_nhwc (N, H, W, cin) and dy_nhwc (N, H, W, dy_channels) hold fp16 elements behind
+ * the float-typed pointers of sad_wgrad_level; both are MN-major UMMA operands under the plain 128-byte swizzle (16-bit types,
+ * unlike tf32, have that layout).  dy_channels >= cout is the channel count of the dY tensors: gradient tensors whose channel
+ * count is not a multiple of 8 (the 36 box-regression channels) are stored padded, and the pad channels never leave the partial
+ * buffers.  out_scale multiplies the finished dW / db: 1 / (the loss scale the caller applied to dY to keep fp16 gradients out
+ * of the subnormal range).  Workspace: sad_conv3x3_wgrad_workspace_bytes(levels, n_levels, cin, dy_channels). */
+int sad_conv3x3_wgrad_f16(const sad_wgrad_level* levels, int n_levels, int cin, int dy_channels, int cout, float out_scale,
+                          float* d_weight, float* d_bias, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * The whole RetinaNet FPN head, forward and backward — replaces the operator chains emitted by

@@ -29,7 +29,13 @@
 //     the splits in a fixed order (deterministic, no atomics) and writes dW in the operator's
 //     (Cout, Cin, 3, 3) layout.  db partials come from bias_grad_partial_kernel and are finished by
 //     the same kernel.
+//
+// fp16 operands (template parameter kF16, entry point sad_conv3x3_wgrad_f16; BASELINE.json configs[4]: mixed fp16 compute): the same
+// formulation on tcgen05.mma kind::f16.  16-bit MN-major operands use the PLAIN 128-byte swizzle (TMA CU_TENSOR_MAP_SWIZZLE_128B,
+// UMMA layout type 2): chunk rows hold 64 channels, 8-pixel swizzle atoms are 1024 B apart (SBO), chunks kWgChunkBytes apart
+// (LBO), one MMA covers 16 pixels (+2048 B).  Accumulators, partial buffers and the finished gradients stay fp32.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,6 +54,19 @@ constexpr int kWgChunkBytes = kWgKP * 128;               // one {32 ch x 32 px} 
 constexpr int kWgABytes = (kWgM / 32) * kWgChunkBytes;   // 16 KB
 constexpr int kWgBBytes = (kWgN / 32) * kWgChunkBytes;   // 32 KB
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;     // 48 KB
+// fp16 operands (kF16): a 128-byte chunk row holds 64 channels, so a tile is 2 + 4 chunks = 24 KB per stage and the ring is 8 deep
+// in the same shared memory; one MMA covers 16 pixels, i.e. 2 instead of 4 instructions per stage for twice the flops each.
+template <bool kF16>
+struct WgTraits {
+  static constexpr int kCh = kF16 ? 64 : 32;                        // channels per 128-byte chunk row
+  static constexpr int kAChunks = kWgM / kCh, kBChunks = kWgN / kCh;
+  static constexpr int kABytes = kAChunks * kWgChunkBytes, kBBytes = kBChunks * kWgChunkBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kF16 ? 2 * kWgStages : kWgStages;
+  static constexpr int kKStep = kF16 ? 16 : 8;                      // pixels per MMA
+};
+static_assert(WgTraits<true>::kStages * WgTraits<true>::kStageBytes == kWgStages * kWgStageBytes, "same ring bytes");
+static_assert(2 * (2 * kWgStages) * 8 + 4 * 8 + 4 <= 256, "barrier block");
 constexpr int kWgEpiWarps = 8;                           // two warps per TMEM lane quarter, each draining 4 of the 8 column blocks
 constexpr int kWgThreads = 64 + 32 * kWgEpiWarps;        // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
 constexpr int kWgTmemCols = 512;                         // 2 accumulator buffers x 256 columns
@@ -62,7 +81,7 @@ struct WgLevel {
   uint32_t block_begin, block_end;    // pixel blocks (n, y, xseg) of this level on the global K axis
 };
 struct alignas(64) WgArgs {
-  CUtensorMap tmap_dy[SAD_MAX_LEVELS];   // 4-D {C, W, H, N}, box {32, 32, 1, 1}: one 32-channel chunk (tail tiles)
+  CUtensorMap tmap_dy[SAD_MAX_LEVELS];   // 4-D {C, W, H, N}, box {32, 32, 1, 1}: one 32-channel chunk (tail tiles); fp16: 64 channels
   CUtensorMap tmap_x[SAD_MAX_LEVELS];
   CUtensorMap tmap_dy5[SAD_MAX_LEVELS];  // 5-D {32, W, H, N, C/32}, box {32, 32, 1, 1, 4}: a whole M tile in one copy
   CUtensorMap tmap_x5[SAD_MAX_LEVELS];   // 5-D, box {32, 32, 1, 1, 8}: a whole N tile in one copy
@@ -91,14 +110,17 @@ __device__ __forceinline__ WgItem wg_decode_item(const WgArgs& a, uint32_t item)
   return it;
 }
 
+template <bool kF16>
 __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const __grid_constant__ WgArgs args) {
+  using TR = WgTraits<kF16>;
+  constexpr int kCh = TR::kCh, kStages = TR::kStages, kStageBytes = TR::kStageBytes, kABytes = TR::kABytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWgStages * kWgStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kWgStages;
-  uint64_t* tmem_full = bars + 2 * kWgStages;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -114,7 +136,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kWgStages; ++s) {
+      for (int s = 0; s < kStages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
@@ -148,33 +170,33 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
         r /= args.lv[l].xsegs;
         int y = (int)(r % (uint32_t)args.lv[l].H);
         int n = (int)(r / (uint32_t)args.lv[l].H);
-        const int a_left = (args.cout - it.m0 + 31) / 32, b_left = (args.cin - it.n0 + 31) / 32;
-        const int a_chunks = a_left < kWgM / 32 ? a_left : kWgM / 32, b_chunks = b_left < kWgN / 32 ? b_left : kWgN / 32;
+        const int a_left = (args.cout - it.m0 + kCh - 1) / kCh, b_left = (args.cin - it.n0 + kCh - 1) / kCh;
+        const int a_chunks = a_left < TR::kAChunks ? a_left : TR::kAChunks, b_chunks = b_left < TR::kBChunks ? b_left : TR::kBChunks;
         const bool a_full = it.m0 + kWgM <= args.cout, b_full = it.n0 + kWgN <= args.cin;  // whole tile inside the tensor
         for (uint32_t kb = it.kb_begin; kb < it.kb_end; ++kb) {
           mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
-          uint8_t* sa = smem + (size_t)rs.stage * kWgStageBytes;
-          uint8_t* sb = sa + kWgABytes;
+          uint8_t* sa = smem + (size_t)rs.stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
           // 32-channel chunks that lie entirely past Cout / Cin are not loaded: whatever the stage holds there
           // only reaches accumulator rows / columns the epilogue never writes out
           mbar_arrive_expect_tx(&full_bar[rs.stage], (uint32_t)(a_chunks + b_chunks) * kWgChunkBytes);
           if (a_full) {  // the tile's 4 chunks in one 5-D copy: [chunk][pixel][32 channels], chunks 4 KB apart
-            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y, n, it.m0 / 32);
+            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y, n, it.m0 / kCh);
           } else {
 #pragma unroll
-            for (int j = 0; j < kWgM / 32; ++j)
+            for (int j = 0; j < TR::kAChunks; ++j)
               if (j < a_chunks)
-                tma_load_4d(sa + j * kWgChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + 32 * j, xs * kWgKP, y, n);
+                tma_load_4d(sa + j * kWgChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + kCh * j, xs * kWgKP, y, n);
           }
           if (b_full) {
-            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y + dy, n, it.n0 / 32);
+            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y + dy, n, it.n0 / kCh);
           } else {
 #pragma unroll
-            for (int j = 0; j < kWgN / 32; ++j)
+            for (int j = 0; j < TR::kBChunks; ++j)
               if (j < b_chunks)
-                tma_load_4d(sb + j * kWgChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + 32 * j, xs * kWgKP + dx, y + dy, n);
+                tma_load_4d(sb + j * kWgChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + kCh * j, xs * kWgKP + dx, y + dy, n);
           }
-          rs.advance<kWgStages>();
+          rs.advance<kStages>();
           if (++xs == (int)args.lv[l].xsegs) {
             xs = 0;
             if (++y == args.lv[l].H) {
@@ -192,7 +214,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kWgM, kWgN, /*A MN-major*/ 1, /*B MN-major*/ 1);
+      constexpr uint32_t idesc = kF16 ? umma_idesc_f16(kWgM, kWgN, /*A MN-major*/ 1, /*B MN-major*/ 1)
+                                      : umma_idesc_tf32(kWgM, kWgN, /*A MN-major*/ 1, /*B MN-major*/ 1);
       RingState rs;
       uint32_t itn = 0;
       for (uint32_t item = blockIdx.x; item < args.total_items; item += gridDim.x, ++itn) {
@@ -205,19 +228,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
         for (uint32_t kb = it.kb_begin; kb < it.kb_end; ++kb) {
           mbar_wait(&full_bar[rs.stage], rs.phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kWgStageBytes);
-          const uint32_t b_addr = a_addr + kWgABytes;
+          const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-          for (int k = 0; k < kWgKP / 8; ++k) {
-            // MN-major operands: one K step = 8 pixel rows of 128 B = two 4-row swizzle groups 512 B apart (SBO);
-            // the 32-channel chunks of the M / N axis are kWgChunkBytes apart (LBO)
-            const uint64_t adesc = umma_smem_desc_sw128_base32(a_addr + k * 1024, kWgChunkBytes, 512);
-            const uint64_t bdesc = umma_smem_desc_sw128_base32(b_addr + k * 1024, kWgChunkBytes, 512);
-            umma_tf32(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+          for (int k = 0; k < kWgKP / TR::kKStep; ++k) {
+            if (kF16) {
+              // MN-major 16-bit operands take the plain 128-byte swizzle (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+              // 16-byte units): one K step = 16 pixel rows of 128 B = two 8-row swizzle atoms 1024 B apart (SBO); the
+              // 64-channel chunks of the M / N axis are kWgChunkBytes apart (LBO)
+              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, kWgChunkBytes, 1024);
+              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, kWgChunkBytes, 1024);
+              umma_f16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+            } else {
+              // MN-major tf32 operands: one K step = 8 pixel rows of 128 B = two 4-row swizzle groups 512 B apart (SBO);
+              // the 32-channel chunks of the M / N axis are kWgChunkBytes apart (LBO)
+              const uint64_t adesc = umma_smem_desc_sw128_base32(a_addr + k * 1024, kWgChunkBytes, 512);
+              const uint64_t bdesc = umma_smem_desc_sw128_base32(b_addr + k * 1024, kWgChunkBytes, 512);
+              umma_tf32(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+            }
             first = 0;
           }
           umma_commit(&empty_bar[rs.stage]);
-          rs.advance<kWgStages>();
+          rs.advance<kStages>();
         }
         umma_commit(&tmem_full[buf]);
       }
@@ -309,12 +341,22 @@ __global__ void conv3x3_wgrad_simt_kernel(const WgSimtArgs a) {
 // the 4 pixel lanes are combined through shared memory in a fixed order.
 // ---------------------------------------------------------------------------------------------
 struct BgArgs {
-  const float* dy[SAD_MAX_LEVELS];
+  const float* dy[SAD_MAX_LEVELS];         // fp16 instantiation: __half storage
   uint32_t pix_begin[SAD_MAX_LEVELS + 1];  // prefix of N*H*W over levels
   float* partial;                          // [blocks][cout]
   int32_t n_levels, cout;
   uint32_t chunk;
 };
+__device__ __forceinline__ float4 bg_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 bg_load4(const __half* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float bg_load1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float bg_load1(const __half* p) { return __half2float(*p); }
+
+template <typename InT>
 __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgArgs a) {
   __shared__ float4 red[kBgThreads];
   const uint32_t total = a.pix_begin[a.n_levels];
@@ -330,10 +372,10 @@ __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgA
         for (int l = 0; l < a.n_levels; ++l) {
           const uint32_t lo = p0 > a.pix_begin[l] ? p0 : a.pix_begin[l];
           const uint32_t hi = p1 < a.pix_begin[l + 1] ? p1 : a.pix_begin[l + 1];
-          const float* base = a.dy[l] - (size_t)a.pix_begin[l] * a.cout + (size_t)q * 4;
+          const InT* base = reinterpret_cast<const InT*>(a.dy[l]) - (size_t)a.pix_begin[l] * a.cout + (size_t)q * 4;
 #pragma unroll 4
           for (uint32_t p = lo + ty; p < hi; p += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * a.cout));
+            const float4 v = bg_load4(base + (size_t)p * a.cout);
             acc.x += v.x;
             acc.y += v.y;
             acc.z += v.z;
@@ -363,7 +405,7 @@ __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgA
       int l = 0;
       for (uint32_t p = p0; p < p1; ++p) {
         while (p >= a.pix_begin[l + 1]) ++l;
-        acc += __ldg(a.dy[l] + (size_t)(p - a.pix_begin[l]) * a.cout + c);
+        acc += bg_load1(reinterpret_cast<const InT*>(a.dy[l]) + (size_t)(p - a.pix_begin[l]) * a.cout + c);
       }
       a.partial[(size_t)blockIdx.x * a.cout + c] = acc;
     }
@@ -377,23 +419,25 @@ __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgA
 // run of the (Cout, Cin, 3, 3) tensor.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinThreads = 288;
+// cout_src >= cout: channel count of the partial buffers (the fp16 path pads the gradient tensors' channels to a multiple of 8);
+// out_scale: 1 / loss scale of the fp16 path (a power of two), 1 otherwise.
 __global__ void __launch_bounds__(kFinThreads) conv3x3_wgrad_finish_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
-                                                                          float* __restrict__ d_weight,
+                                                                          int cout_src, float out_scale, float* __restrict__ d_weight,
                                                                           const float* __restrict__ bias_partial, int bias_blocks,
                                                                           float* __restrict__ d_bias, int accumulate) {
   __shared__ float out[kFinThreads];
-  const size_t plane = (size_t)cout * cin;
+  const size_t plane = (size_t)cout * cin, plane_src = (size_t)cout_src * cin;
   const int tap = threadIdx.x >> 5, ii = threadIdx.x & 31;
   const size_t groups = (plane + 31) / 32;
   for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
     const size_t i = g * 32 + ii;  // i = co * cin + ci
     float acc = 0.f;
     if (i < plane) {
-      const float* src = partial + (size_t)tap * plane + i;
+      const float* src = partial + (size_t)tap * plane_src + i;   // i = co * cin + ci is the same in both planes (co < cout)
 #pragma unroll 4
-      for (int s = 0; s < splits; ++s) acc += __ldg(src + (size_t)s * 9 * plane);
+      for (int s = 0; s < splits; ++s) acc += __ldg(src + (size_t)s * 9 * plane_src);
     }
-    out[ii * 9 + tap] = acc;
+    out[ii * 9 + tap] = acc * out_scale;
     __syncthreads();
     const size_t o = g * 288 + threadIdx.x;
     if (o < 9 * plane) d_weight[o] = accumulate ? d_weight[o] + out[threadIdx.x] : out[threadIdx.x];
@@ -405,9 +449,10 @@ __global__ void __launch_bounds__(kFinThreads) conv3x3_wgrad_finish_kernel(const
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t c = warp; c < (size_t)cout; c += warps) {
       float acc = 0.f;
-      for (int b = lane; b < bias_blocks; b += 32) acc += __ldg(bias_partial + (size_t)b * cout + c);
+      for (int b = lane; b < bias_blocks; b += 32) acc += __ldg(bias_partial + (size_t)b * cout_src + c);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      acc *= out_scale;
       if (lane == 0) d_bias[c] = accumulate ? d_bias[c] + acc : acc;
     }
   }
@@ -474,6 +519,14 @@ static int encode_nhwc5_map(CUtensorMap* m, const float* xt, int N, int C, int H
   return encode_map(m, xt, 5, dims, str, box, what, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
+// the same for fp16: {64 c_lo, W, H, N, C/64 c_hi}, plain 128-byte swizzle
+static int encode_nhwc5_map_f16(CUtensorMap* m, const void* xt, int N, int C, int H, int W, int box_x, int chunks, const char* what) {
+  const cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 64)};
+  const cuuint64_t str[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, 128};
+  const cuuint32_t box[5] = {64, (cuuint32_t)box_x, 1, 1, (cuuint32_t)chunks};
+  return encode_map(m, xt, 5, dims, str, box, what, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+}
+
 static int wg_sms(int* sms) {
   // sizing must not depend on a device being present (workspace_bytes is callable on a CPU-only host):
   // fall back to the B200's 148 SMs
@@ -499,20 +552,25 @@ SAD_EXPORT size_t sad_conv3x3_wgrad_workspace_bytes(const sad_wgrad_level* level
   return ((p.partial_bytes + 255) / 256) * 256 + p.bias_partial_bytes;
 }
 
-SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
-                                     int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+// cout_out: channels of d_weight / d_bias; cout (>= cout_out): channel count of the dY tensors (the fp16 path pads it to a multiple
+// of 8; the extra channels never leave the partial buffers); out_scale multiplies the finished gradients (1 / loss scale).
+static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int cout, int cout_out, float out_scale, float* d_weight, float* d_bias,
+                      int accumulate, void* workspace, size_t workspace_bytes, void* stream, bool f16) {
   int sms = 0, rc;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   WgPlan p;
   if ((rc = wg_plan(levels, n_levels, cin, cout, sms, &p)) != SAD_OK) return rc;
   if (!d_weight) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: d_weight is null");
+  if (cout_out < 1 || cout_out > cout) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: output channels must be in [1, dY channels]");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bool tma_ok = (cin % 4 == 0) && (cout % 4 == 0);
+  bool tma_ok = f16 ? (cin % 8 == 0) && (cout % 8 == 0) : (cin % 4 == 0) && (cout % 4 == 0);
   for (int l = 0; l < n_levels; ++l) {
     const sad_wgrad_level& L = levels[l];
     if ((uint64_t)L.N * L.H * L.W && (!L.x_nhwc || !L.dy_nhwc)) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: null tensor");
     if ((reinterpret_cast<uintptr_t>(L.x_nhwc) | reinterpret_cast<uintptr_t>(L.dy_nhwc)) & 15) tma_ok = false;
   }
+  if (!tma_ok && f16)
+    return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 wgrad fp16: needs channel counts that are multiples of 8 and 16-byte aligned tensors");
   if (!tma_ok) p.splits = 1, p.partial_bytes = (size_t)9 * cout * cin * sizeof(float);
   const size_t partial_padded = ((p.partial_bytes + 255) / 256) * 256;
   if (!workspace || workspace_bytes < partial_padded + p.bias_partial_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255))
@@ -522,8 +580,8 @@ SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels
 
   if (p.pixels == 0) {  // nothing to reduce: the gradients are zero
     if (!accumulate) {
-      if ((rc = check_cuda(cudaMemsetAsync(d_weight, 0, (size_t)9 * cin * cout * sizeof(float), st), "memset dW")) != SAD_OK) return rc;
-      if (d_bias && (rc = check_cuda(cudaMemsetAsync(d_bias, 0, (size_t)cout * sizeof(float), st), "memset db")) != SAD_OK) return rc;
+      if ((rc = check_cuda(cudaMemsetAsync(d_weight, 0, (size_t)9 * cin * cout_out * sizeof(float), st), "memset dW")) != SAD_OK) return rc;
+      if (d_bias && (rc = check_cuda(cudaMemsetAsync(d_bias, 0, (size_t)cout_out * sizeof(float), st), "memset db")) != SAD_OK) return rc;
     }
     return SAD_OK;
   }
@@ -543,6 +601,16 @@ SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels
       blocks += (uint64_t)L.N * L.H * D.xsegs;
       D.block_end = (uint32_t)blocks;
       if (D.block_end == D.block_begin) continue;
+      if (f16) {
+        if ((rc = encode_nhwc_map_f16(&a.tmap_dy[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, 1, "wgrad fp16 dY {C,W,H,N}")) != SAD_OK) return rc;
+        if ((rc = encode_nhwc_map_f16(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, 1, "wgrad fp16 X {C,W,H,N}")) != SAD_OK) return rc;
+        if (cout >= kWgM && (rc = encode_nhwc5_map_f16(&a.tmap_dy5[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, kWgM / 64, "wgrad fp16 dY 5-D")) != SAD_OK) return rc;
+        if (cin >= kWgN && (rc = encode_nhwc5_map_f16(&a.tmap_x5[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, kWgN / 64, "wgrad fp16 X 5-D")) != SAD_OK) return rc;
+        if (cout < kWgM) a.tmap_dy5[l] = a.tmap_dy[l];
+        if (cin < kWgN) a.tmap_x5[l] = a.tmap_x[l];
+        if (first_valid < 0) first_valid = l;
+        continue;
+      }
       if ((rc = encode_nhwc_map(&a.tmap_dy[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, 1, "wgrad dY {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
       if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, 1, "wgrad X {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
       // 5-D views {32 c_lo, W, H, N, C/32 c_hi} (c_hi stride 128 B) so one copy brings a whole tile of full chunks
@@ -568,11 +636,12 @@ SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels
     a.splits = p.splits;
     a.total_blocks = p.total_blocks;
     a.total_items = p.tiles * p.splits;
-    if ((rc = check_cuda(cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes),
+    auto kern = f16 ? conv3x3_wgrad_tf32_kernel<true> : conv3x3_wgrad_tf32_kernel<false>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes),
                          "cudaFuncSetAttribute(wgrad)")) != SAD_OK)
       return rc;
     const uint32_t grid = a.total_items < (uint32_t)sms ? a.total_items : (uint32_t)sms;
-    conv3x3_wgrad_tf32_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
+    kern<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
     count_launch(1);
     if ((rc = check_cuda(cudaGetLastError(), "conv3x3 wgrad launch")) != SAD_OK) return rc;
   } else {
@@ -607,16 +676,27 @@ SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels
     b.n_levels = n_levels;
     b.cout = cout;
     b.chunk = p.bias_chunk;
-    bias_grad_partial_kernel<<<p.bias_blocks, kBgThreads, 0, st>>>(b);
+    if (f16) bias_grad_partial_kernel<__half><<<p.bias_blocks, kBgThreads, 0, st>>>(b);
+    else bias_grad_partial_kernel<float><<<p.bias_blocks, kBgThreads, 0, st>>>(b);
     count_launch(1);
     if ((rc = check_cuda(cudaGetLastError(), "bias grad launch")) != SAD_OK) return rc;
   }
-  const size_t groups = ((size_t)cin * cout + 31) / 32;
+  const size_t groups = ((size_t)cin * cout_out + 31) / 32;
   const unsigned fblocks = (unsigned)(groups < (size_t)sms * 16 ? groups : (size_t)sms * 16);
-  conv3x3_wgrad_finish_kernel<<<fblocks, kFinThreads, 0, st>>>(partial, (int)p.splits, cin, cout, d_weight, bias_partial, (int)p.bias_blocks,
-                                                       d_bias, accumulate);
+  conv3x3_wgrad_finish_kernel<<<fblocks, kFinThreads, 0, st>>>(partial, (int)p.splits, cin, cout_out, cout, out_scale, d_weight, bias_partial,
+                                                       (int)p.bias_blocks, d_bias, accumulate);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "conv3x3 wgrad finish launch");
+}
+
+SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
+                                     int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return wgrad_impl(levels, n_levels, cin, cout, cout, 1.f, d_weight, d_bias, accumulate, workspace, workspace_bytes, stream, false);
+}
+
+SAD_EXPORT int sad_conv3x3_wgrad_f16(const sad_wgrad_level* levels, int n_levels, int cin, int dy_channels, int cout, float out_scale,
+                                     float* d_weight, float* d_bias, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return wgrad_impl(levels, n_levels, cin, dy_channels, cout, out_scale, d_weight, d_bias, accumulate, workspace, workspace_bytes, stream, true);
 }
 
 }  // extern "C"

@@ -9,10 +9,13 @@
 // A chunk is a run of whole ANCHORS of one image of one level: the (A*C, H, W) block of an image is contiguous and the
 // kernel's label indexing (loss_op.cu:35-42: t = gt[n*H*W*A + a*H*W + y*W + x]) only needs the label base moved by
 // a0*H*W, so anchors [a0, a0 + k) of image n are a valid (N = 1, D = k*C, H, W) level of their own.  Chunks are capped at
-// ~4 MB (SAD_HOST_CHUNK_BYTES) and ordered largest first so the un-overlapped D2H tail is the smallest chunk.
-// The normaliser needs every teacher probability (PowSum runs over all levels, reference retinanet_heads.py:320-328),
-// hence T goes first and the critical path is  H2D(T) + H2D(first X chunk) + kernel + D2H(all dX):  with whole images as
-// chunks the middle term was a 29.5 MB copy (0.54 ms of 3.65 ms per step at configs[1], measured r01j/r01k).
+// 16 MB (SAD_HOST_CHUNK_BYTES / sad_ctx_set_host_chunk_bytes) and ordered largest first so the un-overlapped D2H tail is the
+// smallest chunk.  The normaliser needs every teacher probability (PowSum runs over all levels, reference
+// retinanet_heads.py:320-328), hence T (and the small label tensors) go first and the critical path is
+//   H2D(T) + H2D(first X chunk) + kernel + D2H(all dX).
+// Measured at configs[1] (profiles/r01l_e2e_chunk_sweep.json): whole images 3.64 ms, 16 MB 3.56 ms, 8 MB 3.67, 4 MB 3.96, 1 MB 4.21 —
+// the copies of both directions contend on this host (236.7 MB in 3.56 ms = 66 GB/s aggregate) and every extra chunk costs
+// launches, so the cap stays coarse.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -62,7 +65,7 @@ size_t host_chunk_bytes() {
   static const size_t v = [] {
     const char* e = std::getenv("SAD_HOST_CHUNK_BYTES");
     const long long x = e ? std::atoll(e) : 0;
-    return x > 0 ? (size_t)x : (size_t)4 << 20;
+    return x > 0 ? (size_t)x : (size_t)16 << 20;
   }();
   return v;
 }
@@ -194,6 +197,12 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
       return rc;
   cudaEventRecord(c->ev_T, c->s_in);
   cudaStreamWaitEvent(c->s_k, c->ev_T, 0);
+  // labels: 1/80 of the logits' bytes; one copy per level here instead of one small copy per chunk
+  for (int l = 0; l < n_levels; ++l) {
+    const sad_host_level& L = levels[l];
+    const size_t lab = (size_t)L.N * (L.D / params->num_classes) * L.H * L.W;
+    if (lab && (rc = check_cuda(cudaMemcpyAsync(c->G[l].p, L.labels, lab * 4, cudaMemcpyHostToDevice, c->s_in), "H2D G")) != SAD_OK) return rc;
+  }
   if ((rc = sad_pow_sum_f32(t_dev, sizes, n_levels, power, d_norm, c->ws_pow.p, c->ws_pow.cap, c->s_k)) != SAD_OK) return rc;
 
   // ---- per chunk: H2D X,G -> loss+grad -> D2H dX --------------------------------------------
@@ -204,10 +213,8 @@ SAD_EXPORT int sad_distill_step_host(sad_ctx* c, const sad_host_level* levels, i
     const size_t xoff = ((size_t)ch.n * L.D + (size_t)ch.a0 * params->num_classes) * hw;
     const size_t lab_per_img = (size_t)(L.D / params->num_classes) * hw;
     const size_t goff = (size_t)ch.n * lab_per_img + (size_t)ch.a0 * hw;
-    const size_t lab_elems = (size_t)ch.k * hw;
     float* dXd = static_cast<float*>(c->dX[ch.level].p) + xoff;
-    if ((rc = check_cuda(cudaMemcpyAsync(static_cast<float*>(c->X[ch.level].p) + xoff, L.logits + xoff, ch.elems * 4, cudaMemcpyHostToDevice, c->s_in), "H2D X")) != SAD_OK ||
-        (rc = check_cuda(cudaMemcpyAsync(static_cast<int32_t*>(c->G[ch.level].p) + goff, L.labels + goff, lab_elems * 4, cudaMemcpyHostToDevice, c->s_in), "H2D G")) != SAD_OK)
+    if ((rc = check_cuda(cudaMemcpyAsync(static_cast<float*>(c->X[ch.level].p) + xoff, L.logits + xoff, ch.elems * 4, cudaMemcpyHostToDevice, c->s_in), "H2D X")) != SAD_OK)
       return rc;
     cudaEventRecord(c->ev_in[i], c->s_in);
     cudaStreamWaitEvent(c->s_k, c->ev_in[i], 0);

@@ -155,6 +155,8 @@ def lib():
         l.sad_nchw_to_nhwc_f16.argtypes = [C.POINTER(LayoutLevel), C.c_int, C.c_int, C.c_void_p]
         l.sad_conv3x3_pack_weights_multi_f16.argtypes = [C.POINTER(PackItem), C.c_int, C.c_void_p]
         l.sad_conv3x3_fwd_f16.argtypes = [C.POINTER(ConvLevel), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.sad_conv3x3_wgrad_f16.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_scale_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
         l.sad_affine_channel_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
         l.sad_upsample_nearest_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -241,7 +241,7 @@ class HostStep:
         check(lib().sad_ctx_create(int(device), C.byref(self.handle)))
 
     def set_chunk_bytes(self, nbytes):
-        """Pipeline granularity (sad_ctx_set_host_chunk_bytes): logits bytes per chunk of whole anchors; 0 = default (4 MB)."""
+        """Pipeline granularity (sad_ctx_set_host_chunk_bytes): logits bytes per chunk of whole anchors; 0 = default (16 MB)."""
         check(lib().sad_ctx_set_host_chunk_bytes(self.handle, int(nbytes)))
 
     def close(self):
@@ -518,3 +518,28 @@ def conv3x3_forward_f16(xs_nhwc_f16, packed_f16, cout, bias=None, relu=0, want_n
     b = C.c_void_p(bias.data_ptr()) if bias is not None else None
     check(lib().sad_conv3x3_fwd_f16(arr, len(xs_nhwc_f16), C.c_void_p(packed_f16.data_ptr()), b, cin, cout, int(relu), _stream()))
     return ys, yts
+
+
+def conv3x3_wgrad_f16(xs_nhwc_f16, dys_nhwc_f16, cout=None, out_scale=1.0, want_bias=True):
+    """Weight (+ bias) gradient summed over every level with fp16 operands.  xs: (N, H, W, Cin) fp16; dys: (N, H, W, C_dy) fp16 with
+    C_dy >= cout (channel-padded gradient tensors); the result is multiplied by out_scale (1 / loss scale).  Returns (dW, db) fp32."""
+    n = len(xs_nhwc_f16)
+    arr = (WgradLevel * n)()
+    cin, cdy = xs_nhwc_f16[0].shape[3], dys_nhwc_f16[0].shape[3]
+    cout = cdy if cout is None else int(cout)
+    for i, (xt, dt) in enumerate(zip(xs_nhwc_f16, dys_nhwc_f16)):
+        _require_cuda(xt, torch.float16, "x_nhwc[%d]" % i)
+        _require_cuda(dt, torch.float16, "dy_nhwc[%d]" % i)
+        if xt.shape[:3] != dt.shape[:3] or xt.shape[3] != cin or dt.shape[3] != cdy:
+            raise ValueError("level %d: x (N,H,W,Cin) and dy (N,H,W,C_dy) do not match" % i)
+        arr[i].x_nhwc, arr[i].dy_nhwc = xt.data_ptr(), dt.data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = xt.shape[:3]
+    dev = xs_nhwc_f16[0].device
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
+    db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
+    nbytes = lib().sad_conv3x3_wgrad_workspace_bytes(arr, n, cin, cdy)
+    workspace = torch.empty(max(256, nbytes), dtype=torch.uint8, device=dev)
+    check(lib().sad_conv3x3_wgrad_f16(arr, n, cin, cdy, cout, float(out_scale), C.c_void_p(dw.data_ptr()),
+                                      C.c_void_p(db.data_ptr()) if db is not None else None, 0,
+                                      C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+    return dw, db

@@ -121,3 +121,35 @@ def test_f16_teacher_head_matches_tf32_head():
     assert (p_ref[0].std() > 1e-4).item(), "the comparison must not be between constant outputs"
     with pytest.raises(native.SadError, match="forward-only"):
         f16.forward(fpn, training=True)
+
+
+WG_CASES = [
+    # (N, Cin, C_dy, Cout, [(H, W), ...])
+    ((2, 256, 256, 256, [(20, 32), (10, 16)]), "tower shape, two levels on one K axis"),
+    ((1, 256, 720, 720, [(10, 16), (5, 8)]), "cls_pred: 720 = 5 full M tiles + 80 (one full + one partial 64-channel chunk)"),
+    ((2, 64, 128, 128, [(8, 40)]), "Cin = 64: one chunk of the 256-wide N tile, ragged 40-pixel rows"),
+    ((1, 256, 40, 36, [(12, 20), (3, 4)]), "bbox_pred: 36 real channels stored padded to 40"),
+]
+
+
+@pytest.mark.parametrize("shape,name", WG_CASES, ids=[c[1] for c in WG_CASES])
+def test_f16_wgrad_matches_oracle(oracle, shape, name):
+    """dW / db of the fp16 weight-gradient kernel (MN-major fp16 operands, plain 128-byte swizzle) against the oracle's ConvGradient
+    (conv_op_impl.h:182-420) on the same fp16-rounded operands, summed over the levels; out_scale = 1 / 8 stands for the loss scale."""
+    from sad_b200 import ops
+    N, Cin, Cdy, Cout, levels = shape
+    rng = np.random.default_rng(Cin + Cdy + len(levels))
+    wdummy = np.zeros((Cout, Cin, 3, 3), np.float32)
+    xs, dys, ref_dw, ref_db = [], [], 0.0, 0.0
+    for (H, W) in levels:
+        x = np.maximum(rng.standard_normal((N, Cin, H, W)), 0).astype(np.float32)
+        dy = rng.standard_normal((N, Cdy, H, W)).astype(np.float32)     # pad channels (>= Cout) hold values too: they must not leak
+        dW, db, _ = oracle.conv2d_bwd(_h(x), wdummy, _h(dy)[:, :Cout].copy(), need_dx=False)
+        ref_dw, ref_db = ref_dw + dW.astype(np.float64), ref_db + db.astype(np.float64)
+        xs.append(torch.from_numpy(x).cuda().permute(0, 2, 3, 1).contiguous().half())
+        dys.append(torch.from_numpy(dy).cuda().permute(0, 2, 3, 1).contiguous().half())
+    dw, db = ops.conv3x3_wgrad_f16(xs, dys, cout=Cout, out_scale=0.125)
+    torch.cuda.synchronize()
+    assert tuple(dw.shape) == (Cout, Cin, 3, 3) and tuple(db.shape) == (Cout,)
+    _close(dw.cpu().numpy(), ref_dw * 0.125, 5e-4, 2e-4, "fp16 dW: " + name)
+    _close(db.cpu().numpy(), ref_db * 0.125, 5e-4, 2e-4, "fp16 db: " + name)
