@@ -244,12 +244,17 @@ int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float*
  * counterpart is the fp16 branch of CudnnConvOp (caffe2/caffe2/operators/conv_op_cudnn.cc:623-643, unused by its configs).
  * The three *_f16 entry points take the SAME structs as the fp32 ones; the channels-last tensors (sad_layout_level.dst_nhwc,
  * sad_conv_level.x_nhwc / y_nhwc) and the packed weights (sad_pack_item.packed, sad_conv3x3_packed_bytes / 2 bytes) then hold
- * IEEE fp16 elements behind the float-typed pointers.  Forward only: relu_mask_nhwc, relu_bits_*, accumulate_nchw must be
- * 0 / NULL.  Needs Cin % 8 == 0 and 16-byte aligned tensors (SAD_ERR_UNSUPPORTED otherwise: there is no SIMT fp16 path). */
-int sad_nchw_to_nhwc_f16(const sad_layout_level* levels, int n_levels, int channels, void* stream);
+ * IEEE fp16 elements behind the float-typed pointers.  relu_mask_nhwc must be NULL (ReluGradient is taken from relu_bits_in).
+ * Needs Cin % 8 == 0 and 16-byte aligned tensors (SAD_ERR_UNSUPPORTED otherwise: there is no SIMT fp16 path). */
+/* channels_dst: channel count of the destination rows (0 = channels; larger = zero padding, e.g. 36 -> 40 for the box-regression
+ * gradient); scale: multiplied in before rounding to fp16 (1 for activations, the loss scale for gradient tensors). */
+int sad_nchw_to_nhwc_f16(const sad_layout_level* levels, int n_levels, int channels, int channels_dst, float scale, void* stream);
 int sad_conv3x3_pack_weights_multi_f16(const sad_pack_item* items, int n_items, void* stream);
+/* nchw_scale multiplies what is stored to y_nchw (1 for the forward operator; 1 / loss scale on the data-gradient pass that
+ * produces d(fpn_L)); the fp16 channels-last output is not rescaled.  The data gradient is this entry point on mode-1 packed
+ * weights: cin = the padded K of the pack (sad_conv3x3_pack_weights_multi_f16 pads K with zeros to a multiple of 8). */
 int sad_conv3x3_fwd_f16(const sad_conv_level* levels, int n_levels, const void* packed_f16, const float* bias, int cin, int cout,
-                        int relu, void* stream);
+                        int relu, float nchw_scale, void* stream);
 
 /* Relu / ReluGradient as stand-alone operators — replace ReluOp / ReluGradientOp<float, CUDAContext>::RunOnDevice
  * (caffe2/caffe2/operators/relu_op.cu:22-62): y = x > 0 ? x : 0;  dx = y > 0 ? dy : 0.  In place allowed (y == x,
@@ -331,8 +336,11 @@ typedef struct sad_head_config {
   int32_t cls_output_sigmoid;   /* 0: cls output = logits (retnet_cls_pred_fpnL, the student).  1: = Sigmoid(logits)
                                    (retnet_cls_prob_fpnL: what the graph adds when model.train is False, i.e. for the
                                    teacher, retinanet_heads.py:153-163) fused into the prediction convolution's epilogue */
-  int32_t compute_f16;          /* 1: fp16 operands (sad_conv3x3_fwd_f16) for every convolution of a FORWARD-ONLY head (the teacher);
-                                   sad_head_forward(training != 0) then fails with SAD_ERR_UNSUPPORTED */
+  int32_t compute_f16;          /* 1: fp16 operands (tcgen05 kind::f16, fp32 accumulation) for every convolution of the head, forward
+                                   and backward: activations, packed weights and the channels-last gradient tensors are fp16;
+                                   parameters, parameter gradients and the NCHW boundary tensors stay fp32 */
+  float f16_grad_scale;         /* compute_f16 only: loss scale applied to d(logits) / d(box deltas) when they are rounded to fp16
+                                   and divided out of every gradient the head returns; a power of two (0 = default 4096) */
 } sad_head_config;
 typedef struct sad_head_weights {
   const float* cls_tower_w[SAD_HEAD_MAX_CONVS];  /* (dim, dim, 3, 3) */

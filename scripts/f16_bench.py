@@ -71,6 +71,22 @@ def main():
         flops = 2.0 * pixels * 2304 * (8 * 256 + 720 + 36)
         res["teacher_head_forward_" + name] = {"ms": ms, "tflops": flops / ms / 1e9}
         h.close()
+    # the student head: forward (training) + backward (data + weight gradients of all 10 convolutions) in both precisions
+    for name, f16 in (("tf32", False), ("f16", True)):
+        h = head.RetinaNetHead(a.bs, shapes, seed=5, compute_f16=f16)
+        cls, box = h.alloc_outputs()
+        d_cls = [torch.randn(c.shape, device="cuda", generator=g) * 1e-5 for c in cls]
+        d_box = [torch.randn(c.shape, device="cuda", generator=g) * 1e-5 for c in box]
+        d_fpn = [torch.empty_like(x) for x in fpn]
+
+        def step():
+            h.forward(fpn, training=True, out=(cls, box))
+            h.backward(d_cls, d_box, d_fpn=d_fpn)
+
+        ms = timeit(step, a.iters)
+        flops = 3 * 2.0 * pixels * 2304 * (8 * 256 + 720 + 36)
+        res["student_head_fwd_bwd_" + name] = {"ms": ms, "tflops": flops / ms / 1e9}
+        h.close()
     # body operators (HBM streams): res2-sized AffineChannel, the FPN top-down upsamples, momentum-sized Scale
     x = rnd(a.bs, 256, 160, 256)
     s, b = rnd(256), rnd(256)

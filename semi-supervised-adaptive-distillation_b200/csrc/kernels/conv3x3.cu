@@ -87,6 +87,7 @@ struct alignas(64) ConvArgs {
   const float* bias;
   int32_t n_levels, cin, cout, relu;
   uint32_t m_tiles, k_blocks, total_tiles;
+  float nchw_scale;   // fp16 instantiations only: multiplies what is stored to y_nchw (1 / loss scale on the last data-gradient pass)
 };
 
 struct ConvTile {
@@ -338,11 +339,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
           }
           if (yrow) {
             float* dst = yrow + (size_t)y * L.W + t.x0;
+            const float ns = kF16 ? args.nchw_scale : 1.f;
             if (vec_ok) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
                 if (t.x0 + i < L.W) {
                   float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                  if (kF16) o = make_float4(o.x * ns, o.y * ns, o.z * ns, o.w * ns);
                   if (L.accumulate) {
                     const float4 p = *reinterpret_cast<const float4*>(dst + i);
                     o.x += p.x;
@@ -355,7 +358,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (t.x0 + i < L.W) dst[i] = L.accumulate ? dst[i] + v[i] : v[i];
+                if (t.x0 + i < L.W) {
+                  if (kF16) dst[i] = L.accumulate ? dst[i] + v[i] * ns : v[i] * ns;
+                  else dst[i] = L.accumulate ? dst[i] + v[i] : v[i];
+                }
             }
           }
           if (ycl) {
@@ -424,13 +430,16 @@ __global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
   OutT* __restrict__ out = reinterpret_cast<OutT*>(p.dst[k_]);
   const int cout = p.cout[k_], cin = p.cin[k_], mode = p.mode[k_];
   const uint32_t M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
-  const uint32_t plane = M * K;
+  // 16-bit output: the K axis is padded with zeros to a multiple of 8 (16-byte tensor-map strides), e.g. the 36 box-regression
+  // channels of the data-gradient pack become 40; the convolution is then called with cin = the padded K
+  const uint32_t Kp = sizeof(OutT) == 2 ? (K + 7u) & ~7u : K;
+  const uint32_t plane = M * Kp;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
-    const uint32_t k = i % K, m = i / K;
+    const uint32_t k = i % Kp, m = i / Kp;
     const float* src = mode == 0 ? w + ((size_t)m * cin + k) * 9 : w + ((size_t)k * cin + m) * 9;
     float v[9];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) v[tap] = __ldg(src + tap);
+    for (int tap = 0; tap < 9; ++tap) v[tap] = k < K ? __ldg(src + tap) : 0.f;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) store_operand(out + (size_t)tap * plane + i, mode == 0 ? v[tap] : v[8 - tap]);
   }
@@ -485,6 +494,8 @@ struct LayoutArgs {
   LayoutLevel lv[SAD_MAX_LEVELS];
   int32_t n_levels, C;
   uint32_t tiles_c, total_tiles;
+  int32_t C_dst;   // channels of the destination rows (>= C: zero padding, fp16 gradient tensors); tiles_c covers C_dst
+  float scale;     // fp16 instantiation only: values are multiplied before rounding (the loss scale of the gradient tensors)
 };
 template <typename OutT>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant__ LayoutArgs a) {
@@ -501,7 +512,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
     const uint32_t n = r / a.tiles_c;
     const uint32_t hw0 = th * 32, c0 = tc * 32;
     const float* src = L.src + (size_t)n * a.C * L.HW;
-    OutT* dst = reinterpret_cast<OutT*>(L.dst) + (size_t)n * a.C * L.HW;
+    OutT* dst = reinterpret_cast<OutT*>(L.dst) + (size_t)n * a.C_dst * L.HW;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t c = c0 + ty + k * 8, hw = hw0 + tx;
@@ -511,7 +522,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t hw = hw0 + ty + k * 8, c = c0 + tx;
-      if (c < (uint32_t)a.C && hw < L.HW) store_operand(dst + (size_t)hw * a.C + c, tile[tx][ty + k * 8]);
+      if (c < (uint32_t)a.C_dst && hw < L.HW)
+        store_operand(dst + (size_t)hw * a.C_dst + c, sizeof(OutT) == 2 ? tile[tx][ty + k * 8] * a.scale : tile[tx][ty + k * 8]);
     }
     __syncthreads();
   }
@@ -570,12 +582,17 @@ static int pack_weights_multi_impl(const sad_pack_item* items, int n_items, void
   return check_cuda(cudaGetLastError(), "conv3x3 pack multi launch");
 }
 
-static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int channels, void* stream, bool f16) {
+static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int channels, void* stream, bool f16, int channels_dst = 0,
+                             float scale = 1.f) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || channels < 1) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: bad argument");
+  if (channels_dst == 0) channels_dst = channels;
+  if (channels_dst < channels) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: destination channels < source channels");
   LayoutArgs a{};
   a.n_levels = n_levels;
   a.C = channels;
-  a.tiles_c = (uint32_t)((channels + 31) / 32);
+  a.C_dst = channels_dst;
+  a.scale = scale;
+  a.tiles_c = (uint32_t)((channels_dst + 31) / 32);
   uint64_t tiles = 0;
   for (int l = 0; l < n_levels; ++l) {
     const sad_layout_level& L = levels[l];
@@ -605,7 +622,7 @@ static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int c
 // `packed` has layout [tap][cout][cin] (sad_conv3x3_pack_weights_f32 mode 0 for the forward operator,
 // mode 1 — with cin/cout swapped by the caller — for the data gradient).
 static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
-                            int cout, int relu, void* stream, bool f16) {
+                            int cout, int relu, void* stream, bool f16, float nchw_scale = 1.f) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3: n_levels must be in [1, 8]");
   if (!packed || cin < 1 || cout < 1) return set_error(SAD_ERR_INVALID, "conv3x3: bad weights/channels");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -645,8 +662,8 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
     return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 fp16: needs Cin % 8 == 0 and 16-byte aligned tensors (there is no SIMT fp16 path)");
   if (f16) {
     for (int l = 0; l < n_levels; ++l)
-      if (levels[l].relu_mask_nhwc || levels[l].relu_bits_in || levels[l].relu_bits_out || levels[l].accumulate_nchw)
-        return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 fp16: forward only (no ReLU masks / sign bits / accumulation)");
+      if (levels[l].relu_mask_nhwc)
+        return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 fp16: ReluGradient comes from sign bits (relu_bits_in), not from a float mask tensor");
   }
   if (!tma_ok) {  // channel count / alignment the TMA path cannot address
     for (int l = 0; l < n_levels; ++l) {
@@ -695,6 +712,7 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
       return rc;
   }
   a.bias = bias;
+  a.nchw_scale = nchw_scale;
   a.n_levels = n_levels;
   a.cin = cin;
   a.cout = cout;
@@ -750,16 +768,16 @@ SAD_EXPORT int sad_conv3x3_pack_weights_multi_f16(const sad_pack_item* items, in
 SAD_EXPORT int sad_nchw_to_nhwc_f32(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
   return nchw_to_nhwc_impl(levels, n_levels, channels, stream, false);
 }
-SAD_EXPORT int sad_nchw_to_nhwc_f16(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
-  return nchw_to_nhwc_impl(levels, n_levels, channels, stream, true);
+SAD_EXPORT int sad_nchw_to_nhwc_f16(const sad_layout_level* levels, int n_levels, int channels, int channels_dst, float scale, void* stream) {
+  return nchw_to_nhwc_impl(levels, n_levels, channels, stream, true, channels_dst, scale);
 }
 SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                                    int cout, int relu, void* stream) {
   return conv3x3_fwd_impl(levels, n_levels, packed, bias, cin, cout, relu, stream, false);
 }
 SAD_EXPORT int sad_conv3x3_fwd_f16(const sad_conv_level* levels, int n_levels, const void* packed_f16, const float* bias, int cin,
-                                   int cout, int relu, void* stream) {
-  return conv3x3_fwd_impl(levels, n_levels, static_cast<const float*>(packed_f16), bias, cin, cout, relu, stream, true);
+                                   int cout, int relu, float nchw_scale, void* stream) {
+  return conv3x3_fwd_impl(levels, n_levels, static_cast<const float*>(packed_f16), bias, cin, cout, relu, stream, true, nchw_scale);
 }
 
 }  // extern "C"

@@ -61,6 +61,8 @@ struct sad_head {
 namespace {
 
 size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+int pad8(int c) { return (c + 7) & ~7; }   // fp16 gradient tensors: channel counts padded to 16-byte rows (36 -> 40)
+float grad_scale(const sad_head* h) { return h->cfg.f16_grad_scale > 0.f ? h->cfg.f16_grad_scale : 4096.f; }
 
 int pred_out(const sad_head_config& c, int tower) { return tower == 0 ? c.cls_out : c.bbox_out; }
 
@@ -100,7 +102,7 @@ int pack_all(sad_head* h, const sad_head_weights* w, bool with_bwd, cudaStream_t
 
 int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float* const* y_nhwc, uint32_t* const* bits_out,
                 uint32_t* const* bits_in, int accumulate, const float* packed, const float* bias, int cin, int cout, int relu,
-                cudaStream_t st) {
+                cudaStream_t st, float nchw_scale = 1.f) {
   sad_conv_level lv[SAD_MAX_LEVELS];
   for (int l = 0; l < h->cfg.n_levels; ++l) {
     lv[l].x_nhwc = x[l];
@@ -115,11 +117,12 @@ int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float*
     lv[l].accumulate_nchw = accumulate;
   }
   // fp16 head: the arena's channels-last / packed buffers hold fp16 elements (half of each fp32-sized slot is used)
-  if (h->cfg.compute_f16) return sad_conv3x3_fwd_f16(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
+  if (h->cfg.compute_f16) return sad_conv3x3_fwd_f16(lv, h->cfg.n_levels, packed, bias, pad8(cin), cout, relu, nchw_scale, st);
   return sad_conv3x3_fwd_f32(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
 }
 
-int layout_levels(const sad_head* h, const float* const* src, float* const* dst, int channels, cudaStream_t st) {
+// scale: fp16 head only (the loss scale of gradient tensors; 1 for activations)
+int layout_levels(const sad_head* h, const float* const* src, float* const* dst, int channels, cudaStream_t st, float scale = 1.f) {
   sad_layout_level lv[SAD_MAX_LEVELS];
   for (int l = 0; l < h->cfg.n_levels; ++l) {
     lv[l].src_nchw = src[l];
@@ -128,7 +131,8 @@ int layout_levels(const sad_head* h, const float* const* src, float* const* dst,
     lv[l].H = h->cfg.H[l];
     lv[l].W = h->cfg.W[l];
   }
-  return h->cfg.compute_f16 ? sad_nchw_to_nhwc_f16(lv, h->cfg.n_levels, channels, st) : sad_nchw_to_nhwc_f32(lv, h->cfg.n_levels, channels, st);
+  return h->cfg.compute_f16 ? sad_nchw_to_nhwc_f16(lv, h->cfg.n_levels, channels, pad8(channels), scale, st)
+                            : sad_nchw_to_nhwc_f32(lv, h->cfg.n_levels, channels, st);
 }
 
 int wgrad_levels(const sad_head* h, float* const* x, float* const* dy, int cin, int cout, float* dw, float* db, int accumulate, void* ws,
@@ -141,6 +145,8 @@ int wgrad_levels(const sad_head* h, float* const* x, float* const* dy, int cin, 
     lv[l].H = h->cfg.H[l];
     lv[l].W = h->cfg.W[l];
   }
+  if (h->cfg.compute_f16)
+    return sad_conv3x3_wgrad_f16(lv, h->cfg.n_levels, cin, pad8(cout), cout, 1.f / grad_scale(h), dw, db, accumulate, ws, h->wg_ws_bytes, st);
   return sad_conv3x3_wgrad_f32(lv, h->cfg.n_levels, cin, cout, dw, db, accumulate, ws, h->wg_ws_bytes, st);
 }
 
@@ -193,7 +199,7 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
   }
   size_t wsb = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, dim);
   const size_t wsb_cls = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, cfg->cls_out);
-  const size_t wsb_box = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, cfg->bbox_out);
+  const size_t wsb_box = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, pad8(cfg->bbox_out));   // the fp16 path pads dY's channels
   if (wsb_cls > wsb) wsb = wsb_cls;
   if (wsb_box > wsb) wsb = wsb_box;
   h->wg_ws_bytes = align256(wsb);
@@ -285,8 +291,8 @@ SAD_EXPORT int sad_head_forward(sad_head* h, const sad_head_weights* w, const fl
   if (!h || !fpn_nchw || !cls_logits_nchw || !bbox_pred_nchw) return set_error(SAD_ERR_INVALID, "sad_head_forward: null argument");
   int rc;
   if ((rc = validate_weights(h, w, "sad_head_forward")) != SAD_OK) return rc;
-  if (h->cfg.compute_f16 && training)
-    return set_error(SAD_ERR_UNSUPPORTED, "sad_head_forward: an fp16 head is forward-only (the teacher); the gradient kernels are tf32");
+  if (h->cfg.compute_f16 && (h->cfg.dim % 8))
+    return set_error(SAD_ERR_UNSUPPORTED, "sad_head_forward: an fp16 head needs dim % 8 == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = h->cfg.num_convs, dim = h->cfg.dim;
   if ((rc = layout_levels(h, fpn_nchw, h->x0, dim, st)) != SAD_OK) return rc;
@@ -320,7 +326,6 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
   if (!d_cls_logits_nchw && !d_bbox_pred_nchw) return set_error(SAD_ERR_INVALID, "sad_head_backward: no output gradient given");
   if (h->cfg.cls_output_sigmoid)
     return set_error(SAD_ERR_UNSUPPORTED, "sad_head_backward: a head whose classification output is Sigmoid(logits) is forward-only (the teacher)");
-  if (h->cfg.compute_f16) return set_error(SAD_ERR_UNSUPPORTED, "sad_head_backward: an fp16 head is forward-only (the teacher)");
   if (!h->packed_bwd_valid)
     return set_error(SAD_ERR_INVALID, "sad_head_backward: call sad_head_forward(training = 1) first (it keeps the activations and packs the weights)");
   int rc;
@@ -350,7 +355,9 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
       if (r != SAD_OK) return r;
       return check_cuda(cudaStreamWaitEvent(sw, h->ev_dy[t][i], 0), "cudaStreamWaitEvent");
     };
-    if ((rc = layout_levels(h, dpred, h->gpred[t], po, s)) != SAD_OK) return rc;
+    // fp16 head: the output gradients are multiplied by the loss scale as they are rounded to fp16 (d_logits ~ 1e-6 would
+    // otherwise sit in fp16's subnormal range); every gradient that leaves the head is divided by it again
+    if ((rc = layout_levels(h, dpred, h->gpred[t], po, s, grad_scale(h))) != SAD_OK) return rc;
     if ((rc = dy_ready(nc)) != SAD_OK) return rc;
     if ((rc = wgrad_levels(h, pred_in, h->gpred[t], dim, po, dwp, dbp, accumulate, ws, sw)) != SAD_OK) return rc;
     // data gradient of the prediction conv; its input is the last tower activation (post-ReLU) -> ReluGradient fused
@@ -368,7 +375,8 @@ SAD_EXPORT int sad_head_backward(sad_head* h, const sad_head_weights* w, const f
         }
         acc = fpn_written ? 1 : 0;
       }
-      if ((rc = conv_levels(h, dy, last ? d_fpn_nchw : nullptr, out_cl, nullptr, mask, acc, h->packed[1][t][i], nullptr, dy_c, dim, 0, s)) != SAD_OK)
+      if ((rc = conv_levels(h, dy, last ? d_fpn_nchw : nullptr, out_cl, nullptr, mask, acc, h->packed[1][t][i], nullptr, dy_c, dim, 0, s,
+                            1.f / grad_scale(h))) != SAD_OK)
         return rc;
       if (last) {
         fpn_written = true;

@@ -34,7 +34,7 @@ def param_names(num_convs=4, k_min=K_MIN):
 
 class RetinaNetHead:
     def __init__(self, n_images, level_shapes, dim=256, num_convs=4, num_anchors=9, num_classes=80, prior_prob=0.01,
-                 device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False, param_buffer=None, compute_f16=False):
+                 device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False, param_buffer=None, compute_f16=False, f16_grad_scale=0.0):
         self.N, self.level_shapes = int(n_images), [tuple(s) for s in level_shapes]
         self.dim, self.num_convs = int(dim), int(num_convs)
         self.cls_out, self.bbox_out = num_anchors * num_classes, num_anchors * 4
@@ -47,8 +47,10 @@ class RetinaNetHead:
         cfg.dim, cfg.num_convs, cfg.cls_out, cfg.bbox_out = self.dim, self.num_convs, self.cls_out, self.bbox_out
         # teacher mode (retinanet_heads.py:153-163): the classification output is retnet_cls_prob_fpnL = Sigmoid(logits)
         cfg.cls_output_sigmoid = 1 if cls_output_sigmoid else 0
-        # fp16 operands for a forward-only head (BASELINE.json configs[4]: mixed fp16 compute); forward(training=True) then fails
+        # fp16 operands for every convolution of the head, forward and backward (BASELINE.json configs[4]: mixed fp16 compute, fp32
+        # accumulation, fp32 parameters and parameter gradients); f16_grad_scale: loss scale of the fp16 gradient tensors (0 = 4096)
         cfg.compute_f16 = 1 if compute_f16 else 0
+        cfg.f16_grad_scale = float(f16_grad_scale)
         self.compute_f16 = bool(compute_f16)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -463,21 +463,24 @@ def scale_(x, alpha):
 # ---------------------------------------------------------------------------------------------
 # fp16-operand forward convolution (BASELINE.json configs[4]: mixed fp16 compute, fp32 accumulate) — forward only
 # ---------------------------------------------------------------------------------------------
-def conv3x3_pack_f16(weight):
-    """(Cout, Cin, 3, 3) fp32 -> [tap][Cout][Cin] fp16 (round to nearest) for sad_conv3x3_fwd_f16."""
+def conv3x3_pack_f16(weight, mode=0):
+    """(Cout, Cin, 3, 3) fp32 -> fp16 (round to nearest) for sad_conv3x3_fwd_f16: mode 0 [tap][Cout][Cin] (forward), mode 1
+    [tap][Cin][pad8(Cout)] with flipped taps (data gradient; the K axis is zero-padded to a multiple of 8)."""
     _require_cuda(weight, torch.float32, "weight")
     cout, cin = weight.shape[0], weight.shape[1]
     if tuple(weight.shape[2:]) != (3, 3):
         raise ValueError("weight must be (Cout, Cin, 3, 3)")
-    packed = torch.empty(9 * cin * cout, dtype=torch.float16, device=weight.device)
+    m, k = (cout, cin) if mode == 0 else (cin, cout)
+    packed = torch.empty(9 * m * ((k + 7) // 8 * 8), dtype=torch.float16, device=weight.device)
     item = (native.PackItem * 1)()
-    item[0].weight, item[0].packed, item[0].cin, item[0].cout, item[0].mode = weight.data_ptr(), packed.data_ptr(), cin, cout, 0
+    item[0].weight, item[0].packed, item[0].cin, item[0].cout, item[0].mode = weight.data_ptr(), packed.data_ptr(), cin, cout, int(mode)
     check(lib().sad_conv3x3_pack_weights_multi_f16(item, 1, _stream()))
     return packed
 
 
-def to_nhwc_f16(xs):
-    """NCHW fp32 -> channels-last (N, H, W, C) fp16, every level in one launch."""
+def to_nhwc_f16(xs, channels_dst=None, scale=1.0):
+    """NCHW fp32 -> channels-last (N, H, W, channels_dst or C) fp16, every level in one launch; values are multiplied by `scale`
+    before rounding (the loss scale of gradient tensors) and channels beyond C are zero."""
     xs = list(xs)
     arr = (native.LayoutLevel * len(xs))()
     outs = []
@@ -486,18 +489,19 @@ def to_nhwc_f16(xs):
         if x.shape[1] != xs[0].shape[1]:
             raise ValueError("all levels must have the same channel count")
         n, c, h, w = x.shape
-        outs.append(torch.empty((n, h, w, c), dtype=torch.float16, device=x.device))
+        outs.append(torch.empty((n, h, w, channels_dst or c), dtype=torch.float16, device=x.device))
         arr[i].src_nchw, arr[i].dst_nhwc = x.data_ptr(), outs[-1].data_ptr()
         arr[i].N, arr[i].H, arr[i].W = n, h, w
-    check(lib().sad_nchw_to_nhwc_f16(arr, len(xs), xs[0].shape[1], _stream()))
+    check(lib().sad_nchw_to_nhwc_f16(arr, len(xs), xs[0].shape[1], int(channels_dst or 0), float(scale), _stream()))
     return outs
 
 
-def conv3x3_forward_f16(xs_nhwc_f16, packed_f16, cout, bias=None, relu=0, want_nchw=True, want_nhwc=False):
+def conv3x3_forward_f16(xs_nhwc_f16, packed_f16, cout, bias=None, relu=0, want_nchw=True, want_nhwc=False, nchw_scale=1.0, relu_bits=None,
+                        want_bits=False):
     """Conv (+bias, + activation: 0 none, 1 ReLU, 2 Sigmoid) of every level in one launch with fp16 operands.
     xs_nhwc_f16: channels-last fp16 inputs (to_nhwc_f16 or a previous call's fp16 output).  Returns (ys_nchw fp32, ys_nhwc fp16)."""
     arr = (ConvLevel * len(xs_nhwc_f16))()
-    ys, yts = [], []
+    ys, yts, bits = [], [], []
     cin = xs_nhwc_f16[0].shape[3]
     for i, xt in enumerate(xs_nhwc_f16):
         _require_cuda(xt, torch.float16, "x_nhwc[%d]" % i)
@@ -512,12 +516,17 @@ def conv3x3_forward_f16(xs_nhwc_f16, packed_f16, cout, bias=None, relu=0, want_n
         if want_nhwc:
             yts.append(torch.empty((n, h, w, cout), dtype=torch.float16, device=xt.device))
             arr[i].y_nhwc = yts[-1].data_ptr()
+        if relu_bits is not None:      # ReluGradient fused into a data-gradient pass: sign bits a forward pass left
+            arr[i].relu_bits_in = relu_bits[i].data_ptr()
+        if want_bits:
+            bits.append(sign_bits_like(n, cout, h, w, xt.device))
+            arr[i].relu_bits_out = bits[-1].data_ptr()
     _require_cuda(packed_f16, torch.float16, "packed")
     if packed_f16.numel() != 9 * cin * cout:
         raise ValueError("packed weights must hold 9 * Cin * Cout fp16 elements")
     b = C.c_void_p(bias.data_ptr()) if bias is not None else None
-    check(lib().sad_conv3x3_fwd_f16(arr, len(xs_nhwc_f16), C.c_void_p(packed_f16.data_ptr()), b, cin, cout, int(relu), _stream()))
-    return ys, yts
+    check(lib().sad_conv3x3_fwd_f16(arr, len(xs_nhwc_f16), C.c_void_p(packed_f16.data_ptr()), b, cin, cout, int(relu), float(nchw_scale), _stream()))
+    return (ys, yts, bits) if want_bits else (ys, yts)
 
 
 def conv3x3_wgrad_f16(xs_nhwc_f16, dys_nhwc_f16, cout=None, out_scale=1.0, want_bias=True):

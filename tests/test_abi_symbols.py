@@ -81,10 +81,14 @@ def test_new_entry_points_validate_arguments_without_device():
     assert lib.sad_upsample_nearest_grad_f32(None, p, 1, 2, 2, 2, None) == -1
     assert lib.sad_scale_f32(None, p, 4, 1.0, None) == -1 and lib.sad_scale_f32(p, p, 0, 1.0, None) == 0
     lv = (native.ConvLevel * 1)()
-    assert lib.sad_conv3x3_fwd_f16(lv, 0, p, None, 64, 64, 0, None) == -1
-    assert lib.sad_conv3x3_fwd_f16(lv, 1, None, None, 64, 64, 0, None) == -1
+    assert lib.sad_conv3x3_fwd_f16(lv, 0, p, None, 64, 64, 0, 1.0, None) == -1
+    assert lib.sad_conv3x3_fwd_f16(lv, 1, None, None, 64, 64, 0, 1.0, None) == -1
     lv[0].N, lv[0].H, lv[0].W = 1, 4, 4
     lv[0].x_nhwc, lv[0].y_nchw = 256, 256
-    assert lib.sad_conv3x3_fwd_f16(lv, 1, p, None, 36, 64, 0, None) == -4 and b"Cin % 8" in lib.sad_last_error()
-    lv[0].accumulate_nchw = 1
-    assert lib.sad_conv3x3_fwd_f16(lv, 1, p, None, 64, 64, 0, None) == -4 and b"forward only" in lib.sad_last_error()
+    assert lib.sad_conv3x3_fwd_f16(lv, 1, p, None, 36, 64, 0, 1.0, None) == -4 and b"Cin % 8" in lib.sad_last_error()
+    lv[0].relu_mask_nhwc = 256
+    assert lib.sad_conv3x3_fwd_f16(lv, 1, p, None, 64, 64, 0, 1.0, None) == -4 and b"sign bits" in lib.sad_last_error()
+    wl = (native.WgradLevel * 1)()
+    wl[0].N, wl[0].H, wl[0].W = 1, 4, 4
+    wl[0].x_nhwc = wl[0].dy_nhwc = 256
+    assert lib.sad_conv3x3_wgrad_f16(wl, 1, 64, 40, 44, 1.0, p, None, 0, p, 1 << 30, None) in (-1, -2)   # cout > dY channels (-2: no device)

@@ -1,5 +1,5 @@
-"""GPU parity of the fp16-operand forward convolution (tcgen05 kind::f16; BASELINE.json configs[4]: "mixed fp16 compute / fp32 loss
-accumulate") and of the forward-only fp16 head (the teacher) against the CPU oracle (oracle/conv_oracle.c restating
+"""GPU parity of the fp16-operand convolutions (forward, data gradient, weight gradient: tcgen05 kind::f16; BASELINE.json configs[4]:
+"mixed fp16 compute / fp32 loss accumulate") and of the fp16 head (teacher forward; student forward + backward) against the CPU oracle (oracle/conv_oracle.c restating
 conv_op_impl.h:31-180).
 
 Two gates, both written here:
@@ -119,8 +119,8 @@ def test_f16_teacher_head_matches_tf32_head():
         d = (a - b).abs().max().item()
         assert d <= 3e-3 * a.abs().max().item(), "fp16 head vs tf32 head: max|d| %.3g of max %.3g" % (d, a.abs().max().item())
     assert (p_ref[0].std() > 1e-4).item(), "the comparison must not be between constant outputs"
-    with pytest.raises(native.SadError, match="forward-only"):
-        f16.forward(fpn, training=True)
+    with pytest.raises(native.SadError, match="forward-only"):      # Sigmoid(logits) output = the teacher: no backward
+        f16.backward([torch.zeros_like(p) for p in p_f16], None)
 
 
 WG_CASES = [
@@ -153,3 +153,66 @@ def test_f16_wgrad_matches_oracle(oracle, shape, name):
     assert tuple(dw.shape) == (Cout, Cin, 3, 3) and tuple(db.shape) == (Cout,)
     _close(dw.cpu().numpy(), ref_dw * 0.125, 5e-4, 2e-4, "fp16 dW: " + name)
     _close(db.cpu().numpy(), ref_db * 0.125, 5e-4, 2e-4, "fp16 db: " + name)
+
+
+def test_f16_dgrad_with_relu_bits_channel_padding_and_loss_scale(oracle):
+    """The data gradient is the forward kernel on mode-1 weights.  Here with everything the fp16 head's backward uses: dY of the 36
+    box-regression channels stored padded to 40 and multiplied by a loss scale S as it is rounded to fp16, K-padded packed weights,
+    ReluGradient from the sign bits a forward pass left, 1 / S on the NCHW output, the channels-last fp16 output left scaled."""
+    from sad_b200 import ops
+    N, C, Cout, H, W, S = 2, 256, 36, 12, 20, 256.0
+    rng = np.random.default_rng(11)
+    x0 = np.maximum(rng.standard_normal((N, 64, H, W)), 0).astype(np.float32)
+    w0 = (rng.standard_normal((C, 64, 3, 3)) / 24.0).astype(np.float32)
+    b0 = rng.standard_normal((C,)).astype(np.float32)
+    w = (rng.standard_normal((Cout, C, 3, 3)) / 48.0).astype(np.float32)
+    dy = (rng.standard_normal((N, Cout, H, W)) * 1e-4).astype(np.float32)
+    # the layer below: Y = relu(conv(x0)) leaves its sign bits
+    (y,), _, bits = ops.conv3x3_forward_f16(ops.to_nhwc_f16([torch.from_numpy(x0).cuda()]), ops.conv3x3_pack_f16(torch.from_numpy(w0).cuda()), C,
+                                            torch.from_numpy(b0).cuda(), relu=1, want_bits=True)
+    dys = ops.to_nhwc_f16([torch.from_numpy(dy).cuda()], channels_dst=40, scale=S)
+    assert tuple(dys[0].shape) == (N, H, W, 40) and not dys[0][..., 36:].any().item()
+    assert np.array_equal(dys[0][..., :36].permute(0, 3, 1, 2).float().cpu().numpy(), _h(dy * S))
+    packed1 = ops.conv3x3_pack_f16(torch.from_numpy(w).cuda(), mode=1)
+    assert packed1.numel() == 9 * C * 40
+    (dx,), (dx_cl,) = ops.conv3x3_forward_f16(dys, packed1, C, None, relu=0, want_nhwc=True, nchw_scale=1.0 / S, relu_bits=bits)
+    torch.cuda.synchronize()
+    _, _, ref = oracle.conv2d_bwd(np.zeros((N, C, H, W), np.float32), _h(w), _h(dy * S) / np.float32(S), need_dx=True)
+    mask = (y.cpu().numpy() > 0)
+    _close(dx.cpu().numpy(), ref * mask, 5e-4, 2e-4, "fp16 data gradient (masked, unscaled)")
+    assert not dx.cpu().numpy()[~mask].any(), "ReluGradient from sign bits: exact zeros where Y <= 0"
+    assert torch.equal(dx_cl.permute(0, 3, 1, 2), (dx * S).half()), "channels-last output stays scaled: fp16(S * dX)"
+
+
+def test_f16_head_backward_matches_tf32_head():
+    """Forward (training) + backward of the fp16 head against the tf32 head on the same parameters, inputs and output gradients
+    (d_logits of the size the losses produce, ~1e-5: without the loss scale they would sit in fp16's subnormal range).  Both carry
+    10-bit-mantissa operands with fp32 accumulation; measured agreement is far inside the gate max|d| <= 1e-2 max|ref|, rms <= 3e-3."""
+    from sad_b200 import head
+    shapes = [(20, 32), (10, 16), (5, 8)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    fpn = [torch.randn(2, 256, h, w, device="cuda", generator=g).clamp_(min=0) * 0.5 for h, w in shapes]
+    ref = head.RetinaNetHead(2, shapes, seed=5)
+    f16 = head.RetinaNetHead(2, shapes, seed=5, compute_f16=True)
+    for h_ in (ref, f16):
+        for n in h_.names:
+            if n.endswith("_w"):
+                h_.params[n].mul_(4.0)
+    out_r, out_h = ref.forward(fpn, training=True), f16.forward(fpn, training=True)
+    d_cls = [torch.randn(o.shape, device="cuda", generator=g) * 1e-5 for o in out_r[0]]
+    d_box = [torch.randn(o.shape, device="cuda", generator=g) * 1e-5 for o in out_r[1]]
+    dfpn_r = ref.backward(d_cls, d_box)
+    dfpn_h = f16.backward(d_cls, d_box)
+    torch.cuda.synchronize()
+    for a, b in zip(out_r[0] + out_r[1], out_h[0] + out_h[1]):
+        assert (a - b).abs().max().item() <= 3e-3 * a.abs().max().item()
+    pairs = [("d_fpn level %d" % i, a, b) for i, (a, b) in enumerate(zip(dfpn_r, dfpn_h))]
+    pairs += [(n, ref.grads[n], f16.grads[n]) for n in ref.names]
+    for name, a, b in pairs:
+        assert torch.isfinite(b).all(), name
+        m = a.abs().max().item()
+        assert m > 0, name
+        d = (a - b).abs()
+        assert d.max().item() <= 1e-2 * m, "%s: max|d| %.3g of max|ref| %.3g" % (name, d.max().item(), m)
+        rms = (d.pow(2).mean().sqrt() / a.pow(2).mean().sqrt()).item()
+        assert rms <= 3e-3, "%s: relative rms %.3g" % (name, rms)
