@@ -54,19 +54,23 @@ constexpr int kWgChunkBytes = kWgKP * 128;               // one {32 ch x 32 px} 
 constexpr int kWgABytes = (kWgM / 32) * kWgChunkBytes;   // 16 KB
 constexpr int kWgBBytes = (kWgN / 32) * kWgChunkBytes;   // 32 KB
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;     // 48 KB
-// fp16 operands (kF16): a 128-byte chunk row holds 64 channels, so a tile is 2 + 4 chunks = 24 KB per stage and the ring is 8 deep
-// in the same shared memory; one MMA covers 16 pixels, i.e. 2 instead of 4 instructions per stage for twice the flops each.
+// fp16 operands (kF16): a 128-byte chunk row holds 64 channels and one MMA covers 16 pixels.  A stage therefore takes TWO image
+// rows of a 32-pixel segment (TMA box {64 ch, 32 x, 2 y}): 64 pixels x (2 + 4 chunks) = the same 48 KB and 4 MMAs per stage as the
+// tf32 form.  (With 32-pixel stages — 24 KB, 2 MMAs — the kernel was bound by the producer's per-stage work, not by the tensor
+// pipe: 38 % active, 48 us against the tf32 form's 51 us; profiles/r01m_f16_kernels_digest.txt.)
 template <bool kF16>
 struct WgTraits {
   static constexpr int kCh = kF16 ? 64 : 32;                        // channels per 128-byte chunk row
+  static constexpr int kRows = kF16 ? 2 : 1;                        // image rows per stage
+  static constexpr int kKP = kWgKP * kRows;                         // pixels per stage
+  static constexpr int kChunkBytes = kKP * 128;                     // one {kCh channels x kKP pixels} box
   static constexpr int kAChunks = kWgM / kCh, kBChunks = kWgN / kCh;
-  static constexpr int kABytes = kAChunks * kWgChunkBytes, kBBytes = kBChunks * kWgChunkBytes;
+  static constexpr int kABytes = kAChunks * kChunkBytes, kBBytes = kBChunks * kChunkBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kF16 ? 2 * kWgStages : kWgStages;
+  static constexpr int kStages = kWgStages;
   static constexpr int kKStep = kF16 ? 16 : 8;                      // pixels per MMA
 };
-static_assert(WgTraits<true>::kStages * WgTraits<true>::kStageBytes == kWgStages * kWgStageBytes, "same ring bytes");
-static_assert(2 * (2 * kWgStages) * 8 + 4 * 8 + 4 <= 256, "barrier block");
+static_assert(WgTraits<true>::kStageBytes == kWgStageBytes && WgTraits<false>::kStageBytes == kWgStageBytes, "same stage bytes");
 constexpr int kWgEpiWarps = 8;                           // two warps per TMEM lane quarter, each draining 4 of the 8 column blocks
 constexpr int kWgThreads = 64 + 32 * kWgEpiWarps;        // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
 constexpr int kWgTmemCols = 512;                         // 2 accumulator buffers x 256 columns
@@ -78,7 +82,8 @@ constexpr int kBgMaxBlocks = 1024;
 struct WgLevel {
   int32_t N, H, W;
   uint32_t xsegs;                     // ceil(W / 32)
-  uint32_t block_begin, block_end;    // pixel blocks (n, y, xseg) of this level on the global K axis
+  uint32_t yblocks;                   // ceil(H / rows per stage)
+  uint32_t block_begin, block_end;    // pixel blocks (n, y block, xseg) of this level on the global K axis
 };
 struct alignas(64) WgArgs {
   CUtensorMap tmap_dy[SAD_MAX_LEVELS];   // 4-D {C, W, H, N}, box {32, 32, 1, 1}: one 32-channel chunk (tail tiles); fp16: 64 channels
@@ -114,6 +119,7 @@ template <bool kF16>
 __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const __grid_constant__ WgArgs args) {
   using TR = WgTraits<kF16>;
   constexpr int kCh = TR::kCh, kStages = TR::kStages, kStageBytes = TR::kStageBytes, kABytes = TR::kABytes;
+  constexpr int kChunkBytes = TR::kChunkBytes, kRows = TR::kRows;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -168,8 +174,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
         uint32_t r = it.kb_begin - args.lv[l].block_begin;
         int xs = (int)(r % args.lv[l].xsegs);
         r /= args.lv[l].xsegs;
-        int y = (int)(r % (uint32_t)args.lv[l].H);
-        int n = (int)(r / (uint32_t)args.lv[l].H);
+        int y = (int)(r % args.lv[l].yblocks);   // row block: image rows y * kRows .. + kRows - 1 (rows past H are zero-filled)
+        int n = (int)(r / args.lv[l].yblocks);
         const int a_left = (args.cout - it.m0 + kCh - 1) / kCh, b_left = (args.cin - it.n0 + kCh - 1) / kCh;
         const int a_chunks = a_left < TR::kAChunks ? a_left : TR::kAChunks, b_chunks = b_left < TR::kBChunks ? b_left : TR::kBChunks;
         const bool a_full = it.m0 + kWgM <= args.cout, b_full = it.n0 + kWgN <= args.cin;  // whole tile inside the tensor
@@ -179,27 +185,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
           uint8_t* sb = sa + kABytes;
           // 32-channel chunks that lie entirely past Cout / Cin are not loaded: whatever the stage holds there
           // only reaches accumulator rows / columns the epilogue never writes out
-          mbar_arrive_expect_tx(&full_bar[rs.stage], (uint32_t)(a_chunks + b_chunks) * kWgChunkBytes);
+          mbar_arrive_expect_tx(&full_bar[rs.stage], (uint32_t)(a_chunks + b_chunks) * kChunkBytes);
           if (a_full) {  // the tile's 4 chunks in one 5-D copy: [chunk][pixel][32 channels], chunks 4 KB apart
-            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y, n, it.m0 / kCh);
+            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y * kRows, n, it.m0 / kCh);
           } else {
 #pragma unroll
             for (int j = 0; j < TR::kAChunks; ++j)
               if (j < a_chunks)
-                tma_load_4d(sa + j * kWgChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + kCh * j, xs * kWgKP, y, n);
+                tma_load_4d(sa + j * kChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + kCh * j, xs * kWgKP, y * kRows, n);
           }
           if (b_full) {
-            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y + dy, n, it.n0 / kCh);
+            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y * kRows + dy, n, it.n0 / kCh);
           } else {
 #pragma unroll
             for (int j = 0; j < TR::kBChunks; ++j)
               if (j < b_chunks)
-                tma_load_4d(sb + j * kWgChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + kCh * j, xs * kWgKP + dx, y + dy, n);
+                tma_load_4d(sb + j * kChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + kCh * j, xs * kWgKP + dx, y * kRows + dy, n);
           }
           rs.advance<kStages>();
           if (++xs == (int)args.lv[l].xsegs) {
             xs = 0;
-            if (++y == args.lv[l].H) {
+            if (++y == (int)args.lv[l].yblocks) {
               y = 0;
               if (++n == args.lv[l].N) {
                 n = 0;
@@ -231,13 +237,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
           const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-          for (int k = 0; k < kWgKP / TR::kKStep; ++k) {
+          for (int k = 0; k < TR::kKP / TR::kKStep; ++k) {
             if (kF16) {
               // MN-major 16-bit operands take the plain 128-byte swizzle (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
               // 16-byte units): one K step = 16 pixel rows of 128 B = two 8-row swizzle atoms 1024 B apart (SBO); the
-              // 64-channel chunks of the M / N axis are kWgChunkBytes apart (LBO)
-              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, kWgChunkBytes, 1024);
-              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, kWgChunkBytes, 1024);
+              // 64-channel chunks of the M / N axis are kChunkBytes (64 pixel rows) apart (LBO)
+              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, kChunkBytes, 1024);
+              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, kChunkBytes, 1024);
               umma_f16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
             } else {
               // MN-major tf32 operands: one K step = 8 pixel rows of 128 B = two 4-row swizzle groups 512 B apart (SBO);
@@ -467,14 +473,14 @@ struct WgPlan {
   size_t partial_bytes, bias_partial_bytes;
 };
 
-static int wg_plan(const sad_wgrad_level* levels, int n_levels, int cin, int cout, int sms, WgPlan* p) {
+static int wg_plan(const sad_wgrad_level* levels, int n_levels, int cin, int cout, int sms, WgPlan* p, int rows = 1) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: n_levels must be in [1, 8]");
   if (cin < 1 || cout < 1) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: bad channel counts");
   uint64_t blocks = 0, pixels = 0;
   for (int l = 0; l < n_levels; ++l) {
     const sad_wgrad_level& L = levels[l];
     if (L.N < 0 || L.H < 0 || L.W < 0) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: negative dimension");
-    blocks += (uint64_t)L.N * L.H * ((L.W + kWgKP - 1) / kWgKP);
+    blocks += (uint64_t)L.N * ((L.H + rows - 1) / rows) * ((L.W + kWgKP - 1) / kWgKP);
     pixels += (uint64_t)L.N * L.H * L.W;
   }
   if (blocks > 0x7fffffffull || pixels > 0x7fffffffull) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: too many pixels");
@@ -520,10 +526,10 @@ static int encode_nhwc5_map(CUtensorMap* m, const float* xt, int N, int C, int H
 }
 
 // the same for fp16: {64 c_lo, W, H, N, C/64 c_hi}, plain 128-byte swizzle
-static int encode_nhwc5_map_f16(CUtensorMap* m, const void* xt, int N, int C, int H, int W, int box_x, int chunks, const char* what) {
+static int encode_nhwc5_map_f16(CUtensorMap* m, const void* xt, int N, int C, int H, int W, int box_x, int box_y, int chunks, const char* what) {
   const cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 64)};
   const cuuint64_t str[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, 128};
-  const cuuint32_t box[5] = {64, (cuuint32_t)box_x, 1, 1, (cuuint32_t)chunks};
+  const cuuint32_t box[5] = {64, (cuuint32_t)box_x, (cuuint32_t)box_y, 1, (cuuint32_t)chunks};
   return encode_map(m, xt, 5, dims, str, box, what, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
 }
 
@@ -559,7 +565,8 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
   int sms = 0, rc;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   WgPlan p;
-  if ((rc = wg_plan(levels, n_levels, cin, cout, sms, &p)) != SAD_OK) return rc;
+  const int rows = f16 ? WgTraits<true>::kRows : 1;
+  if ((rc = wg_plan(levels, n_levels, cin, cout, sms, &p, rows)) != SAD_OK) return rc;
   if (!d_weight) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: d_weight is null");
   if (cout_out < 1 || cout_out > cout) return set_error(SAD_ERR_INVALID, "conv3x3 wgrad: output channels must be in [1, dY channels]");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -597,15 +604,16 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
       D.H = L.H;
       D.W = L.W;
       D.xsegs = (uint32_t)((L.W + kWgKP - 1) / kWgKP);
+      D.yblocks = (uint32_t)((L.H + rows - 1) / rows);
       D.block_begin = (uint32_t)blocks;
-      blocks += (uint64_t)L.N * L.H * D.xsegs;
+      blocks += (uint64_t)L.N * D.yblocks * D.xsegs;
       D.block_end = (uint32_t)blocks;
       if (D.block_end == D.block_begin) continue;
       if (f16) {
-        if ((rc = encode_nhwc_map_f16(&a.tmap_dy[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, 1, "wgrad fp16 dY {C,W,H,N}")) != SAD_OK) return rc;
-        if ((rc = encode_nhwc_map_f16(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, 1, "wgrad fp16 X {C,W,H,N}")) != SAD_OK) return rc;
-        if (cout >= kWgM && (rc = encode_nhwc5_map_f16(&a.tmap_dy5[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, kWgM / 64, "wgrad fp16 dY 5-D")) != SAD_OK) return rc;
-        if (cin >= kWgN && (rc = encode_nhwc5_map_f16(&a.tmap_x5[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, kWgN / 64, "wgrad fp16 X 5-D")) != SAD_OK) return rc;
+        if ((rc = encode_nhwc_map_f16(&a.tmap_dy[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, rows, "wgrad fp16 dY {C,W,H,N}")) != SAD_OK) return rc;
+        if ((rc = encode_nhwc_map_f16(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, rows, "wgrad fp16 X {C,W,H,N}")) != SAD_OK) return rc;
+        if (cout >= kWgM && (rc = encode_nhwc5_map_f16(&a.tmap_dy5[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, rows, kWgM / 64, "wgrad fp16 dY 5-D")) != SAD_OK) return rc;
+        if (cin >= kWgN && (rc = encode_nhwc5_map_f16(&a.tmap_x5[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, rows, kWgN / 64, "wgrad fp16 X 5-D")) != SAD_OK) return rc;
         if (cout < kWgM) a.tmap_dy5[l] = a.tmap_dy[l];
         if (cin < kWgN) a.tmap_x5[l] = a.tmap_x[l];
         if (first_valid < 0) first_valid = l;
