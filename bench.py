@@ -265,7 +265,7 @@ def run_head_step(args, rank, world, barrier, native):
     }
 
 
-def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False, teacher_f16=False):
+def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False, teacher_f16=False, student_f16=False):
     """BASELINE.json configs[3] geometry (n_images = 2 per GPU) or configs[2] (n_images = 16 on one GPU): R-50-FPN student <-
     R-101-FPN teacher, full distillation training step, 600 px, one allreduce of the flat [head | body] gradient buffer.
     Heads, every loss, the exchange and the optimiser step are this repository's kernels; the ResNet/FPN bodies are
@@ -280,7 +280,7 @@ def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False,
     if config5:   # configs[4]: R-101 student <- ResNeXt-101-64x4d teacher, 500 px, one image per GPU
         st = FullDistillStep(n_images=n_images, scale_px=500, world=world, rank=rank, student_blocks=(3, 4, 23, 3),
                              teacher_blocks=(3, 4, 23, 3), teacher_body=dict(groups=64, width_per_group=4, stride_1x1=False),
-                             teacher_head_f16=teacher_f16)
+                             teacher_head_f16=teacher_f16, student_head_f16=student_f16)
     else:
         st = FullDistillStep(n_images=n_images, scale_px=600, world=world, rank=rank)
     for _ in range(3):
@@ -332,6 +332,10 @@ def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False,
                             "gradient bytes, momentum SGD" % (n_images, st.exchange.nbytes))
         line["baseline_config"] = "configs[4] geometry and models (bs=1 per GPU); computed in tf32 / fp32, i.e. at higher precision than the fp16 the config names"
         line["teacher_head_dtype"] = "f16 operands, fp32 accumulate (tcgen05 kind::f16)" if teacher_f16 else "tf32"
+        line["student_head_dtype"] = "f16 operands forward + backward, fp32 accumulate, loss-scaled fp16 gradient tensors" if student_f16 else "tf32"
+        if teacher_f16 and student_f16:
+            line["baseline_config"] = ("configs[4] geometry and models (bs=1 per GPU); both RetinaNet heads in mixed fp16 (fp16 operands, fp32 "
+                                       "accumulation, fp32 losses and parameters) as the config names; the cuDNN bodies (scaffolding) stay tf32")
     st.head.close()
     st.teacher_head.close()
     del st
@@ -349,8 +353,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head-steps", type=int, default=0, help="head distillation steps (0 = min(steps, 100); -1 = skip)")
     ap.add_argument("--full-steps", type=int, default=0, help="full R-50 <- R-101 distillation steps (0 = min(steps, 20); -1 = skip)")
-    ap.add_argument("--teacher-f16", action="store_true", default=os.environ.get("SAD_TEACHER_F16", "") == "1",
-                    help="also run configs[4]'s step with the teacher head on fp16 operands (object full_step_config5_teacher_f16)")
+    ap.add_argument("--teacher-f16", "--heads-f16", dest="teacher_f16", action="store_true", default=os.environ.get("SAD_HEADS_F16", "") == "1",
+                    help="also run configs[4]'s step with both RetinaNet heads on fp16 operands (object full_step_config5_heads_f16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -486,7 +490,7 @@ def main():
         if args.teacher_f16:   # the same step with the forward-only teacher head on fp16 operands (configs[4]: mixed fp16 compute)
             gc.collect()
             torch.cuda.empty_cache()
-            full5_f16_line = run_full_step(args, rank, world, barrier, native, n_images=1, config5=True, teacher_f16=True)
+            full5_f16_line = run_full_step(args, rank, world, barrier, native, n_images=1, config5=True, teacher_f16=True, student_f16=True)
         if world == 1:   # BASELINE.json configs[2]: the same step at bs = 16 on one GPU
             import gc
             gc.collect()
@@ -535,7 +539,7 @@ def main():
         line["full_step_config5"] = full5_line
         line["gpu_launches"] += full5_line["gpu_launches"]
     if full5_f16_line:
-        line["full_step_config5_teacher_f16"] = full5_f16_line
+        line["full_step_config5_heads_f16"] = full5_f16_line
         line["gpu_launches"] += full5_f16_line["gpu_launches"]
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_oracle

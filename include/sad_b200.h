@@ -373,7 +373,8 @@ int sad_head_forward(sad_head* head, const sad_head_weights* weights, const floa
                      float* const* cls_logits_nchw, float* const* bbox_pred_nchw, int training, void* stream);
 /* Introspection: copies a kept activation of the last forward into dst_nhwc (N, H_l, W_l, dim), channels-last,
  * tf32-rounded as stored.  tower 0 = cls, 1 = bbox; conv = -1: the head's input fpn_L, 0..num_convs-1: output of
- * that tower conv after ReLU (the blob retnet_{cls,bbox}_conv_n{conv}_fpn{L}). */
+ * that tower conv after ReLU (the blob retnet_{cls,bbox}_conv_n{conv}_fpn{L}).  For a compute_f16 head dst_nhwc receives
+ * fp16 elements (N * H_l * W_l * dim * 2 bytes), fp16-rounded as stored. */
 int sad_head_copy_activation(const sad_head* head, int tower, int conv, int level, float* dst_nhwc, void* stream);
 /* d_cls_logits_nchw / d_bbox_pred_nchw: gradients of the two predictions (either may be NULL: that branch is
  * skipped and its weight gradients are left untouched).  d_fpn_nchw: NULL, or (N, dim, H_l, W_l) receiving the sum

@@ -278,9 +278,9 @@ SAD_EXPORT size_t sad_head_device_bytes(const sad_head* h) { return h ? h->arena
 SAD_EXPORT int sad_head_copy_activation(const sad_head* h, int tower, int conv, int level, float* dst_nhwc, void* stream) {
   if (!h || !dst_nhwc || tower < 0 || tower > 1 || level < 0 || level >= h->cfg.n_levels || conv < -1 || conv >= h->cfg.num_convs)
     return set_error(SAD_ERR_INVALID, "sad_head_copy_activation: bad argument");
-  if (h->cfg.compute_f16) return set_error(SAD_ERR_UNSUPPORTED, "sad_head_copy_activation: an fp16 head keeps fp16 activations");
   const float* src = conv < 0 ? h->x0[level] : h->act[tower][conv][level];
-  const size_t bytes = h->pixels[level] * h->cfg.dim * sizeof(float);
+  // an fp16 head keeps fp16 activations: dst then receives pixels * dim fp16 elements
+  const size_t bytes = h->pixels[level] * h->cfg.dim * (h->cfg.compute_f16 ? 2 : sizeof(float));
   if (bytes == 0) return SAD_OK;
   return check_cuda(cudaMemcpyAsync(dst_nhwc, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)),
                     "sad_head_copy_activation");

@@ -173,10 +173,11 @@ class ResNetFPN(nn.Module):
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
                  temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4,
-                 fused_body=True, overlap_teacher=True, teacher_body=None, teacher_head_f16=False):
+                 fused_body=True, overlap_teacher=True, teacher_body=None, teacher_head_f16=False, student_head_f16=False):
         """teacher_body: extra ResNetFPN arguments of the teacher, e.g. dict(groups=64, width_per_group=4, stride_1x1=False)
         for the ResNeXt-101-64x4d teacher of BASELINE.json configs[4].  teacher_head_f16: the forward-only teacher head on fp16
-        operands (tcgen05 kind::f16, fp32 accumulation; configs[4]: "mixed fp16 compute / fp32 loss accumulate")."""
+        operands (tcgen05 kind::f16, fp32 accumulation; configs[4]: "mixed fp16 compute / fp32 loss accumulate"); student_head_f16: the
+        student head's forward AND backward on fp16 operands (loss-scaled fp16 gradient tensors, fp32 parameters and parameter gradients)."""
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world, self.rank, self.images = int(world), int(rank), int(n_images)
         self.overlap_teacher = bool(overlap_teacher)
@@ -203,7 +204,7 @@ class FullDistillStep:
         self.flat_grads = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
         self.flat_params = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
         self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head],
-                                  param_buffer=self.flat_params[:n_head])
+                                  param_buffer=self.flat_params[:n_head], compute_f16=student_head_f16)
         self.teacher_head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed + 1, cls_output_sigmoid=True,
                                           compute_f16=teacher_head_f16)
         off = n_head

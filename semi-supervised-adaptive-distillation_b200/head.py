@@ -146,10 +146,10 @@ class RetinaNetHead:
         """Kept activation of the last forward as an NCHW tensor: tower 'cls' / 'bbox'; conv -1 = the input fpn_L,
         i = output of tower conv i after ReLU (blob retnet_<tower>_conv_n<i>_fpn<L>), tf32-rounded as stored."""
         h, w = self.level_shapes[level]
-        out = torch.empty((self.N, h, w, self.dim), dtype=torch.float32, device=self.device)
+        out = torch.empty((self.N, h, w, self.dim), dtype=torch.float16 if self.compute_f16 else torch.float32, device=self.device)
         check(lib().sad_head_copy_activation(self.handle, 0 if tower == "cls" else 1, int(conv), int(level),
                                              C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return out.permute(0, 3, 1, 2).contiguous()
+        return out.float().permute(0, 3, 1, 2).contiguous()
 
     def alloc_outputs(self):
         cls = [torch.empty((self.N, self.cls_out, h, w), dtype=torch.float32, device=self.device) for h, w in self.level_shapes]

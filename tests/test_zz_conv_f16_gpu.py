@@ -184,14 +184,53 @@ def test_f16_dgrad_with_relu_bits_channel_padding_and_loss_scale(oracle):
     assert torch.equal(dx_cl.permute(0, 3, 1, 2), (dx * S).half()), "channels-last output stays scaled: fp16(S * dX)"
 
 
+def test_f16_head_matches_staged_fp64_reference():
+    """Forward (training) + backward of the fp16 head against the staged fp64 reference of tests/test_head_gpu.py with the product's
+    operand rounding reproduced — here fp16 round-to-nearest wherever a tensor-core pass reads a tensor (input, weights, kept
+    activations, incoming and intermediate gradients) — and the ReLU masks taken from the product's own kept activations, so that
+    only the tensor cores' fp32 accumulation differs.  Same gate as the tf32 head: max|d| <= 3e-3 max|ref|, relative rms <= 1e-3.
+    The loss scale (16 here, gradients are N(0, 1)) is a power of two and therefore invisible to the rounding."""
+    import test_head_gpu as T
+    from sad_b200.head import RetinaNetHead
+
+    class F16Backend(T.TorchF64Backend):
+        def rna(self, t):
+            return t.float().half().double()
+
+    shapes = [(20, 32), (10, 16), (5, 8)]
+    head = RetinaNetHead(2, shapes, seed=7, compute_f16=True, f16_grad_scale=16.0)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for name, p in head.params.items():
+        if name.endswith("_w"):
+            p.normal_(0.0, 1.0 / np.sqrt(9 * 256) * 1.4, generator=g)
+        else:
+            p.normal_(0.0, 0.1, generator=g)
+    fpn = [torch.randn(2, 256, h, w, device="cuda", generator=g) for h, w in shapes]
+    d_cls = [torch.randn(2, head.cls_out, h, w, device="cuda", generator=g) for h, w in shapes]
+    d_box = [torch.randn(2, head.bbox_out, h, w, device="cuda", generator=g) for h, w in shapes]
+    cls, box = head.forward(fpn)
+    d_fpn = head.backward(d_cls, d_box)
+    torch.cuda.synchronize()
+    T.check_against(head, cls, box, d_fpn, T.staged_reference(head, fpn, d_cls, d_box, F16Backend(), product_acts=True), tight=(3e-3, 1e-3))
+    # run to run bit-identical, and accumulate doubles
+    g1 = head.flat_grads.clone()
+    head.forward(fpn)
+    head.backward(d_cls, d_box)
+    assert torch.equal(g1, head.flat_grads)
+    head.backward(d_cls, d_box, accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(head.flat_grads, 2 * g1, rtol=1e-6, atol=0)
+
+
 def test_f16_head_backward_matches_tf32_head(capsys):
     """Forward (training) + backward of the fp16 head against the tf32 head on the same parameters, inputs and output gradients
     (d_logits of the size the losses produce, ~1e-5: without the loss scale they would sit in fp16's subnormal range).
     Both heads carry 10-bit-mantissa operands with fp32 accumulation, but their forward passes round differently (K = 8 vs 16 per
     MMA), so a few pre-activations within round-off of zero get opposite ReLU masks and each flipped mask changes the gradients it
-    touches by their full size (DESIGN.md §4 measured the same effect between the tf32 head and an fp32 reference).  The gate is
-    therefore statistical: relative rms <= 2e-2, at most 0.2 % of the elements off by more than 1 % of max|ref|, nothing off by
-    more than half of max|ref| (a scale or layout error moves everything).  The measured statistics are printed (pytest -s)."""
+    touches by their full size (DESIGN.md §4 measured the same effect between the tf32 head and an fp32 reference; measured here
+    on a B200: relative rms 1.2e-2 .. 2.0e-2 on every tensor, profiles/r01o).  The exact check is
+    test_f16_head_matches_staged_fp64_reference; this one is the statistical gate tests/test_head_gpu.py uses for the same
+    situation: max|d| <= 0.15 max|ref|, relative rms <= 6e-2 (a scale or layout error moves everything).  Statistics are printed."""
     from sad_b200 import head
     shapes = [(20, 32), (10, 16), (5, 8)]
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -221,7 +260,7 @@ def test_f16_head_backward_matches_tf32_head(capsys):
         rms = (d.pow(2).mean().sqrt() / a.pow(2).mean().sqrt()).item()
         frac = (d > 1e-2 * m).float().mean().item()
         rows.append("%-34s max|ref| %.3e  max|d|/max %.3e  rel rms %.3e  frac(|d| > 1%% max) %.2e" % (name, m, d.max().item() / m, rms, frac))
-        if not (rms <= 2e-2 and frac <= 2e-3 and d.max().item() <= 0.5 * m):
+        if not (rms <= 6e-2 and d.max().item() <= 0.15 * m):
             bad.append(rows[-1])
     with capsys.disabled():
         print("\nfp16 head vs tf32 head, backward:\n" + "\n".join(rows))
