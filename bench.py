@@ -353,8 +353,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head-steps", type=int, default=0, help="head distillation steps (0 = min(steps, 100); -1 = skip)")
     ap.add_argument("--full-steps", type=int, default=0, help="full R-50 <- R-101 distillation steps (0 = min(steps, 20); -1 = skip)")
-    ap.add_argument("--teacher-f16", "--heads-f16", dest="teacher_f16", action="store_true", default=os.environ.get("SAD_HEADS_F16", "") == "1",
-                    help="also run configs[4]'s step with both RetinaNet heads on fp16 operands (object full_step_config5_heads_f16)")
+    ap.add_argument("--no-heads-f16", dest="teacher_f16", action="store_false", default=True,
+                    help="skip configs[4]'s step with both RetinaNet heads on fp16 operands (object full_step_config5_heads_f16)")
+    ap.add_argument("--teacher-f16", "--heads-f16", dest="teacher_f16", action="store_true", help="(default) run that object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
