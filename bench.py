@@ -204,7 +204,7 @@ def _tensor_peak():
     return 1400.0 / 2.0, "fallback: 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) / 2"
 
 
-def run_head_step(args, rank, world, barrier, native):
+def run_head_step(args, rank, world, barrier, native, f16=False):
     """the widened path on every rank's own 2-image shard — student head forward, PowSum, fused
     distillation loss + gradient, head backward (device work replayed from ONE CUDA graph), then the step's only
     collective (SUM-allreduce of the 25.9 MB flat head-gradient buffer) and the momentum-SGD update (one launch)."""
@@ -213,7 +213,7 @@ def run_head_step(args, rank, world, barrier, native):
     from sad_b200.step import DistillHeadStep
 
     K = args.head_steps or min(args.steps, 100)
-    st = DistillHeadStep(n_images=2, scale_px=600, world=world, rank=rank)
+    st = DistillHeadStep(n_images=2, scale_px=600, world=world, rank=rank, compute_f16=f16)
     n0 = native.lib().sad_launch_count()
     st.forward_backward()
     per_step = int(native.lib().sad_launch_count() - n0)
@@ -247,7 +247,10 @@ def run_head_step(args, rank, world, barrier, native):
     fwd_f, bwd_f = st.flops()
     dev_ms = ms - ar_ms
     peak, src = _tensor_peak()
+    if f16:   # 16-bit operands: the measured sustained bf16 rate itself
+        peak, src = peak * 2.0, src.replace(" / 2 (tf32 = half the bf16 rate)", " (16-bit operands)").replace(" / 2", "")
     achieved = (fwd_f + bwd_f) / (ms * 1e-3) / 1e12
+    kind = "f16" if f16 else "tf32"
     return {
         "metric": "RetinaNet head distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s",
         "ms_per_step": ms, "steps": K, "images_per_gpu": st.images, "scaling": "weak",
@@ -256,12 +259,12 @@ def run_head_step(args, rank, world, barrier, native):
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
         "conv_gflop_per_step": (fwd_f + bwd_f) / 1e9,
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_tf32_kernel + conv3x3_wgrad_tf32_kernel (tcgen05 kind::tf32, 30 launches/step)",
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tf32_kernel + conv3x3_wgrad_tf32_kernel (tcgen05 kind::%s, 30 launches/step)" % kind,
                      "achieved": achieved, "peak": peak, "peak_source": src, "unit": "TFLOP/s", "frac": achieved / peak,
                      "note": "achieved = algorithmic conv flops of the step / WHOLE step time (loss kernels, layout passes, allreduce and "
                              "SGD included); device-only step %.3f ms" % dev_ms},
         "gpu_launches": per_step * (K + 5), "launches_per_step": per_step, "cuda_graph": True,
-        "dtype": "tf32 operands, fp32 accumulate (convs); f32 (loss)", "distill_losses": losses,
+        "dtype": "%s operands, fp32 accumulate (convs); f32 (loss)" % kind, "distill_losses": losses,
     }
 
 
@@ -477,9 +480,11 @@ def main():
     e2e_value2 = world * anchors / float(e2e_dt2.item()) / 1e6
     step2.close()
 
-    head_line = None
+    head_line = head_f16_line = None
     if args.head_steps >= 0:
         head_line = run_head_step(args, rank, world, barrier, native)
+        if args.teacher_f16:
+            head_f16_line = run_head_step(args, rank, world, barrier, native, f16=True)
 
     full_line = full16_line = full5_line = full5_f16_line = None
     if args.full_steps >= 0:
@@ -528,6 +533,9 @@ def main():
         "gpu_launches": int(launches) + (head_line["gpu_launches"] if head_line else 0),
         "clocks": sampler.result(),
     }
+    if head_f16_line:
+        line["head_step_f16"] = head_f16_line
+        line["gpu_launches"] += head_f16_line["gpu_launches"]
     if head_line:
         line["head_step"] = head_line
     if full_line:
