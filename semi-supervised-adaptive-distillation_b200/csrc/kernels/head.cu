@@ -198,7 +198,7 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
     wl[l].W = cfg->W[l];
   }
   size_t wsb = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, dim);
-  const size_t wsb_cls = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, cfg->cls_out);
+  const size_t wsb_cls = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, pad8(cfg->cls_out));
   const size_t wsb_box = sad_conv3x3_wgrad_workspace_bytes(wl, L, dim, pad8(cfg->bbox_out));   // the fp16 path pads dY's channels
   if (wsb_cls > wsb) wsb = wsb_cls;
   if (wsb_box > wsb) wsb = wsb_box;
@@ -220,13 +220,14 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
         slot(&h->act[t][i][l], h->pixels[l] * dim);
         slot(reinterpret_cast<float**>(&h->bits[t][i][l]), sad_conv3x3_sign_bits_bytes(cfg->N, dim, cfg->H[l], cfg->W[l]) / sizeof(float));
       }
-      slot(&h->gpred[t][l], h->pixels[l] * pred_out(*cfg, t));
+      // sized for the fp16 form too: channels padded to a multiple of 8 (2-byte elements; pad8(c) * 2 <= c * 4 only for c >= 4)
+      slot(&h->gpred[t][l], h->pixels[l] * pad8(pred_out(*cfg, t)));
       for (int k = 0; k < nc; ++k) slot(&h->g[t][k][l], h->pixels[l] * dim);
     }
   }
   for (int mode = 0; mode < 2; ++mode)
     for (int t = 0; t < 2; ++t)
-      for (int i = 0; i <= nc; ++i) slot(&h->packed[mode][t][i], (size_t)9 * dim * (i < nc ? dim : pred_out(*cfg, t)));
+      for (int i = 0; i <= nc; ++i) slot(&h->packed[mode][t][i], (size_t)9 * pad8(dim) * pad8(i < nc ? dim : pred_out(*cfg, t)));
   const size_t ws_off0 = take(h->wg_ws_bytes), ws_off1 = take(h->wg_ws_bytes);
   h->arena_bytes = off ? off : 256;
   if ((rc = check_cuda(cudaMalloc(reinterpret_cast<void**>(&h->arena), h->arena_bytes), "sad_head_create: cudaMalloc")) != SAD_OK) {
