@@ -222,6 +222,34 @@ def test_f16_head_matches_staged_fp64_reference():
     assert torch.allclose(head.flat_grads, 2 * g1, rtol=1e-6, atol=0)
 
 
+def test_f16_small_head_matches_cpu_oracle_staged(oracle):
+    """The fp16 head at the tiny geometry of tests/test_head_gpu.py::test_head_matches_cpu_oracle_small (dim 32 = half a 64-channel
+    chunk, 2 tower convolutions, 12 + 12 output channels stored padded to 16) against the CPU oracle chained layer by layer with
+    fp16 operand rounding (oracle/conv_oracle.c restating conv_op_impl.h:31-180, relu_op.cu:22-35)."""
+    import test_head_gpu as T
+    from sad_b200.head import RetinaNetHead
+
+    class F16OracleBackend(T.OracleBackend):
+        rna = staticmethod(lambda a: np.asarray(a, np.float32).astype(np.float16).astype(np.float32))
+
+    shapes = [(8, 12), (4, 6), (2, 3)]
+    head = RetinaNetHead(2, shapes, dim=32, num_convs=2, num_anchors=3, num_classes=4, seed=3, compute_f16=True, f16_grad_scale=16.0)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for name, p in head.params.items():
+        if name.endswith("_w"):
+            p.normal_(0.0, 1.0 / np.sqrt(9 * 32) * 1.4, generator=g)
+        else:
+            p.normal_(0.0, 0.1, generator=g)
+    fpn = [torch.randn(2, 32, h, w, device="cuda", generator=g) for h, w in shapes]
+    d_cls = [torch.randn(2, head.cls_out, h, w, device="cuda", generator=g) for h, w in shapes]
+    d_box = [torch.randn(2, head.bbox_out, h, w, device="cuda", generator=g) for h, w in shapes]
+    cls, box = head.forward(fpn)
+    d_fpn = head.backward(d_cls, d_box)
+    torch.cuda.synchronize()
+    T.check_against(head, cls, box, d_fpn, T.staged_reference(head, fpn, d_cls, d_box, F16OracleBackend(oracle), product_acts=True),
+                    tight=(1e-3, 3e-4))
+
+
 def test_f16_head_backward_matches_tf32_head(capsys):
     """Forward (training) + backward of the fp16 head against the tf32 head on the same parameters, inputs and output gradients
     (d_logits of the size the losses produce, ~1e-5: without the loss scale they would sit in fp16's subnormal range).
