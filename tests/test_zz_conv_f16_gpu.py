@@ -279,7 +279,7 @@ def test_f16_head_backward_matches_tf32_head(capsys):
         assert (a - b).abs().max().item() <= 3e-3 * a.abs().max().item()
     pairs = [("d_fpn level %d" % i, a, b) for i, (a, b) in enumerate(zip(dfpn_r, dfpn_h))]
     pairs += [(n, ref.grads[n], f16.grads[n]) for n in ref.names]
-    rows, bad = [], []
+    rows, bad, all_rms = [], [], []
     for name, a, b in pairs:
         assert torch.isfinite(b).all(), name
         m = a.abs().max().item()
@@ -287,9 +287,10 @@ def test_f16_head_backward_matches_tf32_head(capsys):
         d = (a - b).abs()
         rms = (d.pow(2).mean().sqrt() / a.pow(2).mean().sqrt()).item()
         frac = (d > 1e-2 * m).float().mean().item()
+        all_rms.append(rms)
         rows.append("%-34s max|ref| %.3e  max|d|/max %.3e  rel rms %.3e  frac(|d| > 1%% max) %.2e" % (name, m, d.max().item() / m, rms, frac))
         if not (rms <= 6e-2 and d.max().item() <= 0.15 * m):
             bad.append(rows[-1])
-    with capsys.disabled():
-        print("\nfp16 head vs tf32 head, backward:\n" + "\n".join(rows))
+    with capsys.disabled():   # one line; the per-tensor table of a B200 run is kept in profiles/r01o_f16_head_vs_tf32_head_stats.txt
+        print(" [fp16 vs tf32 head backward: relative rms %.1e .. %.1e over %d tensors]" % (min(all_rms), max(all_rms), len(all_rms)), end="")
     assert not bad, "\n".join(bad)
