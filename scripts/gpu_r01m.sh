@@ -3,7 +3,7 @@
 TAG=${1:-r01m}
 OUT=gpurun_out
 mkdir -p $OUT
-echo "== fp16 wgrad tests"; timeout 200 python -m pytest tests/test_zz_conv_f16_gpu.py -m gpu -q -k "wgrad" 2>&1 | tail -30 | tee $OUT/pytest_wgrad_f16_${TAG}.log
+echo "== fp16 wgrad tests"; timeout 200 python -m pytest tests/test_conv_f16_gpu.py -m gpu -q -k "wgrad" 2>&1 | tail -30 | tee $OUT/pytest_wgrad_f16_${TAG}.log
 echo "== whole gpu suite"; timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee $OUT/pytest_gpu_${TAG}.log
 echo "== e2e sweep"; timeout 200 python scripts/e2e_sweep.py 2>&1 | tail -2 | tee $OUT/e2e_sweep_${TAG}.json
 echo "== ncu full: fp16 convolution / wgrad, AffineChannel, UpsampleNearest"
