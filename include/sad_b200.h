@@ -239,11 +239,12 @@ int sad_conv3x3_pack_weights_multi_f32(const sad_pack_item* items, int n_items, 
 int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                         int cout, int relu, void* stream);
 
-/* The forward convolution with fp16 operands (tcgen05 kind::f16, fp32 accumulation, bias / activation / NCHW output in fp32) —
- * BASELINE.json configs[4]'s "mixed fp16 compute / fp32 loss accumulate" for the forward-only teacher head; the reference's
- * counterpart is the fp16 branch of CudnnConvOp (caffe2/caffe2/operators/conv_op_cudnn.cc:623-643, unused by its configs).
- * The three *_f16 entry points take the SAME structs as the fp32 ones; the channels-last tensors (sad_layout_level.dst_nhwc,
- * sad_conv_level.x_nhwc / y_nhwc) and the packed weights (sad_pack_item.packed, sad_conv3x3_packed_bytes / 2 bytes) then hold
+/* The convolution with fp16 operands (tcgen05 kind::f16, fp32 accumulation, bias / activation / NCHW output in fp32) —
+ * BASELINE.json configs[4]'s "mixed fp16 compute / fp32 loss accumulate": forward and, on mode-1 packed weights, data gradient
+ * (the weight gradient is sad_conv3x3_wgrad_f16); the reference's counterpart is the fp16 branch of CudnnConvOp /
+ * CudnnConvGradientOp (caffe2/caffe2/operators/conv_op_cudnn.cc:623-643, 1082-1100, unused by its configs).
+ * The *_f16 entry points take the SAME structs as the fp32 ones; the channels-last tensors (sad_layout_level.dst_nhwc,
+ * sad_conv_level.x_nhwc / y_nhwc) and the packed weights (sad_pack_item.packed: 9 * M * pad8(K) fp16 elements) then hold
  * IEEE fp16 elements behind the float-typed pointers.  relu_mask_nhwc must be NULL (ReluGradient is taken from relu_bits_in).
  * Needs Cin % 8 == 0 and 16-byte aligned tensors (SAD_ERR_UNSUPPORTED otherwise: there is no SIMT fp16 path). */
 /* channels_dst: channel count of the destination rows (0 = channels; larger = zero padding, e.g. 36 -> 40 for the box-regression
