@@ -42,3 +42,27 @@ def test_bench_constants_and_peaks():
     if os.path.exists(p):
         t = json.load(open(p))
         assert "distill" in t["kernel"] and t["dram_bytes_per_launch"] > 1e8
+
+
+def test_bench_default_line_includes_the_fp16_objects(monkeypatch):
+    """The driver runs `python bench.py` without flags: the configs[4] step with both heads in fp16 and head_step_f16 are part of
+    the default line; --no-heads-f16 drops them.  (Argument parsing only: no device needed.)"""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    seen = {}
+
+    def fake_parse(self, *a, **k):
+        ns = real(self, *a, **k)
+        seen["ns"] = ns
+        raise SystemExit(0)
+
+    real = argparse.ArgumentParser.parse_args
+    monkeypatch.setattr(argparse.ArgumentParser, "parse_args", fake_parse)
+    for argv, want in ((["bench.py"], True), (["bench.py", "--no-heads-f16"], False), (["bench.py", "--heads-f16"], True)):
+        monkeypatch.setattr(sys, "argv", argv)
+        try:
+            bench.main()
+        except SystemExit:
+            pass
+        assert seen["ns"].teacher_f16 is want and seen["ns"].gpus == 1 and seen["ns"].impl == "b200"
