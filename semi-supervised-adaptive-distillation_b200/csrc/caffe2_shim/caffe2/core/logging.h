@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <exception>
 #include <sstream>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -95,6 +96,19 @@ class EnforceNotMet : public std::exception {
 #define DCHECK_LT(x, y) SAD_SHIM_DCHECK_(x, y)
 #define DCHECK_GE(x, y) SAD_SHIM_DCHECK_(x, y)
 #define DCHECK_GT(x, y) SAD_SHIM_DCHECK_(x, y)
+
+// reference logging.h:115 / logging.cc:41-58 — in-place substring replacement used by schema doc generators
+inline size_t ReplaceAll(std::string& s, const char* from, const char* to) {
+  size_t n = 0, pos = 0;
+  const size_t lf = strlen(from), lt = strlen(to);
+  if (!lf) return 0;
+  while ((pos = s.find(from, pos)) != std::string::npos) {
+    s.replace(pos, lf, to);
+    pos += lt;
+    ++n;
+  }
+  return n;
+}
 
 // CUDA_ENFORCE lives in common_gpu.h
 }  // namespace caffe2

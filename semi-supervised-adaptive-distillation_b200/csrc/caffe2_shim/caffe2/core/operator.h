@@ -22,6 +22,20 @@ namespace caffe2 {
 // stored in Argument.f, an int/bool argument in Argument.i, a string in Argument.s.
 class ArgumentHelper {
  public:
+  // instance form (proto_utils.h:227-251): ArgumentHelper helper(def); helper.GetSingleArgument<T>(name, default)
+  explicit ArgumentHelper(const OperatorDef& def) : def_(&def) {}
+  bool HasArgument(const string& name) const { return HasArgument(*def_, name); }
+  template <typename T>
+  T GetSingleArgument(const string& name, const T& default_value) const {
+    return GetSingleArgument<OperatorDef, T>(*def_, name, default_value);
+  }
+  template <typename T>
+  bool HasSingleArgumentOfType(const string& name) const { return HasSingleArgumentOfType<OperatorDef, T>(*def_, name); }
+  template <typename T>
+  vector<T> GetRepeatedArgument(const string& name, const vector<T>& default_value = vector<T>()) const {
+    return GetRepeatedArgument<OperatorDef, T>(*def_, name, default_value);
+  }
+
   template <typename Def>
   static bool HasArgument(const Def& def, const string& name) {
     for (const auto& a : def.arg()) if (a.name() == name) return true;
@@ -41,7 +55,22 @@ class ArgumentHelper {
     for (const auto& a : def.arg()) if (a.name() == name) return &a;
     return nullptr;
   }
+  const OperatorDef* def_ = nullptr;
 };
+
+// reference proto_utils.h:253-262 / proto_utils.cc:302-330
+template <typename T>
+Argument MakeArgument(const string& name, const T& value);
+template <>
+inline Argument MakeArgument(const string& name, const int& value) { Argument a; a.set_name(name); a.set_i(value); return a; }
+template <>
+inline Argument MakeArgument(const string& name, const int64_t& value) { Argument a; a.set_name(name); a.set_i(value); return a; }
+template <>
+inline Argument MakeArgument(const string& name, const bool& value) { Argument a; a.set_name(name); a.set_i(value); return a; }
+template <>
+inline Argument MakeArgument(const string& name, const float& value) { Argument a; a.set_name(name); a.set_f(value); return a; }
+template <>
+inline Argument MakeArgument(const string& name, const string& value) { Argument a; a.set_name(name); a.set_s(value); return a; }
 
 #define SAD_SHIM_SINGLE_ARG(T, fieldname)                                                            \
   template <>                                                                                        \

@@ -32,6 +32,25 @@ class OpSchema {
   OpSchema& IdenticalTypeAndShape() { return *this; }
   OpSchema& IdenticalTypeAndShapeOfInput(int) { return *this; }
   OpSchema& SetDoc(const string& doc) { doc_ = doc; return *this; }
+  // reference operator_schema.h:150-214 — shape / cost inference hooks and FillUsing; kept so reference .cc files
+  // that chain them compile and so callers can query them
+  struct Cost {
+    uint64_t flops = 0;
+    uint64_t bytes_moved = 0;
+    uint64_t params_bytes = 0;
+  };
+  typedef std::function<vector<TensorShape>(const OperatorDef&, const vector<TensorShape>&)> TensorInferenceFunctionType;
+  typedef std::function<struct Cost(const OperatorDef&, const vector<TensorShape>&)> CostInferenceFunctionType;
+  OpSchema& TensorInferenceFunction(TensorInferenceFunctionType f) { tensor_inference_function_ = f; return *this; }
+  OpSchema& CostInferenceFunction(CostInferenceFunctionType f) { cost_inference_function_ = f; return *this; }
+  bool HasCostInferenceFunction() const { return !!cost_inference_function_; }
+  vector<TensorShape> InferTensor(const OperatorDef& def, const vector<TensorShape>& in) const {
+    return tensor_inference_function_(def, in);
+  }
+  struct Cost InferCost(const OperatorDef& def, const vector<TensorShape>& in) const {
+    return cost_inference_function_(def, in);
+  }
+  OpSchema& FillUsing(std::function<void(OpSchema&)> populator) { if (populator) populator(*this); return *this; }
   OpSchema& Arg(const char* name, const char* description) { args_.emplace_back(name, description); return *this; }
   OpSchema& Input(const int n, const char* name, const char* description) {
     if ((int)input_desc_.size() <= n) input_desc_.resize(n + 1);
@@ -55,7 +74,23 @@ class OpSchema {
   int min_input_ = 0, max_input_ = INT_MAX, min_output_ = 0, max_output_ = INT_MAX;
   std::function<bool(int, int)> inplace_allowed_ = [](int, int) { return false; };
   std::vector<std::pair<const char*, const char*>> args_, input_desc_, output_desc_;
+  TensorInferenceFunctionType tensor_inference_function_;
+  CostInferenceFunctionType cost_inference_function_;
 };
+
+// reference proto_utils.h:48-60 / proto_utils.cc — shape descriptor helpers used by inference functions
+inline TensorShape CreateTensorShape(vector<int> dims, TensorProto::DataType dt) {
+  TensorShape ts;
+  for (int d : dims) ts.add_dims(d);
+  ts.set_data_type(dt);
+  ts.set_unknown_shape(false);
+  return ts;
+}
+inline vector<TIndex> GetDimsVector(const TensorShape& shape) {
+  vector<TIndex> dims;
+  for (auto d : shape.dims()) dims.push_back(d);
+  return dims;
+}
 
 class OpSchemaRegistry {
  public:

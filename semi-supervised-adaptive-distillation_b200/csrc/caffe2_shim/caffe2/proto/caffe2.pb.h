@@ -50,6 +50,32 @@ class Argument {
   std::vector<std::string> strings_;
 };
 
+// caffe2.proto:16-68 — the shape-only descriptors schema inference functions exchange
+// (operator_schema.h:150-185; conv_pool_op_base.h:375-520 builds them for Conv / pooling).
+class TensorProto {
+ public:
+  enum DataType { UNDEFINED = 0, FLOAT = 1, INT32 = 2, BYTE = 3, STRING = 4, BOOL = 5, UINT8 = 6, INT8 = 7,
+                  UINT16 = 8, INT16 = 9, INT64 = 10, FLOAT16 = 12, DOUBLE = 13 };
+};
+const TensorProto::DataType TensorProto_DataType_FLOAT = TensorProto::FLOAT;
+class TensorShape {
+ public:
+  const std::vector<int64_t>& dims() const { return dims_; }
+  int64_t dims(int i) const { return dims_.at(i); }
+  int dims_size() const { return (int)dims_.size(); }
+  void add_dims(int64_t d) { dims_.push_back(d); }
+  void clear_dims() { dims_.clear(); }
+  TensorProto::DataType data_type() const { return data_type_; }
+  void set_data_type(TensorProto::DataType t) { data_type_ = t; }
+  bool unknown_shape() const { return unknown_shape_; }
+  void set_unknown_shape(bool b) { unknown_shape_ = b; }
+
+ private:
+  std::vector<int64_t> dims_;
+  TensorProto::DataType data_type_ = TensorProto::FLOAT;
+  bool unknown_shape_ = false;
+};
+
 // caffe2.proto:122-137
 class DeviceOption {
  public:
