@@ -257,6 +257,25 @@ int sad_conv3x3_pack_weights_multi_f16(const sad_pack_item* items, int n_items, 
 int sad_conv3x3_fwd_f16(const sad_conv_level* levels, int n_levels, const void* packed_f16, const float* bias, int cin, int cout,
                         int relu, float nchw_scale, void* stream);
 
+/* The convolution in "3xTF32" arithmetic — the fp32-accurate mode.  The reference's head convolution is fp32 (cuDNN without tensor-op
+ * math: caffe2/caffe2/operators/conv_op_cudnn.cc:494-498 enables it for fp16 only); tf32 operands keep 10 mantissa bits and sit at
+ * ~5e-4 of max|ref| per convolution, which cannot meet a 1e-4 gate.  Here every fp32 operand v is carried as two tf32 numbers,
+ * hi = rna_tf32(v) and lo = rna_tf32(v - hi), and a product is accumulated (fp32, TMEM) as W_hi X_hi + W_hi X_lo + W_lo X_hi:
+ * three tensor-core passes, error ~1e-6 of max|ref| (measured: tests/test_conv_gpu.py), 3x the tensor work of the tf32 mode.
+ * The *_f32x3 entry points take the SAME structs as the fp32 ones; channels-last tensors (sad_layout_level.dst_nhwc,
+ * sad_conv_level.x_nhwc / y_nhwc, sad_wgrad_level.x_nhwc / dy_nhwc) are then SPLIT tensors: per pixel a row of
+ * 2 * sad_conv3x3_split_channels(C) floats, [hi(0..C) zero pad | lo(0..C) zero pad]; packed weights (sad_pack_item.packed) are
+ * [tap][M][2 * sad_conv3x3_split_channels(K)] floats laid out the same way (sad_conv3x3_packed_bytes_f32x3).  Pad channels of a
+ * y_nhwc the caller allocates must be zero-initialised once (the kernels never write them).  NCHW outputs, weights, gradients
+ * and biases are plain fp32.  relu_mask_nhwc must be NULL (ReluGradient is taken from relu_bits_in).  16-byte aligned tensors
+ * (SAD_ERR_UNSUPPORTED otherwise: there is no SIMT split path). */
+int sad_conv3x3_split_channels(int channels); /* round_up(channels, 32) */
+size_t sad_conv3x3_packed_bytes_f32x3(int cin, int cout, int mode);
+int sad_nchw_to_nhwc_f32x3(const sad_layout_level* levels, int n_levels, int channels, void* stream);
+int sad_conv3x3_pack_weights_multi_f32x3(const sad_pack_item* items, int n_items, void* stream);
+int sad_conv3x3_fwd_f32x3(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin, int cout,
+                          int relu, void* stream);
+
 /* Relu / ReluGradient as stand-alone operators — replace ReluOp / ReluGradientOp<float, CUDAContext>::RunOnDevice
  * (caffe2/caffe2/operators/relu_op.cu:22-62): y = x > 0 ? x : 0;  dx = y > 0 ? dy : 0.  In place allowed (y == x,
  * dx == dy), as the towers use them (retinanet_heads.py:124,209). */
@@ -312,6 +331,11 @@ int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, 
 int sad_conv3x3_wgrad_f16(const sad_wgrad_level* levels, int n_levels, int cin, int dy_channels, int cout, float out_scale,
                           float* d_weight, float* d_bias, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight (+ bias) gradient in 3xTF32 arithmetic: x_nhwc and dy_nhwc are split tensors (see sad_conv3x3_fwd_f32x3); every pixel
+ * block is accumulated as dY_hi X_hi + dY_hi X_lo + dY_lo X_hi; db sums hi + lo.  Same workspace as sad_conv3x3_wgrad_f32. */
+int sad_conv3x3_wgrad_f32x3(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
+                            int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * The whole RetinaNet FPN head, forward and backward — replaces the operator chains emitted by
  *   add_fpn_retinanet_outputs              (detectron/lib/modeling/retinanet_heads.py:63-245)
@@ -342,6 +366,10 @@ typedef struct sad_head_config {
                                    parameters, parameter gradients and the NCHW boundary tensors stay fp32 */
   float f16_grad_scale;         /* compute_f16 only: loss scale applied to d(logits) / d(box deltas) when they are rounded to fp16
                                    and divided out of every gradient the head returns; a power of two (0 = default 4096) */
+  int32_t compute_f32x3;        /* 1: 3xTF32, the fp32-accurate mode (sad_conv3x3_fwd_f32x3 / sad_conv3x3_wgrad_f32x3) for every
+                                   convolution of the head, forward and backward: what matches the reference's fp32 cuDNN convolution
+                                   to 1e-4; the kept activations and gradient tensors are split [hi | lo] tensors (2x the memory,
+                                   3x the tensor-core work of the default tf32 mode).  Excludes compute_f16. */
 } sad_head_config;
 typedef struct sad_head_weights {
   const float* cls_tower_w[SAD_HEAD_MAX_CONVS];  /* (dim, dim, 3, 3) */

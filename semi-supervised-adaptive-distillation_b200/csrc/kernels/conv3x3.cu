@@ -88,6 +88,10 @@ struct alignas(64) ConvArgs {
   int32_t n_levels, cin, cout, relu;
   uint32_t m_tiles, k_blocks, total_tiles;
   float nchw_scale;   // fp16 instantiations only: multiplies what is stored to y_nchw (1 / loss scale on the last data-gradient pass)
+  // 3xTF32 ("f32x3") instantiations only: operands are split tensors [hi | lo] (see kX3 below)
+  uint32_t k_part;      // K blocks of ONE part (k_blocks = 3 * k_part)
+  int32_t k_split;      // channel offset of the lo part in the packed weights and the input rows: round_up(cin, 32)
+  int32_t cout_split;   // channel offset of the lo part in y_nhwc rows: round_up(cout, 32); the rows are 2 * cout_split long
 };
 
 struct ConvTile {
@@ -131,12 +135,20 @@ __device__ __forceinline__ ConvTile conv_decode_tile(const ConvArgs& a, uint32_t
 //              empty[s]     one per CTA: the leader's commit multicasts "stage read" to both producers
 //              tmem_full[b] one per CTA: the leader's commit multicasts "accumulator complete" to both epilogues
 //              tmem_empty[b] lives in the LEADER: 256 arrivals, both CTAs' epilogue threads (the partner's remotely)
+// kX3: "3xTF32", the fp32-accurate mode (the reference's head convolution is fp32: conv_op_cudnn.cc:494-498 enables tensor-op math
+// for fp16 only).  Every fp32 operand v is carried as two tf32 numbers hi = rna_tf32(v), lo = rna_tf32(v - hi) (v = hi + lo to
+// 2^-22 |v|), stored side by side: channels-last rows [hi(0..C) pad | lo(0..C) pad] of 2 * round_up(C, 32) floats, packed weights
+// [tap][M][hi(0..K) pad | lo(0..K) pad].  The K loop of a tap runs three passes over the same accumulator,
+//     W_hi * X_hi  +  W_hi * X_lo  +  W_lo * X_hi        (W_lo * X_lo ~ 2^-22 is dropped),
+// which only moves the producer's TMA coordinates (pass 1: activations' lo half, pass 2: weights' lo half); the MMA issuer
+// just sees 3x as many stages.  The channels-last output is written as such a split row.  3x the tensor-core work of tf32.
 // kF16: fp16 operands (tcgen05.mma kind::f16, K = 16 per instruction): the channels-last input, the packed weights and the
 // channels-last output are fp16; a stage still holds 128-byte rows, i.e. 64 instead of 32 input channels, so a tile takes
 // half as many stages and MMAs.  Accumulation, bias, activation and the NCHW output stay fp32 (BASELINE.json configs[4]:
 // "mixed fp16 compute / fp32 loss accumulate").  fp16 keeps the 10-bit mantissa of tf32; values beyond 65504 become inf.
-template <bool kC2, bool kSigmoid, bool kF16 = false>
+template <bool kC2, bool kSigmoid, bool kF16 = false, bool kX3 = false>
 __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __grid_constant__ ConvArgs args) {
+  static_assert(!(kF16 && kX3), "the split mode is a tf32 mode");
   constexpr int kKCe = kF16 ? 2 * kCvKC : kCvKC;   // input channels per stage (one 128-byte row)
   constexpr int kStages = kC2 ? kCvStagesPair : kCvStages;
   constexpr int kBBytes = kC2 ? kCvBBytes / 2 : kCvBBytes;
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t k_blocks = args.k_blocks;  // ceil(Cin / kKCe)
+  const uint32_t k_blocks = args.k_blocks;  // ceil(Cin / kKCe); kX3: 3 passes of k_part blocks
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
@@ -203,15 +215,22 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
             uint8_t* sa = smem + (size_t)rs.stage * kStageBytes;
             uint8_t* sb = sa + kCvABytes;
+            int ka = (int)kb * kKCe, kx = ka;   // K coordinate in the packed weights / channel coordinate in the input rows
+            if (kX3) {
+              const uint32_t pass = kb / args.k_part;   // 0: hi x hi, 1: W_hi x X_lo, 2: W_lo x X_hi
+              const int kk = (int)(kb - pass * args.k_part) * kKCe;
+              ka = kk + (pass == 2 ? args.k_split : 0);
+              kx = kk + (pass == 1 ? args.k_split : 0);
+            }
             if (kC2) {
               mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
-              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kKCe, t.m0, tap);
+              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], ka, t.m0, tap);
               // my half of the pixel tile: rows y0 + 4 * rank .. + 3 (= accumulator columns 128 * rank .. + 127)
-              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kKCe, t.x0 + dx, t.y0 + (int)crank * (kCvRows / 2) + dy, t.n);
+              tma_load_4d(sb, mx, &full_bar[rs.stage], kx, t.x0 + dx, t.y0 + (int)crank * (kCvRows / 2) + dy, t.n);
             } else {
               mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
-              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], (int)kb * kKCe, t.m0, tap);
-              tma_load_4d(sb, mx, &full_bar[rs.stage], (int)kb * kKCe, t.x0 + dx, t.y0 + dy, t.n);
+              tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], ka, t.m0, tap);
+              tma_load_4d(sb, mx, &full_bar[rs.stage], kx, t.x0 + dx, t.y0 + dy, t.n);
             }
             rs.advance<kStages>();
           }
@@ -294,7 +313,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kCvN;
       const size_t HW = (size_t)L.H * L.W;
       float* yrow = L.y_nchw ? L.y_nchw + ((size_t)t.n * args.cout + (co_ok ? co : 0)) * HW : nullptr;
-      float* ycl = L.y_nhwc ? L.y_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
+      // channels-last output rows: cout floats; kX3: split rows of 2 * cout_split floats, hi at co, lo at cout_split + co
+      const size_t ycl_row = kX3 ? 2 * (size_t)args.cout_split : (size_t)args.cout;
+      float* ycl = L.y_nhwc ? L.y_nhwc + (size_t)t.n * HW * ycl_row + (co_ok ? co : 0) : nullptr;
       const float* mcl = L.mask_nhwc ? L.mask_nhwc + (size_t)t.n * HW * args.cout + (co_ok ? co : 0) : nullptr;
       // sign-bit planes: one word per (image row, 32-pixel segment, channel); this tile owns segment t.x0 / 32
       const size_t bits_row0 = (((size_t)t.n * L.H) * L.tiles_x + (t.x0 >> 5)) * args.cout + (co_ok ? co : 0);
@@ -371,6 +392,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (t.x0 + i < L.W) dst[(size_t)i * args.cout] = __float2half_rn(v[i]);
+            } else if (kX3) {
+              // split rows: two 128 B lines per pixel and warp (hi, lo)
+              float* dst = ycl + ((size_t)y * L.W + t.x0) * ycl_row;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (t.x0 + i < L.W) {
+                  const float hi = to_tf32_rna(v[i]);
+                  dst[(size_t)i * ycl_row] = hi;
+                  dst[(size_t)i * ycl_row + args.cout_split] = to_tf32_rna(v[i] - hi);
+                }
             } else {
               // channels-last: for a fixed pixel the warp's 32 lanes (consecutive co) write one 128 B line
               float* dst = ycl + ((size_t)y * L.W + t.x0) * args.cout;
@@ -420,6 +451,7 @@ struct PackMulti {
   const float* src[SAD_MAX_PACK_ITEMS];
   float* dst[SAD_MAX_PACK_ITEMS];   // fp16 instantiation: __half storage
   int32_t cin[SAD_MAX_PACK_ITEMS], cout[SAD_MAX_PACK_ITEMS], mode[SAD_MAX_PACK_ITEMS];
+  int32_t split;   // float output only: 3xTF32 rows [hi(0..K) pad | lo(0..K) pad] of 2 * round_up(K, 32) floats
 };
 // every weight tensor of the head in one launch: blockIdx.y selects the tensor; one thread per (row m, column k)
 // of the packed planes moves the 9 taps (writes coalesced along k in each tap plane)
@@ -432,14 +464,21 @@ __global__ void conv3x3_pack_multi_kernel(const PackMulti p) {
   const uint32_t M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
   // 16-bit output: the K axis is padded with zeros to a multiple of 8 (16-byte tensor-map strides), e.g. the 36 box-regression
   // channels of the data-gradient pack become 40; the convolution is then called with cin = the padded K
-  const uint32_t Kp = sizeof(OutT) == 2 ? (K + 7u) & ~7u : K;
+  const bool split = sizeof(OutT) == 4 && p.split != 0;
+  const uint32_t Ks = (K + 31u) & ~31u;   // offset of the lo half of a split row
+  const uint32_t Kp = sizeof(OutT) == 2 ? (K + 7u) & ~7u : (split ? 2u * Ks : K);
   const uint32_t plane = M * Kp;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
-    const uint32_t k = i % Kp, m = i / Kp;
+    const uint32_t kcol = i % Kp, m = i / Kp;
+    const bool lo = split && kcol >= Ks;
+    const uint32_t k = lo ? kcol - Ks : kcol;
     const float* src = mode == 0 ? w + ((size_t)m * cin + k) * 9 : w + ((size_t)k * cin + m) * 9;
     float v[9];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) v[tap] = k < K ? __ldg(src + tap) : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      v[tap] = k < K ? __ldg(src + tap) : 0.f;
+      if (lo) v[tap] -= to_tf32_rna(v[tap]);   // exact in fp32; store_operand rounds it to tf32
+    }
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) store_operand(out + (size_t)tap * plane + i, mode == 0 ? v[tap] : v[8 - tap]);
   }
@@ -496,6 +535,7 @@ struct LayoutArgs {
   uint32_t tiles_c, total_tiles;
   int32_t C_dst;   // channels of the destination rows (>= C: zero padding, fp16 gradient tensors); tiles_c covers C_dst
   float scale;     // fp16 instantiation only: values are multiplied before rounding (the loss scale of the gradient tensors)
+  int32_t split;   // float output only: 3xTF32 rows of 2 * C_dst floats, hi at c, lo at C_dst + c (C_dst = round_up(C, 32))
 };
 template <typename OutT>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant__ LayoutArgs a) {
@@ -512,7 +552,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
     const uint32_t n = r / a.tiles_c;
     const uint32_t hw0 = th * 32, c0 = tc * 32;
     const float* src = L.src + (size_t)n * a.C * L.HW;
-    OutT* dst = reinterpret_cast<OutT*>(L.dst) + (size_t)n * a.C_dst * L.HW;
+    const uint32_t row = (sizeof(OutT) == 4 && a.split) ? 2u * (uint32_t)a.C_dst : (uint32_t)a.C_dst;
+    OutT* dst = reinterpret_cast<OutT*>(L.dst) + (size_t)n * row * L.HW;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t c = c0 + ty + k * 8, hw = hw0 + tx;
@@ -522,8 +563,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t hw = hw0 + ty + k * 8, c = c0 + tx;
-      if (c < (uint32_t)a.C_dst && hw < L.HW)
-        store_operand(dst + (size_t)hw * a.C_dst + c, sizeof(OutT) == 2 ? tile[tx][ty + k * 8] * a.scale : tile[tx][ty + k * 8]);
+      if (c < (uint32_t)a.C_dst && hw < L.HW) {
+        const float v = tile[tx][ty + k * 8];
+        store_operand(dst + (size_t)hw * row + c, sizeof(OutT) == 2 ? v * a.scale : v);
+        if (sizeof(OutT) == 4 && a.split) store_operand(dst + (size_t)hw * row + a.C_dst + c, v - to_tf32_rna(v));
+      }
     }
     __syncthreads();
   }
@@ -559,7 +603,7 @@ SAD_EXPORT int sad_conv3x3_pack_weights_f32(const float* weight, int cin, int co
   return check_cuda(cudaGetLastError(), "conv3x3 pack launch");
 }
 
-static int pack_weights_multi_impl(const sad_pack_item* items, int n_items, void* stream, bool f16) {
+static int pack_weights_multi_impl(const sad_pack_item* items, int n_items, void* stream, bool f16, bool split = false) {
   if (!items || n_items < 1 || n_items > SAD_MAX_PACK_ITEMS) return set_error(SAD_ERR_INVALID, "conv3x3 pack multi: n_items must be in [1, 32]");
   PackMulti p{};
   size_t most = 0;
@@ -572,9 +616,10 @@ static int pack_weights_multi_impl(const sad_pack_item* items, int n_items, void
     p.cin[i] = it.cin;
     p.cout[i] = it.cout;
     p.mode[i] = it.mode;
-    const size_t total = (size_t)it.cin * it.cout;
+    const size_t total = (size_t)it.cin * it.cout * (split ? 4 : 1);   // split rows are 2 * round_up(K, 32) long (the kernel is grid-stride: this only sizes the grid)
     if (total > most) most = total;
   }
+  p.split = split ? 1 : 0;
   const unsigned bx = (unsigned)((most + 255) / 256 < 1024 ? (most + 255) / 256 : 1024);
   if (f16) conv3x3_pack_multi_kernel<__half><<<dim3(bx, (unsigned)n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   else conv3x3_pack_multi_kernel<float><<<dim3(bx, (unsigned)n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -583,7 +628,7 @@ static int pack_weights_multi_impl(const sad_pack_item* items, int n_items, void
 }
 
 static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int channels, void* stream, bool f16, int channels_dst = 0,
-                             float scale = 1.f) {
+                             float scale = 1.f, bool split = false) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || channels < 1) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: bad argument");
   if (channels_dst == 0) channels_dst = channels;
   if (channels_dst < channels) return set_error(SAD_ERR_INVALID, "nchw_to_nhwc: destination channels < source channels");
@@ -592,6 +637,7 @@ static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int c
   a.C = channels;
   a.C_dst = channels_dst;
   a.scale = scale;
+  a.split = split ? 1 : 0;
   a.tiles_c = (uint32_t)((channels_dst + 31) / 32);
   uint64_t tiles = 0;
   for (int l = 0; l < n_levels; ++l) {
@@ -622,7 +668,7 @@ static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int c
 // `packed` has layout [tap][cout][cin] (sad_conv3x3_pack_weights_f32 mode 0 for the forward operator,
 // mode 1 — with cin/cout swapped by the caller — for the data gradient).
 static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
-                            int cout, int relu, void* stream, bool f16, float nchw_scale = 1.f) {
+                            int cout, int relu, void* stream, bool f16, float nchw_scale = 1.f, bool x3 = false) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3: n_levels must be in [1, 8]");
   if (!packed || cin < 1 || cout < 1) return set_error(SAD_ERR_INVALID, "conv3x3: bad weights/channels");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -660,6 +706,18 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
   if (tiles == 0) return SAD_OK;
   if (!tma_ok && f16)
     return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 fp16: needs Cin % 8 == 0 and 16-byte aligned tensors (there is no SIMT fp16 path)");
+  const int cin_s = (cin + 31) & ~31;   // x3: the lo half of a split row / packed K row starts here; rows are 2 * cin_s long
+  if (x3) {
+    bool ok = (reinterpret_cast<uintptr_t>(packed) & 15) == 0;
+    for (int l = 0; l < n_levels; ++l) {
+      if ((reinterpret_cast<uintptr_t>(levels[l].x_nhwc) | reinterpret_cast<uintptr_t>(levels[l].y_nchw)) & 15) ok = false;
+      if (levels[l].relu_mask_nhwc)
+        return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 f32x3: ReluGradient comes from sign bits (relu_bits_in), not from a float mask tensor");
+    }
+    if (!ok) return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 f32x3: needs 16-byte aligned tensors (there is no SIMT split path)");
+    tma_ok = true;
+  }
+  const int cin_map = x3 ? 2 * cin_s : cin;   // innermost extent of the packed-weight and activation tensor maps
   if (f16) {
     for (int l = 0; l < n_levels; ++l)
       if (levels[l].relu_mask_nhwc)
@@ -686,8 +744,8 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
   }
   {
     const cuuint64_t esz = f16 ? 2 : 4;
-    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
-    const cuuint64_t str[2] = {(cuuint64_t)cin * esz, (cuuint64_t)cin * cout * esz};
+    const cuuint64_t dims[3] = {(cuuint64_t)cin_map, (cuuint64_t)cout, 9};
+    const cuuint64_t str[2] = {(cuuint64_t)cin_map * esz, (cuuint64_t)cin_map * cout * esz};
     const cuuint32_t box[3] = {(cuuint32_t)(f16 ? 2 * kCvKC : kCvKC), kCvM, 1};
     if ((rc = encode_map(&a.tmap_w, packed, 3, dims, str, box, "packed weights", CU_TENSOR_MAP_SWIZZLE_128B,
                          f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) != SAD_OK)
@@ -707,8 +765,8 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
         return rc;
       continue;
     }
-    if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows, "activations {C,W,H,N}")) != SAD_OK) return rc;
-    if ((rc = encode_nhwc_map(&a.tmap_xh[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows / 2, "activations {C,W,H,N}, half tile")) != SAD_OK)
+    if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kCvCols, kCvRows, "activations {C,W,H,N}")) != SAD_OK) return rc;
+    if ((rc = encode_nhwc_map(&a.tmap_xh[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kCvCols, kCvRows / 2, "activations {C,W,H,N}, half tile")) != SAD_OK)
       return rc;
   }
   a.bias = bias;
@@ -720,13 +778,20 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
   a.m_tiles = m_tiles;
   const int kc = f16 ? 2 * kCvKC : kCvKC;
   a.k_blocks = (uint32_t)((cin + kc - 1) / kc);
+  if (x3) {
+    a.k_part = (uint32_t)(cin_s / kCvKC);
+    a.k_blocks = 3 * a.k_part;
+    a.k_split = cin_s;
+    a.cout_split = (cout + 31) & ~31;
+  }
   a.total_tiles = (uint32_t)tiles;
 
   int sms = 0;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   if (pair) {
-    auto kern = f16 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true> : conv3x3_tf32_kernel<true, false, true>)
-                    : (relu == 2 ? conv3x3_tf32_kernel<true, true, false> : conv3x3_tf32_kernel<true, false, false>);
+    auto kern = f16  ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true> : conv3x3_tf32_kernel<true, false, true>)
+                : x3 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, false, true> : conv3x3_tf32_kernel<true, false, false, true>)
+                     : (relu == 2 ? conv3x3_tf32_kernel<true, true, false> : conv3x3_tf32_kernel<true, false, false>);
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
                          "cudaFuncSetAttribute(conv3x3 pair)")) != SAD_OK)
       return rc;
@@ -747,8 +812,9 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
     cfg.numAttrs = 1;
     if ((rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "conv3x3 pair launch")) != SAD_OK) return rc;
   } else {
-    auto kern = f16 ? (relu == 2 ? conv3x3_tf32_kernel<false, true, true> : conv3x3_tf32_kernel<false, false, true>)
-                    : (relu == 2 ? conv3x3_tf32_kernel<false, true, false> : conv3x3_tf32_kernel<false, false, false>);
+    auto kern = f16  ? (relu == 2 ? conv3x3_tf32_kernel<false, true, true> : conv3x3_tf32_kernel<false, false, true>)
+                : x3 ? (relu == 2 ? conv3x3_tf32_kernel<false, true, false, true> : conv3x3_tf32_kernel<false, false, false, true>)
+                     : (relu == 2 ? conv3x3_tf32_kernel<false, true, false> : conv3x3_tf32_kernel<false, false, false>);
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
                          "cudaFuncSetAttribute(conv3x3)")) != SAD_OK)
       return rc;
@@ -774,6 +840,23 @@ SAD_EXPORT int sad_nchw_to_nhwc_f16(const sad_layout_level* levels, int n_levels
 SAD_EXPORT int sad_conv3x3_fwd_f32(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                                    int cout, int relu, void* stream) {
   return conv3x3_fwd_impl(levels, n_levels, packed, bias, cin, cout, relu, stream, false);
+}
+// 3xTF32: split operands (sad_b200.h)
+SAD_EXPORT int sad_conv3x3_split_channels(int channels) { return channels < 1 ? 0 : (channels + 31) & ~31; }
+SAD_EXPORT size_t sad_conv3x3_packed_bytes_f32x3(int cin, int cout, int mode) {
+  if (cin < 1 || cout < 1 || (mode != 0 && mode != 1)) return 0;
+  const int M = mode == 0 ? cout : cin, K = mode == 0 ? cin : cout;
+  return (size_t)9 * M * 2 * sad_conv3x3_split_channels(K) * sizeof(float);
+}
+SAD_EXPORT int sad_nchw_to_nhwc_f32x3(const sad_layout_level* levels, int n_levels, int channels, void* stream) {
+  return nchw_to_nhwc_impl(levels, n_levels, channels, stream, false, sad_conv3x3_split_channels(channels), 1.f, true);
+}
+SAD_EXPORT int sad_conv3x3_pack_weights_multi_f32x3(const sad_pack_item* items, int n_items, void* stream) {
+  return pack_weights_multi_impl(items, n_items, stream, false, true);
+}
+SAD_EXPORT int sad_conv3x3_fwd_f32x3(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
+                                     int cout, int relu, void* stream) {
+  return conv3x3_fwd_impl(levels, n_levels, packed, bias, cin, cout, relu, stream, false, 1.f, true);
 }
 SAD_EXPORT int sad_conv3x3_fwd_f16(const sad_conv_level* levels, int n_levels, const void* packed_f16, const float* bias, int cin,
                                    int cout, int relu, float nchw_scale, void* stream) {

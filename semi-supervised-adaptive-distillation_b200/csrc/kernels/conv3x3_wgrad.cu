@@ -94,6 +94,10 @@ struct alignas(64) WgArgs {
   float* partial;                     // [splits][9][cout][cin]
   int32_t n_levels, cin, cout;
   uint32_t m_tiles, n_tiles, splits, total_blocks, total_items;
+  // 3xTF32 (sad_conv3x3_wgrad_f32x3): dY and X are split tensors [hi | lo] (conv3x3.cu, kX3).  Every pixel block is staged npass = 3
+  // times — (dY_hi, X_hi), (dY_hi, X_lo), (dY_lo, X_hi) — into the same accumulator; only the producer's channel coordinates move.
+  uint32_t npass;            // 1, or 3
+  int32_t dy_lo, x_lo;       // channel offset of the lo half: round_up(cout, 32) / round_up(cin, 32)
 };
 
 struct WgItem {
@@ -180,6 +184,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
         const int a_chunks = a_left < TR::kAChunks ? a_left : TR::kAChunks, b_chunks = b_left < TR::kBChunks ? b_left : TR::kBChunks;
         const bool a_full = it.m0 + kWgM <= args.cout, b_full = it.n0 + kWgN <= args.cin;  // whole tile inside the tensor
         for (uint32_t kb = it.kb_begin; kb < it.kb_end; ++kb) {
+         for (uint32_t pass = 0; pass < args.npass; ++pass) {
+          const int ma = it.m0 + (pass == 2 ? args.dy_lo : 0);   // first dY channel of this stage (lo half on pass 2)
+          const int nb = it.n0 + (pass == 1 ? args.x_lo : 0);    // first X channel of this stage (lo half on pass 1)
           mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
           uint8_t* sa = smem + (size_t)rs.stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
@@ -187,22 +194,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
           // only reaches accumulator rows / columns the epilogue never writes out
           mbar_arrive_expect_tx(&full_bar[rs.stage], (uint32_t)(a_chunks + b_chunks) * kChunkBytes);
           if (a_full) {  // the tile's 4 chunks in one 5-D copy: [chunk][pixel][32 channels], chunks 4 KB apart
-            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y * kRows, n, it.m0 / kCh);
+            tma_load_5d(sa, &args.tmap_dy5[l], &full_bar[rs.stage], 0, xs * kWgKP, y * kRows, n, ma / kCh);
           } else {
 #pragma unroll
             for (int j = 0; j < TR::kAChunks; ++j)
               if (j < a_chunks)
-                tma_load_4d(sa + j * kChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], it.m0 + kCh * j, xs * kWgKP, y * kRows, n);
+                tma_load_4d(sa + j * kChunkBytes, &args.tmap_dy[l], &full_bar[rs.stage], ma + kCh * j, xs * kWgKP, y * kRows, n);
           }
           if (b_full) {
-            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y * kRows + dy, n, it.n0 / kCh);
+            tma_load_5d(sb, &args.tmap_x5[l], &full_bar[rs.stage], 0, xs * kWgKP + dx, y * kRows + dy, n, nb / kCh);
           } else {
 #pragma unroll
             for (int j = 0; j < TR::kBChunks; ++j)
               if (j < b_chunks)
-                tma_load_4d(sb + j * kChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], it.n0 + kCh * j, xs * kWgKP + dx, y * kRows + dy, n);
+                tma_load_4d(sb + j * kChunkBytes, &args.tmap_x[l], &full_bar[rs.stage], nb + kCh * j, xs * kWgKP + dx, y * kRows + dy, n);
           }
           rs.advance<kStages>();
+         }
           if (++xs == (int)args.lv[l].xsegs) {
             xs = 0;
             if (++y == (int)args.lv[l].yblocks) {
@@ -231,7 +239,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_tf32_kernel(const
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * kWgN;
         uint32_t first = 1;
-        for (uint32_t kb = it.kb_begin; kb < it.kb_end; ++kb) {
+        const uint32_t n_stages = (it.kb_end - it.kb_begin) * args.npass;
+        for (uint32_t kb = 0; kb < n_stages; ++kb) {
           mbar_wait(&full_bar[rs.stage], rs.phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + (size_t)rs.stage * kStageBytes);
@@ -352,6 +361,8 @@ struct BgArgs {
   float* partial;                          // [blocks][cout]
   int32_t n_levels, cout;
   uint32_t chunk;
+  int32_t row, lo_off;   // floats per pixel row of dY (= cout unless the tensor is a split one: 2 * round_up(cout, 32)); lo_off != 0: offset
+                         // of the lo half, which is added in (dY = hi + lo)
 };
 __device__ __forceinline__ float4 bg_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 bg_load4(const __half* p) {
@@ -378,10 +389,17 @@ __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgA
         for (int l = 0; l < a.n_levels; ++l) {
           const uint32_t lo = p0 > a.pix_begin[l] ? p0 : a.pix_begin[l];
           const uint32_t hi = p1 < a.pix_begin[l + 1] ? p1 : a.pix_begin[l + 1];
-          const InT* base = reinterpret_cast<const InT*>(a.dy[l]) - (size_t)a.pix_begin[l] * a.cout + (size_t)q * 4;
+          const InT* base = reinterpret_cast<const InT*>(a.dy[l]) - (size_t)a.pix_begin[l] * a.row + (size_t)q * 4;
 #pragma unroll 4
           for (uint32_t p = lo + ty; p < hi; p += 4) {
-            const float4 v = bg_load4(base + (size_t)p * a.cout);
+            float4 v = bg_load4(base + (size_t)p * a.row);
+            if (a.lo_off) {   // split tensor: the element is hi + lo (exact in fp32)
+              const float4 w = bg_load4(base + (size_t)p * a.row + a.lo_off);
+              v.x += w.x;
+              v.y += w.y;
+              v.z += w.z;
+              v.w += w.w;
+            }
             acc.x += v.x;
             acc.y += v.y;
             acc.z += v.z;
@@ -411,7 +429,8 @@ __global__ void __launch_bounds__(kBgThreads) bias_grad_partial_kernel(const BgA
       int l = 0;
       for (uint32_t p = p0; p < p1; ++p) {
         while (p >= a.pix_begin[l + 1]) ++l;
-        acc += bg_load1(reinterpret_cast<const InT*>(a.dy[l]) + (size_t)(p - a.pix_begin[l]) * a.cout + c);
+        const InT* e = reinterpret_cast<const InT*>(a.dy[l]) + (size_t)(p - a.pix_begin[l]) * a.row + c;
+        acc += a.lo_off ? bg_load1(e) + bg_load1(e + a.lo_off) : bg_load1(e);
       }
       a.partial[(size_t)blockIdx.x * a.cout + c] = acc;
     }
@@ -561,7 +580,7 @@ SAD_EXPORT size_t sad_conv3x3_wgrad_workspace_bytes(const sad_wgrad_level* level
 // cout_out: channels of d_weight / d_bias; cout (>= cout_out): channel count of the dY tensors (the fp16 path pads it to a multiple
 // of 8; the extra channels never leave the partial buffers); out_scale multiplies the finished gradients (1 / loss scale).
 static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int cout, int cout_out, float out_scale, float* d_weight, float* d_bias,
-                      int accumulate, void* workspace, size_t workspace_bytes, void* stream, bool f16) {
+                      int accumulate, void* workspace, size_t workspace_bytes, void* stream, bool f16, bool x3 = false) {
   int sms = 0, rc;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   WgPlan p;
@@ -578,6 +597,16 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
   }
   if (!tma_ok && f16)
     return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 wgrad fp16: needs channel counts that are multiples of 8 and 16-byte aligned tensors");
+  // 3xTF32: the tensors are split rows [hi | lo] of 2 * round_up(C, 32) floats; cin / cout stay the logical channel counts
+  const int cin_s = (cin + 31) & ~31, cout_s = (cout + 31) & ~31;
+  const int cin_map = x3 ? 2 * cin_s : cin, cout_map = x3 ? 2 * cout_s : cout;
+  if (x3) {
+    bool ok = true;
+    for (int l = 0; l < n_levels; ++l)
+      if ((reinterpret_cast<uintptr_t>(levels[l].x_nhwc) | reinterpret_cast<uintptr_t>(levels[l].dy_nhwc)) & 15) ok = false;
+    if (!ok) return set_error(SAD_ERR_UNSUPPORTED, "conv3x3 wgrad f32x3: needs 16-byte aligned tensors (there is no SIMT split path)");
+    tma_ok = true;
+  }
   if (!tma_ok) p.splits = 1, p.partial_bytes = (size_t)9 * cout * cin * sizeof(float);
   const size_t partial_padded = ((p.partial_bytes + 255) / 256) * 256;
   if (!workspace || workspace_bytes < partial_padded + p.bias_partial_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255))
@@ -619,11 +648,11 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
         if (first_valid < 0) first_valid = l;
         continue;
       }
-      if ((rc = encode_nhwc_map(&a.tmap_dy[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, 1, "wgrad dY {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
-      if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, 1, "wgrad X {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
+      if ((rc = encode_nhwc_map(&a.tmap_dy[l], L.dy_nhwc, L.N, cout_map, L.H, L.W, kWgKP, 1, "wgrad dY {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
+      if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kWgKP, 1, "wgrad X {C,W,H,N}", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != SAD_OK) return rc;
       // 5-D views {32 c_lo, W, H, N, C/32 c_hi} (c_hi stride 128 B) so one copy brings a whole tile of full chunks
-      if (cout >= kWgM && (rc = encode_nhwc5_map(&a.tmap_dy5[l], L.dy_nhwc, L.N, cout, L.H, L.W, kWgKP, kWgM / 32, "wgrad dY 5-D")) != SAD_OK) return rc;
-      if (cin >= kWgN && (rc = encode_nhwc5_map(&a.tmap_x5[l], L.x_nhwc, L.N, cin, L.H, L.W, kWgKP, kWgN / 32, "wgrad X 5-D")) != SAD_OK) return rc;
+      if (cout >= kWgM && (rc = encode_nhwc5_map(&a.tmap_dy5[l], L.dy_nhwc, L.N, cout_map, L.H, L.W, kWgKP, kWgM / 32, "wgrad dY 5-D")) != SAD_OK) return rc;
+      if (cin >= kWgN && (rc = encode_nhwc5_map(&a.tmap_x5[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kWgKP, kWgN / 32, "wgrad X 5-D")) != SAD_OK) return rc;
       if (cout < kWgM) a.tmap_dy5[l] = a.tmap_dy[l];  // never used (no full tile)
       if (cin < kWgN) a.tmap_x5[l] = a.tmap_x[l];
       if (first_valid < 0) first_valid = l;
@@ -644,6 +673,9 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
     a.splits = p.splits;
     a.total_blocks = p.total_blocks;
     a.total_items = p.tiles * p.splits;
+    a.npass = x3 ? 3 : 1;
+    a.dy_lo = cout_s;
+    a.x_lo = cin_s;
     auto kern = f16 ? conv3x3_wgrad_tf32_kernel<true> : conv3x3_wgrad_tf32_kernel<false>;
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes),
                          "cudaFuncSetAttribute(wgrad)")) != SAD_OK)
@@ -684,6 +716,8 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
     b.n_levels = n_levels;
     b.cout = cout;
     b.chunk = p.bias_chunk;
+    b.row = cout_map;
+    b.lo_off = x3 ? cout_s : 0;
     if (f16) bias_grad_partial_kernel<__half><<<p.bias_blocks, kBgThreads, 0, st>>>(b);
     else bias_grad_partial_kernel<float><<<p.bias_blocks, kBgThreads, 0, st>>>(b);
     count_launch(1);
@@ -700,6 +734,11 @@ static int wgrad_impl(const sad_wgrad_level* levels, int n_levels, int cin, int 
 SAD_EXPORT int sad_conv3x3_wgrad_f32(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
                                      int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   return wgrad_impl(levels, n_levels, cin, cout, cout, 1.f, d_weight, d_bias, accumulate, workspace, workspace_bytes, stream, false);
+}
+
+SAD_EXPORT int sad_conv3x3_wgrad_f32x3(const sad_wgrad_level* levels, int n_levels, int cin, int cout, float* d_weight, float* d_bias,
+                                       int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return wgrad_impl(levels, n_levels, cin, cout, cout, 1.f, d_weight, d_bias, accumulate, workspace, workspace_bytes, stream, false, true);
 }
 
 SAD_EXPORT int sad_conv3x3_wgrad_f16(const sad_wgrad_level* levels, int n_levels, int cin, int dy_channels, int cout, float out_scale,

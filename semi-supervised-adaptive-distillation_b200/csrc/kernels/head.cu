@@ -61,6 +61,7 @@ struct sad_head {
 namespace {
 
 size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+int split32(int c) { return (c + 31) & ~31; }   // 3xTF32 head: offset of the lo half of a split row (rows are 2 * split32(C) floats)
 int pad8(int c) { return (c + 7) & ~7; }   // fp16 gradient tensors: channel counts padded to 16-byte rows (36 -> 40)
 float grad_scale(const sad_head* h) { return h->cfg.f16_grad_scale > 0.f ? h->cfg.f16_grad_scale : 4096.f; }
 
@@ -97,6 +98,7 @@ int pack_all(sad_head* h, const sad_head_weights* w, bool with_bwd, cudaStream_t
         it.mode = mode;
       }
   h->packed_bwd_valid = with_bwd;
+  if (h->cfg.compute_f32x3) return sad_conv3x3_pack_weights_multi_f32x3(items, n, st);
   return h->cfg.compute_f16 ? sad_conv3x3_pack_weights_multi_f16(items, n, st) : sad_conv3x3_pack_weights_multi_f32(items, n, st);
 }
 
@@ -118,6 +120,8 @@ int conv_levels(const sad_head* h, float* const* x, float* const* y_nchw, float*
   }
   // fp16 head: the arena's channels-last / packed buffers hold fp16 elements (half of each fp32-sized slot is used)
   if (h->cfg.compute_f16) return sad_conv3x3_fwd_f16(lv, h->cfg.n_levels, packed, bias, pad8(cin), cout, relu, nchw_scale, st);
+  // 3xTF32 head: every channels-last tensor of the arena is a split [hi | lo] tensor
+  if (h->cfg.compute_f32x3) return sad_conv3x3_fwd_f32x3(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
   return sad_conv3x3_fwd_f32(lv, h->cfg.n_levels, packed, bias, cin, cout, relu, st);
 }
 
@@ -131,6 +135,7 @@ int layout_levels(const sad_head* h, const float* const* src, float* const* dst,
     lv[l].H = h->cfg.H[l];
     lv[l].W = h->cfg.W[l];
   }
+  if (h->cfg.compute_f32x3) return sad_nchw_to_nhwc_f32x3(lv, h->cfg.n_levels, channels, st);
   return h->cfg.compute_f16 ? sad_nchw_to_nhwc_f16(lv, h->cfg.n_levels, channels, pad8(channels), scale, st)
                             : sad_nchw_to_nhwc_f32(lv, h->cfg.n_levels, channels, st);
 }
@@ -147,6 +152,7 @@ int wgrad_levels(const sad_head* h, float* const* x, float* const* dy, int cin, 
   }
   if (h->cfg.compute_f16)
     return sad_conv3x3_wgrad_f16(lv, h->cfg.n_levels, cin, pad8(cout), cout, 1.f / grad_scale(h), dw, db, accumulate, ws, h->wg_ws_bytes, st);
+  if (h->cfg.compute_f32x3) return sad_conv3x3_wgrad_f32x3(lv, h->cfg.n_levels, cin, cout, dw, db, accumulate, ws, h->wg_ws_bytes, st);
   return sad_conv3x3_wgrad_f32(lv, h->cfg.n_levels, cin, cout, dw, db, accumulate, ws, h->wg_ws_bytes, st);
 }
 
@@ -171,6 +177,7 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
     return set_error(SAD_ERR_INVALID, "sad_head_create: N, dim, cls_out, bbox_out must be positive");
   if (cfg->num_convs < 0 || cfg->num_convs > SAD_HEAD_MAX_CONVS) return set_error(SAD_ERR_INVALID, "sad_head_create: num_convs must be in [0, 8]");
   if (2 * 2 * (cfg->num_convs + 1) > SAD_MAX_PACK_ITEMS) return set_error(SAD_ERR_INVALID, "sad_head_create: too many convolutions");
+  if (cfg->compute_f16 && cfg->compute_f32x3) return set_error(SAD_ERR_INVALID, "sad_head_create: compute_f16 and compute_f32x3 exclude each other");
   sad_head* h = new (std::nothrow) sad_head();
   if (!h) return set_error(SAD_ERR_CUDA, "sad_head_create: out of host memory");
   h->cfg = *cfg;
@@ -213,24 +220,36 @@ SAD_EXPORT int sad_head_create(const sad_head_config* cfg, sad_head** out) {
   };
   std::vector<std::pair<float**, size_t>> slots;
   auto slot = [&](float** p, size_t floats) { slots.emplace_back(p, take(floats * sizeof(float))); };
+  const bool x3 = cfg->compute_f32x3 != 0;
+  const size_t dim_row = x3 ? 2 * (size_t)split32(dim) : (size_t)dim;   // floats per pixel of a dim-channel channels-last tensor
   for (int l = 0; l < L; ++l) {
-    slot(&h->x0[l], h->pixels[l] * dim);
+    slot(&h->x0[l], h->pixels[l] * dim_row);
     for (int t = 0; t < 2; ++t) {
       for (int i = 0; i < nc; ++i) {
-        slot(&h->act[t][i][l], h->pixels[l] * dim);
+        slot(&h->act[t][i][l], h->pixels[l] * dim_row);
         slot(reinterpret_cast<float**>(&h->bits[t][i][l]), sad_conv3x3_sign_bits_bytes(cfg->N, dim, cfg->H[l], cfg->W[l]) / sizeof(float));
       }
       // sized for the fp16 form too: channels padded to a multiple of 8 (2-byte elements; pad8(c) * 2 <= c * 4 only for c >= 4)
-      slot(&h->gpred[t][l], h->pixels[l] * pad8(pred_out(*cfg, t)));
-      for (int k = 0; k < nc; ++k) slot(&h->g[t][k][l], h->pixels[l] * dim);
+      slot(&h->gpred[t][l], h->pixels[l] * (x3 ? 2 * (size_t)split32(pred_out(*cfg, t)) : (size_t)pad8(pred_out(*cfg, t))));
+      for (int k = 0; k < nc; ++k) slot(&h->g[t][k][l], h->pixels[l] * dim_row);
     }
   }
   for (int mode = 0; mode < 2; ++mode)
     for (int t = 0; t < 2; ++t)
-      for (int i = 0; i <= nc; ++i) slot(&h->packed[mode][t][i], (size_t)9 * pad8(dim) * pad8(i < nc ? dim : pred_out(*cfg, t)));
+      for (int i = 0; i <= nc; ++i) {
+        const int co = i < nc ? dim : pred_out(*cfg, t);
+        const int M = mode == 0 ? co : dim, K = mode == 0 ? dim : co;   // packed [tap][M][K]
+        slot(&h->packed[mode][t][i], x3 ? (size_t)9 * M * 2 * split32(K) : (size_t)9 * pad8(dim) * pad8(co));
+      }
   const size_t ws_off0 = take(h->wg_ws_bytes), ws_off1 = take(h->wg_ws_bytes);
   h->arena_bytes = off ? off : 256;
   if ((rc = check_cuda(cudaMalloc(reinterpret_cast<void**>(&h->arena), h->arena_bytes), "sad_head_create: cudaMalloc")) != SAD_OK) {
+    delete h;
+    return rc;
+  }
+  // pad channels of split (3xTF32) and padded (fp16) rows are never written by the kernels and must read as zero
+  if ((rc = check_cuda(cudaMemset(h->arena, 0, h->arena_bytes), "sad_head_create: cudaMemset")) != SAD_OK) {
+    cudaFree(h->arena);
     delete h;
     return rc;
   }
@@ -281,7 +300,9 @@ SAD_EXPORT int sad_head_copy_activation(const sad_head* h, int tower, int conv, 
     return set_error(SAD_ERR_INVALID, "sad_head_copy_activation: bad argument");
   const float* src = conv < 0 ? h->x0[level] : h->act[tower][conv][level];
   // an fp16 head keeps fp16 activations: dst then receives pixels * dim fp16 elements
-  const size_t bytes = h->pixels[level] * h->cfg.dim * (h->cfg.compute_f16 ? 2 : sizeof(float));
+  // a 3xTF32 head keeps split rows [hi | lo]: dst then receives pixels * 2 * round_up(dim, 32) floats
+  const size_t bytes = h->cfg.compute_f32x3 ? h->pixels[level] * 2 * (size_t)split32(h->cfg.dim) * sizeof(float)
+                                            : h->pixels[level] * h->cfg.dim * (h->cfg.compute_f16 ? 2 : sizeof(float));
   if (bytes == 0) return SAD_OK;
   return check_cuda(cudaMemcpyAsync(dst_nhwc, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)),
                     "sad_head_copy_activation");

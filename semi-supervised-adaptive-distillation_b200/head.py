@@ -34,7 +34,8 @@ def param_names(num_convs=4, k_min=K_MIN):
 
 class RetinaNetHead:
     def __init__(self, n_images, level_shapes, dim=256, num_convs=4, num_anchors=9, num_classes=80, prior_prob=0.01,
-                 device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False, param_buffer=None, compute_f16=False, f16_grad_scale=0.0):
+                 device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False, param_buffer=None, compute_f16=False, f16_grad_scale=0.0,
+                 compute_f32x3=False):
         self.N, self.level_shapes = int(n_images), [tuple(s) for s in level_shapes]
         self.dim, self.num_convs = int(dim), int(num_convs)
         self.cls_out, self.bbox_out = num_anchors * num_classes, num_anchors * 4
@@ -52,6 +53,9 @@ class RetinaNetHead:
         cfg.compute_f16 = 1 if compute_f16 else 0
         cfg.f16_grad_scale = float(f16_grad_scale)
         self.compute_f16 = bool(compute_f16)
+        # 3xTF32: the fp32-accurate mode (the reference's head convolution is fp32, conv_op_cudnn.cc:494-498); split [hi | lo] operands
+        cfg.compute_f32x3 = 1 if compute_f32x3 else 0
+        self.compute_f32x3 = bool(compute_f32x3)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib().sad_head_create(C.byref(cfg), C.byref(self.handle)))
@@ -146,9 +150,13 @@ class RetinaNetHead:
         """Kept activation of the last forward as an NCHW tensor: tower 'cls' / 'bbox'; conv -1 = the input fpn_L,
         i = output of tower conv i after ReLU (blob retnet_<tower>_conv_n<i>_fpn<L>), tf32-rounded as stored."""
         h, w = self.level_shapes[level]
-        out = torch.empty((self.N, h, w, self.dim), dtype=torch.float16 if self.compute_f16 else torch.float32, device=self.device)
+        cs = lib().sad_conv3x3_split_channels(self.dim)
+        shape = (self.N, h, w, 2 * cs) if self.compute_f32x3 else (self.N, h, w, self.dim)
+        out = torch.empty(shape, dtype=torch.float16 if self.compute_f16 else torch.float32, device=self.device)
         check(lib().sad_head_copy_activation(self.handle, 0 if tower == "cls" else 1, int(conv), int(level),
                                              C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        if self.compute_f32x3:   # split rows [hi | lo]: the stored value is hi + lo (exact in fp32)
+            out = out[..., :self.dim] + out[..., cs:cs + self.dim]
         return out.float().permute(0, 3, 1, 2).contiguous()
 
     def alloc_outputs(self):

@@ -58,7 +58,8 @@ SAD_HEAD_MAX_CONVS = 8
 class HeadConfig(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("N", C.c_int32), ("H", C.c_int32 * SAD_MAX_LEVELS), ("W", C.c_int32 * SAD_MAX_LEVELS),
                 ("dim", C.c_int32), ("num_convs", C.c_int32), ("cls_out", C.c_int32), ("bbox_out", C.c_int32),
-                ("cls_output_sigmoid", C.c_int32), ("compute_f16", C.c_int32), ("f16_grad_scale", C.c_float)]
+                ("cls_output_sigmoid", C.c_int32), ("compute_f16", C.c_int32), ("f16_grad_scale", C.c_float),
+                ("compute_f32x3", C.c_int32)]
 
 
 class PackItem(C.Structure):
@@ -157,6 +158,14 @@ def lib():
         l.sad_conv3x3_fwd_f16.argtypes = [C.POINTER(ConvLevel), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
         l.sad_conv3x3_wgrad_f16.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_size_t, C.c_void_p]
+        l.sad_conv3x3_split_channels.argtypes = [C.c_int]
+        l.sad_conv3x3_packed_bytes_f32x3.restype = C.c_size_t
+        l.sad_conv3x3_packed_bytes_f32x3.argtypes = [C.c_int, C.c_int, C.c_int]
+        l.sad_nchw_to_nhwc_f32x3.argtypes = [C.POINTER(LayoutLevel), C.c_int, C.c_int, C.c_void_p]
+        l.sad_conv3x3_pack_weights_multi_f32x3.argtypes = [C.POINTER(PackItem), C.c_int, C.c_void_p]
+        l.sad_conv3x3_fwd_f32x3.argtypes = [C.POINTER(ConvLevel), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.sad_conv3x3_wgrad_f32x3.argtypes = [C.POINTER(WgradLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_scale_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
         l.sad_affine_channel_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
         l.sad_upsample_nearest_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -552,3 +552,98 @@ def conv3x3_wgrad_f16(xs_nhwc_f16, dys_nhwc_f16, cout=None, out_scale=1.0, want_
                                       C.c_void_p(db.data_ptr()) if db is not None else None, 0,
                                       C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
     return dw, db
+
+
+# ---------------------------------------------------------------------------------------------
+# 3xTF32: the fp32-accurate convolution mode (split [hi | lo] operands; include/sad_b200.h, sad_conv3x3_fwd_f32x3)
+# ---------------------------------------------------------------------------------------------
+def split_channels(c):
+    """Offset of the lo half of a split row: round_up(c, 32); rows are 2 * split_channels(c) floats long."""
+    return lib().sad_conv3x3_split_channels(int(c))
+
+
+def join_split(t_nhwc_split, channels):
+    """Split channels-last tensor (N, H, W, 2 * split_channels(C)) -> the fp32 values it carries, NCHW: hi + lo."""
+    cs = t_nhwc_split.shape[3] // 2
+    return (t_nhwc_split[..., :channels] + t_nhwc_split[..., cs:cs + channels]).permute(0, 3, 1, 2).contiguous()
+
+
+def conv3x3_pack_f32x3(weight, mode=0):
+    """(Cout, Cin, 3, 3) fp32 -> [tap][M][hi(0..K) pad | lo(0..K) pad] tf32 pairs: mode 0 forward (M = Cout, K = Cin), mode 1 data
+    gradient (M = Cin, K = Cout, taps flipped)."""
+    _require_cuda(weight, torch.float32, "weight")
+    cout, cin = weight.shape[0], weight.shape[1]
+    if tuple(weight.shape[2:]) != (3, 3):
+        raise ValueError("weight must be (Cout, Cin, 3, 3)")
+    packed = torch.empty(lib().sad_conv3x3_packed_bytes_f32x3(cin, cout, int(mode)) // 4, dtype=torch.float32, device=weight.device)
+    item = (native.PackItem * 1)()
+    item[0].weight, item[0].packed, item[0].cin, item[0].cout, item[0].mode = weight.data_ptr(), packed.data_ptr(), cin, cout, int(mode)
+    check(lib().sad_conv3x3_pack_weights_multi_f32x3(item, 1, _stream()))
+    return packed
+
+
+def to_nhwc_f32x3(xs):
+    """NCHW fp32 -> split channels-last (N, H, W, 2 * split_channels(C)), every level in one launch."""
+    xs = list(xs)
+    arr = (native.LayoutLevel * len(xs))()
+    outs = []
+    for i, x in enumerate(xs):
+        _require_cuda(x, torch.float32, "x[%d]" % i)
+        if x.shape[1] != xs[0].shape[1]:
+            raise ValueError("all levels must have the same channel count")
+        n, c, h, w = x.shape
+        outs.append(torch.empty((n, h, w, 2 * split_channels(c)), dtype=torch.float32, device=x.device))
+        arr[i].src_nchw, arr[i].dst_nhwc = x.data_ptr(), outs[-1].data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = n, h, w
+    check(lib().sad_nchw_to_nhwc_f32x3(arr, len(xs), xs[0].shape[1], _stream()))
+    return outs
+
+
+def conv3x3_forward_f32x3(xs_split, packed_x3, cin, cout, bias=None, relu=0, want_nchw=True, want_nhwc=False, relu_bits=None, want_bits=False):
+    """Conv (+bias, + activation: 0 none, 1 ReLU, 2 Sigmoid) of every level in one launch in 3xTF32 arithmetic; with mode-1 packed
+    weights (and cin / cout swapped) the data gradient.  xs_split: split channels-last inputs.  Returns (ys_nchw, ys_split)."""
+    arr = (ConvLevel * len(xs_split))()
+    ys, yts, bits = [], [], []
+    for i, xt in enumerate(xs_split):
+        _require_cuda(xt, torch.float32, "x_split[%d]" % i)
+        n, h, w, c = xt.shape
+        if c != 2 * split_channels(cin):
+            raise ValueError("x_split rows must be 2 * split_channels(cin) floats")
+        arr[i].x_nhwc = xt.data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = n, h, w
+        if want_nchw:
+            ys.append(torch.empty((n, cout, h, w), dtype=torch.float32, device=xt.device))
+            arr[i].y_nchw = ys[-1].data_ptr()
+        if want_nhwc:   # pad channels are never written by the kernel and must read as zero
+            yts.append(torch.zeros((n, h, w, 2 * split_channels(cout)), dtype=torch.float32, device=xt.device))
+            arr[i].y_nhwc = yts[-1].data_ptr()
+        if relu_bits is not None:
+            arr[i].relu_bits_in = relu_bits[i].data_ptr()
+        if want_bits:
+            bits.append(sign_bits_like(n, cout, h, w, xt.device))
+            arr[i].relu_bits_out = bits[-1].data_ptr()
+    b = C.c_void_p(bias.data_ptr()) if bias is not None else None
+    check(lib().sad_conv3x3_fwd_f32x3(arr, len(xs_split), C.c_void_p(packed_x3.data_ptr()), b, int(cin), int(cout), int(relu), _stream()))
+    return (ys, yts, bits) if want_bits else (ys, yts)
+
+
+def conv3x3_wgrad_f32x3(xs_split, dys_split, cin, cout, want_bias=True):
+    """Weight (+ bias) gradient summed over every level in 3xTF32 arithmetic from split tensors.  Returns (dW, db) fp32."""
+    n = len(xs_split)
+    arr = (WgradLevel * n)()
+    for i, (xt, dt) in enumerate(zip(xs_split, dys_split)):
+        _require_cuda(xt, torch.float32, "x_split[%d]" % i)
+        _require_cuda(dt, torch.float32, "dy_split[%d]" % i)
+        if xt.shape[:3] != dt.shape[:3] or xt.shape[3] != 2 * split_channels(cin) or dt.shape[3] != 2 * split_channels(cout):
+            raise ValueError("level %d: split x / dy rows do not match cin / cout" % i)
+        arr[i].x_nhwc, arr[i].dy_nhwc = xt.data_ptr(), dt.data_ptr()
+        arr[i].N, arr[i].H, arr[i].W = xt.shape[:3]
+    dev = xs_split[0].device
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
+    db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
+    nbytes = lib().sad_conv3x3_wgrad_workspace_bytes(arr, n, int(cin), int(cout))
+    workspace = torch.empty(max(256, nbytes), dtype=torch.uint8, device=dev)
+    check(lib().sad_conv3x3_wgrad_f32x3(arr, n, int(cin), int(cout), C.c_void_p(dw.data_ptr()),
+                                        C.c_void_p(db.data_ptr()) if db is not None else None, 0,
+                                        C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+    return dw, db
