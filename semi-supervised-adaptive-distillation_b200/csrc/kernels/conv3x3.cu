@@ -257,12 +257,18 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
       RingState rs;
       uint32_t it = 0;
       for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
-        const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+        // kX3: the tile's stage sequence is cut into TWO accumulation chains, one per TMEM buffer, which the epilogue adds in
+        // fp32 (round to nearest): the tensor core's accumulator add rounds toward zero (measured: the result of a K = 2304
+        // chain is 1.6e-5 too small in magnitude, growing linearly with the number of MMAs in the chain), so halving the
+        // chains halves that bias.  The price is the epilogue / main-loop overlap, < 10 % of a 3x longer main loop.
+        const uint32_t buf = kX3 ? 0u : (it & 1u), aphase = kX3 ? (it & 1u) : ((it >> 1) & 1u);
         mbar_wait(&tmem_empty[buf], aphase ^ 1u);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * kCvN;
         const uint32_t n_kb = 9u * k_blocks;
+        const uint32_t chain_b = kX3 ? n_kb / 2u : n_kb;   // first stage of the second chain
         for (uint32_t kb = 0; kb < n_kb; ++kb) {
+          const uint32_t d_tmem = tmem_base + ((kX3 ? (kb >= chain_b ? 1u : 0u) : buf) * kCvN);
+          const uint32_t kb_chain = (kX3 && kb >= chain_b) ? kb - chain_b : kb;   // 0 at the first stage of a chain: overwrite
           mbar_wait(&full_bar[rs.stage], rs.phase);
           if (kC2) mbar_wait_cluster(&peer_full[rs.stage], rs.phase);
           tc_fence_after_sync();
@@ -275,11 +281,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
             const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             if (kF16) {
-              if (kC2) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
-              else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+              if (kC2) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb_chain | (uint32_t)k) != 0u);
+              else umma_f16(d_tmem, adesc, bdesc, idesc, (kb_chain | (uint32_t)k) != 0u);
             } else {
-              if (kC2) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
-              else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+              if (kC2) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, (kb_chain | (uint32_t)k) != 0u);
+              else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb_chain | (uint32_t)k) != 0u);
             }
           }
           // frees the smem stage when these MMAs have read it (pair: in both CTAs)
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
     uint32_t it = 0;
     int l_hint = 0;
     for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
-      const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+      const uint32_t buf = kX3 ? 0u : (it & 1u), aphase = kX3 ? (it & 1u) : ((it >> 1) & 1u);
       ConvTile t = conv_decode_tile(args, tile, l_hint);
       if (kC2) t.m0 = (2 * (t.m0 / kCvM) + (int)crank) * kCvM;
       const ConvLevel& L = args.lv[t.l];
@@ -324,6 +330,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
       for (int j = jhalf * kRowsPerWarp; j < (jhalf + 1) * kRowsPerWarp; ++j) {
         float v[32];
         tmem_ld_32x32(taddr + j * kCvCols, v);
+        if (kX3) {   // second accumulation chain (the other TMEM buffer)
+          float w2[32];
+          tmem_ld_32x32(taddr + kCvN + j * kCvCols, w2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w2[i];
+        }
         const int y = t.y0 + j;
         if (co_ok && y < L.H) {
 #pragma unroll
