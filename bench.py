@@ -155,6 +155,12 @@ def run_reference_arm(args, rank):
     import numpy as np
     from oracle import cpu_oracle
     from sad_b200 import synthetic
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm runs on rank 0 alone and takes every host core it may use
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cpu_oracle.set_num_threads(max(1, avail))
     cores = cpu_oracle.num_threads()
     full = synthetic.make_pyramid(1234, 2, 600)
     # bounded sample: the largest suffix of the pyramid (P3..P7, P4..P7, ...) whose pass keeps the
@@ -430,7 +436,10 @@ def main():
     sampler.stop_flag = True
     launches = native.lib().sad_launch_count() - launches0
     total_ms = ev0.elapsed_time(ev1)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / max(1, args.steps)
+    kernel_times = sorted(a.elapsed_time(b) for a, b in kev)
+    kernel_ms = sum(kernel_times) / max(1, args.steps)
+    kernel_ms_median = kernel_times[len(kernel_times) // 2]
+    kernel_ms_min = kernel_times[0]
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -480,6 +489,34 @@ def main():
     e2e_value2 = world * anchors / float(e2e_dt2.item()) / 1e6
     step2.close()
 
+    # ---- copy-only baseline of the e2e path: the SAME bytes over the same two directions (all inputs up on one stream, all
+    # gradients down on another, concurrently), no kernels: what this host's PCIe / memory path allows for that step
+    cp_in, cp_out = torch.cuda.Stream(), torch.cuda.Stream()
+    dev_in = [tuple(torch.empty_like(a, device="cuda") for a in l) for l in cpu]
+    dev_out = [torch.empty_like(l[0], device="cuda") for l in cpu]
+
+    def copy_only():
+        with torch.cuda.stream(cp_in):
+            for l, d in zip(cpu, dev_in):
+                for a, b in zip(l, d):
+                    b.copy_(a, non_blocking=True)
+        with torch.cuda.stream(cp_out):
+            for o, d in zip(outs, dev_out):
+                o.copy_(d, non_blocking=True)
+
+    for _ in range(3):
+        copy_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_only()
+    torch.cuda.synchronize()
+    copy_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(copy_dt, op=dist.ReduceOp.MAX)
+    copy_only_ms = float(copy_dt.item()) * 1e3
+    del dev_in, dev_out
+
     head_line = head_f16_line = None
     if args.head_steps >= 0:
         head_line = run_head_step(args, rank, world, barrier, native)
@@ -523,10 +560,18 @@ def main():
                      "traffic": _traffic_per_launch(), "algorithmic_bytes_per_launch": BYTES_PER_ELEMENT * elements,
                      "algorithmic_bytes_per_element": "16.05 = PowSum 4 (T) + loss+grad 12.05 (X 4 + T 4 + dX 4 + labels 4/80), SURVEY.md 8(d); "
                                                       "the second read of T can be served by L2, so achieved may exceed the DRAM copy peak",
-                     "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step},
+                     "kernel_ms": kernel_ms, "kernel_ms_median": kernel_ms_median, "kernel_ms_min": kernel_ms_min,
+                     "frac_median": BYTES_PER_ELEMENT * elements / (kernel_ms_median * 1e-3) / 1e9 / peak,
+                     "timing": "one CUDA event pair around every launch of the timed region (%d steps): achieved / frac use the mean, "
+                               "kernel_ms_median / frac_median the median" % args.steps,
+                     "kernel_share_of_step": kernel_ms / ms_per_step},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_dt.item()) * 1e3, "steps": e2e_steps,
                 "api": "sad_distill_step_host (pinned host buffers in, losses + normaliser + gradients out)",
+                "copy_only": {"ms_per_step": copy_only_ms, "value": world * anchors / (copy_only_ms * 1e-3) / 1e6, "unit": UNIT,
+                              "e2e_over_copy_only": float(e2e_dt.item()) * 1e3 / copy_only_ms,
+                              "what": "the same %d H2D + %d D2H bytes per step and rank as two concurrent copy streams with NO kernels "
+                                      "(max over ranks): the bound this host's PCIe / memory path sets for the e2e step" % (h2d, d2h)},
                 "gradients_on_device": {"value": e2e_value2, "unit": UNIT, "ms_per_step": float(e2e_dt2.item()) * 1e3,
                                         "d2h_bytes_per_step": 4 * (len(host) * 2 + 1),
                                         "note": "same call with d_logits = NULL: gradients stay in HBM for ConvGradient, only losses + normaliser return"}},
@@ -550,6 +595,15 @@ def main():
     if full5_f16_line:
         line["full_step_config5_heads_f16"] = full5_f16_line
         line["gpu_launches"] += full5_f16_line["gpu_launches"]
+    step_imgs = {}
+    for key, obj in (("head_step", head_line), ("head_step_f16", head_f16_line), ("full_step", full_line), ("full_step_bs16", full16_line),
+                     ("full_step_config5", full5_line), ("full_step_config5_heads_f16", full5_f16_line)):
+        if obj:
+            step_imgs[key] = {"imgs_s": obj["value"], "ms_per_step": obj["ms_per_step"], "allreduce_ms": obj.get("allreduce_ms"),
+                              "allreduce_exposed_ms": obj.get("allreduce_exposed_ms"), "multi_gpu_check": obj.get("multi_gpu_check")}
+    line["config"]["step_imgs_s"] = step_imgs
+    line["config"]["e2e_ms_per_step"] = float(e2e_dt.item()) * 1e3
+    line["config"]["e2e_copy_only_ms_per_step"] = copy_only_ms
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_oracle
         sample = host  # the full configs[1] batch; passes are repeated until >= 10 core-seconds of CPU work were timed

@@ -42,7 +42,7 @@ constexpr int kFWarps = kFConsumers / 32;
 constexpr int kFThreads = kFConsumers + 32;
 constexpr int kFPer = kFCT / 2;
 constexpr int kF1Chunk = 2048;      // floats per phase-1 unit (8 KB)
-constexpr int kF1Stages = 6;
+constexpr int kF1Stages = 4;         // the phase-1 ring lives inside phase-2 stage 0 (4 x 8 KB <= 34 KB)
 
 struct FusedLevel {
   const float* X;
@@ -54,6 +54,8 @@ struct FusedLevel {
   uint32_t HW, hw_tiles, unit_begin, unit_end;  // phase-2 units
   uint32_t p1_begin, p1_end;                    // phase-1 units (chunks of T)
   uint32_t elems;                               // N * D * HW
+  uint32_t D;                                   // channels (A * num_classes)
+  uint32_t tail;                                // 1: H*W % 4 != 0 — no ring units, done by the scalar tail pass
 };
 struct FusedArgs {
   FusedLevel lv[SAD_MAX_LEVELS];
@@ -80,7 +82,7 @@ struct __align__(128) FStage {
   int32_t G[kFHW];
 };
 constexpr size_t kFusedSmemBytes = sizeof(FStage) * kFStages;
-static_assert(kFusedSmemBytes >= (size_t)kF1Chunk * 4 * kF1Stages, "phase-1 ring must fit in the phase-2 ring");
+static_assert(sizeof(FStage) >= (size_t)kF1Chunk * 4 * kF1Stages, "phase-1 ring must fit in stage 0 of the phase-2 ring");
 
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
@@ -102,7 +104,7 @@ template <bool kAlphaHalf, bool kPowAccurate>
 __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __grid_constant__ FusedArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FStage* stages = reinterpret_cast<FStage*>(smem_raw);
-  float(*p1_stages)[kF1Chunk] = reinterpret_cast<float(*)[kF1Chunk]>(smem_raw);
+  float(*p1_stages)[kF1Chunk] = reinterpret_cast<float(*)[kF1Chunk]>(smem_raw);   // phase-1 ring: inside phase-2 stage 0
   __shared__ FUnitDesc desc[kFStages];
   __shared__ int32_t p1_desc[kF1Stages][2];  // {input, count}
   __shared__ __align__(8) uint64_t full_bar[kFStages], empty_bar[kFStages], p1_full[kF1Stages], p1_empty[kF1Stages];
@@ -124,6 +126,10 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
       mbar_init(&p1_full[s], 1);
       mbar_init(&p1_empty[s], kFWarps);
     }
+    // The phase-2 ring starts at stage 1: stage 0 holds the phase-1 ring and joins when phase 1 has been consumed (the
+    // consumer warps' arrivals on empty_bar[0] after phase 1 are that barrier's first completion).  This dummy first
+    // completion of full_bar[0] keeps both barriers of stage 0 one phase ahead of the ring's phase bit.
+    mbar_arrive(&full_bar[0]);
     mbar_fence_init();
   }
   if (tid < SAD_MAX_LEVELS) {
@@ -134,29 +140,77 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
   const bool stamp = (args.dbg & 8u) && tid == 0;
   if (stamp) args.stamps[blockIdx.x * 5 + 0] = gtimer();
 
-  // ================= phase 1: PowSum over the teacher probabilities, last chunk first =================
-  {
-    // unit j of this CTA = global chunk (p1_total - 1 - (blockIdx.x + j * gridDim.x))
+  if (tid >= kFConsumers) {
+    // ================= producer thread: phase-1 chunks, then (without waiting for the normaliser) phase-2 units ==========
     if (tid == kFConsumers) {
-      const uint64_t pol = (args.dbg & 1u) ? policy_evict_first() : policy_evict_last();
-      RingState rs;
-      int k = args.n_levels - 1;
+      {
+        // unit j of this CTA = global chunk (p1_total - 1 - (blockIdx.x + j * gridDim.x)): last chunk first
+        const uint64_t pol = (args.dbg & 1u) ? policy_evict_first() : policy_evict_last();
+        RingState rs;
+        int k = args.n_levels - 1;
 #pragma unroll 1
-      for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
-        const uint32_t u = args.p1_total - 1u - r;
-        while (u < args.lv[k].p1_begin) --k;
-        const uint32_t start = (u - args.lv[k].p1_begin) * (uint32_t)kF1Chunk;
-        const uint32_t left = args.lv[k].elems - start;
-        const uint32_t cnt = left < (uint32_t)kF1Chunk ? left : (uint32_t)kF1Chunk;
-        mbar_wait(&p1_empty[rs.stage], rs.phase ^ 1u);
-        p1_desc[rs.stage][0] = k;
-        p1_desc[rs.stage][1] = (int32_t)cnt;
-        mbar_arrive_expect_tx(&p1_full[rs.stage], cnt * 4u);
-        bulk_g2s(p1_stages[rs.stage], args.lv[k].T + start, cnt * 4u, &p1_full[rs.stage], pol);
-        rs.advance<kF1Stages>();
+        for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
+          const uint32_t u = args.p1_total - 1u - r;
+          while (u < args.lv[k].p1_begin) --k;
+          const uint32_t start = (u - args.lv[k].p1_begin) * (uint32_t)kF1Chunk;
+          const uint32_t left = args.lv[k].elems - start;
+          const uint32_t cnt = left < (uint32_t)kF1Chunk ? left : (uint32_t)kF1Chunk;
+          mbar_wait(&p1_empty[rs.stage], rs.phase ^ 1u);
+          p1_desc[rs.stage][0] = k;
+          p1_desc[rs.stage][1] = (int32_t)cnt;
+          mbar_arrive_expect_tx(&p1_full[rs.stage], cnt * 4u);
+          bulk_g2s(p1_stages[rs.stage], args.lv[k].T + start, cnt * 4u, &p1_full[rs.stage], pol);
+          rs.advance<kF1Stages>();
+        }
       }
-    } else if (tid < kFConsumers) {
+      // phase 2: X and T rows and the label row of each unit.  Nothing here depends on the normaliser, so the first units
+      // (stages 1 and 2 at once, stage 0 as soon as the consumers are through with phase 1) land while the grid barrier
+      // is still being crossed.
+      const uint64_t pol = policy_evict_first();
+      const uint32_t C = (uint32_t)args.num_classes, cg = (uint32_t)args.class_groups;
+      RingState rs;
+      rs.stage = 1;
+      int l = 0;
+#pragma unroll 1
+      for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
+        mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
+        while (u >= args.lv[l].unit_end) ++l;
+        const FusedLevel& L = args.lv[l];
+        const uint32_t local = u - L.unit_begin;
+        const uint32_t item = local / cg, chunk = local - item * cg;
+        const uint32_t na = item / L.hw_tiles, ht = item - na * L.hw_tiles;
+        const uint32_t hw0 = ht * kFHW;
+        const uint32_t n_hw = min((uint32_t)kFHW, L.HW - hw0);
+        const uint32_t c0 = chunk * kFCT;
+        const uint32_t n_cls = min((uint32_t)kFCT, C - c0);
+        const size_t off = ((size_t)na * C + c0) * L.HW + hw0;
+        FStage& st = stages[rs.stage];
+        FUnitDesc d;
+        d.dX = L.dX + off;
+        d.n_hw = n_hw;
+        d.n_cls = n_cls;
+        d.plane = L.HW;
+        d.unit = u;
+        d.level = l;
+        d.kg = 0.f;
+        desc[rs.stage] = d;
+        const uint32_t row_bytes = n_hw * 4u;
+        mbar_arrive_expect_tx(&full_bar[rs.stage], (2u * n_cls + 1u) * row_bytes);
+        const float* xs = L.X + off;
+        const float* ts = L.T + off;
+        for (uint32_t c = 0; c < n_cls; ++c) {
+          bulk_g2s(st.X[c], xs + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
+          bulk_g2s(st.T[c], ts + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
+        }
+        bulk_g2s(st.G, L.G + (size_t)na * L.HW + hw0, row_bytes, &full_bar[rs.stage], pol);
+        rs.advance<kFStages>();
+      }
+    }
+  } else {
+    // ================= consumers, phase 1: PowSum over the teacher probabilities =================
+    {
       const float power = args.power;
+      const f32x2 power2 = pk2(power, power);
       float acc = 0.f;
       int cur = -1;
       RingState rs;
@@ -183,8 +237,11 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
               acc += powf(v.x, power) + powf(v.y, power);
               acc += powf(v.z, power) + powf(v.w, power);
             } else {  // x^p = 2^(p log2 x) for x >= 0 (NaN for x < 0, like powf with a non-integer exponent)
-              acc += ex2_approx(power * lg2_approx(v.x)) + ex2_approx(power * lg2_approx(v.y));
-              acc += ex2_approx(power * lg2_approx(v.z)) + ex2_approx(power * lg2_approx(v.w));
+              float a, b, c, d;
+              upk2(mul2(power2, pk2(lg2_approx(v.x), lg2_approx(v.y))), a, b);
+              upk2(mul2(power2, pk2(lg2_approx(v.z), lg2_approx(v.w))), c, d);
+              acc += ex2_approx(a) + ex2_approx(b);
+              acc += ex2_approx(c) + ex2_approx(d);
             }
           }
         }
@@ -197,86 +254,40 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
         if (tid == 0) in_sum[cur] = s;
       }
     }
-  }
-  __syncthreads();
+    // phase 1 consumed: stage 0 of the phase-2 ring (which held the phase-1 ring) is free
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[0]);
+    named_bar_sync(2, kFConsumers);
 
-  // ================= grid barrier; every CTA derives the same normaliser =================
-  if (stamp) args.stamps[blockIdx.x * 5 + 1] = gtimer();
-  if (tid < SAD_MAX_LEVELS) args.p1_partials[(size_t)blockIdx.x * SAD_MAX_LEVELS + tid] = in_sum[tid];
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    atomicAdd(&args.ctrl[0], 1u);
-    while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(32);
-    __threadfence();
-  }
-  __syncthreads();
-  // per input: fp64 sum of the CTA partials in a fixed order, rounded to float (one warp per input); then the
-  // reference's running float add over the inputs (pow_sum_op.cu:39)
-  for (int j = warp; j < args.n_levels; j += kFThreads / 32) {
-    const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p1_partials, j, lane);
-    if (lane == 0) in_sum[j] = (float)s;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float res = 0.f;
-    for (int j = 0; j < args.n_levels; ++j) res = res + in_sum[j];
-    np_smem = res;
-    if (blockIdx.x == 0) args.norm_out[0] = res;
-  }
-  __syncthreads();
-  const float Np = fmaxf(np_smem, 1.0f);   // max(weight_pos[0], 1.0): ...loss_op.cu:49,87
-  if (stamp) args.stamps[blockIdx.x * 5 + 2] = gtimer();
-
-  // ================= phase 2: loss + gradient, units dealt round-robin =================
-  if (tid >= kFConsumers) {
-    if (tid == kFConsumers) {
-      const uint64_t pol = policy_evict_first();
-      const uint32_t C = (uint32_t)args.num_classes, cg = (uint32_t)args.class_groups;
-      RingState rs;
-      int l = 0;
-      float kg = 0.f;
-      int kg_level = -1;
-#pragma unroll 1
-      for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
-        mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
-        while (u >= args.lv[l].unit_end) ++l;
-        const FusedLevel& L = args.lv[l];
-        if (kg_level != l) {
-          kg = (L.d_loss ? __ldg(L.d_loss) : 1.f) * args.scale / Np;
-          kg_level = l;
-        }
-        const uint32_t local = u - L.unit_begin;
-        const uint32_t item = local / cg, chunk = local - item * cg;
-        const uint32_t na = item / L.hw_tiles, ht = item - na * L.hw_tiles;
-        const uint32_t hw0 = ht * kFHW;
-        const uint32_t n_hw = min((uint32_t)kFHW, L.HW - hw0);
-        const uint32_t c0 = chunk * kFCT;
-        const uint32_t n_cls = min((uint32_t)kFCT, C - c0);
-        const size_t off = ((size_t)na * C + c0) * L.HW + hw0;
-        FStage& st = stages[rs.stage];
-        FUnitDesc d;
-        d.dX = L.dX + off;
-        d.n_hw = n_hw;
-        d.n_cls = n_cls;
-        d.plane = L.HW;
-        d.unit = u;
-        d.level = l;
-        d.kg = kg;
-        desc[rs.stage] = d;
-        const uint32_t row_bytes = n_hw * 4u;
-        mbar_arrive_expect_tx(&full_bar[rs.stage], (2u * n_cls + 1u) * row_bytes);
-        const float* xs = L.X + off;
-        const float* ts = L.T + off;
-        for (uint32_t c = 0; c < n_cls; ++c) {
-          bulk_g2s(st.X[c], xs + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
-          bulk_g2s(st.T[c], ts + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
-        }
-        bulk_g2s(st.G, L.G + (size_t)na * L.HW + hw0, row_bytes, &full_bar[rs.stage], pol);
-        rs.advance<kFStages>();
-      }
+    // ================= grid barrier; every CTA derives the same normaliser =================
+    if (stamp) args.stamps[blockIdx.x * 5 + 1] = gtimer();
+    if (tid < SAD_MAX_LEVELS) args.p1_partials[(size_t)blockIdx.x * SAD_MAX_LEVELS + tid] = in_sum[tid];
+    named_bar_sync(2, kFConsumers);
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&args.ctrl[0], 1u);
+      while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(20);
+      __threadfence();
     }
-  } else {
+    named_bar_sync(2, kFConsumers);
+    // per input: fp64 sum of the CTA partials in a fixed order, rounded to float (one warp per input); then the
+    // reference's running float add over the inputs (pow_sum_op.cu:39)
+    for (int j = warp; j < args.n_levels; j += kFWarps) {
+      const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p1_partials, j, lane);
+      if (lane == 0) in_sum[j] = (float)s;
+    }
+    named_bar_sync(2, kFConsumers);
+    if (tid == 0) {
+      float res = 0.f;
+      for (int j = 0; j < args.n_levels; ++j) res = res + in_sum[j];
+      np_smem = res;
+      if (blockIdx.x == 0) args.norm_out[0] = res;
+    }
+    named_bar_sync(2, kFConsumers);
+    const float Np = fmaxf(np_smem, 1.0f);   // max(weight_pos[0], 1.0): ...loss_op.cu:49,87
+    if (stamp) args.stamps[blockIdx.x * 5 + 2] = gtimer();
+
+    // ================= consumers, phase 2: loss + gradient, units dealt round-robin =================
     const uint32_t h = (uint32_t)(tid & 127) * 4u;
     const uint32_t cbase = (uint32_t)(tid >> 7) * kFPer;
     const float alpha = args.alpha;
@@ -285,9 +296,12 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     fc.cb2 = 2.f * (1.f - alpha) * kLn2;
     fc.alpha = alpha;
     fc.om2a = 1.f - 2.f * alpha;
+    const PairConsts pc = pair_consts();
     const int32_t ignored = args.ignored_label;
+    const float kscale = args.scale / Np;
     RingState rs;
-    float acc = 0.f;
+    rs.stage = 1;
+    float acc = 0.f, kg = 0.f;
     int cur_level = -1;
 #pragma unroll 1
     for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
@@ -301,6 +315,8 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           acc = 0.f;
         }
         cur_level = d.level;
+        const float* dl = args.lv[cur_level].d_loss;
+        kg = (dl ? __ldg(dl) : 1.f) * kscale;   // d_loss * scale / Np of this level
       }
       if (h < d.n_hw) {
         const int4 g = *reinterpret_cast<const int4*>(&st.G[h]);
@@ -309,25 +325,70 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
         keep[1] = g.y != ignored ? 1.f : 0.f;
         keep[2] = g.z != ignored ? 1.f : 0.f;
         keep[3] = g.w != ignored ? 1.f : 0.f;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) kk[v] = keep[v] * d.kg;
-        float4 xv[kFPer], tv[kFPer];
-#pragma unroll
-        for (int j = 0; j < kFPer; ++j) {
-          xv[j] = *reinterpret_cast<const float4*>(&st.X[cbase + j][h]);
-          tv[j] = *reinterpret_cast<const float4*>(&st.T[cbase + j][h]);
-        }
         float* out = d.dX + (size_t)cbase * d.plane + h;
+        if (kAlphaHalf && cbase + kFPer <= d.n_cls) {
+          // packed arithmetic (distill_math.cuh, distill_pair_half): 2 elements per FMA-pipe instruction
 #pragma unroll
-        for (int j = 0; j < kFPer; ++j) {
-          if (cbase + j < d.n_cls) {
-            const float xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
-            const float ts[4] = {tv[j].x, tv[j].y, tv[j].z, tv[j].w};
-            float gv[4];
+          for (int v = 0; v < 4; ++v) kk[v] = keep[v] * (kg * kLn2);
+          const f32x2 kk01 = pk2(kk[0], kk[1]), kk23 = pk2(kk[2], kk[3]);
+          f32x2 a01 = pk2(0.f, 0.f), a23 = a01;   // sum over this thread's classes of AT^2 * D per hw position
+          float vmin = 1.f;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) distill_elem_fast<kAlphaHalf, true, true>(xs[v], ts[v], keep[v], kk[v], fc, acc, gv[v]);
-            if (args.dbg & 2u) *reinterpret_cast<float4*>(out + (size_t)j * d.plane) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-            else __stcs(reinterpret_cast<float4*>(out + (size_t)j * d.plane), make_float4(gv[0], gv[1], gv[2], gv[3]));
+          for (int j = 0; j < kFPer; ++j) {
+            const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&st.X[cbase + j][h]);
+            const ulonglong2 tv = *reinterpret_cast<const ulonglong2*>(&st.T[cbase + j][h]);
+            const f32x2 g01 = distill_pair_half(xv.x, tv.x, kk01, pc, a01, vmin);
+            const f32x2 g23 = distill_pair_half(xv.y, tv.y, kk23, pc, a23, vmin);
+            float4 o;
+            upk2(g01, o.x, o.y);
+            upk2(g23, o.z, o.w);
+            __stcs(reinterpret_cast<float4*>(out + (size_t)j * d.plane), o);
+          }
+          if (vmin > 0.f) {
+            float s0, s1, s2, s3;
+            upk2(a01, s0, s1);
+            upk2(a23, s2, s3);
+            // acc gathers twice the (positive) loss summand: -(AT^2) * D2 * keep with D2 = ln2 * D
+            acc = fmaf(-kLn2 * keep[0], s0, acc);
+            acc = fmaf(-kLn2 * keep[1], s1, acc);
+            acc = fmaf(-kLn2 * keep[2], s2, acc);
+            acc = fmaf(-kLn2 * keep[3], s3, acc);
+          } else {
+            // some teacher probability of this thread's 16 elements is <= 0, >= 1 or NaN: the reference's result there is NaN
+            // (...loss_op.cu:59,93).  Redo them with the scalar function, which carries that rule per element.
+#pragma unroll
+            for (int v = 0; v < 4; ++v) kk[v] = keep[v] * kg;
+#pragma unroll 1
+            for (int j = 0; j < kFPer; ++j) {
+              const float4 xq = *reinterpret_cast<const float4*>(&st.X[cbase + j][h]);
+              const float4 tq = *reinterpret_cast<const float4*>(&st.T[cbase + j][h]);
+              const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+              const float ts[4] = {tq.x, tq.y, tq.z, tq.w};
+              float gv[4];
+#pragma unroll
+              for (int v = 0; v < 4; ++v) distill_elem_fast<true, true, true>(xs[v], ts[v], keep[v], kk[v], fc, acc, gv[v]);
+              __stcs(reinterpret_cast<float4*>(out + (size_t)j * d.plane), make_float4(gv[0], gv[1], gv[2], gv[3]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) kk[v] = keep[v] * kg;
+          float4 xv[kFPer], tv[kFPer];
+#pragma unroll
+          for (int j = 0; j < kFPer; ++j) {
+            xv[j] = *reinterpret_cast<const float4*>(&st.X[cbase + j][h]);
+            tv[j] = *reinterpret_cast<const float4*>(&st.T[cbase + j][h]);
+          }
+#pragma unroll
+          for (int j = 0; j < kFPer; ++j) {
+            if (cbase + j < d.n_cls) {
+              const float xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+              const float ts[4] = {tv[j].x, tv[j].y, tv[j].z, tv[j].w};
+              float gv[4];
+#pragma unroll
+              for (int v = 0; v < 4; ++v) distill_elem_fast<kAlphaHalf, true, true>(xs[v], ts[v], keep[v], kk[v], fc, acc, gv[v]);
+              __stcs(reinterpret_cast<float4*>(out + (size_t)j * d.plane), make_float4(gv[0], gv[1], gv[2], gv[3]));
+            }
           }
         }
       }
@@ -339,12 +400,36 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
       const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
       if (tid == 0) lvl_sum[cur_level] = s;
     }
+
+    // ================= tail levels: H*W % 4 != 0 (e.g. P7 = 5 x 7 of a 640 x 896 input) =================
+    // Their rows are not 16-byte aligned, so they cannot ride the bulk-copy ring; they are a fraction of a per cent of the
+    // elements (coarsest levels only) and are done here with scalar accesses, strided over the whole grid, in the same
+    // launch.  Index arithmetic of ...loss_op.cu:35-42.
+    for (int l = 0; l < args.n_levels; ++l) {
+      const FusedLevel& L = args.lv[l];
+      if (!L.tail) continue;
+      const float* dl = L.d_loss;
+      const float kgl = (dl ? __ldg(dl) : 1.f) * kscale;
+      const uint32_t C = (uint32_t)args.num_classes, A = L.D / C;
+      float tacc = 0.f;
+      for (uint32_t i = blockIdx.x * kFConsumers + tid; i < L.elems; i += gridDim.x * kFConsumers) {
+        const uint32_t hw = i % L.HW, c = (i / L.HW) % L.D, n = i / (L.HW * L.D);
+        const int32_t t = __ldg(L.G + ((size_t)n * A + c / C) * L.HW + hw);
+        const float keep = t != ignored ? 1.f : 0.f;
+        float gv;
+        distill_elem_fast<kAlphaHalf, true, true>(ld_stream1(L.X + i), ld_stream1(L.T + i), keep, keep * kgl, fc, tacc, gv);
+        L.dX[i] = gv;
+      }
+      const float s = group_sum<kFConsumers>(tacc, red_f, tid, 1);
+      if (tid == 0) lvl_sum[l] = s;
+    }
   }
 
   // ================= last CTA: per-level loss from the per-CTA partials, fixed order, fp64 =================
   if (stamp) args.stamps[blockIdx.x * 5 + 3] = gtimer();
   if (publish_and_ticket<SAD_MAX_LEVELS>(lvl_sum, args.p2_partials, &args.ctrl[1], &is_last)) {
     __threadfence();
+    const float Np = fmaxf(np_smem, 1.0f);
     for (int k = warp; k < args.n_levels; k += kFThreads / 32) {
       const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane);
       // the fast path accumulates twice the summand
@@ -358,13 +443,16 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
   }
 }
 
+// a level whose rows the bulk-copy ring cannot address (H*W % 4 != 0): scalar tail pass
+static bool fused_tail_level(const sad_distill_level& L) { return (((uint64_t)L.H * L.W) & 3) != 0; }
+
 static size_t fused_units(const sad_distill_level* levels, int n_levels, int num_classes, uint64_t* p1_units) {
   uint64_t t = 0, p1 = 0;
   const uint32_t C = (uint32_t)num_classes, cg = (C + kFCT - 1) / kFCT;
   for (int l = 0; l < n_levels; ++l) {
     const sad_distill_level& L = levels[l];
     const uint64_t HW = (uint64_t)L.H * L.W, NA = (uint64_t)L.N * ((uint32_t)L.D / C);
-    t += NA * ((HW + kFHW - 1) / kFHW) * cg;
+    if (!fused_tail_level(L)) t += NA * ((HW + kFHW - 1) / kFHW) * cg;
     p1 += ((uint64_t)L.N * L.D * HW + kF1Chunk - 1) / kF1Chunk;
   }
   if (p1_units) *p1_units = p1;
@@ -378,13 +466,22 @@ static size_t fused_ws_bytes(size_t) {
 
 bool distill_fused_supported(const sad_distill_level* levels, int n_levels, const sad_distill_params* p, float power) {
   if (!(p->gamma == 2.0f && p->beta == 0.0f)) return false;
-  if (!distill_ring_supported(levels, n_levels, p->num_classes)) return false;
+  uint64_t ring_elems = 0;
   for (int l = 0; l < n_levels; ++l) {
     const sad_distill_level& L = levels[l];
     if (!L.loss || !L.d_logits) return false;
-    const uint64_t n = (uint64_t)L.N * L.D * L.H * L.W;
+    const uint64_t HW = (uint64_t)L.H * L.W;
+    const uint64_t n = (uint64_t)L.N * L.D * HW;
     if (n == 0 || n > 0xfffffff0ull) return false;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(L.logits) | reinterpret_cast<uintptr_t>(L.teacher_prob) |
+                           reinterpret_cast<uintptr_t>(L.labels) | reinterpret_cast<uintptr_t>(L.d_logits);
+    if (bits & 15) return false;
+    // phase 1 streams T in 16-byte multiples whatever the row length: the level's element count must be a multiple of 4
+    // (true for every D % 4 == 0, e.g. 9 anchors x 80 classes)
+    if (n & 3) return false;
+    if (!fused_tail_level(L)) ring_elems += n;
   }
+  if (ring_elems == 0) return false;   // nothing for the ring: the SIMT kernels are the better fit
   uint64_t p1 = 0;
   const size_t units = fused_units(levels, n_levels, p->num_classes, &p1);
   return units > 0 && units < 0x3fffffffull && p1 < 0x3fffffffull && power == power;
@@ -408,8 +505,10 @@ int launch_distill_fused(const sad_distill_level* levels, int n_levels, float po
     D.d_loss = L.d_loss;
     D.HW = (uint32_t)HW;
     D.hw_tiles = (uint32_t)tiles;
+    D.tail = fused_tail_level(L) ? 1u : 0u;
+    D.D = (uint32_t)L.D;
     D.unit_begin = (uint32_t)t;
-    t += NA * tiles * cg;
+    if (!D.tail) t += NA * tiles * cg;
     D.unit_end = (uint32_t)t;
     D.elems = (uint32_t)((uint64_t)L.N * L.D * HW);
     D.p1_begin = (uint32_t)p1;

@@ -478,6 +478,22 @@ SAD_EXPORT int sad_distill_f32(const sad_distill_level* levels, int n_levels, co
 
   if (vec == 4 && distill_ring_supported(levels, n_levels, params->num_classes))  // persistent TMA ring
     return launch_distill_ring(levels, n_levels, normalizer, params, workspace, workspace_bytes, st);
+  if (vec == 1 && n_levels > 1) {
+    // Dispatch per level: one level with H*W % 4 != 0 (P7 = 5 x 7 of a 640 x 896 input) must not push the other levels — 99.9 %
+    // of the elements — off the ring.  Ring-capable levels go to the ring kernel, the rest to the scalar SIMT kernel below:
+    // two launches on the same stream sharing the workspace one after the other.
+    sad_distill_level ring_lv[SAD_MAX_LEVELS], rest_lv[SAD_MAX_LEVELS];
+    int n_ring = 0, n_rest = 0;
+    for (int l = 0; l < n_levels; ++l) {
+      if (distill_ring_supported(levels + l, 1, params->num_classes)) ring_lv[n_ring++] = levels[l];
+      else rest_lv[n_rest++] = levels[l];
+    }
+    if (n_ring > 0 && n_rest > 0) {
+      rc = launch_distill_ring(ring_lv, n_ring, normalizer, params, workspace, workspace_bytes, st);
+      if (rc != SAD_OK) return rc;
+      return sad_distill_f32(rest_lv, n_rest, normalizer, params, workspace, workspace_bytes, stream);
+    }
+  }
 
   DistillArgs a{};
   uint32_t tiles = 0;

@@ -181,6 +181,101 @@ __device__ __forceinline__ void distill_elem_fast(float x, float pt, float keep,
   }
 }
 
+// -------------------------------------------------------------------------------------------
+// packed fast path (gamma == 2, beta == 0, alpha == 0.5): TWO elements per instruction on the FMA pipe
+// (fma/add/mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2, sm_100), the 4 MUFU per element stay scalar.
+// The r01 kernel was issue-bound (ncu profiles/r01h_distill_fused: issue active 54 %, 31 FP + 4 MUFU
+// instructions per element in this function alone); per element this form issues
+//   4.5 FMUL2 + 3.5 FADD2 + 2 FFMA2 + 4 MUFU + 4.5 scalar (2 FMNMX, FSETP + FSEL, half a FMNMX3) = 18.5.
+// Same formulas as distill_elem_fast (comments there), with
+//   * the "teacher probability outside (0, 1) -> NaN" rule (the reference evaluates pt*logf(pt) + (1-pt)*logf(1-pt)
+//     even for beta == 0, ...loss_op.cu:59,93) taken out of the per-element code: vmin collects min(pt * (1 - pt))
+//     over everything a thread touches (FMNMX3.NAN), and the caller re-runs the scalar function for the unit when
+//     !(vmin > 0), i.e. when some pt was <= 0, >= 1 or NaN;
+//   * ln2 and the ignore mask folded into the per-position factors: acc2 gathers AT^2 * D with D = D2 / ln2 per hw
+//     position (the caller applies keep, -ln2/2 and 1/Np), the gradient is multiplied by kk2 = keep * kg * ln2.
+// -------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float min3_nan(float a, float b, float c) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+struct PairConsts {
+  f32x2 log2e, one, neg_c;   // (log2 e, log2 e), (1, 1), (-0.5 / ln2, -0.5 / ln2)
+};
+__device__ __forceinline__ PairConsts pair_consts() {
+  PairConsts k;
+  k.log2e = pk2(kLog2e, kLog2e);
+  k.one = pk2(1.f, 1.f);
+  k.neg_c = pk2(-0.5f / kLn2, -0.5f / kLn2);
+  return k;
+}
+
+// two elements (x, pt packed): returns the two gradients times kk2; acc2 += AT^2 * D; vmin = min(vmin, pt * (1 - pt))
+__device__ __forceinline__ f32x2 distill_pair_half(f32x2 x, f32x2 pt, f32x2 kk2, const PairConsts& k, f32x2& acc2, float& vmin) {
+  const f32x2 x2 = mul2(x, k.log2e);
+  float x2a, x2b;
+  upk2(x2, x2a, x2b);
+  const float ea = ex2_approx(-fabsf(x2a)), eb = ex2_approx(-fabsf(x2b));
+  const f32x2 e = pk2(ea, eb);
+  const f32x2 u = add2(e, k.one);
+  float ua, ub;
+  upk2(u, ua, ub);
+  const f32x2 l = pk2(lg2_approx(ua), lg2_approx(ub));
+  const f32x2 nmx = pk2(fminf(-x2a, 0.f), fminf(-x2b, 0.f));   // -max(x2, 0)
+  const f32x2 a0 = sub2(add2(x2, nmx), l);                     // min(x2, 0) - l = log2 p
+  const f32x2 b = sub2(nmx, l);                                // -(max(x2, 0) + l) = log2(1 - p)
+  const f32x2 q = sub2(k.one, pt);
+  const f32x2 B = mul2(q, b);
+  const f32x2 S = fma2(pt, a0, B);                             // -DL * log2 e
+  float va, vb;
+  upk2(mul2(pt, q), va, vb);
+  vmin = min3_nan(vmin, va, vb);
+  float Sa, Sb;
+  upk2(S, Sa, Sb);
+  const f32x2 E = pk2(ex2_approx(Sa), ex2_approx(Sb));
+  const f32x2 AT = sub2(k.one, E);
+  float a0a, a0b;
+  upk2(a0, a0a, a0b);
+  const f32x2 D = fma2(pt, pk2(fmaxf(a0a, -126.f), fmaxf(a0b, -126.f)), B);   // FLT_MIN clamp on log p: loss term only (...loss_op.cu:63)
+  acc2 = fma2(mul2(AT, AT), D, acc2);
+  const float ra = rcp_approx(ua), rb = rcp_approx(ub);
+  float era, erb;
+  upk2(mul2(e, pk2(ra, rb)), era, erb);
+  const f32x2 p = pk2(x2a >= 0.f ? ra : era, x2b >= 0.f ? rb : erb);
+  const f32x2 d = sub2(pt, p);
+  const f32x2 t = fma2(E, D, mul2(AT, k.neg_c));               // (E * D2 - 0.5 * AT) / ln2
+  return mul2(mul2(mul2(AT, d), t), kk2);
+}
+
 // Sum over a group of kThreads threads that share named barrier `bar_id`; result valid in the group's thread 0.
 template <int kThreads, typename T>
 __device__ __forceinline__ T group_sum(T v, T* smem, int tid, uint32_t bar_id) {

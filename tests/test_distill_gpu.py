@@ -402,3 +402,126 @@ def test_config5_geometry_one_image_500px(ops, oracle):
         # the one-launch step computes its own normaliser (<= 1e-4 from the reference-order one)
         assert abs(losses[i].item() - exact_loss) <= 3e-4 * abs(exact_loss)
         assert torch.allclose(grads[i], g2[i], rtol=3e-4, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: packed arithmetic of the fused kernel, levels with H*W % 4 != 0 inside the one launch, configs[2] size
+# ---------------------------------------------------------------------------------------------
+def _launches(ops):
+    from sad_b200 import native
+    return native.lib().sad_launch_count()
+
+
+@pytest.mark.parametrize("padded", [(640, 896), (896, 1408)], ids=["640x896 (P7 = 5x7)", "896x1408 (P6 = 14x22... P7 = 7x11)"])
+def test_fused_step_keeps_the_ring_when_coarse_levels_have_odd_planes(ops, oracle, padded):
+    """The reference's config (SCALES 600, MAX_SIZE 1000) pads the common 4:3 COCO image to 640 x 896: P7 is 5 x 7 = 35
+    positions, not a multiple of 4.  That level is done by the scalar tail pass of the SAME launch; every other level stays
+    on the bulk-copy ring (one launch, not the two-kernel SIMT fallback for all levels)."""
+    from sad_b200 import synthetic
+    host = synthetic.make_pyramid(777, 1, padded)
+    assert any((l[0].shape[2] * l[0].shape[3]) % 4 for l in host)
+    dev = [_dev(l) for l in host]
+    wp = oracle.pow_sum([l[1] for l in host], 1.8)
+    ops.distill_step(dev, power=1.8, **HEAD)          # warm (workspace allocation is not a launch, but keep the count clean)
+    before = _launches(ops)
+    norm, losses, grads = ops.distill_step(dev, power=1.8, **HEAD)
+    torch.cuda.synchronize()
+    assert _launches(ops) - before == 1, "PowSum + loss + gradient of all 5 levels must be ONE launch"
+    assert_loss_close(norm.item(), wp, "normaliser")
+    n = _scalar(wp)
+    l2, g2 = ops.distill(dev, n, **HEAD)              # two-launch path, per-level dispatch (ring + scalar kernel)
+    for i, l in enumerate(host):
+        ref_loss, elems = oracle.distill_loss(*l, wp, return_elements=True, **HEAD)
+        exact_loss = float(elems.astype(np.float64).sum()) * HEAD["scale"]
+        assert_reduced_close(l2[i].item(), ref_loss, exact_loss, "loss level %d" % i)
+        assert_grad_close(g2[i].cpu().numpy(), oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)
+        assert abs(losses[i].item() - exact_loss) <= 3e-4 * abs(exact_loss)
+        assert torch.allclose(grads[i], g2[i], rtol=3e-4, atol=1e-12)
+
+
+def test_fused_packed_path_keeps_the_nan_rule_and_the_flt_min_clamp(ops, oracle):
+    """Teacher probabilities of exactly 0 / 1 (NaN in the reference even for beta = 0, ...loss_op.cu:59,93) and logits below
+    log(FLT_MIN) (the clamp of ...loss_op.cu:63 that the gradient's DL does not have, :92-93) inside full 8-class x 512-position
+    ring units, including under an ignored anchor (NaN * 0 stays NaN)."""
+    host = _pyr(2, [(16, 32), (8, 16)], 300)
+    x, t, g = host[0]
+    t[0, 5, 3, 7] = 1.0          # anchor 0, class 5
+    t[1, 81, 2, 9] = 0.0         # anchor 1, class 1
+    g[1, 2, 4, 4] = -1
+    t[1, 2 * 80 + 17, 4, 4] = 1.0   # under an ignored anchor
+    x[0, 300, 10, 20] = -95.0    # log p < log(FLT_MIN): clamp in the loss term only
+    x[1, 301, 10, 21] = -120.0
+    x[0, 302, 10, 22] = 95.0
+    wp = oracle.pow_sum([l[1] for l in host], 1.8)
+    norm, losses, grads = ops.distill_step([_dev(l) for l in host], power=1.8, **HEAD)
+    torch.cuda.synchronize()
+    assert_loss_close(norm.item(), wp, "normaliser")
+    assert np.isnan(losses[0].item()) and np.isnan(oracle.distill_loss(*host[0], wp, **HEAD))
+    assert_loss_close(losses[1].item(), oracle.distill_loss(*host[1], wp, **HEAD))
+    for i, l in enumerate(host):
+        assert_grad_close(grads[i].cpu().numpy(), oracle.distill_grad(*l, wp, d_loss=1.0, **HEAD), "grad level %d" % i)
+    # the clamp alone (no NaN anywhere): the loss must match too
+    host2 = _pyr(2, [(16, 32)], 301)
+    host2[0][0][0, 300, 10, 20] = -95.0
+    host2[0][0][1, 11, 0, 0] = -110.0
+    wp2 = oracle.pow_sum([host2[0][1]], 1.8)
+    _, l2, g2 = ops.distill_step([_dev(host2[0])], power=1.8, **HEAD)
+    assert_loss_close(l2[0].item(), oracle.distill_loss(*host2[0], wp2, **HEAD), "loss with clamped elements")
+    assert_grad_close(g2[0].cpu().numpy(), oracle.distill_grad(*host2[0], wp2, d_loss=1.0, **HEAD), "grad with clamped elements")
+
+
+def test_fused_step_d_loss_and_scale(ops, oracle):
+    host = _pyr(2, [(8, 16), (4, 8)], 310)
+    args = dict(HEAD, scale=0.125)
+    wp = oracle.pow_sum([l[1] for l in host], 1.8)
+    norm, losses, grads = ops.distill_step([_dev(l) for l in host], power=1.8, d_loss=_scalar(3.0), **args)
+    for i, l in enumerate(host):
+        assert_loss_close(losses[i].item(), oracle.distill_loss(*l, wp, **args), "loss level %d" % i)
+        assert_grad_close(grads[i].cpu().numpy(), oracle.distill_grad(*l, wp, d_loss=3.0, **args), "grad level %d" % i)
+
+
+def test_config3_size_bs16_fused_direct(ops, oracle):
+    """BASELINE.json configs[2]: bs = 16, 600 px: 157 M logits, P3 alone 118 M elements (int-index headroom).  The one-launch
+    step against the oracle directly on the three coarse levels (full tensors) and on image 0 / image 15 of P3 and P4
+    (the oracle is per-image additive in the gradient: the same normaliser, the image's own labels)."""
+    from sad_b200 import synthetic
+    host = synthetic.make_pyramid(2024, 16, 600)
+    assert synthetic.anchors_in(host) == 16 * 122760
+    dev = [_dev(l) for l in host]
+    norm, losses, grads = ops.distill_step(dev, power=1.8, **HEAD)
+    torch.cuda.synchronize()
+    exact = float(sum(np.power(l[1].astype(np.float64), 1.8).sum() for l in host))
+    assert abs(norm.item() - exact) <= 2e-6 * exact, ("normaliser vs exact f64 sum", norm.item(), exact)
+    wp = np.float32(norm.item())
+    for i in (2, 3, 4):
+        l = host[i]
+        ref_loss, elems = oracle.distill_loss(*l, wp, return_elements=True, **HEAD)
+        exact_loss = float(elems.astype(np.float64).sum()) * HEAD["scale"]
+        assert_reduced_close(losses[i].item(), ref_loss, exact_loss, "loss level %d" % i)
+        assert_grad_close(grads[i].cpu().numpy(), oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)
+    for i in (0, 1):
+        x, t, g = host[i]
+        tot = 0.0
+        for k in (0, 15):
+            sub = (x[k:k + 1], t[k:k + 1], g[k:k + 1])
+            assert_grad_close(grads[i][k:k + 1].cpu().numpy(), oracle.distill_grad(*sub, wp, **HEAD), "level %d image %d" % (i, k))
+        # level loss: exact fp64 sum of the oracle's per-element fp32 terms over all 16 images
+        _, elems = oracle.distill_loss(x, t, g, wp, return_elements=True, **HEAD)
+        exact_loss = float(elems.astype(np.float64).sum()) * HEAD["scale"]
+        assert abs(losses[i].item() - exact_loss) <= 2e-5 * abs(exact_loss), ("loss level %d" % i, losses[i].item(), exact_loss)
+
+
+def test_config2_fused_step_directly_against_the_oracle(ops, oracle, config2):
+    """BASELINE.json configs[1] through the ONE-launch entry point, compared with the oracle directly (not via the two-launch
+    path): the oracle is given the normaliser the fused step produced, so loss and gradient are 'on identical inputs'."""
+    host, dev = config2
+    norm, losses, grads = ops.distill_step(dev, power=1.8, **HEAD)
+    torch.cuda.synchronize()
+    exact = float(sum(np.power(l[1].astype(np.float64), 1.8).sum() for l in host))
+    assert abs(norm.item() - exact) <= 1e-6 * exact
+    wp = np.float32(norm.item())
+    for i, l in enumerate(host):
+        ref_loss, elems = oracle.distill_loss(*l, wp, return_elements=True, **HEAD)
+        exact_loss = float(elems.astype(np.float64).sum()) * HEAD["scale"]
+        assert_reduced_close(losses[i].item(), ref_loss, exact_loss, "loss level %d" % i)
+        assert_grad_close(grads[i].cpu().numpy(), oracle.distill_grad(*l, wp, **HEAD), "level %d" % i)

@@ -263,3 +263,15 @@ def test_head_config5_geometry_one_image_500px():
     torch.cuda.synchronize()
     check_against(head, cls, box, d_fpn, staged_reference(head, fpn, d_cls, d_box, TorchF64Backend(), product_acts=True),
                   tight=(3e-3, 1e-3))
+
+
+def test_head_config3_size_bs16():
+    """BASELINE.json configs[2]: bs = 16 on one GPU, 600 px pyramid (218 240 pixels per tower tensor, 118 M logits at P3): the whole
+    head forward + backward against the staged fp64 reference (product's operand rounding, masks from the product's activations)."""
+    shapes = [(80, 128), (40, 64), (20, 32), (10, 16), (5, 8)]
+    head, fpn, d_cls, d_box = _make(16, shapes, 256, 4, 9, 80, seed=17)
+    cls, box = head.forward(fpn)
+    d_fpn = head.backward(d_cls, d_box)
+    torch.cuda.synchronize()
+    check_against(head, cls, box, d_fpn, staged_reference(head, fpn, d_cls, d_box, TorchF64Backend(), product_acts=True),
+                  tight=(3e-3, 1e-3))
