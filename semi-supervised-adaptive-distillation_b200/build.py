@@ -1,6 +1,7 @@
 """In-tree build of the native libraries (nvcc, sm_100a only).
 
     libsad_b200.so                     C-ABI kernels (include/sad_b200.h)
+    libsad_exchange.so                 the gradient exchange: host C++ over NCCL (include/sad_exchange.h)
     libcaffe2_detectron_ops_gpu.so     operator-boundary library: shim runtime + operator classes,
                                        named after the reference module it replaces
                                        (caffe2/modules/detectron/CMakeLists.txt:7-13)
@@ -21,6 +22,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--use_fast_math=false"][:3] + ARCH 
 
 LIB_KERNELS = os.path.join(HERE, "libsad_b200.so")
 LIB_OPS = os.path.join(HERE, "libcaffe2_detectron_ops_gpu.so")
+LIB_EXCHANGE = os.path.join(HERE, "libsad_exchange.so")   # host C++ over NCCL (include/sad_exchange.h); NCCL is resolved at run time
 
 
 def _sources(*rel):
@@ -70,7 +72,11 @@ def build(force=False, verbose=False):
         _run([nvcc] + COMMON + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CSRC, "caffe2_shim"), "-I" + CSRC,
                                 "-x", "cu", "-shared", "-o", LIB_OPS] + osrc +
              ["-L" + HERE, "-l:libsad_b200.so", "-Xlinker", "-rpath=$ORIGIN"], verbose)
-    return LIB_KERNELS, LIB_OPS
+    xsrc = _sources("exchange/sad_exchange.cc")
+    if force or _stale(LIB_EXCHANGE, xsrc + hdrs):
+        _run([nvcc, "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-fvisibility=hidden,-fno-gnu-unique", "-w", "-I" + os.path.join(ROOT, "include"),
+              "-shared", "-o", LIB_EXCHANGE] + xsrc + ["-ldl"], verbose)
+    return LIB_KERNELS, LIB_OPS, LIB_EXCHANGE
 
 
 if __name__ == "__main__":

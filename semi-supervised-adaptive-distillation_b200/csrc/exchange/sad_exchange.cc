@@ -1,0 +1,212 @@
+// Gradient exchange of the data-parallel step: host C++ over NCCL (include/sad_exchange.h).
+//
+// Reference (single process, all GPUs): detectron/lib/modeling/optimizer.py:72-92 adds one NCCLAllreduce operator per gradient
+// blob; caffe2/caffe2/contrib/nccl/cuda_nccl_gpu.cc:139-225 (runNCCL) records an event on every participating context's stream,
+// makes the NCCL stream wait for it, calls ncclAllReduce and makes the context streams wait for the result.  The same
+// event plumbing, one process per GPU: record on the producer stream -> the communication stream waits -> ncclAllReduce ->
+// join: record on the communication stream -> the consumer (optimiser) stream waits.  The host never blocks.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sad_exchange.h"
+
+#define SAD_EXPORT __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+int cuda_check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return SAD_EXCHANGE_OK;
+  return fail(SAD_EXCHANGE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ---- NCCL, resolved at run time (nccl.h: ncclUniqueId is 128 opaque bytes passed by value; ncclFloat32 = 7, ncclSum = 0) ----
+struct NcclUniqueId {
+  char internal[SAD_EXCHANGE_UNIQUE_ID_BYTES];
+};
+typedef void* NcclComm;
+struct Nccl {
+  int (*GetVersion)(int*) = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string why;   // non-empty: NCCL is not usable
+  bool ok = false;
+};
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+
+const Nccl& nccl() {
+  static Nccl n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = nullptr;
+    std::string tried;
+    if (const char* e = getenv("SAD_NCCL_LIBRARY")) {
+      h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+      tried += std::string(e) + " ";
+    }
+    // the copy already mapped into this process (PyTorch's bundled libnccl.so.2) comes first: one NCCL per process
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+      n.why = "NCCL not found (tried " + tried + "libnccl.so.2, libnccl.so): " + (dlerror() ? dlerror() : "");
+      return;
+    }
+    auto sym = [&](const char* name) -> void* {
+      void* p = dlsym(h, name);
+      if (!p && n.why.empty()) n.why = std::string("NCCL symbol missing: ") + name;
+      return p;
+    };
+    n.GetVersion = reinterpret_cast<decltype(n.GetVersion)>(sym("ncclGetVersion"));
+    n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(sym("ncclGetUniqueId"));
+    n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(sym("ncclCommInitRank"));
+    n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
+    n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
+    n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
+    n.ok = n.why.empty();
+  });
+  return n;
+}
+int nccl_check(int rc, const char* what) {
+  if (rc == 0) return SAD_EXCHANGE_OK;
+  const Nccl& n = nccl();
+  return fail(SAD_EXCHANGE_ERR_NCCL, std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "NCCL error") + " (" + std::to_string(rc) + ")");
+}
+
+}  // namespace
+
+struct sad_exchange {
+  int rank = 0, world = 1, device = 0;
+  NcclComm comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  std::vector<cudaEvent_t> ready;   // one "bucket is ready" event per bucket in flight (re-used after a join)
+  size_t in_flight = 0;             // buckets enqueued since the last join
+  cudaEvent_t done = nullptr;
+  uint64_t buckets = 0, bytes = 0;
+};
+
+extern "C" {
+
+SAD_EXPORT const char* sad_exchange_last_error(void) { return g_err.c_str(); }
+
+SAD_EXPORT int sad_exchange_nccl_version(void) {
+  const Nccl& n = nccl();
+  if (!n.ok) return fail(SAD_EXCHANGE_ERR_NCCL, n.why);
+  int v = 0;
+  int rc = nccl_check(n.GetVersion(&v), "ncclGetVersion");
+  return rc != SAD_EXCHANGE_OK ? rc : v;
+}
+
+SAD_EXPORT int sad_exchange_unique_id(void* id_out) {
+  if (!id_out) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_unique_id: null id");
+  const Nccl& n = nccl();
+  if (!n.ok) return fail(SAD_EXCHANGE_ERR_NCCL, n.why);
+  return nccl_check(n.GetUniqueId(static_cast<NcclUniqueId*>(id_out)), "ncclGetUniqueId");
+}
+
+SAD_EXPORT int sad_exchange_create(const void* id, int rank, int world, sad_exchange** out) {
+  if (!out) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: null out");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: rank must be in [0, world)");
+  sad_exchange* ex = new (std::nothrow) sad_exchange();
+  if (!ex) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: out of host memory");
+  ex->rank = rank;
+  ex->world = world;
+  int rc = cuda_check(cudaGetDevice(&ex->device), "cudaGetDevice");
+  if (rc == SAD_EXCHANGE_OK) {
+    int lo = 0, hi = 0;   // the exchange should win the SMs it needs as soon as a bucket is ready: highest stream priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    rc = cuda_check(cudaStreamCreateWithPriority(&ex->comm_stream, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority");
+  }
+  if (rc == SAD_EXCHANGE_OK) rc = cuda_check(cudaEventCreateWithFlags(&ex->done, cudaEventDisableTiming), "cudaEventCreate");
+  if (rc == SAD_EXCHANGE_OK && world > 1) {
+    const Nccl& n = nccl();
+    if (!n.ok) rc = fail(SAD_EXCHANGE_ERR_NCCL, n.why);
+    else if (!id) rc = fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: world > 1 needs the unique id of rank 0");
+    else rc = nccl_check(n.CommInitRank(&ex->comm, world, *static_cast<const NcclUniqueId*>(id), rank), "ncclCommInitRank");
+  }
+  if (rc != SAD_EXCHANGE_OK) {
+    const std::string keep = g_err;
+    sad_exchange_destroy(ex);
+    g_err = keep;
+    return rc;
+  }
+  *out = ex;
+  return SAD_EXCHANGE_OK;
+}
+
+SAD_EXPORT void sad_exchange_destroy(sad_exchange* ex) {
+  if (!ex) return;
+  if (ex->comm_stream) cudaStreamSynchronize(ex->comm_stream);
+  if (ex->comm && nccl().CommDestroy) nccl().CommDestroy(ex->comm);
+  for (cudaEvent_t e : ex->ready) cudaEventDestroy(e);
+  if (ex->done) cudaEventDestroy(ex->done);
+  if (ex->comm_stream) cudaStreamDestroy(ex->comm_stream);
+  delete ex;
+}
+
+SAD_EXPORT int sad_exchange_world(const sad_exchange* ex) { return ex ? ex->world : 0; }
+SAD_EXPORT int sad_exchange_rank(const sad_exchange* ex) { return ex ? ex->rank : -1; }
+SAD_EXPORT uint64_t sad_exchange_buckets(const sad_exchange* ex) { return ex ? ex->buckets : 0; }
+SAD_EXPORT uint64_t sad_exchange_bytes(const sad_exchange* ex) { return ex ? ex->bytes : 0; }
+
+SAD_EXPORT int sad_exchange_allreduce_async_f32(sad_exchange* ex, float* buf, size_t count, void* producer_stream) {
+  if (!ex || (!buf && count)) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_allreduce_async_f32: null argument");
+  if (count == 0) return SAD_EXCHANGE_OK;
+  int rc;
+  if (ex->in_flight == ex->ready.size()) {
+    cudaEvent_t e = nullptr;
+    if ((rc = cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) != SAD_EXCHANGE_OK) return rc;
+    ex->ready.push_back(e);
+  }
+  cudaEvent_t ev = ex->ready[ex->in_flight++];
+  // the bucket is complete once everything enqueued so far on the producer stream has run (cuda_nccl_gpu.cc:157-166)
+  if ((rc = cuda_check(cudaEventRecord(ev, static_cast<cudaStream_t>(producer_stream)), "cudaEventRecord(bucket ready)")) != SAD_EXCHANGE_OK) return rc;
+  if ((rc = cuda_check(cudaStreamWaitEvent(ex->comm_stream, ev, 0), "cudaStreamWaitEvent(comm stream)")) != SAD_EXCHANGE_OK) return rc;
+  if (ex->world > 1) {
+    if ((rc = nccl_check(nccl().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, ex->comm, ex->comm_stream), "ncclAllReduce")) != SAD_EXCHANGE_OK)
+      return rc;
+  }
+  ex->buckets += 1;
+  ex->bytes += (uint64_t)count * sizeof(float);
+  return SAD_EXCHANGE_OK;
+}
+
+SAD_EXPORT int sad_exchange_join(sad_exchange* ex, void* consumer_stream) {
+  if (!ex) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_join: null exchange");
+  if (ex->in_flight == 0) return SAD_EXCHANGE_OK;
+  int rc;
+  // the consumer waits for the communication stream (cuda_nccl_gpu.cc:196-205)
+  if ((rc = cuda_check(cudaEventRecord(ex->done, ex->comm_stream), "cudaEventRecord(exchange done)")) != SAD_EXCHANGE_OK) return rc;
+  if ((rc = cuda_check(cudaStreamWaitEvent(static_cast<cudaStream_t>(consumer_stream), ex->done, 0), "cudaStreamWaitEvent(consumer)")) != SAD_EXCHANGE_OK)
+    return rc;
+  ex->in_flight = 0;
+  return SAD_EXCHANGE_OK;
+}
+
+SAD_EXPORT int sad_exchange_allreduce_f32(sad_exchange* ex, float* buf, size_t count, void* stream) {
+  if (!ex || (!buf && count)) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_allreduce_f32: null argument");
+  if (count == 0 || ex->world == 1) return SAD_EXCHANGE_OK;
+  int rc = nccl_check(nccl().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, ex->comm, static_cast<cudaStream_t>(stream)), "ncclAllReduce");
+  if (rc == SAD_EXCHANGE_OK) {
+    ex->buckets += 1;
+    ex->bytes += (uint64_t)count * sizeof(float);
+  }
+  return rc;
+}
+
+}  // extern "C"

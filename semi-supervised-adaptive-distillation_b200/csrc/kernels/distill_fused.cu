@@ -41,8 +41,8 @@ constexpr int kFConsumers = 256;
 constexpr int kFWarps = kFConsumers / 32;
 constexpr int kFThreads = kFConsumers + 32;
 constexpr int kFPer = kFCT / 2;
-constexpr int kF1Chunk = 2048;      // floats per phase-1 unit (8 KB)
-constexpr int kF1Stages = 4;         // the phase-1 ring lives inside phase-2 stage 0 (4 x 8 KB <= 34 KB)
+constexpr int kF1Chunk = 4096;      // floats per phase-1 unit (16 KB)
+constexpr int kF1Stages = 6;         // the phase-1 ring (96 KB) reuses the whole phase-2 ring's shared memory
 
 struct FusedLevel {
   const float* X;
@@ -67,7 +67,8 @@ struct FusedArgs {
   float* p1_partials;   // [gridDim.x][SAD_MAX_LEVELS]
   float* p2_partials;   // [gridDim.x][SAD_MAX_LEVELS]
   unsigned long long* stamps;  // debug (dbg & 8): [gridDim.x][5] globaltimer values
-  unsigned int* ctrl;   // [0] grid barrier, [1] final ticket; zero between launches
+  float* unit_loss;     // [total_units]: loss sum of every phase-2 unit (fixed summation tree per unit: schedule-independent)
+  unsigned int* ctrl;   // [0] grid barrier, [1] final ticket, [2] phase-2 unit hand-out; zero between launches
 };
 
 struct __align__(16) FUnitDesc {
@@ -82,7 +83,8 @@ struct __align__(128) FStage {
   int32_t G[kFHW];
 };
 constexpr size_t kFusedSmemBytes = sizeof(FStage) * kFStages;
-static_assert(sizeof(FStage) >= (size_t)kF1Chunk * 4 * kF1Stages, "phase-1 ring must fit in stage 0 of the phase-2 ring");
+static_assert(kFusedSmemBytes >= (size_t)kF1Chunk * 4 * kF1Stages, "phase-1 ring must fit in the phase-2 ring");
+constexpr uint32_t kFSentinel = 0xffffffffu;   // FUnitDesc.n_hw of the producer's "no more units" message
 
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
@@ -104,13 +106,16 @@ template <bool kAlphaHalf, bool kPowAccurate>
 __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __grid_constant__ FusedArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FStage* stages = reinterpret_cast<FStage*>(smem_raw);
-  float(*p1_stages)[kF1Chunk] = reinterpret_cast<float(*)[kF1Chunk]>(smem_raw);   // phase-1 ring: inside phase-2 stage 0
+  float(*p1_stages)[kF1Chunk] = reinterpret_cast<float(*)[kF1Chunk]>(smem_raw);   // the phase-1 ring reuses the phase-2 ring's memory
   __shared__ FUnitDesc desc[kFStages];
   __shared__ int32_t p1_desc[kF1Stages][2];  // {input, count}
   __shared__ __align__(8) uint64_t full_bar[kFStages], empty_bar[kFStages], p1_full[kF1Stages], p1_empty[kF1Stages];
   __shared__ float in_sum[SAD_MAX_LEVELS];
   __shared__ float red_f[kFWarps];
+  __shared__ double red_d[kFThreads / 32];
   __shared__ float lvl_sum[SAD_MAX_LEVELS];
+  __shared__ float unit_part[kFStages][kFWarps];   // per-warp loss sums of the unit in a stage
+  __shared__ unsigned int unit_cnt[kFStages];      // warps that have delivered theirs
   __shared__ float np_smem;
   __shared__ bool is_last;
 
@@ -120,16 +125,18 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     for (int s = 0; s < kFStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kFWarps);
+      unit_cnt[s] = 0u;
     }
 #pragma unroll
     for (int s = 0; s < kF1Stages; ++s) {
       mbar_init(&p1_full[s], 1);
       mbar_init(&p1_empty[s], kFWarps);
     }
-    // The phase-2 ring starts at stage 1: stage 0 holds the phase-1 ring and joins when phase 1 has been consumed (the
-    // consumer warps' arrivals on empty_bar[0] after phase 1 are that barrier's first completion).  This dummy first
-    // completion of full_bar[0] keeps both barriers of stage 0 one phase ahead of the ring's phase bit.
-    mbar_arrive(&full_bar[0]);
+    // The phase-2 ring's memory holds the phase-1 ring first.  A stage joins phase 2 when the consumer warps have arrived on
+    // its empty barrier after phase 1 — that barrier's FIRST completion — so the phase-2 ring state starts with phase bit 1
+    // (first wait: parity 0), and this dummy first completion of every full barrier keeps the consumer side in step.
+#pragma unroll
+    for (int s = 0; s < kFStages; ++s) mbar_arrive(&full_bar[s]);
     mbar_fence_init();
   }
   if (tid < SAD_MAX_LEVELS) {
@@ -163,16 +170,19 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           rs.advance<kF1Stages>();
         }
       }
-      // phase 2: X and T rows and the label row of each unit.  Nothing here depends on the normaliser, so the first units
-      // (stages 1 and 2 at once, stage 0 as soon as the consumers are through with phase 1) land while the grid barrier
-      // is still being crossed.
+      // phase 2: X and T rows and the label row of each unit.  Nothing here depends on the normaliser, so the first three
+      // units are requested the moment the consumers are through with phase 1 and land while the grid barrier is crossed.
+      // Units are handed out through a counter (ctrl[2]) in increasing order: phase 2 is DRAM-bound, the CTAs' shares of the
+      // memory system differ (measured with a static deal: finish times 8 us apart in a 27 us phase), and whoever is
+      // faster simply takes more units.  The next ticket is fetched while the current unit's copies are in flight.
       const uint64_t pol = policy_evict_first();
       const uint32_t C = (uint32_t)args.num_classes, cg = (uint32_t)args.class_groups;
       RingState rs;
-      rs.stage = 1;
+      rs.phase = 1u;
       int l = 0;
+      uint32_t u = atomicAdd(&args.ctrl[2], 1u);
 #pragma unroll 1
-      for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
+      while (u < args.total_units) {
         mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
         while (u >= args.lv[l].unit_end) ++l;
         const FusedLevel& L = args.lv[l];
@@ -203,8 +213,13 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           bulk_g2s(st.T[c], ts + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
         }
         bulk_g2s(st.G, L.G + (size_t)na * L.HW + hw0, row_bytes, &full_bar[rs.stage], pol);
+        u = atomicAdd(&args.ctrl[2], 1u);
         rs.advance<kFStages>();
       }
+      // "no more units"
+      mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
+      desc[rs.stage].n_hw = kFSentinel;
+      mbar_arrive(&full_bar[rs.stage]);
     }
   } else {
     // ================= consumers, phase 1: PowSum over the teacher probabilities =================
@@ -254,9 +269,12 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
         if (tid == 0) in_sum[cur] = s;
       }
     }
-    // phase 1 consumed: stage 0 of the phase-2 ring (which held the phase-1 ring) is free
+    // phase 1 consumed: the ring's memory is free for phase 2
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[0]);
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kFStages; ++s) mbar_arrive(&empty_bar[s]);
+    }
     named_bar_sync(2, kFConsumers);
 
     // ================= grid barrier; every CTA derives the same normaliser =================
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     const float Np = fmaxf(np_smem, 1.0f);   // max(weight_pos[0], 1.0): ...loss_op.cu:49,87
     if (stamp) args.stamps[blockIdx.x * 5 + 2] = gtimer();
 
-    // ================= consumers, phase 2: loss + gradient, units dealt round-robin =================
+    // ================= consumers, phase 2: loss + gradient of the units this CTA's producer drew =================
     const uint32_t h = (uint32_t)(tid & 127) * 4u;
     const uint32_t cbase = (uint32_t)(tid >> 7) * kFPer;
     const float alpha = args.alpha;
@@ -300,24 +318,21 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     const int32_t ignored = args.ignored_label;
     const float kscale = args.scale / Np;
     RingState rs;
-    rs.stage = 1;
-    float acc = 0.f, kg = 0.f;
+    rs.phase = 1u;
+    float kg = 0.f;
     int cur_level = -1;
 #pragma unroll 1
-    for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
+    for (;;) {
       mbar_wait(&full_bar[rs.stage], rs.phase);
       const FUnitDesc d = desc[rs.stage];
+      if (d.n_hw == kFSentinel) break;
       const FStage& st = stages[rs.stage];
       if (d.level != cur_level) {
-        if (cur_level >= 0) {
-          const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
-          if (tid == 0) lvl_sum[cur_level] = s;
-          acc = 0.f;
-        }
         cur_level = d.level;
         const float* dl = args.lv[cur_level].d_loss;
         kg = (dl ? __ldg(dl) : 1.f) * kscale;   // d_loss * scale / Np of this level
       }
+      float acc = 0.f;   // this thread's share of the unit's loss (twice the summand, positive)
       if (h < d.n_hw) {
         const int4 g = *reinterpret_cast<const int4*>(&st.G[h]);
         float keep[4], kk[4];
@@ -392,19 +407,30 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           }
         }
       }
+      // the unit's loss: a fixed tree (16 elements per thread, shuffle tree per warp, the 8 warps in order) whatever CTA drew
+      // the unit -> bit-identical run to run although the hand-out is dynamic.  The warp that delivers last adds up.
+      const float ws = warp_sum(acc);
+      if (lane == 0) {
+        unit_part[rs.stage][warp] = ws;
+        __threadfence_block();
+        if (atomicAdd(&unit_cnt[rs.stage], 1u) == (unsigned int)(kFWarps - 1)) {
+          __threadfence_block();
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < kFWarps; ++w) s += unit_part[rs.stage][w];
+          args.unit_loss[d.unit] = s;
+          unit_cnt[rs.stage] = 0u;
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[rs.stage]);
       rs.advance<kFStages>();
     }
-    if (cur_level >= 0) {
-      const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
-      if (tid == 0) lvl_sum[cur_level] = s;
-    }
 
     // ================= tail levels: H*W % 4 != 0 (e.g. P7 = 5 x 7 of a 640 x 896 input) =================
     // Their rows are not 16-byte aligned, so they cannot ride the bulk-copy ring; they are a fraction of a per cent of the
-    // elements (coarsest levels only) and are done here with scalar accesses, strided over the whole grid, in the same
-    // launch.  Index arithmetic of ...loss_op.cu:35-42.
+    // elements (coarsest levels only) and are done here with scalar accesses, strided over the whole grid (static), in the
+    // same launch.  Index arithmetic of ...loss_op.cu:35-42.
     for (int l = 0; l < args.n_levels; ++l) {
       const FusedLevel& L = args.lv[l];
       if (!L.tail) continue;
@@ -425,19 +451,48 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     }
   }
 
-  // ================= last CTA: per-level loss from the per-CTA partials, fixed order, fp64 =================
+  // ================= last CTA: per-level loss, fixed order, fp64 =================
+  //   ring levels: the unit slots of the level in unit order;  tail levels: the per-CTA partials in CTA order
   if (stamp) args.stamps[blockIdx.x * 5 + 3] = gtimer();
   if (publish_and_ticket<SAD_MAX_LEVELS>(lvl_sum, args.p2_partials, &args.ctrl[1], &is_last)) {
     __threadfence();
     const float Np = fmaxf(np_smem, 1.0f);
-    for (int k = warp; k < args.n_levels; k += kFThreads / 32) {
-      const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane);
-      // the fast path accumulates twice the summand
-      if (lane == 0) args.lv[k].loss[0] = (float)(0.5 * s / (double)Np) * args.scale;
+    for (int k = 0; k < args.n_levels; ++k) {
+      const FusedLevel& L = args.lv[k];
+      double s = 0.0;
+      if (L.tail) {
+        if (warp == 0) s = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane);
+      } else {
+        constexpr int kBatch = 8;   // loads issued together; thread t owns units begin + t, + kFThreads, ... (fixed)
+        for (uint32_t u0 = L.unit_begin + (uint32_t)tid; u0 < L.unit_end; u0 += kFThreads * kBatch) {
+          float v[kBatch];
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const uint32_t u = u0 + (uint32_t)i * kFThreads;
+            v[i] = u < L.unit_end ? __ldcg(args.unit_loss + u) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) s += (double)v[i];
+        }
+        s = warp_sum(s);
+        if (lane == 0) red_d[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+          double tot = 0.0;
+          for (int w = 0; w < kFThreads / 32; ++w) tot += red_d[w];
+          red_d[0] = tot;
+        }
+        __syncthreads();
+        s = red_d[0];
+        __syncthreads();
+      }
+      // the arithmetic accumulates twice the summand
+      if (tid == 0) L.loss[0] = (float)(0.5 * s / (double)Np) * args.scale;
     }
     if (tid == 0) {
       args.ctrl[0] = 0u;
       args.ctrl[1] = 0u;
+      args.ctrl[2] = 0u;
     }
     if (stamp) args.stamps[blockIdx.x * 5 + 4] = gtimer();
   }
@@ -459,10 +514,11 @@ static size_t fused_units(const sad_distill_level* levels, int n_levels, int num
   return (size_t)t;
 }
 
-// layout of the fused workspace: [0,256) ctrl | phase-1 partials | phase-2 partials | debug stamps
-static size_t fused_ws_bytes(size_t) {
+// layout of the fused workspace: [0,256) ctrl | phase-1 partials | phase-2 (tail-level) partials | debug stamps | unit loss slots
+static size_t fused_fixed_bytes() {
   return 256 + 2 * (size_t)kMaxRingCtas * SAD_MAX_LEVELS * sizeof(float) + (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long);
 }
+static size_t fused_ws_bytes(size_t units) { return fused_fixed_bytes() + ((units * sizeof(float) + 255) / 256) * 256; }
 
 bool distill_fused_supported(const sad_distill_level* levels, int n_levels, const sad_distill_params* p, float power) {
   if (!(p->gamma == 2.0f && p->beta == 0.0f)) return false;
@@ -531,8 +587,9 @@ int launch_distill_fused(const sad_distill_level* levels, int n_levels, float po
   a.ctrl = static_cast<unsigned int*>(workspace);
   a.p1_partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   a.p2_partials = a.p1_partials + (size_t)kMaxRingCtas * SAD_MAX_LEVELS;
-  a.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + fused_ws_bytes((size_t)t) -
+  a.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + fused_fixed_bytes() -
                                                    (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long));
+  a.unit_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + fused_fixed_bytes());
 
   int dev = 0, sms = 0, rc;
   if ((rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) != SAD_OK) return rc;

@@ -240,14 +240,22 @@ def test_config2_properties(ops, config2):
     plan.run()  # idempotent + deterministic: same bits on a second run with the reused workspace
     assert [l.item() for l in plan.losses] == l0
     assert all(torch.equal(a, b) for a, b in zip(plan.grads, g0))
-    # linearity in d_loss and scale: power-of-two factors are exact in fp32
+    # linearity in d_loss and scale: power-of-two factors are exact in fp32 (within one kernel: the one-launch step and the
+    # two-launch path order their per-element products differently and agree to rounding, not to the bit)
     n = plan.normalizer
+    l1, g1 = ops.distill(dev, n, **HEAD)
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=0) for a, b in zip(g1, g0))
     _, g2 = ops.distill(dev, n, want_loss=False, d_loss=_scalar(2.0), **HEAD)
-    assert all(torch.equal(a, 2 * b) for a, b in zip(g2, g0))
+    assert all(torch.equal(a, 2 * b) for a, b in zip(g2, g1))
     l4, g4 = ops.distill(dev, n, **dict(HEAD, scale=0.25))
-    assert all(torch.equal(a, 0.25 * b) for a, b in zip(g4, g0))
+    assert all(torch.equal(a, 0.25 * b) for a, b in zip(g4, g1))
     for a, b in zip(l4, l0):
         assert abs(a.item() - 0.25 * b) <= 1e-6 * abs(b)
+    # the same two properties through the one-launch step
+    _, _, gs2 = ops.distill_step(dev, power=1.8, d_loss=_scalar(2.0), **HEAD)
+    assert all(torch.equal(a, 2 * b) for a, b in zip(gs2, g0))
+    _, ls4, gs4 = ops.distill_step(dev, power=1.8, **dict(HEAD, scale=0.25))
+    assert all(torch.equal(a, 0.25 * b) for a, b in zip(gs4, g0))
     # additivity over images: loss(level) = sum of the per-image losses
     for i, (x, t, g) in enumerate(dev):
         parts = [ops.distill([(x[k:k + 1], t[k:k + 1], g[k:k + 1])], n, want_grad=False, **HEAD)[0][0].item() for k in range(2)]
