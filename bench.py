@@ -197,6 +197,51 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def multi_gpu_check(flat_params, exchange, world, rank):
+    """caffe2/caffe2/contrib/nccl/nccl_ops_test.py:56-79 on the live job: (1) the exchange's SUM equals the fp64 sum over ranks of
+    rank-seeded buffers (fp32 round-off; bit-exact against the rank-ordered fp32 sum at 2 ranks) and every rank holds the same
+    bits; (2) after the K optimiser steps just timed, all replicas' parameters are bit-identical."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return "n/a (1 GPU)"
+    n = min(exchange.flat.numel(), 1 << 22)
+
+    def seeded(r):
+        g = torch.Generator(device="cuda").manual_seed(4242 + r)
+        return torch.randn(n, device="cuda", generator=g)
+
+    keep = exchange.flat[:n].clone()
+    exchange.flat[:n].copy_(seeded(rank))
+    if hasattr(exchange, "reduce_bucket"):
+        exchange.reduce_bucket(0, n // 3)
+        exchange.reduce_bucket(n // 3, n)
+        exchange.join()
+    else:
+        exchange.allreduce()
+    got = exchange.flat[:n].clone()
+    exchange.flat[:n].copy_(keep)
+    ref = torch.zeros(n, device="cuda", dtype=torch.float64)
+    for r in range(world):
+        ref += seeded(r).double()
+    err = float((got.double() - ref).abs().max() / ref.abs().max())
+
+    def same_on_all_ranks(t):
+        bits = t.contiguous().view(torch.int32)
+        hi, lo = bits.clone(), bits.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        return bool(torch.equal(hi, lo))
+
+    ok = err < 1e-6 and same_on_all_ranks(got)
+    if world == 2:
+        ok = ok and bool(torch.equal(got, seeded(0) + seeded(1)))
+    replicas = same_on_all_ranks(flat_params)
+    flag = torch.tensor([1 if (ok and replicas) else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return "ok" if int(flag.item()) == 1 else "FAILED (sum rel err %.3g, sum identical on ranks / replicas identical: %s / %s)" % (err, ok, replicas)
+
+
 def _tensor_peak():
     """tf32 tensor peak for a kernel timed inside a long step: half the measured sustained bf16 rate (tf32 runs at
     half the bf16 rate on this part: 1.1 vs 2.25 PFLOP/s nominal, B200_PROFILING.md); MEASURED_PEAKS.json holds no tf32 figure."""
@@ -250,6 +295,8 @@ def run_head_step(args, rank, world, barrier, native, f16=False):
     ms, ar_ms = float(t[0].item()), float(t[1].item())
     losses = st.losses()
     assert all(l == l and abs(l) < 1e30 for l in losses), ("non-finite distillation loss", losses)
+    mgc = multi_gpu_check(st.head.flat_params, st.exchange, world, rank)
+    assert not mgc.startswith("FAILED"), mgc
     fwd_f, bwd_f = st.flops()
     dev_ms = ms - ar_ms
     peak, src = _tensor_peak()
@@ -264,6 +311,7 @@ def run_head_step(args, rank, world, barrier, native, f16=False):
                     "600px, then ONE allreduce of %d head-gradient bytes + momentum SGD" % st.exchange.nbytes,
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
+        "exchange": "libsad_exchange.so (host C++ over NCCL), whole flat buffer on the step's stream", "multi_gpu_check": mgc,
         "conv_gflop_per_step": (fwd_f + bwd_f) / 1e9,
         "roofline": {"bound": "tensor", "kernel": "conv3x3_tf32_kernel + conv3x3_wgrad_tf32_kernel (tcgen05 kind::%s, 30 launches/step)" % kind,
                      "achieved": achieved, "peak": peak, "peak_source": src, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -297,26 +345,38 @@ def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False,
     n0 = native.lib().sad_launch_count()
     st.forward_backward()
     per_step = int(native.lib().sad_launch_count() - n0)
-    graphed = st.capture()
-    for _ in range(2):
-        st.step()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    ev0.record()
-    for i in range(K):
-        st.run()
-        ar[i][0].record()
-        st.allreduce()
-        ar[i][1].record()
-        st.sgd()
-    ev1.record()
-    barrier()
-    launches = per_step * K
-    t = torch.tensor([ev0.elapsed_time(ev1) / K, sum(a.elapsed_time(b) for a, b in ar) / K], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ar_ms = float(t[0].item()), float(t[1].item())
+
+    def timed(overlap):
+        """K steps of the captured step; returns (ms per step, ms between the end of the device work and the end of the
+        exchange — 0 by construction when the exchange is inside the graph), max over ranks."""
+        st.overlap_exchange = overlap
+        graphed_ = st.capture()
+        for _ in range(2):
+            st.step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        ev0.record()
+        for i in range(K):
+            st.run()
+            ar[i][0].record()
+            st.allreduce()
+            ar[i][1].record()
+            st.sgd()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / K, sum(a.elapsed_time(b) for a, b in ar) / K], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item()), graphed_
+
+    # the reference's order first (optimizer.py:72-92: every allreduce after the whole backward), then the overlapped form
+    ms_seq, ar_ms, _ = timed(False)
+    ms, _, graphed = timed(True)
+    launches = per_step * 2 * (K + 2)
+    exposed = max(0.0, ms - (ms_seq - ar_ms))
+    mgc = multi_gpu_check(st.flat_params, st.exchange, world, rank)
+    assert not mgc.startswith("FAILED"), mgc
     losses = st.losses()
     assert all(v == v for v in [losses["normalizer"]] + losses["bbox"] + losses["distill"] + losses["focal"]), ("non-finite loss", losses)
     line = {
@@ -331,6 +391,12 @@ def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False,
         "scaffolding": "ResNet/FPN bodies on cuDNN (TF32) under autograd (SURVEY.md 8f rank 3)",
         "allreduce_ms": ar_ms, "allreduce_bytes": st.exchange.nbytes,
         "allreduce_busbw_gbs": (st.exchange.bus_bytes() / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
+        "allreduce_exposed_ms": exposed, "ms_per_step_exchange_after_backward": ms_seq,
+        "exchange": "libsad_exchange.so (host C++ over NCCL): 4 buckets (head | res5 + FPN | res4 | res3 + biases) enqueued on the exchange's "
+                    "stream as the backward pass completes them, inside the captured graph; value / ms_per_step are this overlapped form, "
+                    "ms_per_step_exchange_after_backward + allreduce_ms the reference's order (one allreduce after the whole backward); "
+                    "allreduce_exposed_ms = ms_per_step - (ms_per_step_exchange_after_backward - allreduce_ms)",
+        "multi_gpu_check": mgc,
         "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),
         "cuda_graph_error": getattr(st, "capture_error", None), "losses": losses,
     }

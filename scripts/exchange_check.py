@@ -1,0 +1,90 @@
+"""Multi-GPU check of the native gradient exchange in the style of caffe2/caffe2/contrib/nccl/nccl_ops_test.py:56-79:
+every rank's result equals the sum over ranks (fp64 reference, fp32 round-off; bit-exact at 2 ranks) and all ranks hold
+bit-identical results, for the whole-buffer call, for the bucketed overlapped form, and inside a CUDA graph.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/exchange_check.py
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sad_b200 import exchange
+    n = 6463220 + 31233280 // 8          # the head's parameters + a slice of the body's
+    n -= n % 4
+
+    def mine(r, salt):
+        g = torch.Generator(device="cuda").manual_seed(1000 * salt + r)
+        return torch.randn(n, device="cuda", generator=g)
+
+    def reference(salt):
+        acc = torch.zeros(n, device="cuda", dtype=torch.float64)
+        for r in range(world):
+            acc += mine(r, salt).double()
+        return acc
+
+    ex = None
+    results = {}
+    for name in ("whole", "buckets", "graph"):
+        salt = {"whole": 1, "buckets": 2, "graph": 3}[name]
+        flat = mine(rank, salt)
+        if ex is None:
+            ex = exchange.NativeGradientExchange(flat, world=world, rank=rank)
+        else:
+            ex.flat = flat
+        cuts = [0, n // 5, n // 2, n]
+        if name == "whole":
+            ex.allreduce()
+        elif name == "buckets":
+            for lo, hi in zip(cuts, cuts[1:]):
+                ex.reduce_bucket(lo, hi)
+            ex.join()
+        else:
+            keep = flat.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for lo, hi in zip(cuts, cuts[1:]):
+                    ex.reduce_bucket(lo, hi)
+                ex.join()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            flat.copy_(keep)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for lo, hi in zip(cuts, cuts[1:]):
+                    ex.reduce_bucket(lo, hi)
+                ex.join()
+            flat.copy_(keep)
+            g.replay()
+        torch.cuda.synchronize()
+        ref = reference(salt)
+        err = float((flat.double() - ref).abs().max() / ref.abs().max())
+        exact2 = bool(torch.equal(flat, (mine(0, salt) + mine(1, salt)))) if world == 2 else None
+        # all ranks bit-identical: MAX and MIN over ranks of the int32 view agree
+        bits = flat.view(torch.int32)
+        hi_, lo_ = bits.clone(), bits.clone()
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(hi_, lo_))
+        results[name] = {"rel_err_vs_fp64_sum": err, "bit_exact_vs_rank_ordered_sum_world2": exact2, "ranks_bit_identical": same}
+        assert err < 1e-6 and same and exact2 in (None, True), (name, results[name])
+    if rank == 0:
+        print(json.dumps({"exchange_check": "ok", "world": world, "elements": n, "nccl": exchange.nccl_version(), "results": results,
+                          "stats": ex.stats()}))
+    ex.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

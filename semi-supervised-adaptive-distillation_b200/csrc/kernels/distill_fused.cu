@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
   __shared__ __align__(8) uint64_t full_bar[kFStages], empty_bar[kFStages], p1_full[kF1Stages], p1_empty[kF1Stages];
   __shared__ float in_sum[SAD_MAX_LEVELS];
   __shared__ float red_f[kFWarps];
-  __shared__ double red_d[kFThreads / 32];
   __shared__ float lvl_sum[SAD_MAX_LEVELS];
   __shared__ float unit_part[kFStages][kFWarps];   // per-warp loss sums of the unit in a stage
   __shared__ unsigned int unit_cnt[kFStages];      // warps that have delivered theirs
@@ -181,6 +180,7 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
       rs.phase = 1u;
       int l = 0;
       uint32_t u = atomicAdd(&args.ctrl[2], 1u);
+      uint32_t u_next = atomicAdd(&args.ctrl[2], 1u);   // always one ticket ahead: its round trip (~0.7 us) hides behind a whole unit
 #pragma unroll 1
       while (u < args.total_units) {
         mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           bulk_g2s(st.T[c], ts + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
         }
         bulk_g2s(st.G, L.G + (size_t)na * L.HW + hw0, row_bytes, &full_bar[rs.stage], pol);
-        u = atomicAdd(&args.ctrl[2], 1u);
+        u = u_next;
+        u_next = atomicAdd(&args.ctrl[2], 1u);
         rs.advance<kFStages>();
       }
       // "no more units"
@@ -283,8 +284,10 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     named_bar_sync(2, kFConsumers);
     if (tid == 0) {
       __threadfence();
-      atomicAdd(&args.ctrl[0], 1u);
-      while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(20);
+      // 296 CTAs polling one L2 line with atomics queueing behind the polls is a hot spot: whoever arrives last knows it from
+      // the atomic's return value, everybody else polls with a back-off
+      if (atomicAdd(&args.ctrl[0], 1u) + 1u < gridDim.x)
+        while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(100);
       __threadfence();
     }
     named_bar_sync(2, kFConsumers);
@@ -457,37 +460,44 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
   if (publish_and_ticket<SAD_MAX_LEVELS>(lvl_sum, args.p2_partials, &args.ctrl[1], &is_last)) {
     __threadfence();
     const float Np = fmaxf(np_smem, 1.0f);
-    for (int k = 0; k < args.n_levels; ++k) {
-      const FusedLevel& L = args.lv[k];
-      double s = 0.0;
-      if (L.tail) {
-        if (warp == 0) s = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane);
-      } else {
-        constexpr int kBatch = 8;   // loads issued together; thread t owns units begin + t, + kFThreads, ... (fixed)
-        for (uint32_t u0 = L.unit_begin + (uint32_t)tid; u0 < L.unit_end; u0 += kFThreads * kBatch) {
-          float v[kBatch];
+    // one pass over all unit slots: thread t owns units t, t + 288, ... (loads issued in batches), one fp64 accumulator per
+    // level (levels are contiguous unit ranges), then a fixed shuffle tree per warp and the 9 warps in order.  Walking the
+    // levels one after the other cost 7 us here (five dependent L2 round trips and ten block barriers).
+    double lsum[SAD_MAX_LEVELS];
 #pragma unroll
-          for (int i = 0; i < kBatch; ++i) {
-            const uint32_t u = u0 + (uint32_t)i * kFThreads;
-            v[i] = u < L.unit_end ? __ldcg(args.unit_loss + u) : 0.f;
-          }
+    for (int k = 0; k < SAD_MAX_LEVELS; ++k) lsum[k] = 0.0;
+    constexpr int kBatch = 9;
+    for (uint32_t u0 = (uint32_t)tid; u0 < args.total_units; u0 += kFThreads * kBatch) {
+      float v[kBatch];
 #pragma unroll
-          for (int i = 0; i < kBatch; ++i) s += (double)v[i];
-        }
-        s = warp_sum(s);
-        if (lane == 0) red_d[warp] = s;
-        __syncthreads();
-        if (tid == 0) {
-          double tot = 0.0;
-          for (int w = 0; w < kFThreads / 32; ++w) tot += red_d[w];
-          red_d[0] = tot;
-        }
-        __syncthreads();
-        s = red_d[0];
-        __syncthreads();
+      for (int i = 0; i < kBatch; ++i) {
+        const uint32_t u = u0 + (uint32_t)i * kFThreads;
+        v[i] = u < args.total_units ? __ldcg(args.unit_loss + u) : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const uint32_t u = u0 + (uint32_t)i * kFThreads;
+#pragma unroll
+        for (int k = 0; k < SAD_MAX_LEVELS; ++k)
+          if (k < args.n_levels && u >= args.lv[k].unit_begin && u < args.lv[k].unit_end) lsum[k] += (double)v[i];
+      }
+    }
+    // tail levels: their per-CTA partials (CTA order), lanes of warp 0
+#pragma unroll
+    for (int k = 0; k < SAD_MAX_LEVELS; ++k)   // (/ 32: every lane holds the total and the shuffle tree below adds the lanes up)
+      if (k < args.n_levels && args.lv[k].tail && warp == 0) lsum[k] = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane) / 32.0;
+    __shared__ double red_l[kFThreads / 32][SAD_MAX_LEVELS];
+#pragma unroll
+    for (int k = 0; k < SAD_MAX_LEVELS; ++k) {
+      const double w = warp_sum(lsum[k]);
+      if (lane == 0) red_l[warp][k] = w;
+    }
+    __syncthreads();
+    if (tid < args.n_levels) {
+      double tot = 0.0;
+      for (int w = 0; w < kFThreads / 32; ++w) tot += red_l[w][tid];
       // the arithmetic accumulates twice the summand
-      if (tid == 0) L.loss[0] = (float)(0.5 * s / (double)Np) * args.scale;
+      args.lv[tid].loss[0] = (float)(0.5 * tot / (double)Np) * args.scale;
     }
     if (tid == 0) {
       args.ctrl[0] = 0u;

@@ -162,6 +162,14 @@ class ResNetFPN(nn.Module):
         c3 = self.res3(c2)
         c4 = self.res4(c3)
         c5 = self.res5(c4)
+        # d(c4) is complete once res5 AND every FPN layer have run their backward; d(c3) once res4 has: the points at which
+        # the gradient exchange of those parameters can start (FullDistillStep._bucket_ready)
+        hooks = getattr(self, "grad_ready_hooks", None)
+        if hooks and torch.is_grad_enabled():
+            if c4.requires_grad and "c4" in hooks:
+                c4.register_hook(lambda g, f=hooks["c4"]: f())
+            if c3.requires_grad and "c3" in hooks:
+                c3.register_hook(lambda g, f=hooks["c3"]: f())
         p5 = self.lat[2](c5)
         p4 = self.lat[1](c4) + F.interpolate(p5, scale_factor=2, mode="nearest")
         p3 = self.lat[0](c3) + F.interpolate(p4, scale_factor=2, mode="nearest")
@@ -173,7 +181,8 @@ class ResNetFPN(nn.Module):
 class FullDistillStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, student_blocks=(3, 4, 6, 3), teacher_blocks=(3, 4, 23, 3),
                  temperature=1.0, power=1.8, distill_alpha=0.5, distill_gamma=2.0, lr=0.01, momentum=0.9, weight_decay=1e-4,
-                 fused_body=True, overlap_teacher=True, teacher_body=None, teacher_head_f16=False, student_head_f16=False):
+                 fused_body=True, overlap_teacher=True, teacher_body=None, teacher_head_f16=False, student_head_f16=False,
+                 overlap_exchange=True):
         """teacher_body: extra ResNetFPN arguments of the teacher, e.g. dict(groups=64, width_per_group=4, stride_1x1=False)
         for the ResNeXt-101-64x4d teacher of BASELINE.json configs[4].  teacher_head_f16: the forward-only teacher head on fp16
         operands (tcgen05 kind::f16, fp32 accumulation; configs[4]: "mixed fp16 compute / fp32 loss accumulate"); student_head_f16: the
@@ -181,6 +190,10 @@ class FullDistillStep:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.world, self.rank, self.images = int(world), int(rank), int(n_images)
         self.overlap_teacher = bool(overlap_teacher)
+        # overlap_exchange: the gradient allreduce runs in buckets on the exchange's own stream while the backward pass is still
+        # producing the next bucket (head bucket under the whole body backward, res5 + FPN under res4 + res3, ...), and the
+        # optimiser waits only for the join (optimizer.py:72-92 issues its NCCLAllreduce ops after the whole backward)
+        self.overlap_exchange = bool(overlap_exchange)
         self.teacher_stream = torch.cuda.Stream(device=self.device)
         self.lr, self.mom, self.wd = lr, momentum, weight_decay
         shapes = synthetic.level_shapes(scale_px)
@@ -230,7 +243,35 @@ class FullDistillStep:
         self._fold_g = [c.weight.grad for c, _ in self._fold]
         self.refold()
         self.n_head, self.n_body = n_head, n_body
-        self.exchange = parallel.GradientExchange(self.flat_grads, world=self.world)
+        self.exchange = parallel.make_exchange(self.flat_grads, world=self.world, rank=self.rank)
+        # buckets of the flat gradient buffer in the order the backward pass completes them:
+        #   "head" (after the head's backward) -> "c4" (res5 + FPN weights, when d(c4) is formed) -> "c3" (res4 weights) ->
+        #   "end" (res3 weights + every body bias)
+        stage_of = {}
+        for name in ("res3", "res4", "res5", "lat", "out", "p6", "p7"):
+            for q in getattr(self.student, name).parameters():
+                stage_of[id(q)] = name
+        ranges, off2 = {}, n_head
+        for q in self.body_params:
+            key = ("bias" if q.dim() == 1 else stage_of[id(q)])
+            lo, hi = ranges.get(key, (off2, off2))
+            assert hi == off2, "bucket %s is not contiguous in the flat buffer" % key
+            ranges[key] = (lo, off2 + q.numel())
+            off2 += q.numel()
+        fpn_lo = min(ranges[k][0] for k in ("res5", "lat", "out", "p6", "p7"))
+        fpn_hi = max(ranges[k][1] for k in ("res5", "lat", "out", "p6", "p7"))
+        assert fpn_hi - fpn_lo == sum(ranges[k][1] - ranges[k][0] for k in ("res5", "lat", "out", "p6", "p7"))
+        self.buckets = {"head": [(0, n_head)], "c4": [(fpn_lo, fpn_hi)], "c3": [ranges["res4"]],
+                        "end": [ranges["res3"]] + ([ranges["bias"]] if "bias" in ranges else [])}
+        assert sum(hi - lo for rs in self.buckets.values() for lo, hi in rs) == n_head + n_body
+        # folded convolutions per bucket (their raw weight gradients are scaled into the flat buffer when the bucket closes)
+        conv_stage = {}
+        for name in ("res3", "res4", "res5"):
+            for m in getattr(self.student, name).modules():
+                if isinstance(m, nn.Conv2d):
+                    conv_stage[id(m)] = {"res3": "end", "res4": "c3", "res5": "c4"}[name]
+        self._fold_bucket = [conv_stage[id(c)] for c, _ in self._fold]
+        self.student.grad_ready_hooks = {"c4": lambda: self._bucket_ready("c4"), "c3": lambda: self._bucket_ready("c3")}
         self.momentum = torch.zeros_like(self.flat_params)
         self.lr_dev = torch.tensor(lr, dtype=torch.float32, device=self.device)
         hw, hb = self.head.sgd_segments(weight_decay)
@@ -269,6 +310,21 @@ class FullDistillStep:
                                     alpha=distill_alpha, beta=0.0, scale=parallel.distill_loss_scale(temperature, self.world),
                                     num_classes=synthetic.NUM_CLASSES, ignored_label=-1)
         self.last = {}
+
+    def _bucket_ready(self, key):
+        """Every gradient of bucket `key` has been produced on the current stream: finish the folded convolutions' weight
+        gradients of that bucket (grad += dW_folded * s, one multi-tensor launch) and, when overlapping, hand the bucket to
+        the exchange (returns at once; the allreduce runs on the exchange's stream behind an event)."""
+        if not self._exchanging:
+            return
+        idx = [i for i, b in enumerate(self._fold_bucket) if b == key and self._fold_dw[i] is not None]
+        if idx:
+            torch._foreach_addcmul_([self._fold_g[i] for i in idx], [self._fold_dw[i] for i in idx], [self._fold_s[i] for i in idx])
+            for i in idx:
+                self._fold_dw[i] = None
+        if self.world > 1 or self._count_buckets:
+            for lo, hi in self.buckets[key]:
+                self.exchange.reduce_bucket(lo, hi)
 
     def refold(self):
         """(Re)build what depends on the frozen AffineChannel values: the per-weight expanded scales of the student and the
@@ -313,11 +369,19 @@ class FullDistillStep:
             ops.select_smooth_l1_loss(self.box[l], self.box_targets[l], self.box_locs[l], self.fg_num, beta=0.11, scale=self.loss_scale,
                                       workspace=self.box_ws[l], loss_out=self.box_losses[l], grad_out=self.d_box[l])
         d_fpn = self.head.backward(self.plan.grads, self.d_box, want_d_fpn=True, d_fpn=self.d_fpn)
+        self._exchanging = self.overlap_exchange and hasattr(self.exchange, "reduce_bucket")
+        self._count_buckets = False
+        if self._exchanging:
+            self._bucket_ready("head")                                   # the head's gradients are final: exchange them under the body's backward
         torch.autograd.backward(fpn, d_fpn)                              # ... and resumes here: FPN and ResNet body backward
-        if self._fold:
+        if self._exchanging:
+            self._bucket_ready("end")
+            self.exchange.join()                                         # the optimiser's stream waits for the last bucket
+            assert all(d is None for d in self._fold_dw)
+        elif self._fold:
             # grad (zeroed above) += dW_folded * s for every folded convolution: one multi-tensor launch instead of an
             # AccumulateGrad add per parameter
-            torch._foreach_addcmul_(self._fold_g, self._fold_dw, self._fold_s)
+            torch._foreach_addcmul_(self._fold_g, [d for d in self._fold_dw], self._fold_s)
         self.last = {"bbox": self.box_losses, "focal": self.focal_losses, "distill": [x for x in self.plan.losses],
                      "normalizer": self.plan.normalizer}
 
@@ -350,6 +414,10 @@ class FullDistillStep:
             self.forward_backward()
 
     def allreduce(self):
+        """The step's exchange.  With overlap_exchange the buckets were enqueued (and joined) inside forward_backward / the
+        captured graph, so nothing is left to do here."""
+        if self.overlap_exchange and hasattr(self.exchange, "reduce_bucket"):
+            return None
         return self.exchange.allreduce()
 
     @torch.no_grad()

@@ -108,3 +108,13 @@ class GradientExchange:
     def bus_bytes(self):
         """Bytes each rank moves for one ring/NVLS allreduce: 2 (world - 1) / world x payload (NCCL's busbw convention)."""
         return 0 if self.world == 1 else 2.0 * (self.world - 1) / self.world * self.nbytes
+
+
+def make_exchange(flat_grads, world=1, rank=0, group=None):
+    """The exchange object of a step: on CUDA buffers the native one (libsad_exchange.so: host C++ over NCCL, bucketed and
+    event-ordered so that it overlaps the backward pass — include/sad_exchange.h); on CPU buffers (the gloo tests) the
+    torch.distributed form above.  Same interface: allreduce(), nbytes, bus_bytes(); the native one adds reduce_bucket / join."""
+    if flat_grads.is_cuda:
+        from .exchange import NativeGradientExchange
+        return NativeGradientExchange(flat_grads, world=world, rank=rank, group=group)
+    return GradientExchange(flat_grads, world=world, group=group)

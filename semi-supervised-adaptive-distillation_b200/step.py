@@ -46,7 +46,7 @@ class DistillHeadStep:
         self.d_fpn = [torch.empty_like(x) for x in self.fpn]
         self.plan = ops.DistillPlan(list(zip(self.cls, self.teacher, self.labels)), power=power, gamma=gamma, alpha=alpha, beta=beta,
                                     scale=parallel.distill_loss_scale(temperature, self.world), num_classes=Cc, ignored_label=-1)
-        self.exchange = parallel.GradientExchange(self.head.flat_grads, world=self.world)
+        self.exchange = parallel.make_exchange(self.head.flat_grads, world=self.world, rank=self.rank)
         self.momentum = torch.zeros_like(self.head.flat_params)
         self.lr = torch.tensor(0.01, dtype=torch.float32, device=self.device)
         self.graph = None

@@ -92,3 +92,20 @@ def test_new_entry_points_validate_arguments_without_device():
     wl[0].N, wl[0].H, wl[0].W = 1, 4, 4
     wl[0].x_nhwc = wl[0].dy_nhwc = 256
     assert lib.sad_conv3x3_wgrad_f16(wl, 1, 64, 40, 44, 1.0, p, None, 0, p, 1 << 30, None) in (-1, -2)   # cout > dY channels (-2: no device)
+
+
+def test_exchange_library_exports_every_declared_symbol():
+    """include/sad_exchange.h (the gradient exchange: host C++ over NCCL).  Loads without a GPU and without NCCL (resolved at
+    run time); argument validation needs neither."""
+    from sad_b200 import exchange
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sad_exchange.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(sad_exchange_[a-z0-9_]+)\s*\(", src)))
+    assert "sad_exchange_allreduce_async_f32" in names and "sad_exchange_join" in names and len(names) >= 11
+    lib = exchange.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    out = C.c_void_p()
+    assert lib.sad_exchange_create(None, 2, 2, C.byref(out)) == -1 and b"rank" in lib.sad_exchange_last_error()
+    assert lib.sad_exchange_allreduce_async_f32(None, None, 0, None) == -1
+    assert lib.sad_exchange_join(None, None) == -1
+    assert lib.sad_exchange_world(None) == 0

@@ -1,0 +1,95 @@
+"""GPU: the native gradient exchange (libsad_exchange.so, include/sad_exchange.h) on one device — stream / event ordering of the
+bucketed form, capture into a CUDA graph, and the bucket layout of the full step.  The multi-rank sum itself is checked under
+torchrun by scripts/exchange_check.py (2+ GPUs: gpurun --gpus 2) and by bench.py's multi_gpu_check, and on CPU by the world-2
+gloo tests (tests/test_parallel_gloo.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_nccl_is_resolved_at_run_time():
+    from sad_b200 import exchange
+    v = exchange.nccl_version()
+    assert v >= 20000, v
+
+
+def test_single_rank_buckets_are_ordered_behind_the_producer_and_ahead_of_the_consumer():
+    from sad_b200 import exchange
+    n = 1 << 22
+    flat = torch.zeros(n, device="cuda")
+    ex = exchange.NativeGradientExchange(flat, world=1, rank=0)
+    big = torch.randn(4096, 4096, device="cuda")
+    for it in range(3):
+        flat.zero_()
+        (big @ big).sum()                       # keep the producer stream busy so that ordering, not luck, decides
+        flat[: n // 2].fill_(float(it + 1))     # bucket 0 is produced ...
+        ex.reduce_bucket(0, n // 2)             # ... and handed over
+        flat[n // 2:].fill_(2.0 * (it + 1))
+        ex.reduce_bucket(n // 2, n)
+        ex.join()                               # consumer (this stream) waits for both
+        total = flat.sum()
+        torch.cuda.synchronize()
+        assert float(total) == (n // 2) * (it + 1) + (n // 2) * 2.0 * (it + 1)
+    assert ex.stats()["buckets"] == 6 and ex.stats()["bytes"] == 3 * 4 * n
+    ex.allreduce()                              # un-overlapped form: identity at world 1
+    ex.close()
+
+
+def test_buckets_inside_a_cuda_graph():
+    from sad_b200 import exchange
+    n = 1 << 20
+    flat = torch.zeros(n, device="cuda")
+    src = torch.arange(n, device="cuda", dtype=torch.float32)
+    ex = exchange.NativeGradientExchange(flat, world=1, rank=0)
+
+    def step():
+        flat.copy_(src)
+        ex.reduce_bucket(0, n // 4)
+        flat[n // 4:].mul_(2.0)
+        ex.reduce_bucket(n // 4, n)
+        ex.join()
+        flat.add_(1.0)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    flat.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    ref = src.clone()
+    ref[n // 4:] *= 2.0
+    ref += 1.0
+    assert torch.equal(flat, ref)
+    ex.close()
+
+
+def test_full_step_buckets_cover_the_flat_buffer_and_overlap_changes_nothing():
+    from sad_b200.full_step import FullDistillStep
+    kw = dict(n_images=1, scale_px=(128, 256), student_blocks=(1, 1, 1, 1), teacher_blocks=(1, 1, 1, 1), seed=7)
+    a = FullDistillStep(overlap_exchange=True, **kw)
+    n = a.flat_grads.numel()
+    spans = sorted(r for rs in a.buckets.values() for r in rs)
+    assert spans[0][0] == 0 and spans[-1][1] == n and all(x[1] == y[0] for x, y in zip(spans, spans[1:]))
+    assert a.buckets["head"] == [(0, a.n_head)]
+    a.forward_backward()
+    torch.cuda.synchronize()
+    ga = a.flat_grads.clone()
+    assert a.exchange.stats()["buckets"] == 0      # world 1: nothing is sent ...
+    b = FullDistillStep(overlap_exchange=False, **kw)
+    b.forward_backward()
+    torch.cuda.synchronize()
+    # ... and closing the buckets early (per-stage multi-tensor folds) gives the same gradients as one fold at the end
+    assert float((ga - b.flat_grads).abs().max()) <= 1e-5 * float(b.flat_grads.abs().max())
+    # graph capture with the hooks in place
+    assert a.capture(), getattr(a, "capture_error", None)
+    a.run()
+    torch.cuda.synchronize()
+    assert float((a.flat_grads - ga).abs().max()) <= 2e-3 * float(ga.abs().max())
