@@ -64,11 +64,12 @@ struct FusedArgs {
   float alpha, scale, power;
   uint32_t dbg;  // experiment switches (SAD_FUSED_DEBUG): 1 = evict-first in phase 1, 2 = plain stores, 8 = globaltimer stamps
   float* norm_out;
-  float* p1_partials;   // [gridDim.x][SAD_MAX_LEVELS]
-  float* p2_partials;   // [gridDim.x][SAD_MAX_LEVELS]
   unsigned long long* stamps;  // debug (dbg & 8): [gridDim.x][5] globaltimer values
-  float* unit_loss;     // [total_units]: loss sum of every phase-2 unit (fixed summation tree per unit: schedule-independent)
-  unsigned int* ctrl;   // [0] grid barrier, [1] final ticket, [2] phase-2 unit hand-out; zero between launches
+  // control block (zero between launches; the last CTA leaves it zeroed):
+  unsigned int* ctrl;          // [0] grid barrier, [1] final ticket, [2] phase-1 chunk hand-out
+  unsigned int* flags;         // [0..8) phase-1 (PowSum) per input, [8..16) phase-2 (loss) per level: kFxNaN / kFxPosInf / kFxNegInf
+  unsigned long long* p1_acc;  // [SAD_MAX_LEVELS][2]: exact fixed-point sum of teacher_prob ^ power per input (distill_math.cuh, Fx128)
+  unsigned long long* p2_acc;  // [SAD_MAX_LEVELS][2]: exact fixed-point sum of the loss terms per level
 };
 
 struct __align__(16) FUnitDesc {
@@ -84,7 +85,6 @@ struct __align__(128) FStage {
 };
 constexpr size_t kFusedSmemBytes = sizeof(FStage) * kFStages;
 static_assert(kFusedSmemBytes >= (size_t)kF1Chunk * 4 * kF1Stages, "phase-1 ring must fit in the phase-2 ring");
-constexpr uint32_t kFSentinel = 0xffffffffu;   // FUnitDesc.n_hw of the producer's "no more units" message
 
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
@@ -102,19 +102,26 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
+// deliver one value per warp (already reduced over the warp, valid in lane 0) into the CTA's exact accumulator `slot`
+__device__ __forceinline__ void fx_deliver(float v, unsigned long long* acc_smem /* [lo, hi] */, unsigned int* flag_smem) {
+  Fx128 x;
+  const unsigned int f = fx_from_float(v, x);
+  if (f) atomicOr(flag_smem, f);
+  else fx_atomic_add(acc_smem, x);
+}
+
 template <bool kAlphaHalf, bool kPowAccurate>
 __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __grid_constant__ FusedArgs args) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FStage* stages = reinterpret_cast<FStage*>(smem_raw);
   float(*p1_stages)[kF1Chunk] = reinterpret_cast<float(*)[kF1Chunk]>(smem_raw);   // the phase-1 ring reuses the phase-2 ring's memory
   __shared__ FUnitDesc desc[kFStages];
-  __shared__ int32_t p1_desc[kF1Stages][2];  // {input, count}
+  __shared__ int32_t p1_desc[kF1Stages][2];  // {input, count}; count < 0: no more chunks
   __shared__ __align__(8) uint64_t full_bar[kFStages], empty_bar[kFStages], p1_full[kF1Stages], p1_empty[kF1Stages];
+  __shared__ __align__(16) unsigned long long acc_s[2][SAD_MAX_LEVELS][2];   // [phase][input / level][lo, hi]: this CTA's exact sums
+  __shared__ unsigned int flag_s[2][SAD_MAX_LEVELS];
   __shared__ float in_sum[SAD_MAX_LEVELS];
   __shared__ float red_f[kFWarps];
-  __shared__ float lvl_sum[SAD_MAX_LEVELS];
-  __shared__ float unit_part[kFStages][kFWarps];   // per-warp loss sums of the unit in a stage
-  __shared__ unsigned int unit_cnt[kFStages];      // warps that have delivered theirs
   __shared__ float np_smem;
   __shared__ bool is_last;
 
@@ -124,7 +131,6 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     for (int s = 0; s < kFStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kFWarps);
-      unit_cnt[s] = 0u;
     }
 #pragma unroll
     for (int s = 0; s < kF1Stages; ++s) {
@@ -138,9 +144,10 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     for (int s = 0; s < kFStages; ++s) mbar_arrive(&full_bar[s]);
     mbar_fence_init();
   }
-  if (tid < SAD_MAX_LEVELS) {
-    in_sum[tid] = 0.f;
-    lvl_sum[tid] = 0.f;
+  if (tid < 2 * SAD_MAX_LEVELS) {
+    acc_s[tid / SAD_MAX_LEVELS][tid % SAD_MAX_LEVELS][0] = 0ull;
+    acc_s[tid / SAD_MAX_LEVELS][tid % SAD_MAX_LEVELS][1] = 0ull;
+    flag_s[tid / SAD_MAX_LEVELS][tid % SAD_MAX_LEVELS] = 0u;
   }
   __syncthreads();
   const bool stamp = (args.dbg & 8u) && tid == 0;
@@ -150,12 +157,18 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     // ================= producer thread: phase-1 chunks, then (without waiting for the normaliser) phase-2 units ==========
     if (tid == kFConsumers) {
       {
-        // unit j of this CTA = global chunk (p1_total - 1 - (blockIdx.x + j * gridDim.x)): last chunk first
+        // Chunks of T are handed out through a counter (ctrl[2]), last chunk first (phase 2 walks forwards and then finds the
+        // head of T most recently used in L2).  A static deal left the CTAs' phase-1 finish times 4.6 us apart (14.4 .. 19.0 us,
+        // profiles/r02_fused_stamps.txt) and the grid barrier waits for the slowest; the sums stay bit-identical run to run
+        // because every warp's partial enters an exact fixed-point accumulator (order does not matter).  The next ticket is
+        // always in flight while the current chunk is requested.
         const uint64_t pol = (args.dbg & 1u) ? policy_evict_first() : policy_evict_last();
         RingState rs;
         int k = args.n_levels - 1;
+        uint32_t r = atomicAdd(&args.ctrl[2], 1u);
+        uint32_t r_next = atomicAdd(&args.ctrl[2], 1u);
 #pragma unroll 1
-        for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
+        while (r < args.p1_total) {
           const uint32_t u = args.p1_total - 1u - r;
           while (u < args.lv[k].p1_begin) --k;
           const uint32_t start = (u - args.lv[k].p1_begin) * (uint32_t)kF1Chunk;
@@ -167,22 +180,24 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           mbar_arrive_expect_tx(&p1_full[rs.stage], cnt * 4u);
           bulk_g2s(p1_stages[rs.stage], args.lv[k].T + start, cnt * 4u, &p1_full[rs.stage], pol);
           rs.advance<kF1Stages>();
+          r = r_next;
+          r_next = atomicAdd(&args.ctrl[2], 1u);
         }
+        mbar_wait(&p1_empty[rs.stage], rs.phase ^ 1u);
+        p1_desc[rs.stage][1] = -1;   // no more chunks
+        mbar_arrive(&p1_full[rs.stage]);
       }
-      // phase 2: X and T rows and the label row of each unit.  Nothing here depends on the normaliser, so the first three
-      // units are requested the moment the consumers are through with phase 1 and land while the grid barrier is crossed.
-      // Units are handed out through a counter (ctrl[2]) in increasing order: phase 2 is DRAM-bound, the CTAs' shares of the
-      // memory system differ (measured with a static deal: finish times 8 us apart in a 27 us phase), and whoever is
-      // faster simply takes more units.  The next ticket is fetched while the current unit's copies are in flight.
+      // phase 2: X and T rows and the label row of each unit, units dealt round-robin (static: a dynamic hand-out was measured
+      // again in round 2 — it evens out the finish times but the phase as a whole is not shorter, 31.1 vs 30.7 us).  Nothing
+      // here depends on the normaliser, so the first three units are requested the moment the consumers are through with
+      // phase 1 and land while the grid barrier is crossed.
       const uint64_t pol = policy_evict_first();
       const uint32_t C = (uint32_t)args.num_classes, cg = (uint32_t)args.class_groups;
       RingState rs;
       rs.phase = 1u;
       int l = 0;
-      uint32_t u = atomicAdd(&args.ctrl[2], 1u);
-      uint32_t u_next = atomicAdd(&args.ctrl[2], 1u);   // always one ticket ahead: its round trip (~0.7 us) hides behind a whole unit
 #pragma unroll 1
-      while (u < args.total_units) {
+      for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
         mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
         while (u >= args.lv[l].unit_end) ++l;
         const FusedLevel& L = args.lv[l];
@@ -213,36 +228,23 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           bulk_g2s(st.T[c], ts + (size_t)c * L.HW, row_bytes, &full_bar[rs.stage], pol);
         }
         bulk_g2s(st.G, L.G + (size_t)na * L.HW + hw0, row_bytes, &full_bar[rs.stage], pol);
-        u = u_next;
-        u_next = atomicAdd(&args.ctrl[2], 1u);
         rs.advance<kFStages>();
       }
-      // "no more units"
-      mbar_wait(&empty_bar[rs.stage], rs.phase ^ 1u);
-      desc[rs.stage].n_hw = kFSentinel;
-      mbar_arrive(&full_bar[rs.stage]);
     }
   } else {
     // ================= consumers, phase 1: PowSum over the teacher probabilities =================
     {
       const float power = args.power;
       const f32x2 power2 = pk2(power, power);
-      float acc = 0.f;
-      int cur = -1;
       RingState rs;
 #pragma unroll 1
-      for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
+      for (;;) {
         mbar_wait(&p1_full[rs.stage], rs.phase);
         const int input = p1_desc[rs.stage][0];
-        const uint32_t n4 = (uint32_t)p1_desc[rs.stage][1] >> 2;
-        if (input != cur) {
-          if (cur >= 0) {
-            const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
-            if (tid == 0) in_sum[cur] = s;
-            acc = 0.f;
-          }
-          cur = input;
-        }
+        const int32_t cnt = p1_desc[rs.stage][1];
+        if (cnt < 0) break;
+        const uint32_t n4 = (uint32_t)cnt >> 2;
+        float acc = 0.f;   // this thread's share of THIS chunk: a fixed tree per chunk, whichever CTA drew it
         const float4* src = reinterpret_cast<const float4*>(p1_stages[rs.stage]);
 #pragma unroll
         for (int j = 0; j < kF1Chunk / 4 / kFConsumers; ++j) {
@@ -261,13 +263,12 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p1_empty[rs.stage]);
+        const float ws = warp_sum(acc);
+        if (lane == 0) {
+          fx_deliver(ws, acc_s[0][input], &flag_s[0][input]);
+          mbar_arrive(&p1_empty[rs.stage]);
+        }
         rs.advance<kF1Stages>();
-      }
-      if (cur >= 0) {
-        const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
-        if (tid == 0) in_sum[cur] = s;
       }
     }
     // phase 1 consumed: the ring's memory is free for phase 2
@@ -278,24 +279,30 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     }
     named_bar_sync(2, kFConsumers);
 
-    // ================= grid barrier; every CTA derives the same normaliser =================
+    // ================= grid barrier; every CTA reads the same exact sums =================
     if (stamp) args.stamps[blockIdx.x * 5 + 1] = gtimer();
-    if (tid < SAD_MAX_LEVELS) args.p1_partials[(size_t)blockIdx.x * SAD_MAX_LEVELS + tid] = in_sum[tid];
+    if (tid < args.n_levels) {
+      Fx128 x;
+      x.lo = acc_s[0][tid][0];
+      x.hi = acc_s[0][tid][1];
+      fx_atomic_add(args.p1_acc + 2 * tid, x);
+      if (flag_s[0][tid]) atomicOr(&args.flags[tid], flag_s[0][tid]);
+      __threadfence();
+    }
     named_bar_sync(2, kFConsumers);
     if (tid == 0) {
       __threadfence();
-      // 296 CTAs polling one L2 line with atomics queueing behind the polls is a hot spot: whoever arrives last knows it from
-      // the atomic's return value, everybody else polls with a back-off
+      // whoever arrives last knows it from the atomic's return value; everybody else polls with a back-off (296 CTAs polling
+      // one L2 line with atomics queueing behind the polls is a hot spot)
       if (atomicAdd(&args.ctrl[0], 1u) + 1u < gridDim.x)
         while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(100);
       __threadfence();
     }
     named_bar_sync(2, kFConsumers);
-    // per input: fp64 sum of the CTA partials in a fixed order, rounded to float (one warp per input); then the
-    // reference's running float add over the inputs (pow_sum_op.cu:39)
-    for (int j = warp; j < args.n_levels; j += kFWarps) {
-      const double s = warp_sum_partials<SAD_MAX_LEVELS>(args.p1_partials, j, lane);
-      if (lane == 0) in_sum[j] = (float)s;
+    // per input: the exact sum rounded to float once; then the reference's running float add over the inputs (pow_sum_op.cu:39)
+    if (tid < args.n_levels) {
+      const unsigned long long lo = __ldcg(args.p1_acc + 2 * tid), hi = __ldcg(args.p1_acc + 2 * tid + 1);
+      in_sum[tid] = (float)fx_to_double(lo, hi, __ldcg(args.flags + tid));
     }
     named_bar_sync(2, kFConsumers);
     if (tid == 0) {
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     const float Np = fmaxf(np_smem, 1.0f);   // max(weight_pos[0], 1.0): ...loss_op.cu:49,87
     if (stamp) args.stamps[blockIdx.x * 5 + 2] = gtimer();
 
-    // ================= consumers, phase 2: loss + gradient of the units this CTA's producer drew =================
+    // ================= consumers, phase 2: loss + gradient, units dealt round-robin =================
     const uint32_t h = (uint32_t)(tid & 127) * 4u;
     const uint32_t cbase = (uint32_t)(tid >> 7) * kFPer;
     const float alpha = args.alpha;
@@ -322,20 +329,23 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     const float kscale = args.scale / Np;
     RingState rs;
     rs.phase = 1u;
-    float kg = 0.f;
+    float acc = 0.f, kg = 0.f;
     int cur_level = -1;
 #pragma unroll 1
-    for (;;) {
+    for (uint32_t u = blockIdx.x; u < args.total_units; u += gridDim.x) {
       mbar_wait(&full_bar[rs.stage], rs.phase);
       const FUnitDesc d = desc[rs.stage];
-      if (d.n_hw == kFSentinel) break;
       const FStage& st = stages[rs.stage];
       if (d.level != cur_level) {
+        if (cur_level >= 0) {   // the level's share of this CTA: thread sums over its units (static deal), shuffle tree, exact delivery
+          const float ws = warp_sum(acc);
+          if (lane == 0) fx_deliver(ws, acc_s[1][cur_level], &flag_s[1][cur_level]);
+          acc = 0.f;
+        }
         cur_level = d.level;
         const float* dl = args.lv[cur_level].d_loss;
         kg = (dl ? __ldg(dl) : 1.f) * kscale;   // d_loss * scale / Np of this level
       }
-      float acc = 0.f;   // this thread's share of the unit's loss (twice the summand, positive)
       if (h < d.n_hw) {
         const int4 g = *reinterpret_cast<const int4*>(&st.G[h]);
         float keep[4], kk[4];
@@ -410,24 +420,13 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           }
         }
       }
-      // the unit's loss: a fixed tree (16 elements per thread, shuffle tree per warp, the 8 warps in order) whatever CTA drew
-      // the unit -> bit-identical run to run although the hand-out is dynamic.  The warp that delivers last adds up.
-      const float ws = warp_sum(acc);
-      if (lane == 0) {
-        unit_part[rs.stage][warp] = ws;
-        __threadfence_block();
-        if (atomicAdd(&unit_cnt[rs.stage], 1u) == (unsigned int)(kFWarps - 1)) {
-          __threadfence_block();
-          float s = 0.f;
-#pragma unroll
-          for (int w = 0; w < kFWarps; ++w) s += unit_part[rs.stage][w];
-          args.unit_loss[d.unit] = s;
-          unit_cnt[rs.stage] = 0u;
-        }
-      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[rs.stage]);
       rs.advance<kFStages>();
+    }
+    if (cur_level >= 0) {
+      const float ws = warp_sum(acc);
+      if (lane == 0) fx_deliver(ws, acc_s[1][cur_level], &flag_s[1][cur_level]);
     }
 
     // ================= tail levels: H*W % 4 != 0 (e.g. P7 = 5 x 7 of a 640 x 896 input) =================
@@ -449,55 +448,41 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
         distill_elem_fast<kAlphaHalf, true, true>(ld_stream1(L.X + i), ld_stream1(L.T + i), keep, keep * kgl, fc, tacc, gv);
         L.dX[i] = gv;
       }
-      const float s = group_sum<kFConsumers>(tacc, red_f, tid, 1);
-      if (tid == 0) lvl_sum[l] = s;
+      const float ws = warp_sum(tacc);
+      if (lane == 0) fx_deliver(ws, acc_s[1][l], &flag_s[1][l]);
     }
   }
 
-  // ================= last CTA: per-level loss, fixed order, fp64 =================
-  //   ring levels: the unit slots of the level in unit order;  tail levels: the per-CTA partials in CTA order
+  // ================= every CTA adds its exact level sums to the global ones; the last CTA rounds them once =================
   if (stamp) args.stamps[blockIdx.x * 5 + 3] = gtimer();
-  if (publish_and_ticket<SAD_MAX_LEVELS>(lvl_sum, args.p2_partials, &args.ctrl[1], &is_last)) {
+  __syncthreads();
+  if (tid < args.n_levels) {
+    Fx128 x;
+    x.lo = acc_s[1][tid][0];
+    x.hi = acc_s[1][tid][1];
+    fx_atomic_add(args.p2_acc + 2 * tid, x);
+    if (flag_s[1][tid]) atomicOr(&args.flags[SAD_MAX_LEVELS + tid], flag_s[1][tid]);
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(&args.ctrl[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
     __threadfence();
     const float Np = fmaxf(np_smem, 1.0f);
-    // one pass over all unit slots: thread t owns units t, t + 288, ... (loads issued in batches), one fp64 accumulator per
-    // level (levels are contiguous unit ranges), then a fixed shuffle tree per warp and the 9 warps in order.  Walking the
-    // levels one after the other cost 7 us here (five dependent L2 round trips and ten block barriers).
-    double lsum[SAD_MAX_LEVELS];
-#pragma unroll
-    for (int k = 0; k < SAD_MAX_LEVELS; ++k) lsum[k] = 0.0;
-    constexpr int kBatch = 9;
-    for (uint32_t u0 = (uint32_t)tid; u0 < args.total_units; u0 += kFThreads * kBatch) {
-      float v[kBatch];
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const uint32_t u = u0 + (uint32_t)i * kFThreads;
-        v[i] = u < args.total_units ? __ldcg(args.unit_loss + u) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const uint32_t u = u0 + (uint32_t)i * kFThreads;
-#pragma unroll
-        for (int k = 0; k < SAD_MAX_LEVELS; ++k)
-          if (k < args.n_levels && u >= args.lv[k].unit_begin && u < args.lv[k].unit_end) lsum[k] += (double)v[i];
-      }
-    }
-    // tail levels: their per-CTA partials (CTA order), lanes of warp 0
-#pragma unroll
-    for (int k = 0; k < SAD_MAX_LEVELS; ++k)   // (/ 32: every lane holds the total and the shuffle tree below adds the lanes up)
-      if (k < args.n_levels && args.lv[k].tail && warp == 0) lsum[k] = warp_sum_partials<SAD_MAX_LEVELS>(args.p2_partials, k, lane) / 32.0;
-    __shared__ double red_l[kFThreads / 32][SAD_MAX_LEVELS];
-#pragma unroll
-    for (int k = 0; k < SAD_MAX_LEVELS; ++k) {
-      const double w = warp_sum(lsum[k]);
-      if (lane == 0) red_l[warp][k] = w;
+    if (tid < args.n_levels) {
+      const double s = fx_to_double(__ldcg(args.p2_acc + 2 * tid), __ldcg(args.p2_acc + 2 * tid + 1), __ldcg(args.flags + SAD_MAX_LEVELS + tid));
+      // the arithmetic accumulates twice the summand
+      args.lv[tid].loss[0] = (float)(0.5 * s / (double)Np) * args.scale;
     }
     __syncthreads();
-    if (tid < args.n_levels) {
-      double tot = 0.0;
-      for (int w = 0; w < kFThreads / 32; ++w) tot += red_l[w][tid];
-      // the arithmetic accumulates twice the summand
-      args.lv[tid].loss[0] = (float)(0.5 * tot / (double)Np) * args.scale;
+    if (tid < SAD_MAX_LEVELS) {   // leave the control block zeroed for the next launch
+      args.p1_acc[2 * tid] = args.p1_acc[2 * tid + 1] = 0ull;
+      args.p2_acc[2 * tid] = args.p2_acc[2 * tid + 1] = 0ull;
+      args.flags[tid] = args.flags[SAD_MAX_LEVELS + tid] = 0u;
     }
     if (tid == 0) {
       args.ctrl[0] = 0u;
@@ -524,11 +509,10 @@ static size_t fused_units(const sad_distill_level* levels, int n_levels, int num
   return (size_t)t;
 }
 
-// layout of the fused workspace: [0,256) ctrl | phase-1 partials | phase-2 (tail-level) partials | debug stamps | unit loss slots
-static size_t fused_fixed_bytes() {
-  return 256 + 2 * (size_t)kMaxRingCtas * SAD_MAX_LEVELS * sizeof(float) + (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long);
-}
-static size_t fused_ws_bytes(size_t units) { return fused_fixed_bytes() + ((units * sizeof(float) + 255) / 256) * 256; }
+// layout of the fused workspace: control block [0, 1024): ctrl (16 B) | flags (64 B at 64) | phase-1 sums (128 B at 256) |
+// phase-2 sums (128 B at 512); debug stamps behind it.  sad_workspace_init zeroes it once; every launch leaves it zeroed.
+constexpr size_t kFusedCtrlBytes = 1024;
+static size_t fused_ws_bytes(size_t) { return kFusedCtrlBytes + (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long); }
 
 bool distill_fused_supported(const sad_distill_level* levels, int n_levels, const sad_distill_params* p, float power) {
   if (!(p->gamma == 2.0f && p->beta == 0.0f)) return false;
@@ -594,12 +578,12 @@ int launch_distill_fused(const sad_distill_level* levels, int n_levels, float po
   if (const char* e = getenv("SAD_FUSED_DEBUG")) a.dbg = (uint32_t)atoi(e);
   if (!workspace || workspace_bytes < fused_ws_bytes((size_t)t) || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return set_error(SAD_ERR_WORKSPACE, "distill fused: workspace must be 256-byte aligned and >= sad_distill_fused_workspace_bytes()");
-  a.ctrl = static_cast<unsigned int*>(workspace);
-  a.p1_partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  a.p2_partials = a.p1_partials + (size_t)kMaxRingCtas * SAD_MAX_LEVELS;
-  a.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + fused_fixed_bytes() -
-                                                   (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long));
-  a.unit_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + fused_fixed_bytes());
+  char* wsb = static_cast<char*>(workspace);
+  a.ctrl = reinterpret_cast<unsigned int*>(wsb);
+  a.flags = reinterpret_cast<unsigned int*>(wsb + 64);
+  a.p1_acc = reinterpret_cast<unsigned long long*>(wsb + 256);
+  a.p2_acc = reinterpret_cast<unsigned long long*>(wsb + 512);
+  a.stamps = reinterpret_cast<unsigned long long*>(wsb + kFusedCtrlBytes);
 
   int dev = 0, sms = 0, rc;
   if ((rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) != SAD_OK) return rc;
@@ -633,18 +617,20 @@ using namespace sad;
 
 extern "C" {
 
+// bytes the two-launch form (PowSum, then loss + gradient) needs at the start of the workspace; the one-launch kernel's control
+// block lives behind it, so a workspace can serve either form call after call
+static size_t fused_two_launch_bytes(const sad_distill_level* levels, int n_levels) {
+  int64_t sizes[SAD_MAX_LEVELS];
+  for (int l = 0; l < n_levels; ++l) sizes[l] = (int64_t)levels[l].N * levels[l].D * levels[l].H * levels[l].W;
+  const size_t a = sad_pow_sum_workspace_bytes(sizes, n_levels), b = sad_distill_workspace_bytes(levels, n_levels);
+  return (((a > b ? a : b) + 255) / 256) * 256;
+}
+
 SAD_EXPORT size_t sad_distill_fused_workspace_bytes(const sad_distill_level* levels, int n_levels, int num_classes) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS || num_classes < 1) return 0;
-  int64_t sizes[SAD_MAX_LEVELS];
-  for (int l = 0; l < n_levels; ++l) {
+  for (int l = 0; l < n_levels; ++l)
     if (levels[l].N < 0 || levels[l].D < 0 || levels[l].H < 0 || levels[l].W < 0 || levels[l].D % num_classes) return 0;
-    sizes[l] = (int64_t)levels[l].N * levels[l].D * levels[l].H * levels[l].W;
-  }
-  size_t need = distill_fused_workspace_bytes(levels, n_levels, num_classes);
-  const size_t a = sad_pow_sum_workspace_bytes(sizes, n_levels), b = sad_distill_workspace_bytes(levels, n_levels);
-  if (a > need) need = a;
-  if (b > need) need = b;
-  return need;
+  return fused_two_launch_bytes(levels, n_levels) + distill_fused_workspace_bytes(levels, n_levels, num_classes);
 }
 
 SAD_EXPORT int sad_distill_fused_f32(const sad_distill_level* levels, int n_levels, float power, float* normalizer_out,
@@ -661,8 +647,11 @@ SAD_EXPORT int sad_distill_fused_f32(const sad_distill_level* levels, int n_leve
   }
   if (!dims_ok) return set_error(SAD_ERR_INVALID, "distill fused: bad level (negative size, D % num_classes != 0 or null tensor)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (distill_fused_supported(levels, n_levels, params, power))
-    return launch_distill_fused(levels, n_levels, power, normalizer_out, params, workspace, workspace_bytes, st);
+  if (distill_fused_supported(levels, n_levels, params, power)) {
+    const size_t off = fused_two_launch_bytes(levels, n_levels);
+    if (!workspace || workspace_bytes < off) return set_error(SAD_ERR_WORKSPACE, "distill fused: workspace smaller than sad_distill_fused_workspace_bytes()");
+    return launch_distill_fused(levels, n_levels, power, normalizer_out, params, static_cast<char*>(workspace) + off, workspace_bytes - off, st);
+  }
   // general arguments / shapes: the same contract as two launches sharing the workspace one after the other
   const float* ins[SAD_MAX_LEVELS];
   int64_t sizes[SAD_MAX_LEVELS];

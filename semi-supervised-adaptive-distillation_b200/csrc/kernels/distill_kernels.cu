@@ -321,7 +321,8 @@ SAD_EXPORT void sad_distill_default_params(sad_distill_params* p) {
 SAD_EXPORT int sad_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (!workspace || workspace_bytes < 256 || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return set_error(SAD_ERR_WORKSPACE, "workspace must be 256-byte aligned and at least 256 bytes");
-  return check_cuda(cudaMemsetAsync(workspace, 0, 256, static_cast<cudaStream_t>(stream)), "workspace init");
+  // the whole workspace: control words sit at its start and, for the one-launch step, in a block behind the two-launch scratch
+  return check_cuda(cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream)), "workspace init");
 }
 
 // ---- PowSum -------------------------------------------------------------------------------

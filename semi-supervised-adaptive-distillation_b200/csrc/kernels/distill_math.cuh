@@ -276,6 +276,74 @@ __device__ __forceinline__ f32x2 distill_pair_half(f32x2 x, f32x2 pt, f32x2 kk2,
   return mul2(mul2(mul2(AT, d), t), kk2);
 }
 
+// -------------------------------------------------------------------------------------------
+// Exact accumulation of fp32 partial sums: a signed 128-bit fixed-point number, LSB = 2^-64, in two 64-bit limbs.
+// Integer addition is associative, so the total is the same bits whatever the ORDER in which warps / CTAs deliver their
+// partials — which is what lets work be handed out dynamically and still be bit-identical run to run — and a CTA that
+// needs the total reads two words instead of re-adding hundreds of per-CTA partials.  Every fp32 value with |v| in
+// [2^-40, 2^62) is represented exactly (24-bit mantissa shifted into place); smaller ones lose bits below 2^-64; larger
+// ones, infinities and NaN raise a flag that the reader turns back into inf / NaN.
+// -------------------------------------------------------------------------------------------
+struct Fx128 {
+  unsigned long long lo;
+  unsigned long long hi;   // two's complement
+};
+constexpr unsigned int kFxNaN = 1u, kFxPosInf = 2u, kFxNegInf = 4u;
+
+// returns 0, or the flag to raise when v is not representable
+__device__ __forceinline__ unsigned int fx_from_float(float v, Fx128& out) {
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t e = (b >> 23) & 0xffu;
+  if (e >= 127u + 62u) {   // |v| >= 2^62, inf, NaN
+    out.lo = out.hi = 0ull;
+    if (e == 0xffu && (b & 0x7fffffu)) return kFxNaN;
+    return (b >> 31) ? kFxNegInf : kFxPosInf;
+  }
+  const unsigned long long m = (unsigned long long)((b & 0x7fffffu) | (e ? 0x800000u : 0u));
+  const int shift = (int)(e ? e : 1u) - 86;   // v = m * 2^(e - 150) = (m << (e - 86)) * 2^-64
+  unsigned long long l, h;
+  if (shift <= -24) {
+    l = 0ull;
+    h = 0ull;
+  } else if (shift < 0) {
+    l = m >> (-shift);
+    h = 0ull;
+  } else if (shift == 0) {
+    l = m;
+    h = 0ull;
+  } else if (shift < 64) {
+    l = m << shift;
+    h = m >> (64 - shift);
+  } else {
+    l = 0ull;
+    h = m << (shift - 64);
+  }
+  if (b >> 31) {   // negate (two's complement over 128 bits)
+    l = ~l + 1ull;
+    h = ~h + (l == 0ull ? 1ull : 0ull);
+  }
+  out.lo = l;
+  out.hi = h;
+  return 0u;
+}
+// acc += x (acc in shared or global memory); exact whatever the interleaving with other adders: the low limbs add up modulo
+// 2^64 and every wrap is seen by exactly one adder, which carries it into the high limb
+__device__ __forceinline__ void fx_atomic_add(unsigned long long* acc /* [lo, hi] */, const Fx128& x) {
+  unsigned long long carry = 0ull;
+  if (x.lo) {
+    const unsigned long long old = atomicAdd(acc, x.lo);
+    carry = (old + x.lo < old) ? 1ull : 0ull;
+  }
+  if (x.hi + carry) atomicAdd(acc + 1, x.hi + carry);
+}
+__device__ __forceinline__ double fx_to_double(unsigned long long lo, unsigned long long hi, unsigned int flags) {
+  if (flags & kFxNaN) return __longlong_as_double(0x7ff8000000000000ll);
+  if ((flags & kFxPosInf) && (flags & kFxNegInf)) return __longlong_as_double(0x7ff8000000000000ll);
+  if (flags & kFxPosInf) return __longlong_as_double(0x7ff0000000000000ll);
+  if (flags & kFxNegInf) return __longlong_as_double(0xfff0000000000000ll);
+  return (double)(long long)hi + (double)lo * 5.421010862427522e-20;   // 2^-64
+}
+
 // Sum over a group of kThreads threads that share named barrier `bar_id`; result valid in the group's thread 0.
 template <int kThreads, typename T>
 __device__ __forceinline__ T group_sum(T v, T* smem, int tid, uint32_t bar_id) {
