@@ -239,6 +239,7 @@ class FullDistillStep:
                 if isinstance(m, Bottleneck) and m.fused:
                     pairs = [(m.c1, m.a1), (m.c2, m.a2), (m.c3, m.a3)] + ([(m.short[0], m.short[1])] if m.short is not None else [])
                     self._fold += [(c, a) for c, a in pairs if c.weight.requires_grad]
+        self._fold_dw = []
         self._fold_w = [c.weight.detach() for c, _ in self._fold]
         self._fold_g = [c.weight.grad for c, _ in self._fold]
         self.refold()
