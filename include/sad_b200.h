@@ -140,6 +140,19 @@ typedef struct sad_sgd_segment {
 int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
                          const float* lr, float momentum, int nesterov, void* stream);
 
+/* The same two optimiser steps as the single-blob operators the reference graph names (operator classes MomentumSGDUpdate,
+ * MomentumSGD and WeightedSum in libcaffe2_detectron_ops_gpu.so forward here):
+ *   MomentumSGDUpdateOp<float, CUDAContext>::RunOnDevice   caffe2/caffe2/sgd/momentum_sgd_op.h:90-127, kernel momentum_sgd_op_gpu.cu:23-54
+ *     adjusted = lr[0] * grad + momentum * mom;  mom_out = grad_out = adjusted;  param_out = param - adjusted   (nesterov: :44-51)
+ *     param == param_out == NULL is MomentumSGDOp (momentum_sgd_op.h:53-88: no parameter update).  In place allowed.
+ *   WeightedSumOp<CUDAContext>::RunOnDevice                 caffe2/caffe2/operators/utility_ops.h:333-378
+ *     out = ws[0][0] * xs[0] + ws[1][0] * xs[1] + ...  (weights are device fp32 scalars; in place only with xs[0])
+ * Element expressions are the reference's, so the results are bit-identical to its operators. */
+int sad_momentum_sgd_update_f32(const float* grad, const float* mom, const float* lr, const float* param /* or NULL */, float* grad_out,
+                                float* mom_out, float* param_out /* or NULL */, int64_t n, float momentum, int nesterov, void* stream);
+int sad_weighted_sum_f32(const float* const* xs, const float* const* ws, int n_inputs /* <= SAD_MAX_INPUTS */, float* out, int64_t n,
+                         void* stream);
+
 /* The whole loss step of add_distill_loss (detectron/lib/modeling/retinanet_heads.py:313-352) in ONE launch:
  *   normalizer_out[0] = PowSum(levels[0..n).teacher_prob, power)           (pow_sum_op.cu:25-43)
  *   levels[l].loss, levels[l].d_logits = SigmoidAdaptiveDistillLoss(+Gradient)(..., normalizer_out)  for every level

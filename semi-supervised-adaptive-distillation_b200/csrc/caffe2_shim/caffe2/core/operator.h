@@ -211,6 +211,28 @@ class Operator : public OperatorBase {
   Context context_;
 };
 
+// reference operator.h:540-645 — run-time dispatch on a tensor's element type: DispatchHelper<TensorTypes<int32_t, int64_t>>::
+// call(this, Input(INDICES)) invokes op->DoRunWithType<T>() for the first listed T the tensor holds
+template <typename... Types>
+struct TensorTypes {};
+template <typename Sizes, typename... ExtraArgs>
+struct DispatchHelper;
+template <typename FirstType, typename... Types, typename... ExtraArgs>
+struct DispatchHelper<TensorTypes<FirstType, Types...>, ExtraArgs...> {
+  template <typename Op, typename Context>
+  static bool call(Op* op, const Tensor<Context>& tensor) {
+    if (tensor.template IsType<FirstType>()) return op->template DoRunWithType<ExtraArgs..., FirstType>();
+    return DispatchHelper<TensorTypes<Types...>, ExtraArgs...>::template call<Op, Context>(op, tensor);
+  }
+};
+template <typename... ExtraArgs>
+struct DispatchHelper<TensorTypes<>, ExtraArgs...> {
+  template <typename Op, typename Context>
+  static bool call(Op* /*op*/, const Tensor<Context>& /*tensor*/) {
+    CAFFE_THROW("Unsupported type of tensor");
+  }
+};
+
 #define USE_OPERATOR_BASE_FUNCTIONS                  \
   /* using override */ using OperatorBase::HasArgument; \
   /* using override */ using OperatorBase::GetSingleArgument; \

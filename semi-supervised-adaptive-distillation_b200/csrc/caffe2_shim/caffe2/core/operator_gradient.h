@@ -107,6 +107,12 @@ GradientRegistryT* GradientRegistry();
       #name, GradientRegistry(), GradientRegisterer::DefaultCreator<__VA_ARGS__>); \
   }
 #define NO_GRADIENT(name) REGISTER_GRADIENT(name, NoGradient)
+// reference operator_gradient.h:281-293,328-332: asking for the gradient of such an operator is an error
+class ThrowInTheTowelIfGradientIsCalled : public GradientMakerBase {
+  using GradientMakerBase::GradientMakerBase;
+  GradientOpsMeta Get() override { CAFFE_THROW("One should not call gradient for operator ", def_.type(), "."); }
+};
+#define SHOULD_NOT_DO_GRADIENT(name) REGISTER_GRADIENT(name, ThrowInTheTowelIfGradientIsCalled)
 
 GradientOpsMeta GetGradientForOp(const OperatorDef& def, const vector<GradientWrapper>& g_output);
 

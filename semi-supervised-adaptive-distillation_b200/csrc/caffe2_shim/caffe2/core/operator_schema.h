@@ -28,6 +28,7 @@ class OpSchema {
   OpSchema& AllowInplace(std::set<std::pair<int, int>> inplace) {
     return AllowInplace([inplace](int in, int out) { return inplace.count(std::make_pair(in, out)) != 0; });
   }
+  OpSchema& EnforceInplace(std::set<std::pair<int, int>> /*inplace*/) { return *this; }
   OpSchema& AllowOneToOneInplace() { return AllowInplace([](int in, int out) { return in == out; }); }
   OpSchema& IdenticalTypeAndShape() { return *this; }
   OpSchema& IdenticalTypeAndShapeOfInput(int) { return *this; }

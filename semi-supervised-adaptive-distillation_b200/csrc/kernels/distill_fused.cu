@@ -66,11 +66,38 @@ struct FusedArgs {
   float* norm_out;
   unsigned long long* stamps;  // debug (dbg & 8): [gridDim.x][5] globaltimer values
   // control block (zero between launches; the last CTA leaves it zeroed):
-  unsigned int* ctrl;          // [0] grid barrier, [1] final ticket, [2] phase-1 chunk hand-out
-  unsigned int* flags;         // [0..8) phase-1 (PowSum) per input, [8..16) phase-2 (loss) per level: kFxNaN / kFxPosInf / kFxNegInf
-  unsigned long long* p1_acc;  // [SAD_MAX_LEVELS][2]: exact fixed-point sum of teacher_prob ^ power per input (distill_math.cuh, Fx128)
-  unsigned long long* p2_acc;  // [SAD_MAX_LEVELS][2]: exact fixed-point sum of the loss terms per level
+  unsigned int* ctrl;          // [1] final ticket
+  unsigned int* flags;         // [8..16) phase-2 (loss) per level: kFxNaN / kFxPosInf / kFxNegInf
+  unsigned long long* bar;     // [SAD_MAX_LEVELS] grid-barrier words, one per input: arrival count and PowSum partials in ONE atomic (below)
+  unsigned long long* p2_acc;  // [SAD_MAX_LEVELS][2]: exact fixed-point sum of the loss terms per level (distill_math.cuh, Fx128)
 };
+
+// Grid barrier that carries the data it is there for.  The only thing the CTAs exchange between the phases is the normaliser, so
+// each CTA delivers its PowSum partial of input k and its arrival with a single fire-and-forget 64-bit atomic on word k:
+//     bits 0..53   the partial in fixed point, 22 fractional bits (a sum of probabilities^power: 0 <= sum < 2^32)
+//     bits 54..62  +1 (arrival count; the grid has at most 2 x 148 CTAs)
+//     bit  63      sticky "not representable" (NaN, negative, or beyond the per-CTA cap that keeps the sum out of the count field)
+// and then polls the words: the load that shows the last arrival also returns the complete sum.  Against "write partials, fence,
+// count, poll, fence, read 296 x 5 partials" this takes three global round trips off the critical path (measured: 3.9 -> x us from
+// the slowest CTA's end of phase 1 to the start of phase 2); integer addition makes the sum independent of the arrival order.
+constexpr int kBarFrac = 22;
+constexpr int kBarCountShift = 54;
+constexpr unsigned long long kBarBad = 1ull << 63;
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bar_deliver(unsigned long long* word, float partial, uint32_t grid) {
+  const double cap = (double)((1ull << kBarCountShift) / grid - 1ull);   // sum over all CTAs stays below 2^54
+  const double q = (double)partial * (double)(1u << kBarFrac);
+  if (!(q >= 0.0 && q <= cap)) {   // NaN, negative or too large
+    atomicOr(word, kBarBad);       // same word, same thread: ordered before the arrival below
+    atomicAdd(word, 1ull << kBarCountShift);
+  } else {
+    atomicAdd(word, (1ull << kBarCountShift) + (unsigned long long)__double2ll_rn(q));
+  }
+}
 
 struct __align__(16) FUnitDesc {
   float* dX;
@@ -144,6 +171,7 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     for (int s = 0; s < kFStages; ++s) mbar_arrive(&full_bar[s]);
     mbar_fence_init();
   }
+  if (tid < SAD_MAX_LEVELS) in_sum[tid] = 0.f;
   if (tid < 2 * SAD_MAX_LEVELS) {
     acc_s[tid / SAD_MAX_LEVELS][tid % SAD_MAX_LEVELS][0] = 0ull;
     acc_s[tid / SAD_MAX_LEVELS][tid % SAD_MAX_LEVELS][1] = 0ull;
@@ -157,18 +185,14 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     // ================= producer thread: phase-1 chunks, then (without waiting for the normaliser) phase-2 units ==========
     if (tid == kFConsumers) {
       {
-        // Chunks of T are handed out through a counter (ctrl[2]), last chunk first (phase 2 walks forwards and then finds the
-        // head of T most recently used in L2).  A static deal left the CTAs' phase-1 finish times 4.6 us apart (14.4 .. 19.0 us,
-        // profiles/r02_fused_stamps.txt) and the grid barrier waits for the slowest; the sums stay bit-identical run to run
-        // because every warp's partial enters an exact fixed-point accumulator (order does not matter).  The next ticket is
-        // always in flight while the current chunk is requested.
+        // unit j of this CTA = global chunk (p1_total - 1 - (blockIdx.x + j * gridDim.x)): last chunk first (phase 2 walks forwards
+        // and then finds the head of T most recently used in L2).  Static deal: handing the chunks out through a counter was
+        // measured in round 2 (per-chunk exact sums so that the result stays deterministic) and made the phase slower, 18.5 vs 16.6 us.
         const uint64_t pol = (args.dbg & 1u) ? policy_evict_first() : policy_evict_last();
         RingState rs;
         int k = args.n_levels - 1;
-        uint32_t r = atomicAdd(&args.ctrl[2], 1u);
-        uint32_t r_next = atomicAdd(&args.ctrl[2], 1u);
 #pragma unroll 1
-        while (r < args.p1_total) {
+        for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
           const uint32_t u = args.p1_total - 1u - r;
           while (u < args.lv[k].p1_begin) --k;
           const uint32_t start = (u - args.lv[k].p1_begin) * (uint32_t)kF1Chunk;
@@ -180,12 +204,7 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
           mbar_arrive_expect_tx(&p1_full[rs.stage], cnt * 4u);
           bulk_g2s(p1_stages[rs.stage], args.lv[k].T + start, cnt * 4u, &p1_full[rs.stage], pol);
           rs.advance<kF1Stages>();
-          r = r_next;
-          r_next = atomicAdd(&args.ctrl[2], 1u);
         }
-        mbar_wait(&p1_empty[rs.stage], rs.phase ^ 1u);
-        p1_desc[rs.stage][1] = -1;   // no more chunks
-        mbar_arrive(&p1_full[rs.stage]);
       }
       // phase 2: X and T rows and the label row of each unit, units dealt round-robin (static: a dynamic hand-out was measured
       // again in round 2 — it evens out the finish times but the phase as a whole is not shorter, 31.1 vs 30.7 us).  Nothing
@@ -236,15 +255,22 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     {
       const float power = args.power;
       const f32x2 power2 = pk2(power, power);
+      float acc = 0.f;
+      int cur = -1;
       RingState rs;
 #pragma unroll 1
-      for (;;) {
+      for (uint32_t r = blockIdx.x; r < args.p1_total; r += gridDim.x) {
         mbar_wait(&p1_full[rs.stage], rs.phase);
         const int input = p1_desc[rs.stage][0];
-        const int32_t cnt = p1_desc[rs.stage][1];
-        if (cnt < 0) break;
-        const uint32_t n4 = (uint32_t)cnt >> 2;
-        float acc = 0.f;   // this thread's share of THIS chunk: a fixed tree per chunk, whichever CTA drew it
+        const uint32_t n4 = (uint32_t)p1_desc[rs.stage][1] >> 2;
+        if (input != cur) {
+          if (cur >= 0) {
+            const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
+            if (tid == 0) in_sum[cur] = s;
+            acc = 0.f;
+          }
+          cur = input;
+        }
         const float4* src = reinterpret_cast<const float4*>(p1_stages[rs.stage]);
 #pragma unroll
         for (int j = 0; j < kF1Chunk / 4 / kFConsumers; ++j) {
@@ -263,12 +289,13 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
             }
           }
         }
-        const float ws = warp_sum(acc);
-        if (lane == 0) {
-          fx_deliver(ws, acc_s[0][input], &flag_s[0][input]);
-          mbar_arrive(&p1_empty[rs.stage]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p1_empty[rs.stage]);
         rs.advance<kF1Stages>();
+      }
+      if (cur >= 0) {
+        const float s = group_sum<kFConsumers>(acc, red_f, tid, 1);
+        if (tid == 0) in_sum[cur] = s;
       }
     }
     // phase 1 consumed: the ring's memory is free for phase 2
@@ -279,37 +306,29 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     }
     named_bar_sync(2, kFConsumers);
 
-    // ================= grid barrier; every CTA reads the same exact sums =================
+    // ================= grid barrier that carries the normaliser (bar_deliver above) =================
     if (stamp) args.stamps[blockIdx.x * 5 + 1] = gtimer();
-    if (tid < args.n_levels) {
-      Fx128 x;
-      x.lo = acc_s[0][tid][0];
-      x.hi = acc_s[0][tid][1];
-      fx_atomic_add(args.p1_acc + 2 * tid, x);
-      if (flag_s[0][tid]) atomicOr(&args.flags[tid], flag_s[0][tid]);
-      __threadfence();
-    }
-    named_bar_sync(2, kFConsumers);
-    if (tid == 0) {
-      __threadfence();
-      // whoever arrives last knows it from the atomic's return value; everybody else polls with a back-off (296 CTAs polling
-      // one L2 line with atomics queueing behind the polls is a hot spot)
-      if (atomicAdd(&args.ctrl[0], 1u) + 1u < gridDim.x)
-        while (ld_acquire_gpu(&args.ctrl[0]) < gridDim.x) __nanosleep(100);
-      __threadfence();
-    }
-    named_bar_sync(2, kFConsumers);
-    // per input: the exact sum rounded to float once; then the reference's running float add over the inputs (pow_sum_op.cu:39)
-    if (tid < args.n_levels) {
-      const unsigned long long lo = __ldcg(args.p1_acc + 2 * tid), hi = __ldcg(args.p1_acc + 2 * tid + 1);
-      in_sum[tid] = (float)fx_to_double(lo, hi, __ldcg(args.flags + tid));
-    }
-    named_bar_sync(2, kFConsumers);
-    if (tid == 0) {
-      float res = 0.f;
-      for (int j = 0; j < args.n_levels; ++j) res = res + in_sum[j];
-      np_smem = res;
-      if (blockIdx.x == 0) args.norm_out[0] = res;
+    if (warp == 0) {
+      const bool mine = lane < args.n_levels;
+      if (mine) bar_deliver(args.bar + lane, in_sum[lane], gridDim.x);
+      unsigned long long v = 0ull;
+      for (;;) {
+        if (mine) v = ld_acquire_gpu_u64(args.bar + lane);
+        const bool done = !mine || ((v >> kBarCountShift) & 0x1ffull) >= (unsigned long long)gridDim.x;
+        if (__all_sync(0xffffffffu, done)) break;
+        __nanosleep(64);
+      }
+      // per input: the exact sum rounded to float once; then the reference's running float add over the inputs (pow_sum_op.cu:39)
+      if (mine)
+        in_sum[lane] = (v & kBarBad) ? __int_as_float(0x7fffffff)
+                                     : (float)((double)(v & ((1ull << kBarCountShift) - 1ull)) * (1.0 / (double)(1u << kBarFrac)));
+      __syncwarp();
+      if (lane == 0) {
+        float res = 0.f;
+        for (int j = 0; j < args.n_levels; ++j) res = res + in_sum[j];
+        np_smem = res;
+        if (blockIdx.x == 0) args.norm_out[0] = res;
+      }
     }
     named_bar_sync(2, kFConsumers);
     const float Np = fmaxf(np_smem, 1.0f);   // max(weight_pos[0], 1.0): ...loss_op.cu:49,87
@@ -480,15 +499,11 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     }
     __syncthreads();
     if (tid < SAD_MAX_LEVELS) {   // leave the control block zeroed for the next launch
-      args.p1_acc[2 * tid] = args.p1_acc[2 * tid + 1] = 0ull;
+      args.bar[tid] = 0ull;
       args.p2_acc[2 * tid] = args.p2_acc[2 * tid + 1] = 0ull;
       args.flags[tid] = args.flags[SAD_MAX_LEVELS + tid] = 0u;
     }
-    if (tid == 0) {
-      args.ctrl[0] = 0u;
-      args.ctrl[1] = 0u;
-      args.ctrl[2] = 0u;
-    }
+    if (tid == 0) args.ctrl[1] = 0u;
     if (stamp) args.stamps[blockIdx.x * 5 + 4] = gtimer();
   }
 }
@@ -509,7 +524,7 @@ static size_t fused_units(const sad_distill_level* levels, int n_levels, int num
   return (size_t)t;
 }
 
-// layout of the fused workspace: control block [0, 1024): ctrl (16 B) | flags (64 B at 64) | phase-1 sums (128 B at 256) |
+// layout of the fused workspace: control block [0, 1024): ctrl (16 B) | flags (64 B at 64) | barrier words (64 B at 256) |
 // phase-2 sums (128 B at 512); debug stamps behind it.  sad_workspace_init zeroes it once; every launch leaves it zeroed.
 constexpr size_t kFusedCtrlBytes = 1024;
 static size_t fused_ws_bytes(size_t) { return kFusedCtrlBytes + (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long); }
@@ -581,7 +596,7 @@ int launch_distill_fused(const sad_distill_level* levels, int n_levels, float po
   char* wsb = static_cast<char*>(workspace);
   a.ctrl = reinterpret_cast<unsigned int*>(wsb);
   a.flags = reinterpret_cast<unsigned int*>(wsb + 64);
-  a.p1_acc = reinterpret_cast<unsigned long long*>(wsb + 256);
+  a.bar = reinterpret_cast<unsigned long long*>(wsb + 256);
   a.p2_acc = reinterpret_cast<unsigned long long*>(wsb + 512);
   a.stamps = reinterpret_cast<unsigned long long*>(wsb + kFusedCtrlBytes);
 

@@ -79,11 +79,91 @@ __global__ void __launch_bounds__(256) momentum_sgd_kernel(const SgdArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The two optimiser operators as the reference graph names them, one blob per call (operator classes in csrc/ops/sgd_ops.cc).
+// The element expressions are written exactly as in the reference sources so that nvcc contracts them into the same FMAs
+// (momentum_sgd_op_gpu.cu:35-51; math_gpu.cu ScaleKernelDeviceAlpha / AxpyKernel behind WeightedSumOp, utility_ops.h:333-378):
+// results are bit-identical to the reference operators (tests/test_sgd_gpu.py runs both).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) momentum_sgd_update_kernel(const int64_t N, const float* __restrict__ g, const float* __restrict__ m,
+                                                                  float* ng, float* nm, const float* __restrict__ lr, const float momentum,
+                                                                  const bool nesterov, const float* param_in, float* param) {
+  const float LR = lr[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!nesterov) {
+      const float adjusted_gradient = LR * g[i] + momentum * m[i];
+      nm[i] = adjusted_gradient;
+      ng[i] = adjusted_gradient;
+      if (param) param[i] = param_in[i] - adjusted_gradient;
+    } else {
+      const float mi = m[i];
+      const float mi_new = momentum * mi + LR * g[i];
+      nm[i] = mi_new;
+      ng[i] = (1 + momentum) * mi_new - momentum * mi;
+      if (param) param[i] = param_in[i] - ng[i];
+    }
+  }
+}
+
+struct WsumArgs {
+  const float* x[SAD_MAX_INPUTS];
+  const float* w[SAD_MAX_INPUTS];
+  int32_t n_inputs;
+};
+__global__ void __launch_bounds__(256) weighted_sum_kernel(const WsumArgs a, float* out, const int64_t N) {
+  float w[SAD_MAX_INPUTS];
+#pragma unroll
+  for (int k = 0; k < SAD_MAX_INPUTS; ++k) w[k] = k < a.n_inputs ? __ldg(a.w[k]) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float y = a.x[0][i] * w[0];                                   // math::Scale (ScaleKernelDeviceAlpha): y = x * (*alpha)
+#pragma unroll
+    for (int k = 1; k < SAD_MAX_INPUTS; ++k)
+      if (k < a.n_inputs) y = fmaf(a.x[k][i], w[k], y);           // math::Axpy (AxpyKernel): y += x * (*a), one FMA as nvcc contracts it
+    out[i] = y;
+  }
+}
+
 }  // namespace sad
 
 using namespace sad;
 
 extern "C" {
+
+SAD_EXPORT int sad_momentum_sgd_update_f32(const float* grad, const float* mom, const float* lr, const float* param, float* grad_out,
+                                           float* mom_out, float* param_out, int64_t n, float momentum, int nesterov, void* stream) {
+  if (n < 0) return set_error(SAD_ERR_INVALID, "MomentumSGDUpdate: negative size");
+  if (n == 0) return SAD_OK;
+  if (!grad || !mom || !lr || !grad_out || !mom_out || (!param != !param_out))
+    return set_error(SAD_ERR_INVALID, "MomentumSGDUpdate: null tensor (param and param_out come together, or both NULL for MomentumSGD)");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n + 255) / 256, cap = (int64_t)sms * 8;
+  momentum_sgd_update_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n, grad, mom, grad_out, mom_out, lr, momentum, nesterov != 0, param, param_out);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "MomentumSGDUpdate launch");
+}
+
+SAD_EXPORT int sad_weighted_sum_f32(const float* const* xs, const float* const* ws, int n_inputs, float* out, int64_t n, void* stream) {
+  if (!xs || !ws || n_inputs < 1 || n_inputs > SAD_MAX_INPUTS) return set_error(SAD_ERR_INVALID, "WeightedSum: 1 .. SAD_MAX_INPUTS (tensor, weight) pairs");
+  if (n < 0) return set_error(SAD_ERR_INVALID, "WeightedSum: negative size");
+  if (n == 0) return SAD_OK;
+  if (!out) return set_error(SAD_ERR_INVALID, "WeightedSum: null output");
+  WsumArgs a{};
+  for (int k = 0; k < n_inputs; ++k) {
+    if (!xs[k] || !ws[k]) return set_error(SAD_ERR_INVALID, "WeightedSum: null input");
+    if (k > 0 && xs[k] == out) return set_error(SAD_ERR_INVALID, "WeightedSum: in-place only with input 0 (utility_ops.h:357-364)");
+    a.x[k] = xs[k];
+    a.w[k] = ws[k];
+  }
+  a.n_inputs = n_inputs;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n + 255) / 256, cap = (int64_t)sms * 8;
+  weighted_sum_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out, n);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "WeightedSum launch");
+}
 
 SAD_EXPORT int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
                                     const float* lr, float momentum, int nesterov, void* stream) {
