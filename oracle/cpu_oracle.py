@@ -68,6 +68,8 @@ def lib():
         l.oracle_select_smooth_l1_loss.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p]
         l.oracle_select_smooth_l1_grad.restype = None
         l.oracle_select_smooth_l1_grad.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p, _f32p]
+        l.oracle_weighted_sum.restype = None
+        l.oracle_weighted_sum.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_void_p), _f32p, _f32p]
         l.oracle_momentum_sgd.restype = None
         l.oracle_momentum_sgd.argtypes = [C.c_int64, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float]
         l.oracle_affine_channel.restype = None
@@ -261,3 +263,13 @@ def upsample_nearest_grad(x_shape, dy, scale=2):
     d1, d2, d3 = _d123(dx.shape)
     lib().oracle_upsample_nearest_grad(dx.reshape(-1), dy.reshape(-1), dx.size, scale, d1, d2, d3)
     return dx
+
+
+def weighted_sum(xs, ws):
+    """WeightedSum (utility_ops.h:333-378): xs[0] * ws[0] + xs[1] * ws[1] + ... with the GPU's one-FMA-per-term rounding."""
+    xs = [np.ascontiguousarray(x, dtype=np.float32).reshape(-1) for x in xs]
+    w = np.ascontiguousarray(ws, dtype=np.float32)
+    out = np.empty_like(xs[0])
+    ptrs = (C.c_void_p * len(xs))(*[x.ctypes.data for x in xs])
+    lib().oracle_weighted_sum(xs[0].size, len(xs), ptrs, w, out)
+    return out

@@ -152,3 +152,13 @@ ORACLE_API void oracle_momentum_sgd(int64_t n, float* param, float* grad, float*
     }
   }
 }
+
+/* WeightedSum (caffe2/caffe2/operators/utility_ops.h:333-378): out = X_0 * w_0 (math::Scale), then out += X_k * w_k (math::Axpy,
+ * which nvcc contracts into one FMA per element on the GPU: caffe2/caffe2/utils/math_gpu.cu AxpyKernel `y[i] += x[i] * (*a)`). */
+ORACLE_API void oracle_weighted_sum(int64_t n, int n_inputs, const float* const* xs, const float* ws, float* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    float y = xs[0][i] * ws[0];
+    for (int k = 1; k < n_inputs; ++k) y = fmaf(xs[k][i], ws[k], y);
+    out[i] = y;
+  }
+}

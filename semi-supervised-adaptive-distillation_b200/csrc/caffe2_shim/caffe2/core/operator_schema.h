@@ -22,6 +22,9 @@ class OpSchema {
 
   OpSchema& NumInputs(int n) { return NumInputs(n, n); }
   OpSchema& NumInputs(int min, int max) { min_input_ = min; max_input_ = max; return *this; }
+  // reference operator_schema.h:70-80: an arbitrary predicate on the input count (WeightedSum: even and positive)
+  OpSchema& NumInputs(std::function<bool(int)> allowed) { num_inputs_allowed_ = allowed; return *this; }
+  bool num_inputs_allowed(int n) const { return !num_inputs_allowed_ || num_inputs_allowed_(n); }
   OpSchema& NumOutputs(int n) { return NumOutputs(n, n); }
   OpSchema& NumOutputs(int min, int max) { min_output_ = min; max_output_ = max; return *this; }
   OpSchema& AllowInplace(std::function<bool(int, int)> inplace) { inplace_allowed_ = inplace; return *this; }
@@ -74,6 +77,7 @@ class OpSchema {
   int line_;
   int min_input_ = 0, max_input_ = INT_MAX, min_output_ = 0, max_output_ = INT_MAX;
   std::function<bool(int, int)> inplace_allowed_ = [](int, int) { return false; };
+  std::function<bool(int)> num_inputs_allowed_;
   std::vector<std::pair<const char*, const char*>> args_, input_desc_, output_desc_;
   TensorInferenceFunctionType tensor_inference_function_;
   CostInferenceFunctionType cost_inference_function_;

@@ -342,6 +342,10 @@ bool OpSchema::Verify(const OperatorDef& def) const {
     fprintf(stderr, "Input size %d not in range [min=%d, max=%d].\n", def.input_size(), min_input_, max_input_);
     return false;
   }
+  if (!num_inputs_allowed(def.input_size())) {
+    fprintf(stderr, "Input size %d is not allowed by the schema of %s.\n", def.input_size(), def.type().c_str());
+    return false;
+  }
   if (def.output_size() < min_output_ || def.output_size() > max_output_) {
     fprintf(stderr, "Output size %d not in range [min=%d, max=%d].\n", def.output_size(), min_output_, max_output_);
     return false;

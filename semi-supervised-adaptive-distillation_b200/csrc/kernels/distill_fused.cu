@@ -10,14 +10,20 @@
 // ramp/drain, and phase 1 walks T backwards with an L2 evict-last policy while phase 2 walks forwards with evict-first
 // loads and streaming stores, so phase 2 finds T still in the 126 MB L2 (ncu: 172 MB read from DRAM per launch instead of
 // 236 MB; with evict-first in phase 1 it is 208 MB).
-// Work units are dealt round-robin (static): a dynamic hand-out through an atomic counter with per-unit loss slots was
-// measured too (globaltimer stamps per CTA, SAD_FUSED_DEBUG=8 + scripts/fused_stamps.py): it narrows the spread of the
-// CTAs' finish times (static: up to 11 us apart) to 3 us but its per-unit overhead delays all of them by 4 us and the
-// fixed-order reduction over the unit slots lengthens the tail; a hybrid (first 50-85 % static, rest dynamic) was
-// slower than the static deal at every split (68.4-74.3 us vs 66.3 us).  16 instead of 8 consumer warps: no change;
-// 3 CTAs per SM with 2-stage rings (72 registers, no spills): 69.5 us.
+// Round 2 (profiles/r02_*): (1) the per-element arithmetic is packed (fma/add/mul.rn.f32x2: two elements per FMA-pipe
+// instruction, distill_math.cuh) and the teacher-probability NaN rule is checked once per thread and unit instead of per element:
+// 34.2 M -> 25.3 M warp instructions per launch, phase 2 is now DRAM-bound (157 MB in 26.5 us); (2) phase-2 loads do not depend
+// on the normaliser, so the producer requests the first three units while the grid barrier is being crossed; (3) the barrier's
+// words carry the PowSum partials themselves (bar_deliver), which takes three global round trips off its critical path; (4) levels
+// whose H*W is not a multiple of 4 (P7 = 5 x 7 of a 640 x 896 input) are done by a scalar tail pass of the same launch instead of
+// pushing every level to the two-launch SIMT path.
+// Work units are dealt round-robin (static) in both phases.  Dynamic hand-outs through atomic counters were measured in round 1
+// (phase 2) and again in round 2 (both phases, with schedule-independent exact sums so that results stay bit-identical): they
+// even out the CTAs' finish times but neither phase gets shorter (phase 1 18.5 vs 16.6 us, phase 2 31.1 vs 30.7 us to the last CTA).
+// 16 instead of 8 consumer warps: no change; 3 CTAs per SM with 2-stage rings (72 registers, no spills): 69.5 us (round 1).
 //
-// Determinism: static unit assignment, per-CTA partial sums, fixed-order fp64 finish: bit-identical run to run.
+// Determinism: static unit assignment; the normaliser and the per-level losses are integer (fixed-point) sums of per-CTA fp32
+// partials, i.e. independent of arrival order: bit-identical run to run.
 //
 // Restricted to the arithmetic fast path (gamma == 2, beta == 0: the reference's headline configs) with both outputs
 // requested; everything else runs as the two ring kernels of distill_ring.cu behind the same entry point.
@@ -615,6 +621,7 @@ int launch_distill_fused(const sad_distill_level* levels, int n_levels, float po
   if (per_sm > 2) per_sm = 2;
   uint32_t grid = (uint32_t)(sms * per_sm);   // every CTA must be resident: the kernel contains a grid-wide barrier
   if (grid > (uint32_t)kMaxRingCtas) grid = kMaxRingCtas;
+  if (grid > 500u) grid = 500u;   // the barrier words count arrivals in 9 bits
   void* params[] = {&a};
   rc = check_cuda(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFThreads), params, kFusedSmemBytes, st), "distill fused launch");
   if (rc != SAD_OK) return rc;

@@ -37,3 +37,89 @@ def test_momentum_sgd_rejects_bad_segments():
     t = torch.zeros(16, device="cuda")
     with pytest.raises(ValueError):
         ops.momentum_sgd(t, t.clone(), t.clone(), [(8, 1.0, 0.0)], torch.tensor(0.1, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------
+# the optimiser OPERATORS under the reference's names (csrc/ops/sgd_ops.cc), op for op against the reference's own
+# MomentumSGDUpdate / MomentumSGD (caffe2/caffe2/sgd/momentum_sgd_op.{h,cc}, momentum_sgd_op_gpu.cu compiled unmodified into
+# oracle/_ref/libref_ops.so) and, for WeightedSum (utility_ops.h:333-378; its .cu is not in _ref), against the oracle restatement
+# ---------------------------------------------------------------------------------------------
+def _libs():
+    import os
+    from oracle import cpu_oracle
+    from sad_b200 import c2
+    ours = c2.OperatorLibrary()
+    ref = c2.OperatorLibrary(cpu_oracle.REF_GPU_LIB) if os.path.exists(cpu_oracle.REF_GPU_LIB) else None
+    return c2, ours, ref
+
+
+@pytest.mark.parametrize("nesterov", [0, 1])
+@pytest.mark.parametrize("n", [1, 1000, 589824 + 3])
+def test_momentum_sgd_update_operator_is_bit_identical_to_the_reference_operator(n, nesterov):
+    c2, ours, ref = _libs()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_ops.so not present")
+    assert ours.SchemaArity("MomentumSGDUpdate") == (4, 4, 3, 3) == ref.SchemaArity("MomentumSGDUpdate")   # momentum_sgd_op.cc:56-58
+    rng = np.random.default_rng(n + nesterov)
+    g, m, p = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    out = {}
+    for name, lib in (("ours", ours), ("ref", ref)):
+        ws = lib.Workspace()
+        for blob, a in (("g", g), ("m", m), ("p", p)):
+            ws.FeedBlob(blob, torch.from_numpy(a.copy()).cuda())
+        ws.FeedBlob("lr", torch.tensor([0.0173], device="cuda"))
+        # in place, as optimizer.py:125-130 emits it
+        op = c2.CreateOperator("MomentumSGDUpdate", ["g", "m", "lr", "p"], ["g", "m", "p"], momentum=0.9, nesterov=nesterov, device_option=dev)
+        ws.RunOperatorOnce(op)
+        ws.RunOperatorOnce(op)       # a second step on the updated blobs
+        out[name] = [ws.FetchBlob(b) for b in ("g", "m", "p")]
+    for a, b, what in zip(out["ours"], out["ref"], ("grad", "momentum", "param")):
+        assert a.tobytes() == b.tobytes(), what
+
+
+def test_momentum_sgd_operator_without_parameter_and_out_of_place():
+    c2, ours, ref = _libs()
+    rng = np.random.default_rng(5)
+    n = 4099
+    g, m, p = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    ws = ours.Workspace()
+    for blob, a in (("g", g), ("m", m), ("p", p)):
+        ws.FeedBlob(blob, torch.from_numpy(a.copy()).cuda())
+    ws.FeedBlob("lr", torch.tensor([0.05], device="cuda"))
+    ws.RunOperatorOnce(c2.CreateOperator("MomentumSGD", ["g", "m", "lr"], ["g2", "m2"], momentum=0.9, device_option=dev))
+    adj = np.float32(0.05) * g + np.float32(0.9) * m
+    np.testing.assert_allclose(ws.FetchBlob("g2"), adj, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(ws.FetchBlob("m2"), adj, rtol=2e-6, atol=1e-7)
+    # out of place: inputs untouched, param_out = param - adjusted
+    ws.RunOperatorOnce(c2.CreateOperator("MomentumSGDUpdate", ["g", "m", "lr", "p"], ["g3", "m3", "p3"], momentum=0.9, device_option=dev))
+    assert ws.FetchBlob("p").tobytes() == p.tobytes() and ws.FetchBlob("g").tobytes() == g.tobytes()
+    np.testing.assert_allclose(ws.FetchBlob("p3"), p - adj, rtol=2e-6, atol=1e-6)
+    if ref is not None:   # the gradient of an optimiser operator is an error in both libraries (SHOULD_NOT_DO_GRADIENT)
+        for lib in (ours, ref):
+            with pytest.raises(c2.EnforceNotMet):
+                lib.GetGradientDefs(c2.CreateOperator("MomentumSGDUpdate", ["g", "m", "lr", "p"], ["g", "m", "p"], device_option=dev), ["g_grad", "", ""])
+
+
+def test_weighted_sum_operator_matches_oracle(oracle):
+    c2, ours, _ = _libs()
+    rng = np.random.default_rng(9)
+    n = 100003
+    grad, param = (rng.standard_normal(n).astype(np.float32) for _ in range(2))
+    dev = c2.DeviceOption(c2.CUDA, 0)
+    ws = ours.Workspace()
+    ws.FeedBlob("grad", torch.from_numpy(grad.copy()).cuda())
+    ws.FeedBlob("param", torch.from_numpy(param.copy()).cuda())
+    ws.FeedBlob("one", torch.tensor([1.0], device="cuda"))
+    ws.FeedBlob("wd", torch.tensor([1e-4], device="cuda"))
+    # optimizer.py:122-124: WeightedSum([param_grad, one, param, wd], param_grad), in place with input 0
+    ws.RunOperatorOnce(c2.CreateOperator("WeightedSum", ["grad", "one", "param", "wd"], ["grad"], device_option=dev))
+    got = ws.FetchBlob("grad")
+    ref = oracle.weighted_sum([grad, param], [1.0, 1e-4])
+    assert got.tobytes() == ref.tobytes()
+    # arity: an odd number of inputs is refused by the schema; in place with an input other than 0 returns false
+    with pytest.raises(c2.EnforceNotMet):
+        ws.RunOperatorOnce(c2.CreateOperator("WeightedSum", ["grad", "one", "param"], ["out"], device_option=dev))
+    with pytest.raises(c2.EnforceNotMet):
+        ws.RunOperatorOnce(c2.CreateOperator("WeightedSum", ["grad", "one", "param", "wd"], ["param"], device_option=dev))
