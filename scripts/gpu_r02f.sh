@@ -3,7 +3,7 @@
 OUT=gpurun_out
 mkdir -p $OUT
 echo "== distill tests"; timeout 900 python -m pytest tests/test_distill_gpu.py tests/test_operator_boundary_gpu.py -q -x 2>&1 | tail -15 | tee $OUT/pytest_distill_r02f.log
-echo "== exchange + full step tests"; timeout 900 python -m pytest tests/test_exchange_gpu.py tests/test_full_step_gpu.py tests/test_head_gpu.py -q 2>&1 | tail -25 | tee $OUT/pytest_exchange_r02f.log
+echo "== exchange + full step tests"; timeout 900 python -m pytest tests/test_exchange_gpu.py tests/test_sgd_gpu.py tests/test_full_step_gpu.py -q 2>&1 | tail -25 | tee $OUT/pytest_exchange_r02f.log
 echo "== bench (short: headline + e2e only)"
 timeout 600 python bench.py --steps 300 --warmup 20 --head-steps -1 --full-steps -1 --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/bench_r02f_short.json | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('value',d['value'],'ms',d['ms_per_step'],'kernel_ms',r['kernel_ms'],'median',r['kernel_ms_median'],'min',r['kernel_ms_min'],'frac',r['frac'])"

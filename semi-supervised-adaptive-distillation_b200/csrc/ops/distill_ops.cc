@@ -432,6 +432,20 @@ int FuseAdaptiveDistillOps(NetDef* net) {
       const float v = ArgumentHelper::GetSingleArgument<OperatorDef, float>(ops[c], "value", 0.f);
       if (grad.empty()) d_loss_value = v;
       else if (v != d_loss_value) { ok = false; break; }
+      // the baked-in d_loss is only the ConstantFill's value if nothing rewrites that blob between the fill and the gradient op
+      // (e.g. a Scale on the loss gradient), and moving the gradient up to the forward op's position is only legal if no op in
+      // between reads or writes the gradient's output blob
+      for (size_t j = c + 1; j < g && ok; ++j)
+        for (const auto& out : ops[j].output())
+          if (out == ops[g].input(4)) ok = false;
+      for (size_t j = i; j < g && ok; ++j) {
+        if (j == f) continue;
+        for (const auto& out : ops[j].output())
+          if (out == ops[g].output(0)) ok = false;
+        for (const auto& in : ops[j].input())
+          if (in == ops[g].output(0)) ok = false;
+      }
+      if (!ok) break;
       // the logits must not be rewritten between the forward and the gradient op
       for (size_t j = f + 1; j < g && ok; ++j)
         for (const auto& out : ops[j].output())

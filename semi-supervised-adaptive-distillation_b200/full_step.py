@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops, parallel, synthetic
-from .head import RetinaNetHead
+from .head import RetinaNetHead, head_param_count
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -211,9 +211,7 @@ class FullDistillStep:
         self.body_params = [p for p in body if p.dim() > 1] + [p for p in body if p.dim() == 1]
         n_body_w = sum(p.numel() for p in self.body_params if p.dim() > 1)
         n_body = sum(p.numel() for p in self.body_params)
-        probe = RetinaNetHead(n_images, shapes, device=self.device, seed=seed)
-        n_head = probe.flat_grads.numel()
-        probe.close()
+        n_head = head_param_count()   # (no throw-away head: its arena is a cudaMalloc of hundreds of MB)
         self.flat_grads = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
         self.flat_params = torch.zeros(n_head + n_body, dtype=torch.float32, device=self.device)
         self.head = RetinaNetHead(n_images, shapes, device=self.device, seed=seed, grad_buffer=self.flat_grads[:n_head],

@@ -32,6 +32,13 @@ def param_names(num_convs=4, k_min=K_MIN):
     return names
 
 
+def head_param_count(dim=256, num_convs=4, num_anchors=9, num_classes=80):
+    """Elements of the head's flat parameter / gradient buffer (retinanet_heads.py:63-245: two towers of num_convs 3x3 convolutions
+    dim -> dim and the two prediction convolutions, each with a bias) — without creating a head."""
+    tower = num_convs * (dim * dim * 9 + dim)
+    return 2 * tower + (num_anchors * num_classes) * (dim * 9 + 1) + (num_anchors * 4) * (dim * 9 + 1)
+
+
 class RetinaNetHead:
     def __init__(self, n_images, level_shapes, dim=256, num_convs=4, num_anchors=9, num_classes=80, prior_prob=0.01,
                  device="cuda", seed=0, grad_buffer=None, cls_output_sigmoid=False, param_buffer=None, compute_f16=False, f16_grad_scale=0.0,

@@ -122,6 +122,9 @@ class LearningRate:
     def __init__(self, solver, lr_blob, momentum_buffers=()):
         self.solver, self.lr_blob, self.momentum_buffers = solver, lr_blob, list(momentum_buffers)
         self.corrections = 0
+        # host copy of the blob's value: the blob is only ever written here, so reading it back every iteration (a full device
+        # synchronisation per training step) is not needed.  One read at construction picks up a value loaded from a checkpoint.
+        self._cur_lr = np.float32(lr_blob.item())
 
     def update(self, cur_iter, new_lr=None):
         """UpdateWorkspaceLr(cur_iter, new_lr): the workspace is the one source of truth for the current rate."""
@@ -129,8 +132,9 @@ class LearningRate:
         if new_lr is None:
             new_lr = get_lr_at_iter(self.solver, cur_iter)
         new_lr = np.float32(new_lr)
-        cur_lr = np.float32(self.lr_blob.item())
+        cur_lr = self._cur_lr
         if cur_lr != new_lr:
+            self._cur_lr = new_lr
             ratio = get_lr_change_ratio(cur_lr, new_lr)
             if ratio > self.solver.LOG_LR_CHANGE_THRESHOLD:
                 logger.info("Changing learning rate {:.6f} -> {:.6f} at iter {:d}".format(cur_lr, new_lr, cur_iter))
