@@ -121,7 +121,56 @@ static bool aligned16(const void* a, const void* b) {
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
 }
 
+// ---- FPN top-down merge: UpsampleNearest(top, 2) + Sum with the lateral (FPN.py:230-249) in one pass ------------------------
+// out[o][Y][X][c] = lateral[o][Y][X][c] + top[o][Y/2][X/2][c] over a tensor viewed as (outer, H_out, W_out, inner):
+// inner = 1 is NCHW (outer = N*C planes), inner = C is channels-last (outer = N).  9 B per output element (4 lateral + 1 top +
+// 4 out) against 17 for the two operators (UpsampleNearest writes 4, Sum reads 4 + 4 and writes 4).  One thread per output
+// float4 along the innermost axis that allows it; exact (a single fp32 add, like math::Add behind SumOp).
+template <bool kVecInner>
+__global__ void __launch_bounds__(256) upsample2_add_kernel(const float* __restrict__ top, const float* __restrict__ lateral,
+                                                            float* __restrict__ out, uint32_t n_vec, uint32_t Wo, uint32_t Ho,
+                                                            uint32_t inner) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  if (kVecInner) {   // inner % 4 == 0: a float4 never crosses a pixel
+    const uint32_t inner4 = inner >> 2, Wi = Wo >> 1, Hi = Ho >> 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      const uint32_t c4 = i % inner4;
+      uint32_t r = i / inner4;
+      const uint32_t X = r % Wo;
+      r /= Wo;
+      const uint32_t Y = r % Ho, o = r / Ho;
+      const float4 a = reinterpret_cast<const float4*>(lateral)[i];
+      const float4 b = __ldg(reinterpret_cast<const float4*>(top) + ((size_t)(o * Hi + (Y >> 1)) * Wi + (X >> 1)) * inner4 + c4);
+      reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+  } else {           // inner == 1, W_out % 4 == 0: a float4 of the output row reads two elements of the top row
+    const uint32_t Wo4 = Wo >> 2, Wi = Wo >> 1, Hi = Ho >> 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      const uint32_t x4 = i % Wo4;
+      uint32_t r = i / Wo4;
+      const uint32_t Y = r % Ho, o = r / Ho;
+      const float4 a = reinterpret_cast<const float4*>(lateral)[i];
+      const float2 b = __ldg(reinterpret_cast<const float2*>(top + ((size_t)o * Hi + (Y >> 1)) * Wi) + x4);
+      reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.x, a.z + b.y, a.w + b.y);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) upsample2_add_scalar_kernel(const float* __restrict__ top, const float* __restrict__ lateral,
+                                                                   float* __restrict__ out, uint32_t n, uint32_t Wo, uint32_t Ho,
+                                                                   uint32_t inner) {
+  const uint32_t stride = gridDim.x * blockDim.x, Wi = Wo >> 1, Hi = Ho >> 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t c = i % inner;
+    uint32_t r = i / inner;
+    const uint32_t X = r % Wo;
+    r /= Wo;
+    const uint32_t Y = r % Ho, o = r / Ho;
+    out[i] = lateral[i] + __ldg(top + ((size_t)(o * Hi + (Y >> 1)) * Wi + (X >> 1)) * inner + c);
+  }
+}
+
 }  // namespace sad
+
 
 using namespace sad;
 
@@ -184,6 +233,33 @@ SAD_EXPORT int sad_upsample_nearest_grad_f32(const float* dy, float* dx, int64_t
     upsample_grad_generic_kernel<<<stream_grid((size_t)n_in), 256, 0, st>>>(dy, dx, (uint32_t)n_in, (uint32_t)H, (uint32_t)W, (uint32_t)scale);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "upsample nearest gradient launch");
+}
+
+SAD_EXPORT int sad_upsample_nearest_add_f32(const float* top, const float* lateral, float* out, int64_t outer, int H_out, int W_out,
+                                            int64_t inner, void* stream) {
+  if (outer < 0 || H_out < 0 || W_out < 0 || inner < 1) return set_error(SAD_ERR_INVALID, "UpsampleNearest+Sum: bad dimension");
+  if ((H_out & 1) || (W_out & 1)) return set_error(SAD_ERR_INVALID, "UpsampleNearest+Sum: the output plane must be twice the top plane (even H, W)");
+  const uint64_t n = (uint64_t)outer * H_out * W_out * inner;
+  if (n == 0) return SAD_OK;
+  if (n >= 0x7fffffffull) return set_error(SAD_ERR_INVALID, "UpsampleNearest+Sum: tensor too large for 32-bit indexing");
+  if (!top || !lateral || !out) return set_error(SAD_ERR_INVALID, "UpsampleNearest+Sum: null tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(top) | reinterpret_cast<uintptr_t>(lateral) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  auto blocks = [&](uint64_t work) {
+    const uint64_t want = (work + 255) / 256, cap = (uint64_t)sms * 16;
+    return (unsigned)(want < cap ? want : cap);
+  };
+  if (aligned && (inner & 3) == 0) {
+    upsample2_add_kernel<true><<<blocks(n / 4), 256, 0, st>>>(top, lateral, out, (uint32_t)(n / 4), (uint32_t)W_out, (uint32_t)H_out, (uint32_t)inner);
+  } else if (aligned && inner == 1 && (W_out & 3) == 0) {
+    upsample2_add_kernel<false><<<blocks(n / 4), 256, 0, st>>>(top, lateral, out, (uint32_t)(n / 4), (uint32_t)W_out, (uint32_t)H_out, 1u);
+  } else {
+    upsample2_add_scalar_kernel<<<blocks(n), 256, 0, st>>>(top, lateral, out, (uint32_t)n, (uint32_t)W_out, (uint32_t)H_out, (uint32_t)inner);
+  }
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "UpsampleNearest+Sum launch");
 }
 
 }  // extern "C"

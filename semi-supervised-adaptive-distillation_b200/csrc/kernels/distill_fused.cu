@@ -75,7 +75,7 @@ struct FusedArgs {
   unsigned int* ctrl;          // [1] final ticket
   unsigned int* flags;         // [8..16) phase-2 (loss) per level: kFxNaN / kFxPosInf / kFxNegInf
   unsigned long long* bar;     // [SAD_MAX_LEVELS] grid-barrier words, one per input: arrival count and PowSum partials in ONE atomic (below)
-  unsigned long long* p2_acc;  // [SAD_MAX_LEVELS][2]: exact fixed-point sum of the loss terms per level (distill_math.cuh, Fx128)
+  unsigned long long* p2_acc;  // [SAD_MAX_LEVELS][4]: exact fixed-point sum of the loss terms per level (distill_math.cuh, Fx128) in four 32-bit pieces
 };
 
 // Grid barrier that carries the data it is there for.  The only thing the CTAs exchange between the phases is the normaliser, so
@@ -479,14 +479,17 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
   }
 
   // ================= every CTA adds its exact level sums to the global ones; the last CTA rounds them once =================
+  // The 128-bit sums travel as four 32-bit pieces, each added into its own 64-bit word (32 bits of headroom: no carries to
+  // propagate, so the adds are fire-and-forget reductions instead of two dependent atomic round trips); the reader puts
+  // the pieces back together modulo 2^128.
   if (stamp) args.stamps[blockIdx.x * 5 + 3] = gtimer();
   __syncthreads();
-  if (tid < args.n_levels) {
-    Fx128 x;
-    x.lo = acc_s[1][tid][0];
-    x.hi = acc_s[1][tid][1];
-    fx_atomic_add(args.p2_acc + 2 * tid, x);
-    if (flag_s[1][tid]) atomicOr(&args.flags[SAD_MAX_LEVELS + tid], flag_s[1][tid]);
+  if (tid < 4 * args.n_levels) {
+    const int k = tid >> 2, piece = tid & 3;
+    const unsigned long long limb = acc_s[1][k][piece >> 1];
+    const unsigned long long v = (piece & 1) ? (limb >> 32) : (limb & 0xffffffffull);
+    if (v) atomicAdd(args.p2_acc + 4 * k + piece, v);
+    if (piece == 0 && flag_s[1][k]) atomicOr(&args.flags[SAD_MAX_LEVELS + k], flag_s[1][k]);
     __threadfence();
   }
   __syncthreads();
@@ -499,14 +502,22 @@ __global__ void __launch_bounds__(kFThreads, 2) distill_fused_kernel(const __gri
     __threadfence();
     const float Np = fmaxf(np_smem, 1.0f);
     if (tid < args.n_levels) {
-      const double s = fx_to_double(__ldcg(args.p2_acc + 2 * tid), __ldcg(args.p2_acc + 2 * tid + 1), __ldcg(args.flags + SAD_MAX_LEVELS + tid));
+      unsigned long long w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = __ldcg(args.p2_acc + 4 * tid + i);
+      // value = w0 + w1 * 2^32 + w2 * 2^64 + w3 * 2^96  (mod 2^128)
+      const unsigned long long lo = w[0] + (w[1] << 32);
+      const unsigned long long c0 = lo < w[0] ? 1ull : 0ull;
+      const unsigned long long hi = (w[1] >> 32) + w[2] + (w[3] << 32) + c0;
+      const double s = fx_to_double(lo, hi, __ldcg(args.flags + SAD_MAX_LEVELS + tid));
       // the arithmetic accumulates twice the summand
       args.lv[tid].loss[0] = (float)(0.5 * s / (double)Np) * args.scale;
     }
     __syncthreads();
     if (tid < SAD_MAX_LEVELS) {   // leave the control block zeroed for the next launch
       args.bar[tid] = 0ull;
-      args.p2_acc[2 * tid] = args.p2_acc[2 * tid + 1] = 0ull;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) args.p2_acc[4 * tid + i] = 0ull;
       args.flags[tid] = args.flags[SAD_MAX_LEVELS + tid] = 0u;
     }
     if (tid == 0) args.ctrl[1] = 0u;
@@ -531,7 +542,7 @@ static size_t fused_units(const sad_distill_level* levels, int n_levels, int num
 }
 
 // layout of the fused workspace: control block [0, 1024): ctrl (16 B) | flags (64 B at 64) | barrier words (64 B at 256) |
-// phase-2 sums (128 B at 512); debug stamps behind it.  sad_workspace_init zeroes it once; every launch leaves it zeroed.
+// phase-2 sums (256 B at 512); debug stamps behind it.  sad_workspace_init zeroes it once; every launch leaves it zeroed.
 constexpr size_t kFusedCtrlBytes = 1024;
 static size_t fused_ws_bytes(size_t) { return kFusedCtrlBytes + (size_t)kMaxRingCtas * 5 * sizeof(unsigned long long); }
 
