@@ -63,3 +63,16 @@ void oracle_upsample_nearest_grad(float* gradInput, const float* gradOutput, int
       for (int j = 0; j < scale_factor; j++) gradInput[ii] += gradOutput[translate_idx_inv((int)ii, d1, d2, d3, scale_factor, i, j)];
   }
 }
+
+/* FPN top-down merge: UpsampleNearest(top, 2) (upsample_nearest_op.cu:102-108) followed by Sum([lateral, td]) (FPN.py:230-249;
+ * math::Add: one fp32 add per element).  Tensors viewed as (outer, H_out, W_out, inner): inner = 1 NCHW, inner = C channels-last. */
+void oracle_upsample2_add(const float* top, const float* lateral, float* out, int64_t outer, int Ho, int Wo, int64_t inner) {
+  const int Hi = Ho / 2, Wi = Wo / 2;
+  for (int64_t o = 0; o < outer; ++o)
+    for (int Y = 0; Y < Ho; ++Y)
+      for (int X = 0; X < Wo; ++X)
+        for (int64_t c = 0; c < inner; ++c) {
+          const int64_t i = ((o * Ho + Y) * Wo + X) * inner + c;
+          out[i] = lateral[i] + top[((o * Hi + Y / 2) * Wi + X / 2) * inner + c];
+        }
+}

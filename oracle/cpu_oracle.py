@@ -68,6 +68,8 @@ def lib():
         l.oracle_select_smooth_l1_loss.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p]
         l.oracle_select_smooth_l1_grad.restype = None
         l.oracle_select_smooth_l1_grad.argtypes = [C.c_int] * 5 + [_f32p] * 4 + [C.c_float, C.c_float, _f32p, _f32p]
+        l.oracle_upsample2_add.restype = None
+        l.oracle_upsample2_add.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int64]
         l.oracle_weighted_sum.restype = None
         l.oracle_weighted_sum.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_void_p), _f32p, _f32p]
         l.oracle_momentum_sgd.restype = None
@@ -272,4 +274,19 @@ def weighted_sum(xs, ws):
     out = np.empty_like(xs[0])
     ptrs = (C.c_void_p * len(xs))(*[x.ctypes.data for x in xs])
     lib().oracle_weighted_sum(xs[0].size, len(xs), ptrs, w, out)
+    return out
+
+
+def upsample2_add(top, lateral, inner=None):
+    """lateral + UpsampleNearest(top, 2).  inner=None: arrays (..., H, W) (NCHW planes); inner=C: channels-last arrays (N, H, W, C)."""
+    top = np.ascontiguousarray(top, dtype=np.float32)
+    lateral = np.ascontiguousarray(lateral, dtype=np.float32)
+    out = np.empty_like(lateral)
+    if inner is None:
+        Ho, Wo = lateral.shape[-2:]
+        outer, inner = lateral.size // (Ho * Wo), 1
+    else:
+        outer, Ho, Wo = lateral.shape[0], lateral.shape[1], lateral.shape[2]
+        assert lateral.shape[3] == inner
+    lib().oracle_upsample2_add(top.reshape(-1), lateral.reshape(-1), out.reshape(-1), outer, Ho, Wo, inner)
     return out

@@ -170,6 +170,10 @@ def lib():
         l.sad_affine_channel_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
         l.sad_upsample_nearest_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.sad_upsample_nearest_grad_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.sad_upsample_nearest_add_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+        l.sad_momentum_sgd_update_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                  C.c_float, C.c_int, C.c_void_p]
+        l.sad_weighted_sum_f32.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
         l.sad_conv3x3_sign_bits_bytes.restype = C.c_size_t
         l.sad_conv3x3_sign_bits_bytes.argtypes = [C.c_int] * 4
         l.sad_conv3x3_pack_weights_multi_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p]

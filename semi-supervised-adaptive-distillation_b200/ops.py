@@ -453,6 +453,31 @@ def upsample_nearest_grad(x, dy, scale=2):
     return dx
 
 
+def upsample_nearest_add(top, lateral, out=None):
+    """FPN top-down merge (FPN.py:230-249) in one pass: lateral + UpsampleNearest(top, 2).  (N, C, H, W) tensors, contiguous NCHW
+    or channels-last (both operands in the same format); out may be `lateral` (in place)."""
+    _require_cuda_any(top, "top")
+    _require_cuda_any(lateral, "lateral")
+    n, c, h, w = lateral.shape
+    if tuple(top.shape) != (n, c, h // 2, w // 2) or h % 2 or w % 2:
+        raise ValueError("top must be (N, C, H/2, W/2) of the lateral's (N, C, H, W)")
+    cl = lateral.is_contiguous(memory_format=torch.channels_last) and not lateral.is_contiguous()
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    if not (top.is_contiguous(memory_format=fmt) and lateral.is_contiguous(memory_format=fmt)):
+        raise ValueError("top and lateral must both be contiguous NCHW or both channels-last")
+    if out is None:
+        out = torch.empty_like(lateral, memory_format=fmt)
+    outer, inner = (n, c) if cl else (n * c, 1)
+    check(lib().sad_upsample_nearest_add_f32(C.c_void_p(top.data_ptr()), C.c_void_p(lateral.data_ptr()), C.c_void_p(out.data_ptr()),
+                                             outer, h, w, inner, _stream()))
+    return out
+
+
+def _require_cuda_any(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError("%s must be a CUDA float32 tensor" % name)
+
+
 def scale_(x, alpha):
     """Scale in place (scale_op.h:31-50): x *= alpha — the momentum correction of a learning-rate change (detector.py:628-648)."""
     _require_cuda(x, torch.float32, "x")

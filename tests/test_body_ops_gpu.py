@@ -142,3 +142,26 @@ def test_scale_and_learning_rate_update_with_momentum_correction():
     for a, b in ((solver.get_lr_at_iter(cfg, 19), solver.get_lr_at_iter(cfg, 20)), (solver.get_lr_at_iter(cfg, 29), solver.get_lr_at_iter(cfg, 30))):
         f = np.float32(f * np.float32(b / a))
     assert torch.all(mom == float(f))
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 40, 64), (1, 7, 10, 14), (2, 256, 10, 14), (1, 3, 4, 6)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fpn_merge_upsample_add_is_exact(oracle, shape, channels_last):
+    """The fused FPN top-down merge (sad_upsample_nearest_add_f32) against the oracle's UpsampleNearest + Sum and against the two
+    stand-alone kernels; float4 paths (W % 4 == 0 / C % 4 == 0) and the scalar path; in place with the lateral."""
+    from sad_b200 import ops
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    lat = torch.randn(n, c, h, w, device="cuda", generator=g)
+    top = torch.randn(n, c, h // 2, w // 2, device="cuda", generator=g)
+    ref = oracle.upsample2_add(top.cpu().numpy(), lat.cpu().numpy())
+    two_kernels = lat + ops.upsample_nearest(top, 2)
+    if channels_last:
+        lat, top = lat.contiguous(memory_format=torch.channels_last), top.contiguous(memory_format=torch.channels_last)
+    out = ops.upsample_nearest_add(top, lat)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert torch.equal(out, two_kernels)
+    assert out.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    ops.upsample_nearest_add(top, lat, out=lat)      # in place with the lateral (FPN.py builds fpn_bottom in a fresh blob; Sum allows in place)
+    assert np.array_equal(lat.cpu().numpy(), ref)

@@ -84,3 +84,16 @@ def test_body_operators_not_implemented_on_cpu_like_the_reference(oplib):
         ws.RunOperatorOnce(c2.CreateOperator("AffineChannel", ["x", "s", "s"], ["y"]))
     with pytest.raises(c2.EnforceNotMet, match="Not Implemented"):
         ws.RunOperatorOnce(c2.CreateOperator("UpsampleNearest", ["x"], ["y"], scale=2))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 4, 6), (1, 5, 2, 2), (1, 1, 10, 14)], ids=lambda s: "x".join(map(str, s)))
+def test_upsample_add_oracle_matches_numpy(oracle, shape):
+    # FPN.py:230-249: td = UpsampleNearest(top, 2); out = Sum([lateral, td]) — in both memory views
+    rng = np.random.default_rng(sum(shape))
+    n, c, h, w = shape
+    lat = rng.standard_normal(shape).astype(np.float32)
+    top = rng.standard_normal((n, c, h // 2, w // 2)).astype(np.float32)
+    ref = lat + top.repeat(2, axis=2).repeat(2, axis=3)
+    assert np.array_equal(oracle.upsample2_add(top, lat), ref)
+    got_cl = oracle.upsample2_add(top.transpose(0, 2, 3, 1), lat.transpose(0, 2, 3, 1), inner=c)
+    assert np.array_equal(got_cl.transpose(0, 3, 1, 2), ref)
