@@ -35,11 +35,15 @@ def main():
 
     ex = None
     results = {}
-    for name in ("whole", "buckets", "graph"):
+    parts = os.environ.get("SAD_EXCHANGE_CHECK_PARTS", "whole,buckets,graph").split(",")
+    for name in parts:
+        print("[rank %d] part %s" % (rank, name), flush=True)
         salt = {"whole": 1, "buckets": 2, "graph": 3}[name]
         flat = mine(rank, salt)
         if ex is None:
+            print("[rank %d] creating the exchange" % rank, flush=True)
             ex = exchange.NativeGradientExchange(flat, world=world, rank=rank)
+            print("[rank %d] exchange created (NCCL %d)" % (rank, exchange.nccl_version()), flush=True)
         else:
             ex.flat = flat
         cuts = [0, n // 5, n // 2, n]
