@@ -304,7 +304,7 @@ def run_head_step(args, rank, world, barrier, native, f16=False):
         peak, src = peak * 2.0, src.replace(" / 2 (tf32 = half the bf16 rate)", " (16-bit operands)").replace(" / 2", "")
     achieved = (fwd_f + bwd_f) / (ms * 1e-3) / 1e12
     kind = "f16" if f16 else "tf32"
-    return {
+    out = {
         "metric": "RetinaNet head distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s",
         "ms_per_step": ms, "steps": K, "images_per_gpu": st.images, "scaling": "weak",
         "workload": "student head fwd (10 convs, 5 levels) + PowSum + fused distill loss+grad + head bwd (dgrad + wgrad) at bs=2/GPU, "
@@ -320,6 +320,8 @@ def run_head_step(args, rank, world, barrier, native, f16=False):
         "gpu_launches": per_step * (K + 5), "launches_per_step": per_step, "cuda_graph": True,
         "dtype": "%s operands, fp32 accumulate (convs); f32 (loss)" % kind, "distill_losses": losses,
     }
+    st.close()
+    return out
 
 
 def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False, teacher_f16=False, student_f16=False):
@@ -411,8 +413,7 @@ def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False,
         if teacher_f16 and student_f16:
             line["baseline_config"] = ("configs[4] geometry and models (bs=1 per GPU); both RetinaNet heads in mixed fp16 (fp16 operands, fp32 "
                                        "accumulation, fp32 losses and parameters) as the config names; the cuDNN bodies (scaffolding) stay tf32")
-    st.head.close()
-    st.teacher_head.close()
+    st.close()     # graph first, then the exchange's communicator (NCCL waits for graphs that captured its collectives), then the heads
     del st
     torch.cuda.empty_cache()
     return line

@@ -71,6 +71,8 @@ def main():
                 ex.join()
             flat.copy_(keep)
             g.replay()
+            torch.cuda.synchronize()
+            del g       # the graph holds a reference on the communicator: it must go before ex.close()
         torch.cuda.synchronize()
         ref = reference(salt)
         err = float((flat.double() - ref).abs().max() / ref.abs().max())

@@ -86,15 +86,17 @@ class NativeGradientExchange:
             _check(lib().sad_exchange_create(uid, self.rank, self.world, C.byref(self.handle)))
 
     def close(self):
+        """Destroy the communicator.  NCCL keeps a reference for every CUDA graph that captured one of its collectives and
+        ncclCommDestroy WAITS until those graphs are gone (measured: an exchange closed while its step's graph was still alive
+        hung the process at exit) — destroy the graphs first (FullDistillStep.close does)."""
         if getattr(self, "handle", None):
             lib().sad_exchange_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        # deliberately not close(): object destruction order at interpreter exit is arbitrary, and tearing the communicator down
+        # before a graph that references it blocks forever; an exchange that was not closed explicitly is left to process exit
+        pass
 
     # ---- whole buffer on the caller's stream (no overlap) ----
     def allreduce(self, async_op=False):

@@ -406,6 +406,18 @@ class FullDistillStep:
             torch.cuda.synchronize()
             return False
 
+    def close(self):
+        """Release the step's native objects in the order NCCL needs: the captured graph (it references the exchange's communicator)
+        before the exchange, then the heads."""
+        torch.cuda.synchronize()
+        self.graph = None
+        import gc
+        gc.collect()
+        if hasattr(self.exchange, "close"):
+            self.exchange.close()
+        self.head.close()
+        self.teacher_head.close()
+
     def run(self):
         if getattr(self, "graph", None) is not None:
             self.graph.replay()

@@ -73,6 +73,13 @@ class DistillHeadStep:
             self.forward_backward()
         return self
 
+    def close(self):
+        torch.cuda.synchronize()
+        self.graph = None
+        if hasattr(self.exchange, "close"):
+            self.exchange.close()
+        self.head.close()
+
     def run(self):
         if self.graph is not None:
             self.graph.replay()
