@@ -255,7 +255,7 @@ def _tensor_peak():
     return 1400.0 / 2.0, "fallback: 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) / 2"
 
 
-def run_head_step(args, rank, world, barrier, native, f16=False):
+def run_head_step(args, rank, world, barrier, native, f16=False, x3=False):
     """the widened path on every rank's own 2-image shard — student head forward, PowSum, fused
     distillation loss + gradient, head backward (device work replayed from ONE CUDA graph), then the step's only
     collective (SUM-allreduce of the 25.9 MB flat head-gradient buffer) and the momentum-SGD update (one launch)."""
@@ -264,7 +264,7 @@ def run_head_step(args, rank, world, barrier, native, f16=False):
     from sad_b200.step import DistillHeadStep
 
     K = args.head_steps or min(args.steps, 100)
-    st = DistillHeadStep(n_images=2, scale_px=600, world=world, rank=rank, compute_f16=f16)
+    st = DistillHeadStep(n_images=2, scale_px=600, world=world, rank=rank, compute_f16=f16, compute_f32x3=x3)
     n0 = native.lib().sad_launch_count()
     st.forward_backward()
     per_step = int(native.lib().sad_launch_count() - n0)
@@ -303,7 +303,9 @@ def run_head_step(args, rank, world, barrier, native, f16=False):
     if f16:   # 16-bit operands: the measured sustained bf16 rate itself
         peak, src = peak * 2.0, src.replace(" / 2 (tf32 = half the bf16 rate)", " (16-bit operands)").replace(" / 2", "")
     achieved = (fwd_f + bwd_f) / (ms * 1e-3) / 1e12
-    kind = "f16" if f16 else "tf32"
+    kind = "f16" if f16 else ("tf32 x3 passes (3xTF32, fp32-accurate)" if x3 else "tf32")
+    if x3:   # three tensor-core passes per product: the tensor work is 3x the algorithmic flops
+        achieved *= 3.0
     out = {
         "metric": "RetinaNet head distill-step imgs/sec", "value": world * st.images / (ms * 1e-3), "unit": "imgs/s",
         "ms_per_step": ms, "steps": K, "images_per_gpu": st.images, "scaling": "weak",
@@ -584,11 +586,13 @@ def main():
     copy_only_ms = float(copy_dt.item()) * 1e3
     del dev_in, dev_out
 
-    head_line = head_f16_line = None
+    head_line = head_f16_line = head_x3_line = None
     if args.head_steps >= 0:
         head_line = run_head_step(args, rank, world, barrier, native)
         if args.teacher_f16:
             head_f16_line = run_head_step(args, rank, world, barrier, native, f16=True)
+        if world == 1:   # the cost of the fp32-accurate mode (what matches the reference's fp32 convolution to 1e-4)
+            head_x3_line = run_head_step(args, rank, world, barrier, native, x3=True)
 
     full_line = full16_line = full5_line = full5_f16_line = None
     if args.full_steps >= 0:
@@ -648,6 +652,11 @@ def main():
     if head_f16_line:
         line["head_step_f16"] = head_f16_line
         line["gpu_launches"] += head_f16_line["gpu_launches"]
+    if head_x3_line:
+        head_x3_line["roofline"]["note"] = ("achieved = 3 x algorithmic conv flops (W_hi X_hi + W_hi X_lo + W_lo X_hi) / whole step time; "
+                                            "imgs/s is the algorithmic rate.  " + head_x3_line["roofline"]["note"])
+        line["head_step_f32x3"] = head_x3_line
+        line["gpu_launches"] += head_x3_line["gpu_launches"]
     if head_line:
         line["head_step"] = head_line
     if full_line:
@@ -663,7 +672,7 @@ def main():
         line["full_step_config5_heads_f16"] = full5_f16_line
         line["gpu_launches"] += full5_f16_line["gpu_launches"]
     step_imgs = {}
-    for key, obj in (("head_step", head_line), ("head_step_f16", head_f16_line), ("full_step", full_line), ("full_step_bs16", full16_line),
+    for key, obj in (("head_step", head_line), ("head_step_f16", head_f16_line), ("head_step_f32x3", head_x3_line), ("full_step", full_line), ("full_step_bs16", full16_line),
                      ("full_step_config5", full5_line), ("full_step_config5_heads_f16", full5_f16_line)):
         if obj:
             step_imgs[key] = {"imgs_s": obj["value"], "ms_per_step": obj["ms_per_step"], "allreduce_ms": obj.get("allreduce_ms"),

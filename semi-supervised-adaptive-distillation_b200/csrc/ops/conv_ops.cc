@@ -57,7 +57,13 @@ struct HeadConvArgs {
     CAFFE_ENFORCE(pt == 1 && pl == 1 && pb == 1 && pr == 1, "B200 head convolution: only pad 1 is implemented");
     CAFFE_ENFORCE(dh == 1 && dw == 1, "B200 head convolution: dilation is not implemented");
     CAFFE_ENFORCE(group == 1, "B200 head convolution: groups are not implemented");
+    // conv_op_cudnn.cc:77-86,494-498: the reference only lets cuDNN use reduced-precision tensor-core math when the operator
+    // carries enable_tensor_core = 1 (default 0: plain fp32).  Here every mode runs on the tensor cores; the flag selects the
+    // arithmetic: 0 (default) = 3xTF32, fp32-accurate (matches the reference's fp32 convolution to ~1e-5), 1 = single-pass tf32
+    // (10-bit operand mantissas, 3x faster).
+    tensor_core_math = op->GetSingleArgument<int>("enable_tensor_core", 0) != 0;
   }
+  bool tensor_core_math = false;
 };
 
 // grows a member tensor to at least `floats` elements and returns its storage (a default-constructed tensor has
@@ -106,18 +112,27 @@ bool HeadConvOp<float, CUDAContext>::RunOnDevice() {
   float* y = Y->mutable_data<float>();
   if (Y->size() == 0) return true;
   void* st = context_.cuda_stream();
-  float* xt = Ensure(&x_nhwc_, (size_t)X.size());
-  float* pk = Ensure(&packed_, sad_conv3x3_packed_bytes(C, M) / sizeof(float));
+  const bool x3 = !args_.tensor_core_math;
+  const size_t pixels = (size_t)N * H * Wd;
+  float* xt = Ensure(&x_nhwc_, x3 ? pixels * 2 * sad_conv3x3_split_channels(C) : (size_t)X.size());
+  float* pk = Ensure(&packed_, (x3 ? sad_conv3x3_packed_bytes_f32x3(C, M, 0) : sad_conv3x3_packed_bytes(C, M)) / sizeof(float));
   sad_layout_level ll{X.data<float>(), xt, N, H, Wd};
-  EnforceSadConv(sad_nchw_to_nhwc_f32(&ll, 1, C, st), "sad_nchw_to_nhwc_f32");
-  EnforceSadConv(sad_conv3x3_pack_weights_f32(W.data<float>(), C, M, 0, pk, st), "sad_conv3x3_pack_weights_f32");
+  sad_pack_item pi{W.data<float>(), pk, C, M, 0};
   sad_conv_level cl{};
   cl.x_nhwc = xt;
   cl.y_nchw = y;
   cl.N = N;
   cl.H = H;
   cl.W = Wd;
-  EnforceSadConv(sad_conv3x3_fwd_f32(&cl, 1, pk, bias, C, M, 0, st), "sad_conv3x3_fwd_f32");
+  if (x3) {
+    EnforceSadConv(sad_nchw_to_nhwc_f32x3(&ll, 1, C, st), "sad_nchw_to_nhwc_f32x3");
+    EnforceSadConv(sad_conv3x3_pack_weights_multi_f32x3(&pi, 1, st), "sad_conv3x3_pack_weights_multi_f32x3");
+    EnforceSadConv(sad_conv3x3_fwd_f32x3(&cl, 1, pk, bias, C, M, 0, st), "sad_conv3x3_fwd_f32x3");
+  } else {
+    EnforceSadConv(sad_nchw_to_nhwc_f32(&ll, 1, C, st), "sad_nchw_to_nhwc_f32");
+    EnforceSadConv(sad_conv3x3_pack_weights_f32(W.data<float>(), C, M, 0, pk, st), "sad_conv3x3_pack_weights_f32");
+    EnforceSadConv(sad_conv3x3_fwd_f32(&cl, 1, pk, bias, C, M, 0, st), "sad_conv3x3_fwd_f32");
+  }
   return true;
 }
 
@@ -159,34 +174,48 @@ bool HeadConvGradientOp<float, CUDAContext>::RunOnDevice() {
   }
   const bool want_dx = OutputSize() == 3 || (no_bias_ && OutputSize() == 2);
   void* st = context_.cuda_stream();
-  float* xt = Ensure(&x_nhwc_, (size_t)X.size());
-  float* dyt = Ensure(&dy_nhwc_, (size_t)dY.size());
+  const bool x3 = !args_.tensor_core_math;
+  const size_t pixels = (size_t)N * H * Wd;
+  float* xt = Ensure(&x_nhwc_, x3 ? pixels * 2 * sad_conv3x3_split_channels(C) : (size_t)X.size());
+  float* dyt = Ensure(&dy_nhwc_, x3 ? pixels * 2 * sad_conv3x3_split_channels(M) : (size_t)dY.size());
   if (X.size()) {
     sad_layout_level lx{X.data<float>(), xt, N, H, Wd};
-    EnforceSadConv(sad_nchw_to_nhwc_f32(&lx, 1, C, st), "sad_nchw_to_nhwc_f32(X)");
     sad_layout_level ld{dY.data<float>(), dyt, N, H, Wd};
-    EnforceSadConv(sad_nchw_to_nhwc_f32(&ld, 1, M, st), "sad_nchw_to_nhwc_f32(dY)");
+    if (x3) {
+      EnforceSadConv(sad_nchw_to_nhwc_f32x3(&lx, 1, C, st), "sad_nchw_to_nhwc_f32x3(X)");
+      EnforceSadConv(sad_nchw_to_nhwc_f32x3(&ld, 1, M, st), "sad_nchw_to_nhwc_f32x3(dY)");
+    } else {
+      EnforceSadConv(sad_nchw_to_nhwc_f32(&lx, 1, C, st), "sad_nchw_to_nhwc_f32(X)");
+      EnforceSadConv(sad_nchw_to_nhwc_f32(&ld, 1, M, st), "sad_nchw_to_nhwc_f32(dY)");
+    }
   }
   sad_wgrad_level wl{xt, dyt, N, H, Wd};
   const size_t wsb = sad_conv3x3_wgrad_workspace_bytes(&wl, 1, C, M);
   // 256-byte aligned scratch inside a float tensor
   float* raw = Ensure(&scratch_, wsb / sizeof(float) + 64);
   void* ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(raw) + 255) & ~(uintptr_t)255);
-  EnforceSadConv(sad_conv3x3_wgrad_f32(&wl, 1, C, M, dw, db, 0, ws, wsb, st), "sad_conv3x3_wgrad_f32");
+  if (x3) EnforceSadConv(sad_conv3x3_wgrad_f32x3(&wl, 1, C, M, dw, db, 0, ws, wsb, st), "sad_conv3x3_wgrad_f32x3");
+  else EnforceSadConv(sad_conv3x3_wgrad_f32(&wl, 1, C, M, dw, db, 0, ws, wsb, st), "sad_conv3x3_wgrad_f32");
   if (want_dx) {
     auto* dX = Output(no_bias_ ? 1 : 2);
     dX->ResizeLike(X);
     float* dx = dX->mutable_data<float>();
     if (X.size()) {
-      float* pk = Ensure(&packed_, sad_conv3x3_packed_bytes(C, M) / sizeof(float));
-      EnforceSadConv(sad_conv3x3_pack_weights_f32(W.data<float>(), C, M, 1, pk, st), "sad_conv3x3_pack_weights_f32");
+      float* pk = Ensure(&packed_, (x3 ? sad_conv3x3_packed_bytes_f32x3(C, M, 1) : sad_conv3x3_packed_bytes(C, M)) / sizeof(float));
       sad_conv_level cl{};
       cl.x_nhwc = dyt;
       cl.y_nchw = dx;
       cl.N = N;
       cl.H = H;
       cl.W = Wd;
-      EnforceSadConv(sad_conv3x3_fwd_f32(&cl, 1, pk, nullptr, M, C, 0, st), "sad_conv3x3_fwd_f32(dgrad)");
+      if (x3) {
+        sad_pack_item pi{W.data<float>(), pk, C, M, 1};
+        EnforceSadConv(sad_conv3x3_pack_weights_multi_f32x3(&pi, 1, st), "sad_conv3x3_pack_weights_multi_f32x3");
+        EnforceSadConv(sad_conv3x3_fwd_f32x3(&cl, 1, pk, nullptr, M, C, 0, st), "sad_conv3x3_fwd_f32x3(dgrad)");
+      } else {
+        EnforceSadConv(sad_conv3x3_pack_weights_f32(W.data<float>(), C, M, 1, pk, st), "sad_conv3x3_pack_weights_f32");
+        EnforceSadConv(sad_conv3x3_fwd_f32(&cl, 1, pk, nullptr, M, C, 0, st), "sad_conv3x3_fwd_f32(dgrad)");
+      }
     }
   }
   return true;

@@ -30,7 +30,7 @@ def get_retinanet_bias_init(cfg=None):
 
 
 def add_fpn_retinanet_outputs(blobs_in, gpu_id=0, train=True, dim_in=FPN_DIM, cfg=None, scope="",
-                              k_min=RPN_MIN_LEVEL, k_max=RPN_MAX_LEVEL):
+                              k_min=RPN_MIN_LEVEL, k_max=RPN_MAX_LEVEL, enable_tensor_core=None):
     """The RetinaNet head as the reference emits it (retinanet_heads.py:63-245): per level two towers of NUM_CONVS
     Conv3x3 + in-place Relu, then the class-logit and box convolutions; level k_min creates the parameters, the other levels
     reuse them (ConvShared = a Conv reading level k_min's `_w` / `_b` blobs); `train=False` (the teacher,
@@ -55,8 +55,11 @@ def add_fpn_retinanet_outputs(blobs_in, gpu_id=0, train=True, dim_in=FPN_DIM, cf
         if lvl == k_min:
             params.append((pre + name + "_w", (cout, dim_in, 3, 3), gauss))
             params.append((pre + name + "_b", (cout,), bias_init))
+        # enable_tensor_core: the reference's own Conv argument (conv_op_cudnn.cc:77-86), absent from the graphs Detectron emits
+        # (= 0: fp32 arithmetic; this library then computes in 3xTF32).  1 selects single-pass tf32.
+        extra = {} if enable_tensor_core is None else {"enable_tensor_core": int(enable_tensor_core)}
         ops.append(c2.CreateOperator("Conv", [bl_in, pre + owner + "_w", pre + owner + "_b"], [pre + name], device_option=dev,
-                                     engine="CUDNN", kernel=3, pad=1, stride=1, order="NCHW"))
+                                     engine="CUDNN", kernel=3, pad=1, stride=1, order="NCHW", **extra))
         return pre + name
 
     def tower(kind, lvl):

@@ -19,12 +19,13 @@ from .head import RetinaNetHead
 
 class DistillHeadStep:
     def __init__(self, n_images=2, scale_px=600, world=1, rank=0, seed=1234, temperature=1.0, power=1.8, alpha=0.5,
-                 gamma=2.0, beta=0.0, device=None, level_shapes=None, dim=256, num_convs=4, with_bbox_branch=True, compute_f16=False):
+                 gamma=2.0, beta=0.0, device=None, level_shapes=None, dim=256, num_convs=4, with_bbox_branch=True, compute_f16=False, compute_f32x3=False):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.world, self.rank = int(world), int(rank)
         shapes = level_shapes if level_shapes is not None else synthetic.level_shapes(scale_px)
         # same weights on every rank; compute_f16: the head's convolutions (forward + backward) on fp16 operands, fp32 everything else
-        self.head = RetinaNetHead(n_images, shapes, dim=dim, num_convs=num_convs, device=self.device, seed=seed, compute_f16=compute_f16)
+        self.head = RetinaNetHead(n_images, shapes, dim=dim, num_convs=num_convs, device=self.device, seed=seed, compute_f16=compute_f16,
+                                  compute_f32x3=compute_f32x3)
         g = torch.Generator(device=self.device).manual_seed(seed + 7919 * (rank + 1))              # different images per rank
         N, A, Cc = n_images, synthetic.NUM_ANCHORS, synthetic.NUM_CLASSES
         # synthetic FPN features: post-conv, zero-mean

@@ -143,8 +143,13 @@ def _conv_close(got, ref, what, max_tol=3e-3, rms_tol=1e-3):
     assert np.sqrt((d ** 2).mean()) <= rms_tol * np.sqrt((ref ** 2).mean()), what
 
 
-def test_head_conv_ops_by_name_forward_and_gradient(oplib, oracle):
+@pytest.mark.parametrize("tensor_core", [None, 1], ids=["default: fp32-accurate (3xTF32)", "enable_tensor_core=1: tf32"])
+def test_head_conv_ops_by_name_forward_and_gradient(oplib, oracle, tensor_core):
+    """Conv / ConvGradient / Relu / ReluGradient through the registry.  Without enable_tensor_core the operators compute like the
+    reference's fp32 convolution (gate 1e-4 max / 1e-4 rms against the reference-pinned oracle); with enable_tensor_core = 1
+    (conv_op_cudnn.cc:77-86) in single-pass tf32 (gate 3e-3 / 1e-3)."""
     from sad_b200 import c2
+    tol = dict(max_tol=1e-4, rms_tol=1e-4) if tensor_core is None else {}
     rng = np.random.default_rng(77)
     N, C, M, H, W = 2, 64, 36, 10, 24
     x = rng.standard_normal((N, C, H, W)).astype(np.float32)
@@ -155,6 +160,8 @@ def test_head_conv_ops_by_name_forward_and_gradient(oplib, oracle):
     dy = rng.standard_normal((N, M, H, W)).astype(np.float32)
     dev = c2.DeviceOption(c2.CUDA, 0)
     conv_args = dict(kernel=3, pad=1, stride=1, order="NCHW")
+    if tensor_core is not None:
+        conv_args["enable_tensor_core"] = tensor_core
     fwd = [c2.CreateOperator("Conv", ["fpn", "w0", "b0"], ["t"], device_option=dev, engine="CUDNN", **conv_args),
            c2.CreateOperator("Relu", ["t"], ["t"], device_option=dev),
            c2.CreateOperator("Conv", ["t", "w1", "b1"], ["pred"], device_option=dev, engine="CUDNN", **conv_args)]
@@ -165,8 +172,8 @@ def test_head_conv_ops_by_name_forward_and_gradient(oplib, oracle):
         ws.RunOperatorOnce(op)
     t_ref = oracle.relu(oracle.conv2d_fwd(x, w0, b0))
     pred_ref = oracle.conv2d_fwd(t_ref, w1, b1)
-    _conv_close(ws.FetchBlob("t"), t_ref, "tower activation")
-    _conv_close(ws.FetchBlob("pred"), pred_ref, "prediction")
+    _conv_close(ws.FetchBlob("t"), t_ref, "tower activation", **tol)
+    _conv_close(ws.FetchBlob("pred"), pred_ref, "prediction", **tol)
     # backward: gradient defs from the registered makers, run through the same registry
     g_out = {"pred": "pred_grad"}
     for op in reversed(fwd):
@@ -181,7 +188,7 @@ def test_head_conv_ops_by_name_forward_and_gradient(oplib, oracle):
     dt = oracle.relu_grad(ws.FetchBlob("t"), dt)
     dw0, db0, dx = oracle.conv2d_bwd(x, w0, dt)
     for name, ref in (("w1_grad", dw1), ("b1_grad", db1), ("w0_grad", dw0), ("b0_grad", db0), ("fpn_grad", dx)):
-        _conv_close(ws.FetchBlob(name), ref, name)
+        _conv_close(ws.FetchBlob(name), ref, name, **tol)
 
 
 def test_head_conv_op_rejects_shapes_outside_its_class(oplib):
@@ -199,15 +206,17 @@ def test_head_conv_op_rejects_shapes_outside_its_class(oplib):
         ws.RunOperatorOnce(c2.CreateOperator("Conv", ["x", "w5"], ["y"], device_option=dev, kernel=3, pad=1, stride=1))
 
 
-def test_head_netdef_through_the_operators_equals_the_fused_head_object(oplib):
+@pytest.mark.parametrize("tensor_core", [1, None], ids=["enable_tensor_core=1 vs the tf32 head", "default vs the 3xTF32 head"])
+def test_head_netdef_through_the_operators_equals_the_fused_head_object(oplib, tensor_core):
     # retinanet_heads.py:63-245 emitted op by op (90 Conv / Relu operators, ConvShared levels reading level 3's blobs) against
     # sad_head_forward, which runs the same graph as 10 launches.  Same kernels, same packed tf32 weights, same rounding points
     # (activations are rounded when their channels-last copy is written), so the results agree to fp32 round-off.
     from sad_b200 import c2, retinanet_heads
     from sad_b200.head import RetinaNetHead
     shapes, n, dim = [(16, 24), (8, 12), (4, 6), (2, 3), (1, 2)], 2, 32
-    student = RetinaNetHead(n, shapes, dim=dim, seed=9)
-    teacher = RetinaNetHead(n, shapes, dim=dim, seed=9, cls_output_sigmoid=True)
+    x3 = tensor_core is None
+    student = RetinaNetHead(n, shapes, dim=dim, seed=9, compute_f32x3=x3)
+    teacher = RetinaNetHead(n, shapes, dim=dim, seed=9, cls_output_sigmoid=True, compute_f32x3=x3)
     g = torch.Generator(device="cuda").manual_seed(4)
     for name, p in student.params.items():
         p.normal_(0.0, 0.08 if name.endswith("_w") else 0.1, generator=g)
@@ -218,7 +227,7 @@ def test_head_netdef_through_the_operators_equals_the_fused_head_object(oplib):
     blobs_in = ["gpu_0/fpn_%d" % l for l in (7, 6, 5, 4, 3)]
     for train, scope, ref_cls in ((True, "", cls), (False, "teacher/", prob)):
         net, params, cls_out, box_out = retinanet_heads.add_fpn_retinanet_outputs(
-            [b.replace("gpu_0/", "gpu_0/" + scope) for b in blobs_in], train=train, dim_in=dim, scope=scope)
+            [b.replace("gpu_0/", "gpu_0/" + scope) for b in blobs_in], train=train, dim_in=dim, scope=scope, enable_tensor_core=tensor_core)
         ws = oplib.Workspace()
         for l, f in zip((3, 4, 5, 6, 7), fpn):
             ws.FeedBlob("gpu_0/%sfpn_%d" % (scope, l), f)
