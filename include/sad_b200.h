@@ -140,6 +140,17 @@ typedef struct sad_sgd_segment {
 int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
                          const float* lr, float momentum, int nesterov, void* stream);
 
+/* Overflow guard of mixed-precision training (BASELINE.json configs[4]: fp16 compute).  The fp16 head scales its gradient tensors by
+ * a loss scale (sad_head_config.f16_grad_scale); when a gradient leaves fp16's range the parameter gradients come out inf / NaN.
+ *   sad_nonfinite_flag_f32        *flag |= 1 if any of x[0 .. n) is inf or NaN (one pass, 4 B/element; run it on the REDUCED gradient
+ *                                 so that every rank of a data-parallel job takes the same decision)
+ *   sad_momentum_sgd_guarded_f32  sad_momentum_sgd_f32 that leaves parameters, gradients and the update history untouched when
+ *                                 *skip_if_nonzero != 0: the step is skipped on the device, no host round trip
+ * The caller lowers the scale (sad_head_set_f16_grad_scale) and clears the flag when it next looks at it (solver.LossScaler). */
+int sad_nonfinite_flag_f32(const float* x, int64_t n, uint32_t* flag, void* stream);
+int sad_momentum_sgd_guarded_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
+                                 const float* lr, float momentum, int nesterov, const uint32_t* skip_if_nonzero, void* stream);
+
 /* The same two optimiser steps as the single-blob operators the reference graph names (operator classes MomentumSGDUpdate,
  * MomentumSGD and WeightedSum in libcaffe2_detectron_ops_gpu.so forward here):
  *   MomentumSGDUpdateOp<float, CUDAContext>::RunOnDevice   caffe2/caffe2/sgd/momentum_sgd_op.h:90-127, kernel momentum_sgd_op_gpu.cu:23-54
@@ -418,6 +429,10 @@ void sad_head_default_config(sad_head_config* cfg); /* dim 256, num_convs 4, cls
 int sad_head_create(const sad_head_config* cfg, sad_head** out); /* on the current device */
 void sad_head_destroy(sad_head* head);
 size_t sad_head_device_bytes(const sad_head* head);
+/* compute_f16 heads: change the loss scale of the gradient tensors (a power of two) for the following backward passes.  The scale is
+ * passed to the kernels by value: a step captured in a CUDA graph has to be captured again after a change. */
+int sad_head_set_f16_grad_scale(sad_head* head, float scale);
+float sad_head_f16_grad_scale(const sad_head* head);
 /* fpn_nchw[l]: (N, dim, H_l, W_l); cls_logits_nchw[l]: (N, cls_out, H_l, W_l); bbox_pred_nchw[l]: (N, bbox_out, H_l, W_l).
  * training != 0 also prepares the data-gradient weights (required before sad_head_backward). */
 int sad_head_forward(sad_head* head, const sad_head_weights* weights, const float* const* fpn_nchw,

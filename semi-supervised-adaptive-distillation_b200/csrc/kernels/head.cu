@@ -295,6 +295,13 @@ SAD_EXPORT void sad_head_destroy(sad_head* h) {
 
 SAD_EXPORT size_t sad_head_device_bytes(const sad_head* h) { return h ? h->arena_bytes : 0; }
 
+SAD_EXPORT int sad_head_set_f16_grad_scale(sad_head* h, float scale) {
+  if (!h || !(scale > 0.f) || !(scale < 3.0e38f)) return set_error(SAD_ERR_INVALID, "sad_head_set_f16_grad_scale: the scale must be positive and finite");
+  h->cfg.f16_grad_scale = scale;
+  return SAD_OK;
+}
+SAD_EXPORT float sad_head_f16_grad_scale(const sad_head* h) { return h ? grad_scale(h) : 0.f; }
+
 SAD_EXPORT int sad_head_copy_activation(const sad_head* h, int tower, int conv, int level, float* dst_nhwc, void* stream) {
   if (!h || !dst_nhwc || tower < 0 || tower > 1 || level < 0 || level >= h->cfg.n_levels || conv < -1 || conv >= h->cfg.num_convs)
     return set_error(SAD_ERR_INVALID, "sad_head_copy_activation: bad argument");

@@ -25,6 +25,7 @@ struct SgdArgs {
   int32_t n_segs, nesterov;
   int64_t total;
   float momentum;
+  const uint32_t* skip_if_nonzero;   // NULL, or a device word: the launch leaves every buffer untouched when it is not 0
 };
 
 __device__ __forceinline__ void sgd_elem(float& p, float& g, float& m, float LR, float momentum, float mult, float wd, bool nesterov) {
@@ -43,6 +44,7 @@ __device__ __forceinline__ void sgd_elem(float& p, float& g, float& m, float LR,
 }
 
 __global__ void __launch_bounds__(256) momentum_sgd_kernel(const SgdArgs a) {
+  if (a.skip_if_nonzero && __ldg(a.skip_if_nonzero) != 0u) return;   // a gradient overflowed (mixed fp16): skip the step
   const float LR = __ldg(a.lr);
   const int64_t n4 = a.total >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -123,11 +125,37 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(const WsumArgs a, flo
   }
 }
 
+// ---- *flag |= (any element of x is inf or NaN): the overflow test of mixed-precision training --------------------------------
+__global__ void __launch_bounds__(256) nonfinite_flag_kernel(const float* __restrict__ x, int64_t n, uint32_t* flag) {
+  const int64_t n4 = n >> 2, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t q = tid; q < n4; q += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + q);
+    // exponent all ones <=> inf or NaN
+    bad |= ((__float_as_uint(v.x) & 0x7f800000u) == 0x7f800000u) | ((__float_as_uint(v.y) & 0x7f800000u) == 0x7f800000u) |
+           ((__float_as_uint(v.z) & 0x7f800000u) == 0x7f800000u) | ((__float_as_uint(v.w) & 0x7f800000u) == 0x7f800000u);
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) bad |= (__float_as_uint(x[i]) & 0x7f800000u) == 0x7f800000u;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
 }  // namespace sad
 
 using namespace sad;
 
 extern "C" {
+
+SAD_EXPORT int sad_nonfinite_flag_f32(const float* x, int64_t n, uint32_t* flag, void* stream) {
+  if (n < 0 || !flag) return set_error(SAD_ERR_INVALID, "nonfinite flag: bad argument");
+  if (n == 0) return SAD_OK;
+  if (!x || (reinterpret_cast<uintptr_t>(x) & 15)) return set_error(SAD_ERR_INVALID, "nonfinite flag: x must be a 16-byte aligned device buffer");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n / 4 + 255) / 256 + 1, cap = (int64_t)sms * 8;
+  nonfinite_flag_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, flag);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "nonfinite flag launch");
+}
 
 SAD_EXPORT int sad_momentum_sgd_update_f32(const float* grad, const float* mom, const float* lr, const float* param, float* grad_out,
                                            float* mom_out, float* param_out, int64_t n, float momentum, int nesterov, void* stream) {
@@ -165,8 +193,8 @@ SAD_EXPORT int sad_weighted_sum_f32(const float* const* xs, const float* const* 
   return check_cuda(cudaGetLastError(), "WeightedSum launch");
 }
 
-SAD_EXPORT int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
-                                    const float* lr, float momentum, int nesterov, void* stream) {
+static int momentum_sgd_impl(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
+                             const float* lr, float momentum, int nesterov, const uint32_t* skip_if_nonzero, void* stream) {
   if (!segments || n_segments < 1 || n_segments > SAD_MAX_SGD_SEGMENTS)
     return set_error(SAD_ERR_INVALID, "momentum sgd: n_segments must be in [1, SAD_MAX_SGD_SEGMENTS]");
   if (!lr) return set_error(SAD_ERR_INVALID, "momentum sgd: null learning rate");
@@ -191,6 +219,7 @@ SAD_EXPORT int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_b
   a.nesterov = nesterov;
   a.total = end;
   a.momentum = momentum;
+  a.skip_if_nonzero = skip_if_nonzero;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t want = (end / 4 + 255) / 256;
@@ -199,6 +228,15 @@ SAD_EXPORT int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_b
   momentum_sgd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   count_launch(1);
   return check_cuda(cudaGetLastError(), "momentum sgd launch");
+}
+
+SAD_EXPORT int sad_momentum_sgd_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
+                                    const float* lr, float momentum, int nesterov, void* stream) {
+  return momentum_sgd_impl(param, grad, momentum_buf, segments, n_segments, lr, momentum, nesterov, nullptr, stream);
+}
+SAD_EXPORT int sad_momentum_sgd_guarded_f32(float* param, float* grad, float* momentum_buf, const sad_sgd_segment* segments, int n_segments,
+                                            const float* lr, float momentum, int nesterov, const uint32_t* skip_if_nonzero, void* stream) {
+  return momentum_sgd_impl(param, grad, momentum_buf, segments, n_segments, lr, momentum, nesterov, skip_if_nonzero, stream);
 }
 
 }  // extern "C"

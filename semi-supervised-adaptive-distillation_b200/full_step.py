@@ -194,6 +194,9 @@ class FullDistillStep:
         # producing the next bucket (head bucket under the whole body backward, res5 + FPN under res4 + res3, ...), and the
         # optimiser waits only for the join (optimizer.py:72-92 issues its NCCLAllreduce ops after the whole backward)
         self.overlap_exchange = bool(overlap_exchange)
+        self.student_head_f16 = bool(student_head_f16)
+        self.overflow = torch.zeros((), dtype=torch.int32, device=self.device)   # set by the device when a reduced gradient is inf / NaN
+        self.loss_scaler = None
         self.teacher_stream = torch.cuda.Stream(device=self.device)
         self.lr, self.mom, self.wd = lr, momentum, weight_decay
         shapes = synthetic.level_shapes(scale_px)
@@ -435,7 +438,27 @@ class FullDistillStep:
     def sgd(self):
         """Scale(2x bias gradients) + WeightedSum weight decay + MomentumSGDUpdate of every trainable blob (optimizer.py:95-130)
         in ONE launch over the flat [head | body] buffers."""
+        if self.student_head_f16:
+            # mixed fp16 (configs[4]): an overflow of the loss-scaled fp16 gradient tensors shows up as inf / NaN in the head's reduced
+            # parameter gradients; the flag makes the optimiser launch a no-op on every rank alike (solver.LossScaler lowers the scale)
+            ops.nonfinite_flag(self.flat_grads[:self.n_head], self.overflow)
+            ops.momentum_sgd(self.flat_params, self.flat_grads, self.momentum, self.sgd_segments, self.lr_dev, momentum=self.mom,
+                             skip_flag=self.overflow)
+            return
         ops.momentum_sgd(self.flat_params, self.flat_grads, self.momentum, self.sgd_segments, self.lr_dev, momentum=self.mom)
+
+    def update_loss_scale(self, force=False):
+        """Host side of dynamic loss scaling (solver.LossScaler): call once per step; looks at the device flag every few dozen steps,
+        halves / doubles the head's loss scale and re-captures the step graph when the scale changed."""
+        if not self.student_head_f16:
+            return False
+        if self.loss_scaler is None:
+            from . import solver
+            self.loss_scaler = solver.LossScaler(self.head, self.overflow, init_scale=self.head.f16_grad_scale())
+        changed = self.loss_scaler.update(force=force)
+        if changed and getattr(self, "graph", None) is not None:
+            self.capture()
+        return changed
 
     def update_lr(self, cur_iter, solver_cfg):
         """model.UpdateWorkspaceLr(cur_iter, lr_policy.get_lr_at_iter(cur_iter)) (utils/train.py loop, detector.py:598-648): sets the

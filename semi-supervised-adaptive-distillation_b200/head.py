@@ -140,6 +140,13 @@ class RetinaNetHead:
         except Exception:
             pass
 
+    def set_f16_grad_scale(self, scale):
+        """Loss scale of the fp16 gradient tensors for the following backward passes (re-capture a CUDA graph after changing it)."""
+        check(lib().sad_head_set_f16_grad_scale(self.handle, float(scale)))
+
+    def f16_grad_scale(self):
+        return float(lib().sad_head_f16_grad_scale(self.handle))
+
     def device_bytes(self):
         return lib().sad_head_device_bytes(self.handle)
 

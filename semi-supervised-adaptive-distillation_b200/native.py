@@ -170,6 +170,12 @@ def lib():
         l.sad_affine_channel_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
         l.sad_upsample_nearest_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.sad_upsample_nearest_grad_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.sad_nonfinite_flag_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        l.sad_momentum_sgd_guarded_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SgdSegment), C.c_int, C.c_void_p, C.c_float, C.c_int,
+                                                   C.c_void_p, C.c_void_p]
+        l.sad_head_set_f16_grad_scale.argtypes = [C.c_void_p, C.c_float]
+        l.sad_head_f16_grad_scale.argtypes = [C.c_void_p]
+        l.sad_head_f16_grad_scale.restype = C.c_float
         l.sad_upsample_nearest_add_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p]
         l.sad_momentum_sgd_update_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                   C.c_float, C.c_int, C.c_void_p]

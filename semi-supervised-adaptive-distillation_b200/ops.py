@@ -160,9 +160,18 @@ def select_smooth_l1_loss(y_hat, y, locs, fg_num, beta=1.0, scale=1.0, want_loss
     return loss, grad
 
 
-def momentum_sgd(param, grad, momentum_buf, segments, lr, momentum=0.9, nesterov=False):
+def nonfinite_flag(x, flag):
+    """flag |= 1 (CUDA int32 scalar tensor) when any element of the fp32 CUDA tensor x is inf or NaN; no host synchronisation."""
+    _require_cuda(x, torch.float32, "x")
+    _require_cuda(flag, torch.int32, "flag")
+    check(lib().sad_nonfinite_flag_f32(C.c_void_p(x.data_ptr()), x.numel(), C.c_void_p(flag.data_ptr()), _stream()))
+    return flag
+
+
+def momentum_sgd(param, grad, momentum_buf, segments, lr, momentum=0.9, nesterov=False, skip_flag=None):
     """In-place momentum SGD over flat buffers.  segments: [(count, grad_multiplier, weight_decay)] tiling the buffers;
-    lr: CUDA fp32 scalar tensor (the `lr` blob, updated by the learning-rate policy between steps)."""
+    lr: CUDA fp32 scalar tensor (the `lr` blob, updated by the learning-rate policy between steps).  skip_flag: CUDA int32 scalar
+    tensor; when it is not 0 the launch leaves every buffer untouched (an overflowed mixed-precision step is skipped on the device)."""
     for name, t in (("param", param), ("grad", grad), ("momentum", momentum_buf)):
         _require_cuda(t, torch.float32, name)
     _require_cuda(lr, torch.float32, "lr")
@@ -171,6 +180,12 @@ def momentum_sgd(param, grad, momentum_buf, segments, lr, momentum=0.9, nesterov
         arr[i].count, arr[i].grad_multiplier, arr[i].weight_decay = int(cnt), float(mult), float(wd)
     if sum(int(c) for c, _, _ in segments) != param.numel() or grad.numel() != param.numel() or momentum_buf.numel() != param.numel():
         raise ValueError("the segments must tile the flat buffers exactly")
+    if skip_flag is not None:
+        _require_cuda(skip_flag, torch.int32, "skip_flag")
+        check(lib().sad_momentum_sgd_guarded_f32(C.c_void_p(param.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(momentum_buf.data_ptr()),
+                                                 arr, len(segments), C.c_void_p(lr.data_ptr()), float(momentum), 1 if nesterov else 0,
+                                                 C.c_void_p(skip_flag.data_ptr()), _stream()))
+        return
     check(lib().sad_momentum_sgd_f32(C.c_void_p(param.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(momentum_buf.data_ptr()),
                                      arr, len(segments), C.c_void_p(lr.data_ptr()), float(momentum), 1 if nesterov else 0, _stream()))
 

@@ -146,3 +146,42 @@ class LearningRate:
                     ops.scale_(buf, correction)
                 self.corrections += 1
         return new_lr
+
+
+class LossScaler:
+    """Dynamic loss scaling for the mixed-fp16 head (BASELINE.json configs[4]) without a host round trip per step.
+
+    On the device, every step: ops.nonfinite_flag over the REDUCED head gradient sets `flag`, and the guarded optimiser launch
+    (ops.momentum_sgd(..., skip_flag=flag)) leaves parameters and update history untouched when it is set — an overflowed step
+    is skipped by all ranks alike.  On the host, every `check_every` steps: `update()` reads the flag (one 4-byte copy); if it is
+    set the scale is halved and the flag cleared, and after `growth_interval` clean steps it is doubled (the usual policy).
+    Returns True when the scale changed: the head takes the scale by value, so a captured step graph has to be captured again."""
+
+    def __init__(self, head, flag, init_scale=4096.0, growth_interval=2000, check_every=50, min_scale=1.0, max_scale=65536.0):
+        self.head, self.flag = head, flag
+        self.scale, self.growth_interval, self.check_every = float(init_scale), int(growth_interval), int(check_every)
+        self.min_scale, self.max_scale = float(min_scale), float(max_scale)
+        self.clean_steps, self.steps, self.skipped_windows = 0, 0, 0
+        head.set_f16_grad_scale(self.scale)
+
+    def update(self, force=False):
+        self.steps += 1
+        if not force and self.steps % self.check_every:
+            return False
+        overflowed = bool(int(self.flag.item()))
+        if overflowed:
+            self.flag.zero_()
+            self.skipped_windows += 1
+            self.clean_steps = 0
+            new = max(self.min_scale, self.scale * 0.5)
+        else:
+            self.clean_steps += self.check_every
+            new = self.scale
+            if self.clean_steps >= self.growth_interval:
+                self.clean_steps = 0
+                new = min(self.max_scale, self.scale * 2.0)
+        if new != self.scale:
+            self.scale = new
+            self.head.set_f16_grad_scale(new)
+            return True
+        return False

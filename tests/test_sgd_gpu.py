@@ -123,3 +123,81 @@ def test_weighted_sum_operator_matches_oracle(oracle):
         ws.RunOperatorOnce(c2.CreateOperator("WeightedSum", ["grad", "one", "param"], ["out"], device_option=dev))
     with pytest.raises(c2.EnforceNotMet):
         ws.RunOperatorOnce(c2.CreateOperator("WeightedSum", ["grad", "one", "param", "wd"], ["param"], device_option=dev))
+
+
+# ---------------------------------------------------------------------------------------------
+# overflow guard of mixed-precision training: non-finite flag + guarded optimiser launch + host-side loss scaler
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bad", [None, float("inf"), float("-inf"), float("nan")])
+@pytest.mark.parametrize("n", [3, 4096, 100003])
+def test_nonfinite_flag_and_guarded_sgd(n, bad):
+    from sad_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n)
+    p, gr, m = (torch.randn(n, device="cuda", generator=g) for _ in range(3))
+    if bad is not None:
+        gr[n - 2] = bad                 # in the scalar tail for n % 4 != 0, in a float4 otherwise
+    flag = torch.zeros((), dtype=torch.int32, device="cuda")
+    ops.nonfinite_flag(gr, flag)
+    assert int(flag.item()) == (0 if bad is None else 1)
+    before = (p.clone(), gr.clone(), m.clone())
+    lr = torch.tensor(0.01, device="cuda")
+    ops.momentum_sgd(p, gr, m, [(n, 1.0, 1e-4)], lr, skip_flag=flag)
+    torch.cuda.synchronize()
+    if bad is None:   # the guarded launch with a clear flag is the plain launch
+        p2, g2, m2 = (t.clone() for t in before)
+        ops.momentum_sgd(p2, g2, m2, [(n, 1.0, 1e-4)], lr)
+        assert torch.equal(p, p2) and torch.equal(gr, g2) and torch.equal(m, m2)
+    else:             # skipped on the device: nothing moved, nothing was poisoned
+        for a, b in zip((p, gr, m), before):
+            assert a.tobytes() == b.tobytes() if hasattr(a, "tobytes") else torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+        assert bool(torch.isfinite(p).all()) and bool(torch.isfinite(m).all())
+
+
+def test_loss_scaler_halves_on_overflow_and_grows_after_clean_steps():
+    from sad_b200 import solver
+    from sad_b200.head import RetinaNetHead
+    head = RetinaNetHead(1, [(8, 32)], dim=32, num_convs=1, num_anchors=3, num_classes=4, compute_f16=True)
+    flag = torch.zeros((), dtype=torch.int32, device="cuda")
+    sc = solver.LossScaler(head, flag, init_scale=4096.0, growth_interval=4, check_every=2)
+    assert head.f16_grad_scale() == 4096.0
+    assert sc.update() is False                 # step 1: not a check step
+    flag.fill_(1)
+    assert sc.update() is True                  # step 2: overflow seen -> halved, flag cleared
+    assert head.f16_grad_scale() == 2048.0 and int(flag.item()) == 0
+    changed = [sc.update() for _ in range(4)]   # 4 clean steps = 2 checks -> grows back
+    assert changed == [False, False, False, True] and head.f16_grad_scale() == 4096.0
+    head.close()
+
+
+def test_fp16_head_overflow_is_caught_and_the_step_skipped():
+    """A loss scale far too large for the incoming gradient overflows the fp16 gradient tensors: the head's parameter gradients come
+    out non-finite, the flag goes up, the guarded optimiser launch leaves the parameters alone, and the scaler's next look halves
+    the scale until a step goes through."""
+    from sad_b200 import ops, solver
+    from sad_b200.head import RetinaNetHead
+    shapes = [(8, 32), (4, 16)]
+    head = RetinaNetHead(1, shapes, dim=64, num_convs=1, num_anchors=3, num_classes=8, compute_f16=True, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    fpn = [torch.randn(1, 64, h, w, device="cuda", generator=g) for h, w in shapes]
+    d_cls = [torch.randn(1, head.cls_out, h, w, device="cuda", generator=g) * 30.0 for h, w in shapes]   # 30 * 4096 > 65504
+    d_box = [torch.randn(1, head.bbox_out, h, w, device="cuda", generator=g) for h, w in shapes]
+    flag = torch.zeros((), dtype=torch.int32, device="cuda")
+    sc = solver.LossScaler(head, flag, init_scale=4096.0, check_every=1)
+    mom = torch.zeros_like(head.flat_params)
+    lr = torch.tensor(0.01, device="cuda")
+    before = head.flat_params.clone()
+    skipped = 0
+    for step in range(12):
+        head.forward(fpn)
+        head.backward(d_cls, d_box)
+        ops.nonfinite_flag(head.flat_grads, flag)
+        ops.momentum_sgd(head.flat_params, head.flat_grads, mom, head.sgd_segments(1e-4), lr, skip_flag=flag)
+        if int(flag.item()):
+            skipped += 1
+            assert torch.equal(head.flat_params, before), "an overflowed step must not touch the parameters"
+        else:
+            break
+        sc.update()
+    assert skipped >= 1 and head.f16_grad_scale() < 4096.0
+    assert not torch.equal(head.flat_params, before) and bool(torch.isfinite(head.flat_params).all())
+    head.close()
