@@ -49,6 +49,13 @@ int sad_exchange_rank(const sad_exchange* ex);
  * so far on producer_stream (cudaStream_t as void*; NULL = legacy default stream).  Returns at once; neither the host nor
  * producer_stream waits.  Several buckets may be in flight; NCCL runs them in issue order. */
 int sad_exchange_allreduce_async_f32(sad_exchange* ex, float* buf, size_t count, void* producer_stream);
+/* CUDA graphs.  When producer_stream is being CAPTURED, sad_exchange_allreduce_async_f32 does not enqueue the collective: it adds
+ * an external event-record node to the graph ("this bucket is final") and remembers the bucket.  After EVERY launch of that graph
+ * call sad_exchange_flush: the communication stream then waits for each bucket's event of that launch and runs the allreduce
+ * eagerly, beside the graph.  sad_exchange_plan_reset forgets the remembered buckets (call it before capturing again). */
+int sad_exchange_flush(sad_exchange* ex);
+int sad_exchange_plan_reset(sad_exchange* ex);
+int sad_exchange_planned(const sad_exchange* ex);
 /* consumer_stream waits (device side) for every bucket enqueued since the previous join */
 int sad_exchange_join(sad_exchange* ex, void* consumer_stream);
 /* the un-overlapped form: the allreduce is enqueued on `stream` itself */

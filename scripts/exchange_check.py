@@ -64,15 +64,24 @@ def main():
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             flat.copy_(keep)
+            ex.plan_reset()
+            big = torch.randn(4096, 4096, device="cuda")
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
+                for _ in range(4):
+                    (big @ big).sum()           # ~1 ms of captured work in front of the producer ...
+                flat.copy_(keep)                # ... which only then writes the buckets' contents
                 for lo, hi in zip(cuts, cuts[1:]):
                     ex.reduce_bucket(lo, hi)
                 ex.join()
-            flat.copy_(keep)
-            g.replay()
-            torch.cuda.synchronize()
-            del g       # the graph holds a reference on the communicator: it must go before ex.close()
+            assert ex.planned() == 3            # captured buckets stay out of the graph: event-record nodes + a plan
+            for _ in range(2):
+                flat.zero_()                    # an exchange that started before its bucket's event would sum these zeros
+                g.replay()
+                ex.flush()                      # the exchanges run beside the graph, behind the events of this launch
+                ex.join()
+                torch.cuda.synchronize()
+            del g
         torch.cuda.synchronize()
         ref = reference(salt)
         err = float((flat.double() - ref).abs().max() / ref.abs().max())

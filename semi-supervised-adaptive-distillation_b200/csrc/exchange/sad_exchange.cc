@@ -89,8 +89,15 @@ int nccl_check(int rc, const char* what) {
 
 }  // namespace
 
+struct PlannedBucket {
+  float* buf;
+  size_t count;
+  cudaEvent_t ready;   // recorded by an EXTERNAL event-record node of the captured graph
+};
+
 struct sad_exchange {
   int rank = 0, world = 1, device = 0;
+  std::vector<PlannedBucket> plan;   // buckets announced while the producer stream was being captured (see sad_exchange_flush)
   NcclComm comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   std::vector<cudaEvent_t> ready;   // one "bucket is ready" event per bucket in flight (re-used after a join)
@@ -154,6 +161,7 @@ SAD_EXPORT void sad_exchange_destroy(sad_exchange* ex) {
   if (ex->comm_stream) cudaStreamSynchronize(ex->comm_stream);
   if (ex->comm && nccl().CommDestroy) nccl().CommDestroy(ex->comm);
   for (cudaEvent_t e : ex->ready) cudaEventDestroy(e);
+  for (auto& b : ex->plan) cudaEventDestroy(b.ready);
   if (ex->done) cudaEventDestroy(ex->done);
   if (ex->comm_stream) cudaStreamDestroy(ex->comm_stream);
   delete ex;
@@ -168,6 +176,24 @@ SAD_EXPORT int sad_exchange_allreduce_async_f32(sad_exchange* ex, float* buf, si
   if (!ex || (!buf && count)) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_allreduce_async_f32: null argument");
   if (count == 0) return SAD_EXCHANGE_OK;
   int rc;
+  cudaStream_t ps = static_cast<cudaStream_t>(producer_stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if ((rc = cuda_check(cudaStreamIsCapturing(ps, &cap), "cudaStreamIsCapturing")) != SAD_EXCHANGE_OK) return rc;
+  if (cap == cudaStreamCaptureStatusActive) {
+    // The producer stream is being captured into a CUDA graph.  The collective itself stays OUT of the graph: the graph only gets
+    // an external event-record node ("this bucket is final"), and sad_exchange_flush — called after every launch of the graph —
+    // makes the communication stream wait for that event and enqueues the allreduce eagerly.  (Capturing the NCCL kernels as a
+    // parallel branch of the graph works — scripts/exchange_check.py — but measured on 8 B200s the branch did not overlap the
+    // backward pass at all: 9.08 ms with and without it.  An eager, high-priority stream beside the graph does.)
+    cudaEvent_t e = nullptr;
+    if ((rc = cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) != SAD_EXCHANGE_OK) return rc;
+    if ((rc = cuda_check(cudaEventRecordWithFlags(e, ps, cudaEventRecordExternal), "cudaEventRecordWithFlags(external)")) != SAD_EXCHANGE_OK) {
+      cudaEventDestroy(e);
+      return rc;
+    }
+    ex->plan.push_back(PlannedBucket{buf, count, e});
+    return SAD_EXCHANGE_OK;
+  }
   if (ex->in_flight == ex->ready.size()) {
     cudaEvent_t e = nullptr;
     if ((rc = cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) != SAD_EXCHANGE_OK) return rc;
@@ -175,7 +201,7 @@ SAD_EXPORT int sad_exchange_allreduce_async_f32(sad_exchange* ex, float* buf, si
   }
   cudaEvent_t ev = ex->ready[ex->in_flight++];
   // the bucket is complete once everything enqueued so far on the producer stream has run (cuda_nccl_gpu.cc:157-166)
-  if ((rc = cuda_check(cudaEventRecord(ev, static_cast<cudaStream_t>(producer_stream)), "cudaEventRecord(bucket ready)")) != SAD_EXCHANGE_OK) return rc;
+  if ((rc = cuda_check(cudaEventRecord(ev, ps), "cudaEventRecord(bucket ready)")) != SAD_EXCHANGE_OK) return rc;
   if ((rc = cuda_check(cudaStreamWaitEvent(ex->comm_stream, ev, 0), "cudaStreamWaitEvent(comm stream)")) != SAD_EXCHANGE_OK) return rc;
   if (ex->world > 1) {
     if ((rc = nccl_check(nccl().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, ex->comm, ex->comm_stream), "ncclAllReduce")) != SAD_EXCHANGE_OK)
@@ -183,6 +209,32 @@ SAD_EXPORT int sad_exchange_allreduce_async_f32(sad_exchange* ex, float* buf, si
   }
   ex->buckets += 1;
   ex->bytes += (uint64_t)count * sizeof(float);
+  return SAD_EXCHANGE_OK;
+}
+
+SAD_EXPORT int sad_exchange_plan_reset(sad_exchange* ex) {
+  if (!ex) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_plan_reset: null exchange");
+  for (auto& b : ex->plan) cudaEventDestroy(b.ready);
+  ex->plan.clear();
+  return SAD_EXCHANGE_OK;
+}
+
+SAD_EXPORT int sad_exchange_planned(const sad_exchange* ex) { return ex ? (int)ex->plan.size() : 0; }
+
+SAD_EXPORT int sad_exchange_flush(sad_exchange* ex) {
+  if (!ex) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_flush: null exchange");
+  int rc;
+  for (auto& b : ex->plan) {
+    // waits for the record node of the graph launch that precedes this call
+    if ((rc = cuda_check(cudaStreamWaitEvent(ex->comm_stream, b.ready, 0), "cudaStreamWaitEvent(planned bucket)")) != SAD_EXCHANGE_OK) return rc;
+    if (ex->world > 1) {
+      if ((rc = nccl_check(nccl().AllReduce(b.buf, b.buf, b.count, kNcclFloat32, kNcclSum, ex->comm, ex->comm_stream), "ncclAllReduce")) != SAD_EXCHANGE_OK)
+        return rc;
+    }
+    ex->buckets += 1;
+    ex->bytes += (uint64_t)b.count * sizeof(float);
+  }
+  if (!ex->plan.empty()) ex->in_flight += 1;   // something for the next join to wait for
   return SAD_EXCHANGE_OK;
 }
 

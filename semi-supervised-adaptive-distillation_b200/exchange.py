@@ -36,6 +36,9 @@ def lib():
         l.sad_exchange_rank.argtypes = [C.c_void_p]
         l.sad_exchange_allreduce_async_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_exchange_join.argtypes = [C.c_void_p, C.c_void_p]
+        l.sad_exchange_flush.argtypes = [C.c_void_p]
+        l.sad_exchange_plan_reset.argtypes = [C.c_void_p]
+        l.sad_exchange_planned.argtypes = [C.c_void_p]
         l.sad_exchange_allreduce_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_exchange_buckets.argtypes = [C.c_void_p]
         l.sad_exchange_buckets.restype = C.c_uint64
@@ -110,6 +113,18 @@ class NativeGradientExchange:
         if not (0 <= begin <= end <= self.flat.numel()):
             raise ValueError("bucket [%d, %d) outside the buffer" % (begin, end))
         _check(lib().sad_exchange_allreduce_async_f32(self.handle, C.c_void_p(self.flat.data_ptr() + 4 * begin), end - begin, _stream()))
+
+    def plan_reset(self):
+        """Forget the buckets announced during a previous graph capture (call before capturing the step again)."""
+        _check(lib().sad_exchange_plan_reset(self.handle))
+
+    def planned(self):
+        return int(lib().sad_exchange_planned(self.handle))
+
+    def flush(self):
+        """After a launch of a graph that captured reduce_bucket calls: run those buckets' exchanges beside the graph, each behind
+        the event its bucket recorded in that launch."""
+        _check(lib().sad_exchange_flush(self.handle))
 
     def join(self):
         """The current stream waits for every bucket enqueued since the last join."""

@@ -399,9 +399,11 @@ class FullDistillStep:
                     self.forward_backward()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
+            if hasattr(self.exchange, "plan_reset"):
+                self.exchange.plan_reset()      # buckets announced by a previous capture
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.forward_backward()
+                self.forward_backward()         # reduce_bucket calls made here only leave event-record nodes in the graph ...
             self.graph = g
             return True
         except Exception as e:  # leave a usable eager step behind
@@ -424,13 +426,16 @@ class FullDistillStep:
     def run(self):
         if getattr(self, "graph", None) is not None:
             self.graph.replay()
+            if self.overlap_exchange and hasattr(self.exchange, "flush"):
+                self.exchange.flush()           # ... and the exchanges run here, beside the graph, each behind its bucket's event
         else:
             self.forward_backward()
 
     def allreduce(self):
-        """The step's exchange.  With overlap_exchange the buckets were enqueued (and joined) inside forward_backward / the
-        captured graph, so nothing is left to do here."""
+        """The step's exchange.  With overlap_exchange the buckets are already on their way (enqueued from inside forward_backward,
+        or by run() beside the captured graph); what is left is to make this stream wait for the last of them."""
         if self.overlap_exchange and hasattr(self.exchange, "reduce_bucket"):
+            self.exchange.join()
             return None
         return self.exchange.allreduce()
 

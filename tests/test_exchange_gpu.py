@@ -37,37 +37,51 @@ def test_single_rank_buckets_are_ordered_behind_the_producer_and_ahead_of_the_co
     ex.close()
 
 
-def test_buckets_inside_a_cuda_graph():
+def test_buckets_announced_inside_a_cuda_graph_run_beside_it():
+    """reduce_bucket on a stream that is being captured leaves an external event-record node in the graph and a planned bucket;
+    flush() after every replay runs the exchange beside the graph, ordered behind that replay's events; join() orders the consumer."""
     from sad_b200 import exchange
     n = 1 << 20
     flat = torch.zeros(n, device="cuda")
     src = torch.arange(n, device="cuda", dtype=torch.float32)
     ex = exchange.NativeGradientExchange(flat, world=1, rank=0)
+    big = torch.randn(2048, 2048, device="cuda")
 
     def step():
         flat.copy_(src)
+        (big @ big).sum()
         ex.reduce_bucket(0, n // 4)
         flat[n // 4:].mul_(2.0)
         ex.reduce_bucket(n // 4, n)
         ex.join()
-        flat.add_(1.0)
 
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        step()
+        step()                      # eager: the buckets go out at once
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
+    eager_buckets = ex.stats()["buckets"]
+    assert eager_buckets == 2 and ex.planned() == 0
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         step()
-    flat.zero_()
-    g.replay()
-    torch.cuda.synchronize()
-    ref = src.clone()
-    ref[n // 4:] *= 2.0
-    ref += 1.0
-    assert torch.equal(flat, ref)
+    assert ex.planned() == 2 and ex.stats()["buckets"] == eager_buckets      # nothing was sent during capture
+    for it in range(3):
+        flat.zero_()
+        g.replay()
+        ex.flush()
+        ex.join()
+        flat.add_(1.0)              # consumer on this stream, behind the join
+        torch.cuda.synchronize()
+        ref = src.clone()
+        ref[n // 4:] *= 2.0
+        ref += 1.0
+        assert torch.equal(flat, ref)
+    assert ex.stats()["buckets"] == eager_buckets + 6
+    ex.plan_reset()
+    assert ex.planned() == 0
+    del g
     ex.close()
 
 
