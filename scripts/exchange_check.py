@@ -66,6 +66,8 @@ def main():
             flat.copy_(keep)
             ex.plan_reset()
             big = torch.randn(4096, 4096, device="cuda")
+            (big @ big).sum()                   # cuBLAS initialises its handle / workspace outside the capture
+            torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 for _ in range(4):
