@@ -41,6 +41,11 @@ int sad_exchange_nccl_version(void);
 int sad_exchange_unique_id(void* id_out /* SAD_EXCHANGE_UNIQUE_ID_BYTES */);
 /* collective over all ranks: joins the communicator on the CURRENT CUDA device.  world == 1 needs neither NCCL nor an id. */
 int sad_exchange_create(const void* id, int rank, int world, sad_exchange** out);
+/* The same with a bound on the CTAs this communicator's kernels may use (ncclConfig_t.maxCTAs; 0 = NCCL's default; the environment
+ * variable SAD_EXCHANGE_MAX_CTAS overrides).  An exchange that has to overlap a backward pass needs kernels small enough to find room
+ * beside the compute kernels. */
+int sad_exchange_create_config(const void* id, int rank, int world, int max_ctas, sad_exchange** out);
+int sad_exchange_max_ctas(const sad_exchange* ex);
 void sad_exchange_destroy(sad_exchange* ex);
 int sad_exchange_world(const sad_exchange* ex);
 int sad_exchange_rank(const sad_exchange* ex);

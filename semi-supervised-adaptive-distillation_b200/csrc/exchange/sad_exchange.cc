@@ -36,7 +36,21 @@ struct NcclUniqueId {
   char internal[SAD_EXCHANGE_UNIQUE_ID_BYTES];
 };
 typedef void* NcclComm;
+// ncclConfig_t as of NCCL 2.27 (nccl.h:70-88).  NCCL reads `size` / `version` first and accepts configuration structs of older
+// releases, so this restatement stays valid for newer libraries; fields left at "undefined" keep the library's defaults.
+struct NcclConfig {
+  size_t size;
+  unsigned int magic;
+  unsigned int version;
+  int blocking, cgaClusterSize, minCTAs, maxCTAs;
+  const char* netName;
+  int splitShare, trafficClass;
+  const char* commName;
+  int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs;
+};
+constexpr int kNcclUndefInt = -2147483647 - 1;   // NCCL_CONFIG_UNDEF_INT = INT_MIN
 struct Nccl {
+  int (*CommInitRankConfig)(NcclComm*, int, NcclUniqueId, int, NcclConfig*) = nullptr;   // optional (NCCL >= 2.14)
   int (*GetVersion)(int*) = nullptr;
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
@@ -78,6 +92,7 @@ const Nccl& nccl() {
     n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
     n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
     n.ok = n.why.empty();
+    n.CommInitRankConfig = reinterpret_cast<decltype(n.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
   });
   return n;
 }
@@ -97,6 +112,7 @@ struct PlannedBucket {
 
 struct sad_exchange {
   int rank = 0, world = 1, device = 0;
+  int max_ctas = 0;                  // CTA bound of this communicator (0 = NCCL's default)
   std::vector<PlannedBucket> plan;   // buckets announced while the producer stream was being captured (see sad_exchange_flush)
   NcclComm comm = nullptr;
   cudaStream_t comm_stream = nullptr;
@@ -125,7 +141,15 @@ SAD_EXPORT int sad_exchange_unique_id(void* id_out) {
   return nccl_check(n.GetUniqueId(static_cast<NcclUniqueId*>(id_out)), "ncclGetUniqueId");
 }
 
+static int exchange_create_impl(const void* id, int rank, int world, int max_ctas, sad_exchange** out);
 SAD_EXPORT int sad_exchange_create(const void* id, int rank, int world, sad_exchange** out) {
+  return exchange_create_impl(id, rank, world, 0, out);
+}
+SAD_EXPORT int sad_exchange_create_config(const void* id, int rank, int world, int max_ctas, sad_exchange** out) {
+  return exchange_create_impl(id, rank, world, max_ctas, out);
+}
+SAD_EXPORT int sad_exchange_max_ctas(const sad_exchange* ex) { return ex ? ex->max_ctas : 0; }
+static int exchange_create_impl(const void* id, int rank, int world, int max_ctas, sad_exchange** out) {
   if (!out) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: null out");
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: rank must be in [0, world)");
@@ -133,6 +157,7 @@ SAD_EXPORT int sad_exchange_create(const void* id, int rank, int world, sad_exch
   if (!ex) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: out of host memory");
   ex->rank = rank;
   ex->world = world;
+  ex->max_ctas = max_ctas;
   int rc = cuda_check(cudaGetDevice(&ex->device), "cudaGetDevice");
   if (rc == SAD_EXCHANGE_OK) {
     int lo = 0, hi = 0;   // the exchange should win the SMs it needs as soon as a bucket is ready: highest stream priority
@@ -144,7 +169,31 @@ SAD_EXPORT int sad_exchange_create(const void* id, int rank, int world, sad_exch
     const Nccl& n = nccl();
     if (!n.ok) rc = fail(SAD_EXCHANGE_ERR_NCCL, n.why);
     else if (!id) rc = fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: world > 1 needs the unique id of rank 0");
-    else rc = nccl_check(n.CommInitRank(&ex->comm, world, *static_cast<const NcclUniqueId*>(id), rank), "ncclCommInitRank");
+    else {
+      // The exchange has to run BESIDE the backward pass.  An NCCL kernel's CTAs want (almost) a whole SM each; with the library's
+      // default CTA count (enough to saturate NVLink on an idle GPU) they do not find room while compute kernels keep every SM
+      // partly occupied, and the "overlapped" exchange ends up running after the backward pass (measured on 8 B200s: 9.03 ms with
+      // and 9.06 ms without the overlap; with 8 CTAs 0.74 ms of a then 1.40 ms exchange is hidden).  max_ctas bounds the CTAs
+      // of THIS communicator only (ncclConfig_t.maxCTAs); 0 keeps NCCL's default.
+      int max_ctas = ex->max_ctas;
+      if (const char* e = getenv("SAD_EXCHANGE_MAX_CTAS")) max_ctas = atoi(e);
+      if (max_ctas > 0 && n.CommInitRankConfig) {
+        NcclConfig cfg{};
+        cfg.size = sizeof(NcclConfig);
+        cfg.magic = 0xcafebeefu;
+        cfg.version = 22703;
+        cfg.blocking = cfg.cgaClusterSize = cfg.minCTAs = cfg.splitShare = cfg.trafficClass = kNcclUndefInt;
+        cfg.collnetEnable = cfg.CTAPolicy = cfg.shrinkShare = cfg.nvlsCTAs = kNcclUndefInt;
+        cfg.netName = cfg.commName = nullptr;
+        cfg.maxCTAs = max_ctas;
+        cfg.minCTAs = max_ctas < 4 ? max_ctas : 4;
+        rc = nccl_check(n.CommInitRankConfig(&ex->comm, world, *static_cast<const NcclUniqueId*>(id), rank, &cfg), "ncclCommInitRankConfig");
+        ex->max_ctas = max_ctas;
+      } else {
+        rc = nccl_check(n.CommInitRank(&ex->comm, world, *static_cast<const NcclUniqueId*>(id), rank), "ncclCommInitRank");
+        ex->max_ctas = 0;
+      }
+    }
   }
   if (rc != SAD_EXCHANGE_OK) {
     const std::string keep = g_err;

@@ -30,6 +30,8 @@ def lib():
         l.sad_exchange_last_error.restype = C.c_char_p
         l.sad_exchange_unique_id.argtypes = [C.c_void_p]
         l.sad_exchange_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        l.sad_exchange_create_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        l.sad_exchange_max_ctas.argtypes = [C.c_void_p]
         l.sad_exchange_destroy.argtypes = [C.c_void_p]
         l.sad_exchange_destroy.restype = None
         l.sad_exchange_world.argtypes = [C.c_void_p]
@@ -68,7 +70,7 @@ class NativeGradientExchange:
     Same interface as parallel.GradientExchange (allreduce / nbytes / bus_bytes) plus reduce_bucket / join for the overlapped
     form.  `world` ranks must construct it collectively (the NCCL id travels through torch.distributed once)."""
 
-    def __init__(self, flat_grads, world=1, rank=0, group=None):
+    def __init__(self, flat_grads, world=1, rank=0, group=None, max_ctas=0):
         if not (flat_grads.is_cuda and flat_grads.dtype == torch.float32 and flat_grads.is_contiguous() and flat_grads.dim() == 1):
             raise ValueError("the gradient buffer must be a contiguous 1-D fp32 CUDA tensor")
         self.flat, self.world, self.rank = flat_grads, int(world), int(rank)
@@ -86,7 +88,8 @@ class NativeGradientExchange:
             uid = (C.c_char * ID_BYTES).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
         self.handle = C.c_void_p()
         with torch.cuda.device(flat_grads.device):
-            _check(lib().sad_exchange_create(uid, self.rank, self.world, C.byref(self.handle)))
+            _check(lib().sad_exchange_create_config(uid, self.rank, self.world, int(max_ctas), C.byref(self.handle)))
+        self.max_ctas = int(lib().sad_exchange_max_ctas(self.handle))
 
     def close(self):
         """Destroy the communicator.  NCCL keeps a reference for every CUDA graph that captured one of its collectives and
