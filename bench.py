@@ -400,6 +400,7 @@ def run_full_step(args, rank, world, barrier, native, n_images=2, config5=False,
                     "stream as the backward pass completes them, inside the captured graph; value / ms_per_step are this overlapped form, "
                     "ms_per_step_exchange_after_backward + allreduce_ms the reference's order (one allreduce after the whole backward); "
                     "allreduce_exposed_ms = ms_per_step - (ms_per_step_exchange_after_backward - allreduce_ms)",
+        "exchange_mode": getattr(st.exchange, "mode", None), "exchange_stats": st.exchange.stats() if hasattr(st.exchange, "stats") else None,
         "multi_gpu_check": mgc,
         "params": st.param_count(), "gpu_launches": launches, "native_launches_per_step": per_step, "cuda_graph": bool(graphed),
         "cuda_graph_error": getattr(st, "capture_error", None), "losses": losses,
@@ -429,6 +430,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="env", choices=["env", "allreduce", "gather"],
+                    help="gradient exchange of the step objects: ncclAllReduce buckets, or the copy-engine all-gather + local sum "
+                         "(include/sad_exchange.h); env = SAD_EXCHANGE_GATHER decides (default allreduce)")
     ap.add_argument("--head-steps", type=int, default=0, help="head distillation steps (0 = min(steps, 100); -1 = skip)")
     ap.add_argument("--full-steps", type=int, default=0, help="full R-50 <- R-101 distillation steps (0 = min(steps, 20); -1 = skip)")
     ap.add_argument("--no-heads-f16", dest="teacher_f16", action="store_false", default=True,
@@ -436,6 +440,8 @@ def main():
     ap.add_argument("--teacher-f16", "--heads-f16", dest="teacher_f16", action="store_true", help="(default) run that object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.exchange != "env":
+        os.environ["SAD_EXCHANGE_GATHER"] = "1" if args.exchange == "gather" else "0"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -30,6 +30,7 @@ extern "C" {
 #define SAD_EXCHANGE_ERR_INVALID (-1)
 #define SAD_EXCHANGE_ERR_CUDA (-2)
 #define SAD_EXCHANGE_ERR_NCCL (-3)      /* NCCL missing or an NCCL call failed */
+#define SAD_EXCHANGE_ERR_UNSUPPORTED (-4) /* the resolved NCCL lacks what the requested form needs */
 #define SAD_EXCHANGE_UNIQUE_ID_BYTES 128 /* sizeof(ncclUniqueId) */
 
 typedef struct sad_exchange sad_exchange;
@@ -46,6 +47,20 @@ int sad_exchange_create(const void* id, int rank, int world, sad_exchange** out)
  * beside the compute kernels. */
 int sad_exchange_create_config(const void* id, int rank, int world, int max_ctas, sad_exchange** out);
 int sad_exchange_max_ctas(const sad_exchange* ex);
+/* The COPY-ENGINE form of the same exchange (NCCL >= 2.28; sad_exchange_gather_supported() says whether the resolved library has it).
+ * Why: an NCCL allreduce kernel holds whole SMs for its whole duration, and beside a backward pass whose kernels are sized for all 148
+ * SMs every held SM turns one wave into two — measured on 8 B200s the overlapped allreduce hid nothing.  Here the
+ * communicator is created with the zero-CTA policy and owns a symmetric NCCL window of world x capacity_floats; a bucket is copied into
+ * this rank's slot, ncclAllGather moves the slots over NVLink with the copy engines (no SMs), and ONE short HBM-bound kernel
+ * (sad_exchange_slot_sum_f32) adds the world slots in rank order back into the bucket: the result is the rank-ordered fp32 sum, bit-identical
+ * on every rank.  Same calls afterwards (allreduce_async / flush / join); a bucket that does not fit what is left of the window in
+ * the current step falls back to ncclAllReduce.  capacity_floats = the most floats one step exchanges (+ 128 per bucket of padding). */
+int sad_exchange_gather_supported(void);
+int sad_exchange_create_gather(const void* id, int rank, int world, size_t capacity_floats, sad_exchange** out);
+size_t sad_exchange_gather_capacity(const sad_exchange* ex);   /* 0 = this exchange runs the ncclAllReduce form */
+uint64_t sad_exchange_gathered(const sad_exchange* ex);         /* buckets that took the copy-engine form since creation */
+/* out[i] = slots[i] + slots[stride + i] + ... + slots[(world-1) * stride + i], fp32, added in that order; returns a cudaError_t */
+int sad_exchange_slot_sum_f32(const float* slots, size_t stride, int world, float* out, size_t count, void* stream);
 void sad_exchange_destroy(sad_exchange* ex);
 int sad_exchange_world(const sad_exchange* ex);
 int sad_exchange_rank(const sad_exchange* ex);

@@ -72,10 +72,10 @@ def build(force=False, verbose=False):
         _run([nvcc] + COMMON + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CSRC, "caffe2_shim"), "-I" + CSRC,
                                 "-x", "cu", "-shared", "-o", LIB_OPS] + osrc +
              ["-L" + HERE, "-l:libsad_b200.so", "-Xlinker", "-rpath=$ORIGIN"], verbose)
-    xsrc = _sources("exchange/sad_exchange.cc")
+    xsrc = _sources("exchange/sad_exchange.cc", "exchange/slot_sum.cu")
     if force or _stale(LIB_EXCHANGE, xsrc + hdrs):
-        _run([nvcc, "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-fvisibility=hidden,-fno-gnu-unique", "-w", "-I" + os.path.join(ROOT, "include"),
-              "-shared", "-o", LIB_EXCHANGE] + xsrc + ["-ldl"], verbose)
+        _run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-fno-gnu-unique",
+              "-w", "-I" + os.path.join(ROOT, "include"), "-shared", "-o", LIB_EXCHANGE] + xsrc + ["-ldl"], verbose)
     return LIB_KERNELS, LIB_OPS, LIB_EXCHANGE
 
 

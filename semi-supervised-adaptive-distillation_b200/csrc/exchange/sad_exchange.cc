@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 
+#include <cstddef>
 #include <cstdlib>
 #include <mutex>
 #include <new>
@@ -47,8 +48,13 @@ struct NcclConfig {
   int splitShare, trafficClass;
   const char* commName;
   int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs;
+  int nChannelsPerNetPeer, nvlinkCentricSched;   // NCCL 2.28 (nccl.h:83-101); only written when the library is >= 2.28
 };
+constexpr size_t kNcclConfigBytesV22703 = offsetof(NcclConfig, nChannelsPerNetPeer);
 constexpr int kNcclUndefInt = -2147483647 - 1;   // NCCL_CONFIG_UNDEF_INT = INT_MIN
+constexpr int kNcclCtaPolicyZero = 2;            // NCCL_CTA_POLICY_ZERO (nccl.h:66, NCCL >= 2.28): collectives on the copy engines where possible
+constexpr int kNcclWinCollSymmetric = 1;         // NCCL_WIN_COLL_SYMMETRIC (nccl.h:59)
+typedef void* NcclWindow;
 struct Nccl {
   int (*CommInitRankConfig)(NcclComm*, int, NcclUniqueId, int, NcclConfig*) = nullptr;   // optional (NCCL >= 2.14)
   int (*GetVersion)(int*) = nullptr;
@@ -57,6 +63,12 @@ struct Nccl {
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  // optional: the copy-engine form (NCCL >= 2.28: symmetric windows + zero-CTA all-gather)
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*MemAlloc)(void**, size_t) = nullptr;
+  int (*MemFree)(void*) = nullptr;
+  int (*CommWindowRegister)(NcclComm, void*, size_t, NcclWindow*, int) = nullptr;
+  int (*CommWindowDeregister)(NcclComm, NcclWindow) = nullptr;
   std::string why;   // non-empty: NCCL is not usable
   bool ok = false;
 };
@@ -93,6 +105,11 @@ const Nccl& nccl() {
     n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
     n.ok = n.why.empty();
     n.CommInitRankConfig = reinterpret_cast<decltype(n.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
+    n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(h, "ncclAllGather"));
+    n.MemAlloc = reinterpret_cast<decltype(n.MemAlloc)>(dlsym(h, "ncclMemAlloc"));
+    n.MemFree = reinterpret_cast<decltype(n.MemFree)>(dlsym(h, "ncclMemFree"));
+    n.CommWindowRegister = reinterpret_cast<decltype(n.CommWindowRegister)>(dlsym(h, "ncclCommWindowRegister"));
+    n.CommWindowDeregister = reinterpret_cast<decltype(n.CommWindowDeregister)>(dlsym(h, "ncclCommWindowDeregister"));
   });
   return n;
 }
@@ -113,6 +130,12 @@ struct PlannedBucket {
 struct sad_exchange {
   int rank = 0, world = 1, device = 0;
   int max_ctas = 0;                  // CTA bound of this communicator (0 = NCCL's default)
+  // copy-engine form (sad_exchange_create_gather): a symmetric NCCL window of world x capacity floats; the buckets of one step take
+  // consecutive regions of it (cursor, reset by the join)
+  float* stage = nullptr;
+  NcclWindow window = nullptr;
+  size_t capacity = 0, cursor = 0;
+  uint64_t gathered = 0;             // buckets that went through the copy-engine form
   std::vector<PlannedBucket> plan;   // buckets announced while the producer stream was being captured (see sad_exchange_flush)
   NcclComm comm = nullptr;
   cudaStream_t comm_stream = nullptr;
@@ -121,6 +144,36 @@ struct sad_exchange {
   cudaEvent_t done = nullptr;
   uint64_t buckets = 0, bytes = 0;
 };
+
+namespace {
+constexpr size_t kSlotAlign = 128;   // floats: every rank's slot of a bucket starts 512-byte aligned
+
+// The exchange of one bucket, enqueued on the communication stream (which already waits for the bucket's producer).
+int enqueue_bucket(sad_exchange* ex, float* buf, size_t count) {
+  int rc;
+  if (ex->world > 1) {
+    const size_t padded = (count + kSlotAlign - 1) / kSlotAlign * kSlotAlign;
+    if (ex->stage && ex->cursor + padded <= ex->capacity) {
+      // Copy-engine form: this rank's bucket goes into its slot of the symmetric window (a local copy), ncclAllGather (in place;
+      // zero-CTA policy: NVLink copies issued by the copy engines, no SMs) fills the other ranks' slots, and one HBM-bound kernel
+      // sums the slots in rank order back into the bucket — the same bits on every rank.
+      float* region = ex->stage + (size_t)ex->world * ex->cursor;
+      float* mine = region + (size_t)ex->rank * padded;
+      if ((rc = cuda_check(cudaMemcpyAsync(mine, buf, count * sizeof(float), cudaMemcpyDeviceToDevice, ex->comm_stream), "cudaMemcpyAsync(bucket -> slot)")) != SAD_EXCHANGE_OK) return rc;
+      if ((rc = nccl_check(nccl().AllGather(mine, region, padded, kNcclFloat32, ex->comm, ex->comm_stream), "ncclAllGather")) != SAD_EXCHANGE_OK) return rc;
+      if ((rc = sad_exchange_slot_sum_f32(region, padded, ex->world, buf, count, ex->comm_stream)) != 0)
+        return fail(SAD_EXCHANGE_ERR_CUDA, std::string("slot sum launch: ") + cudaGetErrorString((cudaError_t)rc));
+      ex->cursor += padded;
+      ex->gathered += 1;
+    } else {
+      if ((rc = nccl_check(nccl().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, ex->comm, ex->comm_stream), "ncclAllReduce")) != SAD_EXCHANGE_OK) return rc;
+    }
+  }
+  ex->buckets += 1;
+  ex->bytes += (uint64_t)count * sizeof(float);
+  return SAD_EXCHANGE_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -141,15 +194,28 @@ SAD_EXPORT int sad_exchange_unique_id(void* id_out) {
   return nccl_check(n.GetUniqueId(static_cast<NcclUniqueId*>(id_out)), "ncclGetUniqueId");
 }
 
-static int exchange_create_impl(const void* id, int rank, int world, int max_ctas, sad_exchange** out);
+static int exchange_create_impl(const void* id, int rank, int world, int max_ctas, size_t gather_capacity, sad_exchange** out);
 SAD_EXPORT int sad_exchange_create(const void* id, int rank, int world, sad_exchange** out) {
-  return exchange_create_impl(id, rank, world, 0, out);
+  return exchange_create_impl(id, rank, world, 0, 0, out);
 }
 SAD_EXPORT int sad_exchange_create_config(const void* id, int rank, int world, int max_ctas, sad_exchange** out) {
-  return exchange_create_impl(id, rank, world, max_ctas, out);
+  return exchange_create_impl(id, rank, world, max_ctas, 0, out);
+}
+SAD_EXPORT int sad_exchange_create_gather(const void* id, int rank, int world, size_t capacity_floats, sad_exchange** out) {
+  if (capacity_floats == 0) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create_gather: capacity must be > 0");
+  return exchange_create_impl(id, rank, world, 0, capacity_floats, out);
+}
+SAD_EXPORT int sad_exchange_gather_supported(void) {
+  const Nccl& n = nccl();
+  if (!n.ok) return 0;
+  int v = 0;
+  if (n.GetVersion(&v) != 0 || v < 22800) return 0;
+  return n.CommInitRankConfig && n.AllGather && n.MemAlloc && n.MemFree && n.CommWindowRegister && n.CommWindowDeregister;
 }
 SAD_EXPORT int sad_exchange_max_ctas(const sad_exchange* ex) { return ex ? ex->max_ctas : 0; }
-static int exchange_create_impl(const void* id, int rank, int world, int max_ctas, sad_exchange** out) {
+SAD_EXPORT size_t sad_exchange_gather_capacity(const sad_exchange* ex) { return ex && ex->stage ? ex->capacity : 0; }
+SAD_EXPORT uint64_t sad_exchange_gathered(const sad_exchange* ex) { return ex ? ex->gathered : 0; }
+static int exchange_create_impl(const void* id, int rank, int world, int max_ctas, size_t gather_capacity, sad_exchange** out) {
   if (!out) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: null out");
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return fail(SAD_EXCHANGE_ERR_INVALID, "sad_exchange_create: rank must be in [0, world)");
@@ -177,18 +243,42 @@ static int exchange_create_impl(const void* id, int rank, int world, int max_cta
       // of THIS communicator only (ncclConfig_t.maxCTAs); 0 keeps NCCL's default.
       int max_ctas = ex->max_ctas;
       if (const char* e = getenv("SAD_EXCHANGE_MAX_CTAS")) max_ctas = atoi(e);
-      if (max_ctas > 0 && n.CommInitRankConfig) {
+      if (gather_capacity && !sad_exchange_gather_supported())
+        rc = fail(SAD_EXCHANGE_ERR_UNSUPPORTED, "sad_exchange_create_gather: needs NCCL >= 2.28 (ncclCommWindowRegister, ncclMemAlloc, zero-CTA policy)");
+      else if ((max_ctas > 0 || gather_capacity) && n.CommInitRankConfig) {
         NcclConfig cfg{};
-        cfg.size = sizeof(NcclConfig);
         cfg.magic = 0xcafebeefu;
-        cfg.version = 22703;
-        cfg.blocking = cfg.cgaClusterSize = cfg.minCTAs = cfg.splitShare = cfg.trafficClass = kNcclUndefInt;
+        cfg.blocking = cfg.cgaClusterSize = cfg.minCTAs = cfg.maxCTAs = cfg.splitShare = cfg.trafficClass = kNcclUndefInt;
         cfg.collnetEnable = cfg.CTAPolicy = cfg.shrinkShare = cfg.nvlsCTAs = kNcclUndefInt;
+        cfg.nChannelsPerNetPeer = cfg.nvlinkCentricSched = kNcclUndefInt;
         cfg.netName = cfg.commName = nullptr;
-        cfg.maxCTAs = max_ctas;
-        cfg.minCTAs = max_ctas < 4 ? max_ctas : 4;
+        if (gather_capacity) {   // NCCL 2.28 layout; collectives that can run on the copy engines take no CTAs
+          cfg.size = sizeof(NcclConfig);
+          cfg.version = 22800;
+          cfg.CTAPolicy = kNcclCtaPolicyZero;
+        } else {
+          cfg.size = kNcclConfigBytesV22703;
+          cfg.version = 22703;
+        }
+        if (max_ctas > 0) {
+          cfg.maxCTAs = max_ctas;
+          cfg.minCTAs = max_ctas < 4 ? max_ctas : 4;
+        }
         rc = nccl_check(n.CommInitRankConfig(&ex->comm, world, *static_cast<const NcclUniqueId*>(id), rank, &cfg), "ncclCommInitRankConfig");
-        ex->max_ctas = max_ctas;
+        ex->max_ctas = max_ctas > 0 ? max_ctas : 0;
+        if (rc == SAD_EXCHANGE_OK && gather_capacity) {
+          // the window: world slots of `capacity` floats, allocated by NCCL (cuMem, shareable over NVLink) and registered
+          // symmetrically — every rank registers the same size at the same point, which is what lets the copy engines address it
+          ex->capacity = (gather_capacity + kSlotAlign - 1) / kSlotAlign * kSlotAlign;
+          size_t bytes = (size_t)world * ex->capacity * sizeof(float);
+          bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+          void* p = nullptr;
+          rc = nccl_check(n.MemAlloc(&p, bytes), "ncclMemAlloc");
+          if (rc == SAD_EXCHANGE_OK) {
+            ex->stage = static_cast<float*>(p);
+            rc = nccl_check(n.CommWindowRegister(ex->comm, p, bytes, &ex->window, kNcclWinCollSymmetric), "ncclCommWindowRegister");
+          }
+        }
       } else {
         rc = nccl_check(n.CommInitRank(&ex->comm, world, *static_cast<const NcclUniqueId*>(id), rank), "ncclCommInitRank");
         ex->max_ctas = 0;
@@ -208,6 +298,8 @@ static int exchange_create_impl(const void* id, int rank, int world, int max_cta
 SAD_EXPORT void sad_exchange_destroy(sad_exchange* ex) {
   if (!ex) return;
   if (ex->comm_stream) cudaStreamSynchronize(ex->comm_stream);
+  if (ex->window && ex->comm && nccl().CommWindowDeregister) nccl().CommWindowDeregister(ex->comm, ex->window);
+  if (ex->stage && nccl().MemFree) nccl().MemFree(ex->stage);
   if (ex->comm && nccl().CommDestroy) nccl().CommDestroy(ex->comm);
   for (cudaEvent_t e : ex->ready) cudaEventDestroy(e);
   for (auto& b : ex->plan) cudaEventDestroy(b.ready);
@@ -252,13 +344,7 @@ SAD_EXPORT int sad_exchange_allreduce_async_f32(sad_exchange* ex, float* buf, si
   // the bucket is complete once everything enqueued so far on the producer stream has run (cuda_nccl_gpu.cc:157-166)
   if ((rc = cuda_check(cudaEventRecord(ev, ps), "cudaEventRecord(bucket ready)")) != SAD_EXCHANGE_OK) return rc;
   if ((rc = cuda_check(cudaStreamWaitEvent(ex->comm_stream, ev, 0), "cudaStreamWaitEvent(comm stream)")) != SAD_EXCHANGE_OK) return rc;
-  if (ex->world > 1) {
-    if ((rc = nccl_check(nccl().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, ex->comm, ex->comm_stream), "ncclAllReduce")) != SAD_EXCHANGE_OK)
-      return rc;
-  }
-  ex->buckets += 1;
-  ex->bytes += (uint64_t)count * sizeof(float);
-  return SAD_EXCHANGE_OK;
+  return enqueue_bucket(ex, buf, count);
 }
 
 SAD_EXPORT int sad_exchange_plan_reset(sad_exchange* ex) {
@@ -276,12 +362,7 @@ SAD_EXPORT int sad_exchange_flush(sad_exchange* ex) {
   for (auto& b : ex->plan) {
     // waits for the record node of the graph launch that precedes this call
     if ((rc = cuda_check(cudaStreamWaitEvent(ex->comm_stream, b.ready, 0), "cudaStreamWaitEvent(planned bucket)")) != SAD_EXCHANGE_OK) return rc;
-    if (ex->world > 1) {
-      if ((rc = nccl_check(nccl().AllReduce(b.buf, b.buf, b.count, kNcclFloat32, kNcclSum, ex->comm, ex->comm_stream), "ncclAllReduce")) != SAD_EXCHANGE_OK)
-        return rc;
-    }
-    ex->buckets += 1;
-    ex->bytes += (uint64_t)b.count * sizeof(float);
+    if ((rc = enqueue_bucket(ex, b.buf, b.count)) != SAD_EXCHANGE_OK) return rc;
   }
   if (!ex->plan.empty()) ex->in_flight += 1;   // something for the next join to wait for
   return SAD_EXCHANGE_OK;
@@ -296,6 +377,7 @@ SAD_EXPORT int sad_exchange_join(sad_exchange* ex, void* consumer_stream) {
   if ((rc = cuda_check(cudaStreamWaitEvent(static_cast<cudaStream_t>(consumer_stream), ex->done, 0), "cudaStreamWaitEvent(consumer)")) != SAD_EXCHANGE_OK)
     return rc;
   ex->in_flight = 0;
+  ex->cursor = 0;   // the next step's buckets reuse the window from its start (ordered behind this step's sums on the communication stream)
   return SAD_EXCHANGE_OK;
 }
 

@@ -32,6 +32,12 @@ def lib():
         l.sad_exchange_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         l.sad_exchange_create_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         l.sad_exchange_max_ctas.argtypes = [C.c_void_p]
+        l.sad_exchange_create_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+        l.sad_exchange_gather_capacity.argtypes = [C.c_void_p]
+        l.sad_exchange_gather_capacity.restype = C.c_size_t
+        l.sad_exchange_gathered.argtypes = [C.c_void_p]
+        l.sad_exchange_gathered.restype = C.c_uint64
+        l.sad_exchange_slot_sum_f32.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         l.sad_exchange_destroy.argtypes = [C.c_void_p]
         l.sad_exchange_destroy.restype = None
         l.sad_exchange_world.argtypes = [C.c_void_p]
@@ -60,8 +66,24 @@ def nccl_version():
     return _check(lib().sad_exchange_nccl_version())
 
 
+def gather_supported():
+    """True when the resolved NCCL has what the copy-engine form needs (>= 2.28: symmetric windows, zero-CTA all-gather)."""
+    return bool(lib().sad_exchange_gather_supported())
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def slot_sum(slots, world, out):
+    """out[i] = slots[0, i] + slots[1, i] + ... in that order (the local half of the copy-engine exchange).  slots: (world, n) fp32."""
+    if not (slots.is_cuda and out.is_cuda and slots.dtype == out.dtype == torch.float32 and slots.dim() == 2 and slots.stride(1) == 1
+            and out.is_contiguous() and slots.shape[0] == world and out.numel() <= slots.shape[1]):
+        raise ValueError("slot_sum: (world, n) fp32 CUDA slots with unit inner stride and a contiguous fp32 output of <= n elements")
+    rc = lib().sad_exchange_slot_sum_f32(C.c_void_p(slots.data_ptr()), slots.stride(0), int(world), C.c_void_p(out.data_ptr()), out.numel(), _stream())
+    if rc != 0:
+        raise ExchangeError("sad_exchange_slot_sum_f32: cudaError %d" % rc)
+    return out
 
 
 class NativeGradientExchange:
@@ -70,12 +92,18 @@ class NativeGradientExchange:
     Same interface as parallel.GradientExchange (allreduce / nbytes / bus_bytes) plus reduce_bucket / join for the overlapped
     form.  `world` ranks must construct it collectively (the NCCL id travels through torch.distributed once)."""
 
-    def __init__(self, flat_grads, world=1, rank=0, group=None, max_ctas=0):
+    def __init__(self, flat_grads, world=1, rank=0, group=None, max_ctas=0, gather=None, max_buckets=16):
+        """gather: True = the copy-engine form (all-gather on the copy engines + a local rank-ordered sum; NCCL >= 2.28), False = the
+        ncclAllReduce form, None = SAD_EXCHANGE_GATHER from the environment ("1" / "0"; default: the ncclAllReduce form).  Asking for
+        the copy-engine form where the library cannot provide it raises — nothing is substituted silently."""
         if not (flat_grads.is_cuda and flat_grads.dtype == torch.float32 and flat_grads.is_contiguous() and flat_grads.dim() == 1):
             raise ValueError("the gradient buffer must be a contiguous 1-D fp32 CUDA tensor")
         self.flat, self.world, self.rank = flat_grads, int(world), int(rank)
         self.nbytes = flat_grads.numel() * 4
         self.calls = 0
+        if gather is None:
+            gather = os.environ.get("SAD_EXCHANGE_GATHER", "0") not in ("0", "", "false", "no")
+        self.gather = bool(gather) and self.world > 1
         uid = (C.c_char * ID_BYTES)()
         if self.world > 1:
             import torch.distributed as dist
@@ -88,8 +116,13 @@ class NativeGradientExchange:
             uid = (C.c_char * ID_BYTES).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
         self.handle = C.c_void_p()
         with torch.cuda.device(flat_grads.device):
-            _check(lib().sad_exchange_create_config(uid, self.rank, self.world, int(max_ctas), C.byref(self.handle)))
+            if self.gather:
+                capacity = flat_grads.numel() + 128 * int(max_buckets)
+                _check(lib().sad_exchange_create_gather(uid, self.rank, self.world, capacity, C.byref(self.handle)))
+            else:
+                _check(lib().sad_exchange_create_config(uid, self.rank, self.world, int(max_ctas), C.byref(self.handle)))
         self.max_ctas = int(lib().sad_exchange_max_ctas(self.handle))
+        self.mode = "copy-engine all-gather (NCCL zero-CTA, symmetric window) + local rank-ordered sum" if self.gather else "ncclAllReduce"
 
     def close(self):
         """Destroy the communicator.  NCCL keeps a reference for every CUDA graph that captured one of its collectives and
@@ -138,4 +171,5 @@ class NativeGradientExchange:
         return 0 if self.world == 1 else 2.0 * (self.world - 1) / self.world * self.nbytes
 
     def stats(self):
-        return {"buckets": int(lib().sad_exchange_buckets(self.handle)), "bytes": int(lib().sad_exchange_bytes(self.handle))}
+        return {"buckets": int(lib().sad_exchange_buckets(self.handle)), "bytes": int(lib().sad_exchange_bytes(self.handle)),
+                "gathered_buckets": int(lib().sad_exchange_gathered(self.handle)), "mode": self.mode}

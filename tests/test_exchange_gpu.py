@@ -107,3 +107,40 @@ def test_full_step_buckets_cover_the_flat_buffer_and_overlap_changes_nothing():
     a.run()
     torch.cuda.synchronize()
     assert float((a.flat_grads - ga).abs().max()) <= 2e-3 * float(ga.abs().max())
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("n,offset", [(1 << 20, 0), (100003, 0), (4099, 1), (3, 0), (70001, 3)])
+def test_slot_sum_adds_the_ranks_slots_in_rank_order(world, n, offset):
+    """The local half of the copy-engine exchange (csrc/exchange/slot_sum.cu): bit-identical to ((s0 + s1) + s2) + ... in fp32, for
+    vectorised, ragged and misaligned buckets; elements beyond the bucket stay untouched."""
+    from sad_b200 import exchange
+    g = torch.Generator(device="cuda").manual_seed(17 * world + n)
+    stride = (n + 127) // 128 * 128
+    slots = torch.randn(world, stride, device="cuda", generator=g) * 100.0
+    backing = torch.full((n + 8,), -7.0, device="cuda")
+    out = backing[offset: offset + n]
+    exchange.slot_sum(slots, world, out)
+    ref = slots[0, :n].clone()
+    for r in range(1, world):
+        ref = ref + slots[r, :n]
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert bool((backing[:offset] == -7.0).all()) and bool((backing[offset + n:] == -7.0).all())
+    # and against the fp64 sum: fp32 round-off only
+    ref64 = slots[:, :n].double().sum(0)
+    assert float((out.double() - ref64).abs().max()) <= 1e-6 * 100.0 * world * 4
+
+
+def test_copy_engine_form_is_reported_not_substituted():
+    """The copy-engine form is a property of the resolved NCCL (>= 2.28); at world 1 there is nothing to gather and the flag is off."""
+    from sad_b200 import exchange
+    assert isinstance(exchange.gather_supported(), bool)
+    flat = torch.ones(1024, device="cuda")
+    ex = exchange.NativeGradientExchange(flat, world=1, rank=0, gather=True)
+    assert ex.gather is False and ex.mode == "ncclAllReduce"
+    ex.reduce_bucket(0, 1024)
+    ex.join()
+    torch.cuda.synchronize()
+    assert float(flat.sum()) == 1024.0 and ex.stats()["gathered_buckets"] == 0
+    ex.close()
