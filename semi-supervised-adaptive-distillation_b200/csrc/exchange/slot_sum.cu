@@ -16,7 +16,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kGrid = 148 * 2;
 
-template <int kWorld>
+// kAlignedOut: out is 16-byte aligned (one float4 store); otherwise the four sums leave as scalar stores — the slot loads, which are
+// world / (world + 1) of the traffic, stay 16-byte vectors either way (the window's regions and strides are 512-byte multiples).
+template <int kWorld, bool kAlignedOut>
 __global__ void __launch_bounds__(kThreads) slot_sum_kernel(const float* __restrict__ slots, size_t stride, int world,
                                                              float* __restrict__ out, size_t count) {
   const size_t n4 = count / 4;
@@ -35,7 +37,11 @@ __global__ void __launch_bounds__(kThreads) slot_sum_kernel(const float* __restr
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
+    if (kAlignedOut) {
+      reinterpret_cast<float4*>(out)[i] = acc;
+    } else {
+      out[4 * i] = acc.x; out[4 * i + 1] = acc.y; out[4 * i + 2] = acc.z; out[4 * i + 3] = acc.w;
+    }
   }
   // the last count % 4 elements
   const size_t tail = n4 * 4 + (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -67,18 +73,25 @@ extern "C" __attribute__((visibility("default"))) int sad_exchange_slot_sum_f32(
   int grid = (int)((n4 + kThreads - 1) / kThreads);
   if (grid > kGrid) grid = kGrid;
   if (grid < 1) grid = 1;
-  const bool vec = ((reinterpret_cast<uintptr_t>(slots) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && stride % 4 == 0;
+  const bool vec = (reinterpret_cast<uintptr_t>(slots) & 15) == 0 && stride % 4 == 0;
+  const bool aligned_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#define SAD_SLOT_SUM(W)                                                                                          \
+  do {                                                                                                           \
+    if (aligned_out) slot_sum_kernel<W, true><<<grid, kThreads, 0, stream>>>(slots, stride, world, out, count);  \
+    else slot_sum_kernel<W, false><<<grid, kThreads, 0, stream>>>(slots, stride, world, out, count);             \
+  } while (0)
   if (!vec) {
     int g = (int)((count + kThreads - 1) / kThreads);
     slot_sum_scalar_kernel<<<g > kGrid ? kGrid : g, kThreads, 0, stream>>>(slots, stride, world, out, count);
   } else if (world == 2) {
-    slot_sum_kernel<2><<<grid, kThreads, 0, stream>>>(slots, stride, world, out, count);
+    SAD_SLOT_SUM(2);
   } else if (world == 4) {
-    slot_sum_kernel<4><<<grid, kThreads, 0, stream>>>(slots, stride, world, out, count);
+    SAD_SLOT_SUM(4);
   } else if (world == 8) {
-    slot_sum_kernel<8><<<grid, kThreads, 0, stream>>>(slots, stride, world, out, count);
+    SAD_SLOT_SUM(8);
   } else {
-    slot_sum_kernel<0><<<grid, kThreads, 0, stream>>>(slots, stride, world, out, count);
+    SAD_SLOT_SUM(0);
   }
+#undef SAD_SLOT_SUM
   return (int)cudaGetLastError();
 }
