@@ -54,7 +54,9 @@ int sad_exchange_max_ctas(const sad_exchange* ex);
  * this rank's slot, ncclAllGather moves the slots over NVLink with the copy engines (no SMs), and ONE short HBM-bound kernel
  * (sad_exchange_slot_sum_f32) adds the world slots in rank order back into the bucket: the result is the rank-ordered fp32 sum, bit-identical
  * on every rank.  Same calls afterwards (allreduce_async / flush / join); a bucket that does not fit what is left of the window in
- * the current step falls back to ncclAllReduce.  capacity_floats = the most floats one step exchanges (+ 128 per bucket of padding). */
+ * the current step falls back to ncclAllReduce.  capacity_floats = the most floats one step exchanges (+ 128 per bucket of padding).
+ * MEASURED (profiles/r02q_exchange_copy_engine.json): correct at 2 and 8 GPUs but slower than the ncclAllReduce
+ * buckets (an all-gather moves (world - 1) x the bytes through every rank's HBM) — opt-in, not the default. */
 int sad_exchange_gather_supported(void);
 int sad_exchange_create_gather(const void* id, int rank, int world, size_t capacity_floats, sad_exchange** out);
 size_t sad_exchange_gather_capacity(const sad_exchange* ex);   /* 0 = this exchange runs the ncclAllReduce form */
