@@ -133,3 +133,45 @@ def test_fused_and_plain_bodies_give_the_same_step_losses(fp32_cudnn):
     for (name, p), (_, q) in zip(a.student.named_parameters(), b.student.named_parameters()):
         if q.grad is not None and float(q.grad.norm()) > 1e-5:
             assert float((p.grad - q.grad).double().norm()) <= 6e-2 * float(q.grad.double().norm()), name
+
+
+def test_full_step_losses_and_logit_gradients_match_the_oracle_chain(oracle):
+    """The step's loss composition against the CPU oracle, on the step's OWN head outputs (so the body / head convolutions, which have
+    their own parity tests, drop out): PowSum over the teacher's five probability maps -> SigmoidAdaptiveDistillLoss per level with
+    scale T^2 / NUM_GPUS (retinanet_heads.py:316-351), SigmoidFocalLoss (gamma 2, alpha 0.25) and SelectSmoothL1Loss (beta 0.11) with
+    scale 1 / NUM_GPUS (retinanet_heads.py:254-312), and d(cls logits) = distillation gradient + focal gradient — the Sum autograd
+    inserts for the two consumers of retnet_cls_pred_fpnL (core.py:695,792-842)."""
+    from parity import assert_grad_close, assert_loss_close
+    from sad_b200 import synthetic
+    from sad_b200.full_step import FullDistillStep
+    world = 4                                   # loss scales 1/4 and T^2/4 without a process group: the exchange is not touched here
+    step = FullDistillStep(n_images=1, scale_px=(128, 256), student_blocks=(1, 1, 1, 1), teacher_blocks=(1, 1, 1, 1), seed=3, temperature=1.0,
+                           world=1)
+    from sad_b200 import ops, parallel
+    step.loss_scale = 1.0 / world
+    step.plan = ops.DistillPlan(list(zip(step.cls, step.t_prob, step.labels)), power=1.8, gamma=2.0, alpha=0.5, beta=0.0,
+                                scale=parallel.distill_loss_scale(1.0, world), num_classes=synthetic.NUM_CLASSES, ignored_label=-1)
+    step.forward_backward()
+    torch.cuda.synchronize()
+    got = step.losses()
+    cls = [t.cpu().numpy() for t in step.cls]
+    box = [t.cpu().numpy() for t in step.box]
+    t_prob = [t.cpu().numpy() for t in step.t_prob]
+    labels = [t.cpu().numpy() for t in step.labels]
+    fg = float(step.fg_num.item())
+    assert fg == float(sum((l > 0).sum() for l in labels)) and fg > 0
+    wp = oracle.pow_sum(t_prob, 1.8)
+    assert_loss_close(got["normalizer"], wp, "PowSum normaliser")
+    head = dict(gamma=2.0, alpha=0.5, beta=0.0, scale=1.0 / world, num_classes=synthetic.NUM_CLASSES, ignored_label=-1)
+    focal = dict(gamma=2.0, alpha=0.25, scale=1.0 / world, num_classes=synthetic.NUM_CLASSES)
+    for l in range(5):
+        assert_loss_close(got["distill"][l], oracle.distill_loss(cls[l], t_prob[l], labels[l], wp, **head), "distill level %d" % l)
+        assert_loss_close(got["focal"][l], oracle.focal_loss(cls[l], labels[l], fg, **focal), "focal level %d" % l)
+        ref_box, ref_dbox = oracle.select_smooth_l1(box[l], step.box_targets[l].cpu().numpy(), step.box_locs[l].cpu().numpy(), fg, beta=0.11,
+                                                    scale=1.0 / world)
+        assert_loss_close(got["bbox"][l], ref_box, "bbox level %d" % l)
+        assert_grad_close(step.d_box[l].cpu().numpy(), ref_dbox, "d(bbox pred) level %d" % l)
+        ref_dcls = (oracle.distill_grad(cls[l], t_prob[l], labels[l], wp, **head).astype(np.float64)
+                    + oracle.focal_grad(cls[l], labels[l], fg, **focal).astype(np.float64)).astype(np.float32)
+        assert_grad_close(step.plan.grads[l].cpu().numpy(), ref_dcls, "d(cls logits) level %d" % l)
+    step.close()
