@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list by kernel name:
-    python scripts/launch_summary.py gpurun_out/launches.csv [out.txt]
-Per-launch times are cold-cache and serialised: compare SHARES, not absolutes."""
+    python scripts/launch_summary.py gpurun_out/launches.csv [out.txt] [--native-share]
+Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.
+--native-share appends the split between this repository's kernels (namespace sad::) and library kernels (cuDNN / CUTLASS / ATen)."""
 import csv
 import re
 import sys
@@ -29,10 +30,17 @@ def main():
     lines = ["%-70s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "avg_us", "share")]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("%-70s %6d %12.1f %10.2f %6.1f%%" % (k[:70], n, t, t / n, 100 * t / total))
+    args = [a for a in sys.argv[2:] if not a.startswith("--")]
+    if "--native-share" in sys.argv:
+        nat = [(n, t) for k, (n, t) in agg.items() if "sad::" in k]
+        lib = [(n, t) for k, (n, t) in agg.items() if "sad::" not in k]
+        lines.append("")
+        lines.append("native (sad::)   %5d launches %10.1f us %5.1f%%" % (sum(n for n, _ in nat), sum(t for _, t in nat), 100 * sum(t for _, t in nat) / total))
+        lines.append("library kernels  %5d launches %10.1f us %5.1f%%" % (sum(n for n, _ in lib), sum(t for _, t in lib), 100 * sum(t for _, t in lib) / total))
     out = "\n".join(lines)
     print(out)
-    if len(sys.argv) > 2:
-        open(sys.argv[2], "w").write(out + "\n")
+    if args:
+        open(args[0], "w").write(out + "\n")
 
 
 if __name__ == "__main__":
