@@ -52,22 +52,27 @@
 
 namespace sad {
 
+#ifndef SAD_CONV_ROWS
+#define SAD_CONV_ROWS 8   // image rows per pixel tile (x 32 columns).  4 was measured too: see there
+#endif
 constexpr int kCvM = 128;
-constexpr int kCvRows = 8;
+constexpr int kCvRows = SAD_CONV_ROWS;
 constexpr int kCvCols = 32;
 constexpr int kCvN = kCvRows * kCvCols;  // 256
+static_assert(kCvRows == 8 || kCvRows == 4, "pixel tile: 8 or 4 rows of 32 pixels");
 constexpr int kCvKC = 32;
-constexpr int kCvStages = 4;
-constexpr int kCvStagesPair = 6;   // CTA-pair kernel: 32 KB stages
 constexpr int kCvABytes = kCvM * kCvKC * 4;            // 16 KB
 constexpr int kCvBBytes = kCvN * kCvKC * 4;            // 32 KB
 constexpr int kCvStageBytes = kCvABytes + kCvBBytes;   // 48 KB
+constexpr int kCvRingBytes = 192 * 1024;               // operand ring of either kernel
+constexpr int kCvStages = kCvRingBytes / kCvStageBytes;                       // 4 (8 rows) / 6 (4 rows)
+constexpr int kCvStagesPair = kCvRingBytes / (kCvABytes + kCvBBytes / 2);     // CTA-pair kernel, half the pixel tile per CTA: 6 / 8
 constexpr int kCvEpiWarps = 8;                         // two warps per TMEM lane quarter, each draining 4 of the tile's 8 pixel rows
                                                        // (measured head step bs=2 / bs=16: 4 warps 2.10 / 14.99 ms, 8: 2.02 / 14.61, 16: 2.02 / 14.39)
 constexpr int kCvThreads = 64 + 32 * kCvEpiWarps;      // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
 constexpr int kCvTmemCols = 512;                       // 2 accumulator buffers x 256 columns
-constexpr size_t kCvSmemBytes = (size_t)kCvStages * kCvStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-static_assert((2 * 6 + 4 + 6) * 8 + 4 <= 256, "barrier block");
+constexpr size_t kCvSmemBytes = (size_t)kCvRingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static_assert((3 * kCvStagesPair + 4) * 8 + 4 <= 256 && kCvStagesPair >= kCvStages, "barrier block");
 
 struct ConvLevel {
   float* y_nchw;            // may be null
