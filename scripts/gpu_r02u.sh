@@ -1,0 +1,25 @@
+#!/bin/bash
+# r02u: A/B of the convolution operand ring: 192 KB (6 stages of the CTA-pair kernel, default build) against 224 KB (7 stages,
+# variants/libsad_b200_ring224.so, -DSAD_CONV_RING_KB=224): head forward / backward / whole head step at bs = 2 and 16, then the tests.
+OUT=gpurun_out
+PKG=semi-supervised-adaptive-distillation_b200
+mkdir -p $OUT
+summ() { python - "$1" <<'PY'
+import json,sys
+tag=sys.argv[1]
+for bs in (2,16):
+    try:
+        d=json.load(open('gpurun_out/head_bench_bs%d.json'%bs))
+        print(tag,'bs',bs,'fwd %.3f ms %.0f TF/s'%(d['head_forward_eager']['ms'],d['head_forward_eager']['tflops']),'bwd %.3f ms %.0f TF/s'%(d['head_backward_eager']['ms'],d['head_backward_eager']['tflops']),'step(graph) %.3f ms %.0f TF/s'%(d['step_graph']['ms'],d['step_graph']['tflops']))
+        import shutil; shutil.copy('gpurun_out/head_bench_bs%d.json'%bs,'gpurun_out/head_bench_r02u_%s_bs%d.json'%(tag,bs))
+    except Exception as e: print(tag,bs,'failed',e)
+PY
+}
+for bs in 2 16; do timeout 200 python scripts/head_bench.py --bs $bs --iters 30 > $OUT/head_bench_r02u_ring192_bs$bs.log 2>&1; done
+summ ring192
+cp $PKG/libsad_b200.so /tmp/libsad_b200_ring192.so
+cp variants/libsad_b200_ring224.so $PKG/libsad_b200.so; touch $PKG/libcaffe2_detectron_ops_gpu.so $PKG/libsad_exchange.so
+for bs in 2 16; do timeout 200 python scripts/head_bench.py --bs $bs --iters 30 > $OUT/head_bench_r02u_ring224_bs$bs.log 2>&1; done
+summ ring224
+echo "== tests on the 224 KB ring build"
+timeout 900 python -m pytest tests/test_conv_gpu.py tests/test_conv_f16_gpu.py tests/test_conv_f32x3_gpu.py tests/test_head_gpu.py tests/test_operator_boundary_gpu.py -x -q 2>&1 | tail -6

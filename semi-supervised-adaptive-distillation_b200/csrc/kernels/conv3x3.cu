@@ -64,7 +64,11 @@ constexpr int kCvKC = 32;
 constexpr int kCvABytes = kCvM * kCvKC * 4;            // 16 KB
 constexpr int kCvBBytes = kCvN * kCvKC * 4;            // 32 KB
 constexpr int kCvStageBytes = kCvABytes + kCvBBytes;   // 48 KB
-constexpr int kCvRingBytes = 192 * 1024;               // operand ring of either kernel
+#ifndef SAD_CONV_RING_KB
+#define SAD_CONV_RING_KB 192
+#endif
+constexpr int kCvRingBytes = SAD_CONV_RING_KB * 1024;   // operand ring of either kernel (+ 1.25 KB of slack and barriers <= 227 KB per CTA)
+static_assert(kCvRingBytes + 1024 + 256 <= 227 * 1024, "shared memory per CTA");
 constexpr int kCvStages = kCvRingBytes / kCvStageBytes;                       // 4 (8 rows) / 6 (4 rows)
 constexpr int kCvStagesPair = kCvRingBytes / (kCvABytes + kCvBBytes / 2);     // CTA-pair kernel, half the pixel tile per CTA: 6 / 8
 constexpr int kCvEpiWarps = 8;                         // two warps per TMEM lane quarter, each draining 4 of the tile's 8 pixel rows
@@ -151,20 +155,13 @@ __device__ __forceinline__ ConvTile conv_decode_tile(const ConvArgs& a, uint32_t
 // channels-last output are fp16; a stage still holds 128-byte rows, i.e. 64 instead of 32 input channels, so a tile takes
 // half as many stages and MMAs.  Accumulation, bias, activation and the NCHW output stay fp32 (BASELINE.json configs[4]:
 // "mixed fp16 compute / fp32 loss accumulate").  fp16 keeps the 10-bit mantissa of tf32; values beyond 65504 become inf.
-// kDual (CTA pairs, not kX3): a work stream takes its tiles TWO at a time — tile i and tile i + nstreams, both under the same weight
-// tile — with one accumulator each (the two TMEM buffers), so that every weight stage is loaded once for two pixel tiles: 48 instead of
-// 2 x 32 KB of TMA traffic per CTA for the same MMAs.  Measured reason: both the 8-row and the 4-row tile forms
-// of this kernel stop at ~36 B per clock and SM of operand traffic from L2, not at the tensor pipe.  The price: both accumulators are
-// live until the last stage, so the epilogue of a tile pair no longer overlaps the next pair's main loop.
-template <bool kC2, bool kSigmoid, bool kF16 = false, bool kX3 = false, bool kDual = false>
+template <bool kC2, bool kSigmoid, bool kF16 = false, bool kX3 = false>
 __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __grid_constant__ ConvArgs args) {
   static_assert(!(kF16 && kX3), "the split mode is a tf32 mode");
-  static_assert(!kDual || (kC2 && !kX3), "two tiles per weight stage: CTA-pair kernel, one accumulation chain per tile");
   constexpr int kKCe = kF16 ? 2 * kCvKC : kCvKC;   // input channels per stage (one 128-byte row)
+  constexpr int kStages = kC2 ? kCvStagesPair : kCvStages;
   constexpr int kBBytes = kC2 ? kCvBBytes / 2 : kCvBBytes;
-  constexpr int kStageBytes = kCvABytes + (kDual ? 2 : 1) * kBBytes;
-  constexpr int kStages = kDual ? kCvRingBytes / kStageBytes : (kC2 ? kCvStagesPair : kCvStages);
-  static_assert(kStages >= 3 && kStages <= kCvStagesPair, "ring depth");
+  constexpr int kStageBytes = kCvABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (128B-swizzle atoms are 1024 B), barriers behind it
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -181,7 +178,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
   const uint32_t crank = kC2 ? cluster_ctarank() : 0u;            // which 128-channel half of the pair
   const uint32_t wstream = kC2 ? blockIdx.x >> 1 : blockIdx.x;    // work stream (both CTAs of a pair walk the same one)
   const uint32_t nstreams = kC2 ? gridDim.x >> 1 : gridDim.x;
-  const uint32_t tstep = kDual ? 2u * nstreams : nstreams;          // kDual: tiles (tile, tile + nstreams) per iteration
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.tmap_w);
@@ -218,14 +214,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
     if (lane == 0) {
       RingState rs;
       int l_hint = 0;
-      for (uint32_t tile = wstream; tile < args.total_tiles; tile += tstep) {
+      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
         ConvTile t = conv_decode_tile(args, tile, l_hint);
         if (kC2) t.m0 = (2 * (t.m0 / kCvM) + (int)crank) * kCvM;
         const CUtensorMap* mx = kC2 ? &args.tmap_xh[t.l] : &args.tmap_x[t.l];
-        const bool has1 = kDual && tile + nstreams < args.total_tiles;
-        ConvTile t1 = t;
-        if (has1) t1 = conv_decode_tile(args, tile + nstreams, l_hint);   // same weight tile: the host keeps nstreams % m_tiles == 0
-        const CUtensorMap* mx1 = &args.tmap_xh[t1.l];
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           for (uint32_t kb = 0; kb < k_blocks; ++kb) {
@@ -240,11 +232,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
               kx = kk + (pass == 1 ? args.k_split : 0);
             }
             if (kC2) {
-              mbar_arrive_expect_tx(&full_bar[rs.stage], kCvABytes + (has1 ? 2 : 1) * kBBytes);
+              mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
               tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], ka, t.m0, tap);
               // my half of the pixel tile: rows y0 + 4 * rank .. + 3 (= accumulator columns 128 * rank .. + 127)
               tma_load_4d(sb, mx, &full_bar[rs.stage], kx, t.x0 + dx, t.y0 + (int)crank * (kCvRows / 2) + dy, t.n);
-              if (has1) tma_load_4d(sb + kBBytes, mx1, &full_bar[rs.stage], kx, t1.x0 + dx, t1.y0 + (int)crank * (kCvRows / 2) + dy, t1.n);
             } else {
               mbar_arrive_expect_tx(&full_bar[rs.stage], kStageBytes);
               tma_load_3d(sa, &args.tmap_w, &full_bar[rs.stage], ka, t.m0, tap);
@@ -260,7 +251,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
     if (kC2 && lane == 0 && crank != 0) {
       // partner CTA: relay "my stage landed" to the leader's MMA thread
       RingState rs;
-      for (uint32_t tile = wstream; tile < args.total_tiles; tile += tstep) {
+      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
         const uint32_t n_kb = 9u * k_blocks;
         for (uint32_t kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full_bar[rs.stage], rs.phase);
@@ -274,14 +265,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
                                       : umma_idesc_tf32(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
       RingState rs;
       uint32_t it = 0;
-      for (uint32_t tile = wstream; tile < args.total_tiles; tile += tstep, ++it) {
-        const bool has1 = kDual && tile + nstreams < args.total_tiles;
+      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
         // kX3: the tile's stage sequence is cut into TWO accumulation chains, one per TMEM buffer, which the epilogue adds in
         // fp32 (round to nearest): the tensor core's accumulator add rounds toward zero (measured: the result of a K = 2304
         // chain is 1.6e-5 too small in magnitude, growing linearly with the number of MMAs in the chain), so halving the
         // chains halves that bias.  The price is the epilogue / main-loop overlap, < 10 % of a 3x longer main loop.
-        // kDual: both buffers are this iteration's accumulators (tile -> buffer 0, tile + nstreams -> buffer 1), handed over as one
-        const uint32_t buf = (kX3 || kDual) ? 0u : (it & 1u), aphase = (kX3 || kDual) ? (it & 1u) : ((it >> 1) & 1u);
+        const uint32_t buf = kX3 ? 0u : (it & 1u), aphase = kX3 ? (it & 1u) : ((it >> 1) & 1u);
         mbar_wait(&tmem_empty[buf], aphase ^ 1u);
         tc_fence_after_sync();
         const uint32_t n_kb = 9u * k_blocks;
@@ -307,11 +296,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
               if (kC2) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, (kb_chain | (uint32_t)k) != 0u);
               else umma_tf32(d_tmem, adesc, bdesc, idesc, (kb_chain | (uint32_t)k) != 0u);
             }
-            if (kDual && has1) {   // the second pixel tile under the same weight stage, into the other accumulator
-              const uint64_t bdesc1 = umma_smem_desc_sw128(b_addr + kBBytes + k * 32, 16, 1024);
-              if (kF16) umma_f16_2sm(d_tmem + kCvN, adesc, bdesc1, idesc, (kb | (uint32_t)k) != 0u);
-              else umma_tf32_2sm(d_tmem + kCvN, adesc, bdesc1, idesc, (kb | (uint32_t)k) != 0u);
-            }
           }
           // frees the smem stage when these MMAs have read it (pair: in both CTAs)
           if (kC2) umma_commit_2sm(&empty_bar[rs.stage], (uint16_t)0x3);
@@ -331,20 +315,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
     const int row = q * 32 + lane;
     uint32_t it = 0;
     int l_hint = 0;
-    for (uint32_t tile = wstream; tile < args.total_tiles; tile += tstep, ++it) {
-      const uint32_t buf = (kX3 || kDual) ? 0u : (it & 1u), aphase = (kX3 || kDual) ? (it & 1u) : ((it >> 1) & 1u);
-      const int n_sub = (kDual && tile + nstreams < args.total_tiles) ? 2 : 1;
-      mbar_wait(&tmem_full[buf], aphase);
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int sub = 0; sub < n_sub; ++sub) {
-      ConvTile t = conv_decode_tile(args, tile + (uint32_t)sub * nstreams, l_hint);
+    for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
+      const uint32_t buf = kX3 ? 0u : (it & 1u), aphase = kX3 ? (it & 1u) : ((it >> 1) & 1u);
+      ConvTile t = conv_decode_tile(args, tile, l_hint);
       if (kC2) t.m0 = (2 * (t.m0 / kCvM) + (int)crank) * kCvM;
       const ConvLevel& L = args.lv[t.l];
       const int co = t.m0 + row;
       const bool co_ok = co < args.cout;
       const float b = (co_ok && args.bias) ? __ldg(args.bias + co) : 0.f;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (kDual ? (uint32_t)sub : buf) * kCvN;
+      mbar_wait(&tmem_full[buf], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kCvN;
       const size_t HW = (size_t)L.H * L.W;
       float* yrow = L.y_nchw ? L.y_nchw + ((size_t)t.n * args.cout + (co_ok ? co : 0)) * HW : nullptr;
       // channels-last output rows: cout floats; kX3: split rows of 2 * cout_split floats, hi at co, lo at cout_split + co
@@ -452,7 +433,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
           }
         }
       }
-      }   // sub
       tc_fence_before_sync();
       if (kC2) mbar_arrive_cluster(map_to_cta(&tmem_empty[buf], 0));   // the leader's MMA thread owns the accumulator hand-over
       else mbar_arrive(&tmem_empty[buf]);
@@ -708,15 +688,6 @@ static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int c
 
 // `packed` has layout [tap][cout][cin] (sad_conv3x3_pack_weights_f32 mode 0 for the forward operator,
 // mode 1 — with cin/cout swapped by the caller — for the data gradient).
-// SAD_CONV_DUAL=0 selects the one-tile-per-stage form of the CTA-pair kernel (A/B measurements; the default is the two-tile form)
-static bool conv_dual_enabled() {
-  static const bool v = [] {
-    const char* e = std::getenv("SAD_CONV_DUAL");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
 static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                             int cout, int relu, void* stream, bool f16, float nchw_scale = 1.f, bool x3 = false) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3: n_levels must be in [1, 8]");
@@ -839,25 +810,15 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
   int sms = 0;
   if ((rc = sm_count(&sms)) != SAD_OK) return rc;
   if (pair) {
-    uint32_t pairs = (uint32_t)sms / 2;
-    if (pairs > a.total_tiles) pairs = a.total_tiles;
-    if (pairs < 1) pairs = 1;
-    // two tiles per weight stage (kDual) when some work stream has more than one tile; tile i and tile i + pairs must then lie under
-    // the same weight tile, i.e. pairs % m_tiles == 0 (256 -> 720: 3 pair tiles, 72 instead of 74 pairs)
-    bool dual = !x3 && conv_dual_enabled() && a.total_tiles > pairs;
-    if (dual && pairs % m_tiles != 0) {
-      if (pairs > m_tiles) pairs -= pairs % m_tiles;
-      else dual = false;
-    }
     auto kern = f16  ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true> : conv3x3_tf32_kernel<true, false, true>)
                 : x3 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, false, true> : conv3x3_tf32_kernel<true, false, false, true>)
                      : (relu == 2 ? conv3x3_tf32_kernel<true, true, false> : conv3x3_tf32_kernel<true, false, false>);
-    if (dual)
-      kern = f16 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true, false, true> : conv3x3_tf32_kernel<true, false, true, false, true>)
-                 : (relu == 2 ? conv3x3_tf32_kernel<true, true, false, false, true> : conv3x3_tf32_kernel<true, false, false, false, true>);
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
                          "cudaFuncSetAttribute(conv3x3 pair)")) != SAD_OK)
       return rc;
+    uint32_t pairs = (uint32_t)sms / 2;
+    if (pairs > a.total_tiles) pairs = a.total_tiles;
+    if (pairs < 1) pairs = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kCvThreads);
