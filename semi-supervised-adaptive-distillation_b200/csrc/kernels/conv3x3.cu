@@ -75,16 +75,8 @@ constexpr int kCvEpiWarps = 8;                         // two warps per TMEM lan
                                                        // (measured head step bs=2 / bs=16: 4 warps 2.10 / 14.99 ms, 8: 2.02 / 14.61, 16: 2.02 / 14.39)
 constexpr int kCvThreads = 64 + 32 * kCvEpiWarps;      // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
 constexpr int kCvTmemCols = 512;                       // 2 accumulator buffers x 256 columns
-constexpr size_t kCvSmemBytes = (size_t)kCvRingBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
-// kHalo (CTA-pair kernel): the pixel operand is loaded with its vertical halo — (kCvRows / 2 + 2) image rows of 32 pixels per CTA, once
-// per (input-channel block, dx) — and the three dy taps read it at row offsets of 4096 B; weights keep their own ring
-constexpr int kCvHaloRows = kCvRows / 2 + 2;
-constexpr int kCvHaloBytes = kCvHaloRows * kCvCols * 128;   // 24 KB
-constexpr int kCvHaloTiles = 4;                             // ring of halo tiles
-constexpr int kCvHaloAStages = (kCvRingBytes - kCvHaloTiles * kCvHaloBytes) / kCvABytes;   // 6 weight stages of 16 KB
-static_assert(kCvHaloAStages >= 4 && kCvHaloAStages <= kCvStagesPair, "weight ring of the halo form");
-static_assert((3 * kCvStagesPair + 4 + 3 * kCvHaloTiles) * 8 + 4 <= 512, "barrier block");
-static_assert(kCvStagesPair >= kCvStages, "barrier block is sized for the pair kernel's ring");
+constexpr size_t kCvSmemBytes = (size_t)kCvRingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static_assert((3 * kCvStagesPair + 4) * 8 + 4 <= 256 && kCvStagesPair >= kCvStages, "barrier block");
 
 struct ConvLevel {
   float* y_nchw;            // may be null
@@ -100,7 +92,6 @@ struct alignas(64) ConvArgs {
   CUtensorMap tmap_w;
   CUtensorMap tmap_x[SAD_MAX_LEVELS];    // box {32 ci, 32 x, 8 y, 1 n}: a whole pixel tile
   CUtensorMap tmap_xh[SAD_MAX_LEVELS];   // box {32 ci, 32 x, 4 y, 1 n}: half a pixel tile (CTA-pair kernel)
-  CUtensorMap tmap_xv[SAD_MAX_LEVELS];   // box {32 ci, 32 x, 4 + 2 y, 1 n}: half a pixel tile with the rows above and below (kHalo)
   ConvLevel lv[SAD_MAX_LEVELS];
   const float* bias;
   int32_t n_levels, cin, cout, relu;
@@ -164,35 +155,24 @@ __device__ __forceinline__ ConvTile conv_decode_tile(const ConvArgs& a, uint32_t
 // channels-last output are fp16; a stage still holds 128-byte rows, i.e. 64 instead of 32 input channels, so a tile takes
 // half as many stages and MMAs.  Accumulation, bias, activation and the NCHW output stay fp32 (BASELINE.json configs[4]:
 // "mixed fp16 compute / fp32 loss accumulate").  fp16 keeps the 10-bit mantissa of tf32; values beyond 65504 become inf.
-// kHalo (CTA pairs, not kX3): the pixel operand with its vertical halo.  The shipped one-box-per-tap form re-reads every pixel row
-// three times (dy = -1, 0, +1) and sits at ~85 % of the L2 -> SM operand ceiling; here a CTA loads its 4 image
-// rows + the row above and the row below ONCE per (input-channel block, dx) — 24 KB instead of 3 x 16 KB — and the three dy taps are
-// the same shared-memory tile read at +0, +4096, +8192 B (one image row = 32 pixel rows of 128 B = four 1024 B swizzle atoms, so the
-// descriptors stay atom-aligned).  Weights keep a ring of their own (one 16 KB stage per tap and channel block, as before).  Operand
-// traffic per CTA and channel block: 9 x 16 + 3 x 24 = 216 KB instead of 288 KB.  The K order becomes (channel block, dx, dy).
-template <bool kC2, bool kSigmoid, bool kF16 = false, bool kX3 = false, bool kHalo = false>
+template <bool kC2, bool kSigmoid, bool kF16 = false, bool kX3 = false>
 __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __grid_constant__ ConvArgs args) {
   static_assert(!(kF16 && kX3), "the split mode is a tf32 mode");
-  static_assert(!kHalo || (kC2 && !kX3), "halo tiles: CTA-pair kernel, single-pass operands");
   constexpr int kKCe = kF16 ? 2 * kCvKC : kCvKC;   // input channels per stage (one 128-byte row)
-  constexpr int kStages = kHalo ? kCvHaloAStages : (kC2 ? kCvStagesPair : kCvStages);
+  constexpr int kStages = kC2 ? kCvStagesPair : kCvStages;
   constexpr int kBBytes = kC2 ? kCvBBytes / 2 : kCvBBytes;
-  constexpr int kStageBytes = kHalo ? kCvABytes : kCvABytes + kBBytes;
+  constexpr int kStageBytes = kCvABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (128B-swizzle atoms are 1024 B), barriers behind it
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* halo = smem + (size_t)kStages * kStageBytes;   // kHalo: kCvHaloTiles tiles of kCvHaloBytes behind the weight ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kCvRingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
   uint64_t* full_bar = bars;                  // [kStages] TMA -> MMA
   uint64_t* empty_bar = bars + kStages;       // [kStages] MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;   // [2] MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;       // [2] epilogue -> MMA
   uint64_t* peer_full = tmem_empty + 2;       // [kStages] pair only: partner's stage landed
-  uint64_t* halo_full = peer_full + kStages;  // [kCvHaloTiles] kHalo only, like full / empty / peer_full for the halo tiles
-  uint64_t* halo_empty = halo_full + kCvHaloTiles;
-  uint64_t* halo_peer = halo_empty + kCvHaloTiles;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_peer + kCvHaloTiles);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = kC2 ? cluster_ctarank() : 0u;            // which 128-channel half of the pair
@@ -202,7 +182,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.tmap_w);
     for (int l = 0; l < args.n_levels; ++l)
-      tma_prefetch_desc(kHalo ? &args.tmap_xv[l] : (kC2 ? &args.tmap_xh[l] : &args.tmap_x[l]));
+      tma_prefetch_desc(kC2 ? &args.tmap_xh[l] : &args.tmap_x[l]);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -210,13 +190,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
         mbar_init(&peer_full[s], 1);
-      }
-      if (kHalo) {
-        for (int s = 0; s < kCvHaloTiles; ++s) {
-          mbar_init(&halo_full[s], 1);
-          mbar_init(&halo_empty[s], 1);
-          mbar_init(&halo_peer[s], 1);
-        }
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full[b], 1);
@@ -238,32 +211,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
-    if (kHalo && lane == 0) {
-      RingState ra, rb;   // weight ring, halo-tile ring
-      int l_hint = 0;
-      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
-        ConvTile t = conv_decode_tile(args, tile, l_hint);
-        t.m0 = (2 * (t.m0 / kCvM) + (int)crank) * kCvM;
-        const CUtensorMap* mv = &args.tmap_xv[t.l];
-        for (uint32_t kb = 0; kb < k_blocks; ++kb) {
-          const int ka = (int)kb * kKCe;
-          for (int dxi = 0; dxi < 3; ++dxi) {
-            mbar_wait(&halo_empty[rb.stage], rb.phase ^ 1u);
-            mbar_arrive_expect_tx(&halo_full[rb.stage], kCvHaloBytes);
-            // rows y0 + 4 * rank - 1 .. + 4 (out-of-range rows and columns are zero-filled: the padding)
-            tma_load_4d(halo + (size_t)rb.stage * kCvHaloBytes, mv, &halo_full[rb.stage], ka, t.x0 + dxi - 1,
-                        t.y0 + (int)crank * (kCvRows / 2) - 1, t.n);
-            rb.advance<kCvHaloTiles>();
-            for (int dyi = 0; dyi < 3; ++dyi) {
-              mbar_wait(&empty_bar[ra.stage], ra.phase ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[ra.stage], kCvABytes);
-              tma_load_3d(smem + (size_t)ra.stage * kStageBytes, &args.tmap_w, &full_bar[ra.stage], ka, t.m0, dyi * 3 + dxi);
-              ra.advance<kStages>();
-            }
-          }
-        }
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       RingState rs;
       int l_hint = 0;
       for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
@@ -300,22 +248,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread; pair: of the leader CTA only) =====================
-    if (kHalo && lane == 0 && crank != 0) {
-      // partner CTA: relay "my halo tile / my weight stage landed" to the leader's MMA thread, in the order the producer issues them
-      RingState ra, rb;
-      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
-        for (uint32_t kb = 0; kb < 3u * k_blocks; ++kb) {   // (channel block, dx)
-          mbar_wait(&halo_full[rb.stage], rb.phase);
-          mbar_arrive_cluster(map_to_cta(&halo_peer[rb.stage], 0));
-          rb.advance<kCvHaloTiles>();
-          for (int dyi = 0; dyi < 3; ++dyi) {
-            mbar_wait(&full_bar[ra.stage], ra.phase);
-            mbar_arrive_cluster(map_to_cta(&peer_full[ra.stage], 0));
-            ra.advance<kStages>();
-          }
-        }
-      }
-    } else if (kC2 && lane == 0 && crank != 0) {
+    if (kC2 && lane == 0 && crank != 0) {
       // partner CTA: relay "my stage landed" to the leader's MMA thread
       RingState rs;
       for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams) {
@@ -327,43 +260,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_tf32_kernel(const __gri
         }
       }
     }
-    if (kHalo && lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = kF16 ? umma_idesc_f16(2 * kCvM, kCvN, 0, 0) : umma_idesc_tf32(2 * kCvM, kCvN, 0, 0);
-      RingState ra, rb;
-      uint32_t it = 0;
-      for (uint32_t tile = wstream; tile < args.total_tiles; tile += nstreams, ++it) {
-        const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
-        mbar_wait(&tmem_empty[buf], aphase ^ 1u);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * kCvN;
-        uint32_t accumulate = 0u;
-        for (uint32_t kb = 0; kb < 3u * k_blocks; ++kb) {   // (channel block, dx)
-          mbar_wait(&halo_full[rb.stage], rb.phase);
-          mbar_wait_cluster(&halo_peer[rb.stage], rb.phase);
-          const uint32_t h_addr = smem_u32(halo + (size_t)rb.stage * kCvHaloBytes);
-          for (int dyi = 0; dyi < 3; ++dyi) {
-            mbar_wait(&full_bar[ra.stage], ra.phase);
-            mbar_wait_cluster(&peer_full[ra.stage], ra.phase);
-            tc_fence_after_sync();
-            const uint32_t a_addr = smem_u32(smem + (size_t)ra.stage * kStageBytes);
-            const uint32_t b_addr = h_addr + (uint32_t)dyi * (kCvCols * 128);   // tap row dy: my 4 output rows start dyi image rows down
-#pragma unroll
-            for (int k = 0; k < kCvKC / 8; ++k) {
-              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              if (kF16) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, accumulate);
-              else umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, accumulate);
-              accumulate = 1u;
-            }
-            umma_commit_2sm(&empty_bar[ra.stage], (uint16_t)0x3);
-            ra.advance<kStages>();
-          }
-          umma_commit_2sm(&halo_empty[rb.stage], (uint16_t)0x3);   // all three dy taps of this tile have been read (both CTAs)
-          rb.advance<kCvHaloTiles>();
-        }
-        umma_commit_2sm(&tmem_full[buf], (uint16_t)0x3);
-      }
-    } else if (lane == 0 && crank == 0) {
+    if (lane == 0 && crank == 0) {
       constexpr uint32_t idesc = kF16 ? umma_idesc_f16(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0)
                                       : umma_idesc_tf32(kC2 ? 2 * kCvM : kCvM, kCvN, /*A K-major*/ 0, /*B K-major*/ 0);
       RingState rs;
@@ -791,15 +688,6 @@ static int nchw_to_nhwc_impl(const sad_layout_level* levels, int n_levels, int c
 
 // `packed` has layout [tap][cout][cin] (sad_conv3x3_pack_weights_f32 mode 0 for the forward operator,
 // mode 1 — with cin/cout swapped by the caller — for the data gradient).
-// SAD_CONV_HALO=0 selects the one-box-per-tap form of the CTA-pair kernel (A/B measurements)
-static bool conv_halo_enabled() {
-  static const bool v = [] {
-    const char* e = std::getenv("SAD_CONV_HALO");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
 static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const float* packed, const float* bias, int cin,
                             int cout, int relu, void* stream, bool f16, float nchw_scale = 1.f, bool x3 = false) {
   if (!levels || n_levels < 1 || n_levels > SAD_MAX_LEVELS) return set_error(SAD_ERR_INVALID, "conv3x3: n_levels must be in [1, 8]");
@@ -889,7 +777,6 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
     if ((uint64_t)L.N * L.H * L.W == 0) {  // empty level: a valid dummy map (never used, no tiles)
       a.tmap_x[l] = a.tmap_w;
       a.tmap_xh[l] = a.tmap_w;
-      a.tmap_xv[l] = a.tmap_w;
       continue;
     }
     if (f16) {
@@ -897,16 +784,10 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
       if ((rc = encode_nhwc_map_f16(&a.tmap_xh[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvRows / 2, "fp16 activations {C,W,H,N}, half tile")) !=
           SAD_OK)
         return rc;
-      if ((rc = encode_nhwc_map_f16(&a.tmap_xv[l], L.x_nhwc, L.N, cin, L.H, L.W, kCvCols, kCvHaloRows, "fp16 activations {C,W,H,N}, half tile + halo rows")) !=
-          SAD_OK)
-        return rc;
       continue;
     }
     if ((rc = encode_nhwc_map(&a.tmap_x[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kCvCols, kCvRows, "activations {C,W,H,N}")) != SAD_OK) return rc;
     if ((rc = encode_nhwc_map(&a.tmap_xh[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kCvCols, kCvRows / 2, "activations {C,W,H,N}, half tile")) != SAD_OK)
-      return rc;
-    if ((rc = encode_nhwc_map(&a.tmap_xv[l], L.x_nhwc, L.N, cin_map, L.H, L.W, kCvCols, kCvHaloRows, "activations {C,W,H,N}, half tile + halo rows")) !=
-        SAD_OK)
       return rc;
   }
   a.bias = bias;
@@ -932,9 +813,6 @@ static int conv3x3_fwd_impl(const sad_conv_level* levels, int n_levels, const fl
     auto kern = f16  ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true> : conv3x3_tf32_kernel<true, false, true>)
                 : x3 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, false, true> : conv3x3_tf32_kernel<true, false, false, true>)
                      : (relu == 2 ? conv3x3_tf32_kernel<true, true, false> : conv3x3_tf32_kernel<true, false, false>);
-    if (!x3 && conv_halo_enabled())
-      kern = f16 ? (relu == 2 ? conv3x3_tf32_kernel<true, true, true, false, true> : conv3x3_tf32_kernel<true, false, true, false, true>)
-                 : (relu == 2 ? conv3x3_tf32_kernel<true, true, false, false, true> : conv3x3_tf32_kernel<true, false, false, false, true>);
     if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCvSmemBytes),
                          "cudaFuncSetAttribute(conv3x3 pair)")) != SAD_OK)
       return rc;
