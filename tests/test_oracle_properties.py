@@ -4,7 +4,7 @@ the normaliser enters as 1 / max(wp, 1); `scale` and `d_loss` are plain multipli
 (sigmoid_adaptive_distillation_loss_op.cu:35-51, 63-64, 98-102, 136-138, 166-168); PowSum is additive over its inputs in input
 order (pow_sum_op.cu:34-40); SigmoidFocalLoss shares the label indexing (sigmoid_focal_loss_op.cu:34-43)."""
 import numpy as np
-from hypothesis import given, settings
+from hypothesis import example, given, settings
 from hypothesis import strategies as st
 
 from oracle import cpu_oracle as O
@@ -20,8 +20,9 @@ def _case(seed, n, a, c, h, w):
     return x, t, g
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(shape_st, st.integers(0, 2 ** 20), st.sampled_from([0.0, 1.0, 2.0]), st.sampled_from([0.25, 0.5]), st.sampled_from([0.0, 1.0]))
+@example(shape=(1, 2, 2, 5, 5), seed=1088, gamma=0.0, alpha=0.25, beta=1.0)   # gamma = 0 with an adaptive target of exactly 0: 0 * powf(0, -1) = NaN
 def test_ignore_mask_is_per_anchor_location_and_class_independent(shape, seed, gamma, alpha, beta):
     n, a, c, h, w = shape
     x, t, g = _case(seed, n, a, c, h, w)
@@ -29,17 +30,23 @@ def test_ignore_mask_is_per_anchor_location_and_class_independent(shape, seed, g
     _, elems = O.distill_loss(x, t, g, 3.0, return_elements=True, **args)
     grad = O.distill_grad(x, t, g, 3.0, **args)
     keep = np.repeat(g != -1, c, axis=1)                      # (N, A, H, W) -> (N, A*C, H, W): channel a*C + d reads anchor a
-    assert np.all(elems[~keep] == 0) and np.all(grad[~keep] == 0)
+    assert np.all(elems[~keep] == 0)
+    # the gradient kernel MULTIPLIES by the mask (loss_op.cu:98-101: ... * d_loss * (t != ignored_label)), so an ignored position is
+    # exactly 0 unless the unmasked expression itself is not finite — gamma = 0 with an adaptive target of 0 gives
+    # 0 * powf(0, -1) = NaN in the reference, and NaN * 0 stays NaN.  Everything else must be an exact zero.
+    unmasked = O.distill_grad(x, t, np.zeros_like(g), 3.0, **args)
+    ignored = grad[~keep]
+    assert np.all((ignored == 0) | (np.isnan(ignored) & ~np.isfinite(unmasked[~keep])))
     # changing the VALUE of a kept label (any class id, background) changes nothing: only `!= ignored_label` is read
     g2 = np.where(g != -1, 55, -1).astype(np.int32)
     _, elems2 = O.distill_loss(x, t, g2, 3.0, return_elements=True, **args)
-    assert np.array_equal(elems, elems2) and np.array_equal(grad, O.distill_grad(x, t, g2, 3.0, **args))
+    assert np.array_equal(elems, elems2) and np.array_equal(grad, O.distill_grad(x, t, g2, 3.0, **args), equal_nan=True)
     # another ignored_label value moves the mask with it
     _, elems3 = O.distill_loss(x, t, g, 3.0, return_elements=True, ignored_label=7, **args)
     assert np.all(elems3[np.repeat(g == 7, c, axis=1)] == 0)
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(shape_st, st.integers(0, 2 ** 20))
 def test_normaliser_clamp_scale_and_upstream_gradient_are_multipliers(shape, seed):
     n, a, c, h, w = shape
@@ -58,7 +65,7 @@ def test_normaliser_clamp_scale_and_upstream_gradient_are_multipliers(shape, see
     assert O.distill_loss(x, t, g, 1.0, scale=0.0, **args) == 0 and not O.distill_grad(x, t, g, 1.0, scale=0.0, **args).any()
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(st.lists(st.integers(1, 300), min_size=1, max_size=5), st.integers(0, 2 ** 20), st.sampled_from([1.0, 1.8, 2.0, 0.5]))
 def test_pow_sum_is_additive_over_inputs_in_input_order(sizes, seed, power):
     rng = np.random.default_rng(seed)
@@ -71,7 +78,7 @@ def test_pow_sum_is_additive_over_inputs_in_input_order(sizes, seed, power):
         assert abs(float(O.pow_sum(xs, 1.0)) - float(sum(x.astype(np.float64).sum() for x in xs))) <= 1e-5 * sum(sizes)
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(shape_st, st.integers(0, 2 ** 20))
 def test_focal_loss_label_semantics(shape, seed):
     n, a, c, h, w = shape
