@@ -109,3 +109,21 @@ def test_exchange_library_exports_every_declared_symbol():
     assert lib.sad_exchange_allreduce_async_f32(None, None, 0, None) == -1
     assert lib.sad_exchange_join(None, None) == -1
     assert lib.sad_exchange_world(None) == 0
+
+
+def test_exchange_fails_loudly_without_a_device_and_validates_the_copy_engine_form():
+    """No CPU path behind the exchange either: creating one where there is no CUDA device reports the CUDA error; the copy-engine
+    form validates its capacity; its capability query and the empty slot sum need neither a device nor NCCL."""
+    import torch
+    from sad_b200 import exchange
+    lib = exchange.lib()
+    out = C.c_void_p()
+    assert lib.sad_exchange_create_gather(None, 0, 1, 0, C.byref(out)) == -1 and b"capacity" in lib.sad_exchange_last_error()
+    assert lib.sad_exchange_gather_supported() in (0, 1)
+    assert lib.sad_exchange_slot_sum_f32(None, 0, 2, None, 0, None) == 0          # nothing to add
+    assert lib.sad_exchange_slot_sum_f32(None, 128, 2, None, 4, None) != 0         # null slots: cudaErrorInvalidValue, not a crash
+    assert lib.sad_exchange_gather_capacity(None) == 0 and lib.sad_exchange_gathered(None) == 0
+    if not torch.cuda.is_available():
+        rc = lib.sad_exchange_create(None, 0, 1, C.byref(out))
+        assert rc == -2 and not out.value, (rc, lib.sad_exchange_last_error())       # SAD_EXCHANGE_ERR_CUDA
+        assert lib.sad_exchange_last_error()
