@@ -66,3 +66,11 @@ def test_bench_default_line_includes_the_fp16_objects(monkeypatch):
         except SystemExit:
             pass
         assert seen["ns"].teacher_f16 is want and seen["ns"].gpus == 1 and seen["ns"].impl == "b200"
+        assert seen["ns"].exchange == "env"        # the exchange form is the environment's / the library default (ncclAllReduce buckets)
+    for form in ("allreduce", "gather"):
+        monkeypatch.setattr(sys, "argv", ["bench.py", "--exchange", form])
+        try:
+            bench.main()
+        except SystemExit:
+            pass
+        assert seen["ns"].exchange == form
