@@ -1,4 +1,7 @@
 #!/bin/bash
+# Build the variant library first (it is not kept in the tree):
+#   K=semi-supervised-adaptive-distillation_b200/csrc/kernels; mkdir -p variants; nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
+#     -Xcompiler -fPIC,-fvisibility=hidden,-fno-gnu-unique -w -DSAD_CONV_ROWS=4 -Iinclude -I$K -shared -o variants/libsad_b200_rows4.so $K/*.cu
 # r02s: A/B of the convolution's pixel tile: 8 rows x 32 (default build) against 4 rows x 32 (variants/libsad_b200_rows4.so, -DSAD_CONV_ROWS=4):
 # head forward / backward / whole head step at bs = 2 and bs = 16, then the convolution + head tests on the 4-row build.
 OUT=gpurun_out

@@ -1,4 +1,7 @@
 #!/bin/bash
+# Build the variant library first (it is not kept in the tree):
+#   K=semi-supervised-adaptive-distillation_b200/csrc/kernels; mkdir -p variants; nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
+#     -Xcompiler -fPIC,-fvisibility=hidden,-fno-gnu-unique -w -DSAD_CONV_RING_KB=224 -Iinclude -I$K -shared -o variants/libsad_b200_ring224.so $K/*.cu
 # r02u: A/B of the convolution operand ring: 192 KB (6 stages of the CTA-pair kernel, default build) against 224 KB (7 stages,
 # variants/libsad_b200_ring224.so, -DSAD_CONV_RING_KB=224): head forward / backward / whole head step at bs = 2 and 16, then the tests.
 OUT=gpurun_out
