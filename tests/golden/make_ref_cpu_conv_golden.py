@@ -51,7 +51,7 @@ def sample(v, limit=16384):
     return flat[::k]
 
 
-def run_reference(reflib, x, w, b, dy):
+def run_reference(reflib, x, w, b, dy, kernel=3, pad=1, stride=1):
     from sad_b200 import c2
     cpu = c2.DeviceOption(c2.CPU)
     ws = reflib.Workspace()
@@ -62,7 +62,7 @@ def run_reference(reflib, x, w, b, dy):
     if b is not None:
         ws.FeedBlob("b", b)
         ins.append("b")
-    fwd = c2.CreateOperator("Conv", ins, ["Y"], kernel=3, pad=1, stride=1, order="NCHW", device_option=cpu)
+    fwd = c2.CreateOperator("Conv", ins, ["Y"], kernel=kernel, pad=pad, stride=stride, order="NCHW", device_option=cpu)
     ws.RunOperatorOnce(fwd)
     # the gradient operator exactly as the reference's own gradient maker emits it (conv_gradient_op.cc:35-77)
     ws.CreateNet("name: \"g\"\n" + reflib.GetGradientDefs(fwd, ["dY"]).split("external_output")[0])

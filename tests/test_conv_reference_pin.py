@@ -76,6 +76,39 @@ def test_conv_oracle_matches_reference_cpu_operator_live(oracle, shape):
     _close(dx, ref["dx"], "dX")
 
 
+# The body's convolution geometries (detectron/lib/modeling/ResNet.py:88-129,157-278, FPN.py:94-249): 1x1
+# (bottleneck reduce / expand, FPN laterals), 1x1 stride 2 (STRIDE_1X1 bottlenecks and projection shortcuts), 3x3 stride 2 (ResNeXt
+# bottlenecks, FPN P6 / P7), 7x7 stride 2 pad 3 (the stem).  The oracle these pin is what a native body convolution is tested against.
+BODY_GEOMETRIES = [
+    # name, (n, cin, cout, h, w), kernel, pad, stride, bias
+    ("1x1", (2, 64, 48, 9, 14), 1, 0, 1, False),
+    ("1x1_lateral_bias", (1, 96, 32, 7, 12), 1, 0, 1, True),
+    ("1x1_s2", (2, 32, 64, 10, 15), 1, 0, 2, False),
+    ("3x3_s2", (1, 24, 40, 11, 16), 3, 1, 2, True),
+    ("7x7_s2_stem", (1, 3, 16, 23, 30), 7, 3, 2, False),
+]
+
+
+@pytest.mark.parametrize("name,shape,kernel,pad,stride,bias", BODY_GEOMETRIES, ids=[g[0] for g in BODY_GEOMETRIES])
+def test_conv_oracle_matches_reference_cpu_operator_on_body_geometries(oracle, name, shape, kernel, pad, stride, bias):
+    n, cin, cout, h, w_ = shape
+    lib = _reflib()
+    rng = np.random.default_rng(sum(shape) + 31 * kernel + stride)
+    x = rng.standard_normal((n, cin, h, w_)).astype(np.float32)
+    w = rng.standard_normal((cout, cin, kernel, kernel)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32) if bias else None
+    ho, wo = (h + 2 * pad - kernel) // stride + 1, (w_ + 2 * pad - kernel) // stride + 1
+    dy = rng.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    ref = gen.run_reference(lib, x, w, b, dy, kernel=kernel, pad=pad, stride=stride)
+    assert ref["y"].shape == (n, cout, ho, wo)
+    _close(oracle.conv2d_fwd(x, w, b, pad=pad, stride=stride), ref["y"], name + " Y")
+    dw, db, dx = oracle.conv2d_bwd(x, w, dy, pad=pad, stride=stride, need_dx=True)
+    _close(dw, ref["dw"], name + " dW")
+    _close(dx, ref["dx"], name + " dX")
+    if bias:
+        _close(db, ref["db"], name + " db")
+
+
 def test_reference_gradient_maker_emits_no_bias_for_two_input_conv():
     # conv_gradient_op.cc:56-71: a bias-less Conv gets ConvGradient(no_bias=1) -> {dW, dX}
     from sad_b200 import c2
